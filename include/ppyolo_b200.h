@@ -1,0 +1,133 @@
+/*
+ * ppyolo_b200.h -- C ABI of the B200-native PP-YOLO hot path (libppyolo_b200.so).
+ *
+ * Every entry point takes raw device pointers, explicit sizes/strides and a CUDA stream, allocates
+ * nothing, keeps no global state besides a launch counter, and returns a ppy_status (0 = ok, <0 = error;
+ * no exceptions cross this boundary).  Kernels are enqueued on `stream` and are NOT synchronised.
+ *
+ * The reference (miemie2013/Pytorch-PPYOLO) has no live C/FFI boundary on this path -- its only native
+ * extension, external/DCNv2 (`_ext`, src/vision.cpp:3-8, src/dcn_v2.h:9-144), is dead code
+ * (model/custom_layers.py:14-19, :102-105).  The entry points below are therefore what a binding of the
+ * reference's *Python* operators would call; each cites the reference operator it replaces.
+ *
+ * Activation layout: NHWC ("channels last"), element (n,h,w,c) at  base + ((n*H + h)*W + w)*ld + c,
+ * where ld >= C is the pixel stride in elements (lets a kernel read/write a channel slice of a wider
+ * concat buffer).  dtype is PPY_F32 or PPY_BF16.
+ */
+#ifndef PPYOLO_B200_H
+#define PPYOLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ppy_stream_t; /* cudaStream_t */
+
+enum ppy_status {
+  PPY_OK = 0,
+  PPY_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported size, misalignment) */
+  PPY_ERR_WORKSPACE = -2,   /* workspace too small */
+  PPY_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed; see ppy_last_cuda_error() */
+  PPY_ERR_UNSUPPORTED = -4  /* configuration not built (e.g. tcgen05 path on a non-sm_100 device) */
+};
+enum ppy_dtype { PPY_F32 = 0, PPY_BF16 = 1 };
+enum ppy_act { PPY_ACT_NONE = 0, PPY_ACT_RELU = 1, PPY_ACT_LEAKY = 2, PPY_ACT_MISH = 3 };
+
+int ppy_abi_version(void);
+const char* ppy_status_string(int status);
+int ppy_last_cuda_error(void);                 /* cudaError_t of the last failing call on this thread */
+long long ppy_kernel_launch_count(void);       /* kernels launched by this library since load */
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / glue (replace torch permute/cat/pool kernels on the path)
+ * ---------------------------------------------------------------------------------------------- */
+/* NCHW fp32 (the tensor Decode.predict uploads, model/decode_np.py:142-147) -> NHWC, channels
+ * [C, y_ld) zero-filled. */
+int ppy_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int w, int y_ld, int y_dtype, ppy_stream_t s);
+/* NHWC -> NCHW fp32 (module-level interop and tests). */
+int ppy_nhwc_to_nchw(const void* x, int x_ld, int x_dtype, float* y, int n, int c, int h, int w, ppy_stream_t s);
+/* MaxPool2d(3,2,1), model/resnet_vd.py:103. Output (h+1)/2 x (w+1)/2. */
+int ppy_maxpool3x3s2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
+/* AvgPool2d(2,2,0) of the "vd" shortcut, model/resnet_vd.py:30. */
+int ppy_avgpool2x2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
+/* SPP, model/custom_layers.py:275-290: y[..., 0:c]=x, [c:2c]=maxpool5, [2c:3c]=maxpool9, [3c:4c]=maxpool13. */
+int ppy_spp(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
+/* nearest x2 upsample (model/head.py:362) written into a channel slice: y is [n,2h,2w,*]. */
+int ppy_upsample2x(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
+/* strided channel-slice copy (concat), rows = n*h*w pixels. */
+int ppy_copy_channels(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, ppy_stream_t s);
+/* CoordConv channels (model/custom_layers.py:256-272): y[h,w,0]=x coord in [-1,1], y[h,w,1]=y coord,
+ * channels [2, y_ld) zero. One image, NHWC. */
+int ppy_coord_channels(void* y, int y_ld, int h, int w, int dtype, ppy_stream_t s);
+/* elementwise activation in place on a dense buffer (Mish etc.; module-level only). */
+int ppy_activation(void* x, long long count, int act, int dtype, ppy_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * conv + folded norm + activation (+ residual), Conv2dUnit.forward model/custom_layers.py:243-253,
+ * block residual add+ReLU model/resnet_vd.py:54-56/:84-86, DCNv2.forward model/custom_layers.py:551-677
+ * ---------------------------------------------------------------------------------------------- */
+/* OIHW fp32 conv weight -> packed K-major [cout_pad][k_pad] rows, K index = (kh*KW + kw)*cin_pad + c,
+ * zero padded; channels [c_begin, c_begin+c_count) of the source are taken (CoordConv weight split). */
+int ppy_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int kh, int kw, int c_begin, int c_count,
+                         void* packed, int cout_pad, int cin_pad, int k_pad, int dtype, ppy_stream_t s);
+
+typedef struct ppy_conv_params {
+  const void* x;            /* input NHWC, dtype = in_dtype */
+  int x_ld;
+  int n, h, w, cin;         /* cin = channels read per tap (multiple of 8) */
+  const void* weight;       /* packed by ppy_pack_conv_weight, same dtype as x */
+  int cout, kh, kw, stride, pad;
+  int k_pad;                /* row length of packed weight (multiple of 64) */
+  int cout_pad;             /* rows of packed weight */
+  const float* scale;       /* [cout] folded norm scale (or 1) */
+  const float* shift;       /* [cout] folded norm shift / bias */
+  const float* bias_map;    /* optional [ho*wo][cout] fp32 added to the accumulator (CoordConv fold) */
+  const void* residual;     /* optional NHWC [n,ho,wo,cout], dtype = out_dtype, added before act */
+  int res_ld;
+  int act;                  /* ppy_act */
+  void* y;                  /* output NHWC */
+  int y_ld;
+  int out_dtype;            /* PPY_F32 or PPY_BF16 */
+  int upsample2x;           /* 1: write every output pixel to its 2x2 block of an [n,2ho,2wo,*] buffer */
+  const float* offset_mask; /* non-null => DCNv2: [n,ho,wo,om_ld] fp32, ch 2t=dy 2t+1=dx, 18+t=mask logit */
+  int om_ld;
+} ppy_conv_params;
+
+/* fp32 SIMT implicit GEMM (the 1e-4 parity path).  x/weight/residual fp32. */
+int ppy_conv_f32(const ppy_conv_params* p, ppy_stream_t s);
+/* bf16 tcgen05 implicit GEMM, fp32 accumulate in TMEM, TMA-fed weights (the throughput path). */
+int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s);
+/* 1 when the tcgen05 path can run on the current device (compute capability 10.x). */
+int ppy_conv_bf16_supported(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * head post-processing
+ * ---------------------------------------------------------------------------------------------- */
+/* get_iou_aware_score, model/head.py:138-141, on an NHWC fp32 head output: [.., A*(6+C)] -> [.., A*(5+C)]. */
+int ppy_iou_aware_score(const float* x, int x_ld, float* y, int y_ld, long long pixels, int an_num, int num_classes,
+                        double factor, ppy_stream_t s);
+/* Fused get_iou_aware_score + yolo_box (model/head.py:21-80) for one scale.
+ * head: NHWC fp32 [n,size,size,ld]; anchors: 2*an_num host floats; im_size: device [n,2] = (h,w).
+ * boxes [n,total_boxes,4], scores [n,total_boxes,C]; this scale fills rows [box_offset, box_offset+size*size*an). */
+int ppy_yolo_decode(const float* head, int ld, int n, int size, int an_num, int num_classes, const float* anchors,
+                    int stride, double scale_x_y, const float* im_size, int clip_bbox, int iou_aware, double factor,
+                    float* boxes, float* scores, int box_offset, int total_boxes, ppy_stream_t s);
+/* jaccard, model/matrix_nms.py:33-47. */
+int ppy_pairwise_iou(const float* a, int na, const float* b, int nb, float* out, ppy_stream_t s);
+
+/* Batched Matrix-NMS, model/matrix_nms.py:102-151 applied to every image (replaces the loop at
+ * model/head.py:462-464).  out: [n,keep_top_k,6] rows [label,score,x0,y0,x1,y1]; counts: [n] int32 rows
+ * valid per image (0 => the reference's [[-1]*6] sentinel; <0 => candidate overflow). */
+int ppy_matrix_nms_workspace_bytes(int n, int num_boxes, int num_classes, size_t* bytes);
+int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
+                           float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
+                           int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
+                           size_t workspace_bytes, ppy_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPYOLO_B200_H */

@@ -1,0 +1,141 @@
+// Head post-processing for sm_100a: IoU-aware objectness fusion + YOLO box decode + score product in one
+// pass over the NHWC fp32 head output (reference model/head.py:21-141).  HBM-bound: reads
+// (A*(6+C))*4 B per pixel once, writes boxes (16 B) and C scores per (pixel, anchor); one warp per
+// (pixel, anchor) so the C-wide score row is a single coalesced store.
+//
+// The arithmetic mirrors the reference's fp32 operation order (explicit _rn intrinsics keep nvcc from
+// contracting mul+add into FMA), so results differ from the CPU path only by the libm ulp of
+// exp/log/pow.
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace ppy {
+namespace {
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+__device__ __forceinline__ float clampf_ref(float v, float lo, float hi) {  // torch.clamp, NaN propagates
+  if (v != v) return v;
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// _de_sigmoid (head.py:97-109) of obj^(1-f) * ioup^f (head.py:125)
+__device__ __forceinline__ float fused_obj_logit(float t_obj, float t_ioup, float e_obj, float e_iou) {
+  float obj = sigmoidf_ref(t_obj);
+  float ip = sigmoidf_ref(t_ioup);
+  float v = __fmul_rn(powf(obj, e_obj), powf(ip, e_iou));
+  const float eps = 1e-7f, inv_eps = 1.f / 1e-7f;
+  v = clampf_ref(v, eps, inv_eps);
+  v = __fsub_rn(__fdiv_rn(1.f, v), 1.f);
+  v = clampf_ref(v, eps, inv_eps);
+  return -logf(v);
+}
+
+struct DecodeArgs {
+  const float* head; int ld; int n; int size; int an; int nc;
+  float aw[4]; float ah[4];
+  float stride; float sxy; float sxy_off;  // (sxy - 1) * 0.5 rounded to fp32 like the reference's python float
+  const float* im_size; int clip; int iou_aware; float e_obj; float e_iou;
+  float* boxes; float* scores; int box_offset; int total_boxes;
+};
+
+__global__ void __launch_bounds__(256) yolo_decode_kernel(DecodeArgs p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long per_img = (long long)p.size * p.size * p.an;
+  if (warp >= per_img * p.n) return;
+  const int img = (int)(warp / per_img);
+  const int r = (int)(warp % per_img);
+  const int a = r % p.an;
+  const int pix = r / p.an;
+  const int gx = pix % p.size, gy = pix / p.size;
+  const float* px = p.head + ((long long)img * p.size * p.size + pix) * p.ld;
+  const int base = (p.iou_aware ? p.an : 0) + a * (5 + p.nc);
+  float t_obj = __ldg(px + base + 4);
+  float conf;
+  if (p.iou_aware) conf = sigmoidf_ref(fused_obj_logit(t_obj, __ldg(px + a), p.e_obj, p.e_iou));
+  else conf = sigmoidf_ref(t_obj);
+  const long long row = (long long)img * p.total_boxes + p.box_offset + r;
+  float* srow = p.scores + row * p.nc;
+  for (int c = lane; c < p.nc; c += 32) srow[c] = __fmul_rn(conf, sigmoidf_ref(__ldg(px + base + 5 + c)));
+  if (lane == 0) {
+    float tx = __ldg(px + base), ty = __ldg(px + base + 1), tw = __ldg(px + base + 2), th = __ldg(px + base + 3);
+    // (scale_x_y * sigmoid(t) + grid - (scale_x_y - 1) * 0.5) * stride      head.py:40
+    float cx = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(tx)), (float)gx), p.sxy_off), p.stride);
+    float cy = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(ty)), (float)gy), p.sxy_off), p.stride);
+    float bw = __fmul_rn(expf(tw), p.aw[a]);                                 // head.py:44
+    float bh = __fmul_rn(expf(th), p.ah[a]);
+    float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
+    float x0 = __fsub_rn(cx, hw), y0 = __fsub_rn(cy, hh), x1 = __fadd_rn(cx, hw), y1 = __fadd_rn(cy, hh);
+    const float im_h = __ldg(p.im_size + 2 * img), im_w = __ldg(p.im_size + 2 * img + 1);
+    const float fs = (float)p.size;
+    x0 = __fmul_rn(__fdiv_rn(__fdiv_rn(x0, fs), p.stride), im_w);            // head.py:66-67
+    y0 = __fmul_rn(__fdiv_rn(__fdiv_rn(y0, fs), p.stride), im_h);
+    x1 = __fmul_rn(__fdiv_rn(__fdiv_rn(x1, fs), p.stride), im_w);
+    y1 = __fmul_rn(__fdiv_rn(__fdiv_rn(y1, fs), p.stride), im_h);
+    if (p.clip) {                                                            // head.py:73-76
+      x0 = x0 < 0.f ? __fmul_rn(x0, 0.f) : x0;
+      y0 = y0 < 0.f ? __fmul_rn(y0, 0.f) : y0;
+      x1 = x1 > im_w ? im_w : x1;
+      y1 = y1 > im_h ? im_h : y1;
+    }
+    reinterpret_cast<float4*>(p.boxes)[row] = make_float4(x0, y0, x1, y1);
+  }
+}
+
+__global__ void iou_aware_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ y, int y_ld, long long pixels,
+                                 int an, int nc, float e_obj, float e_iou) {
+  const int per = 5 + nc;
+  const long long total = pixels * an * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i / (an * per);
+    int rem = (int)(i % (an * per));
+    int a = rem / per, f = rem % per;
+    const float* px = x + pix * x_ld;
+    float v = __ldg(px + an + rem);
+    if (f == 4) v = fused_obj_logit(v, __ldg(px + a), e_obj, e_iou);
+    y[pix * y_ld + rem] = v;
+  }
+}
+
+}  // namespace
+}  // namespace ppy
+
+extern "C" {
+
+int ppy_yolo_decode(const float* head, int ld, int n, int size, int an_num, int num_classes, const float* anchors,
+                    int stride, double scale_x_y, const float* im_size, int clip_bbox, int iou_aware, double factor,
+                    float* boxes, float* scores, int box_offset, int total_boxes, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(head && anchors && im_size && boxes && scores);
+  PPY_REQUIRE(n > 0 && size > 0 && an_num > 0 && an_num <= 4 && num_classes > 0 && stride > 0);
+  PPY_REQUIRE(ld >= an_num * (num_classes + (iou_aware ? 6 : 5)));
+  PPY_REQUIRE(box_offset >= 0 && box_offset + size * size * an_num <= total_boxes);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
+  DecodeArgs p;
+  p.head = head; p.ld = ld; p.n = n; p.size = size; p.an = an_num; p.nc = num_classes;
+  for (int a = 0; a < 4; ++a) { p.aw[a] = a < an_num ? anchors[2 * a] : 0.f; p.ah[a] = a < an_num ? anchors[2 * a + 1] : 0.f; }
+  p.stride = (float)stride; p.sxy = (float)scale_x_y;
+  p.sxy_off = (float)((scale_x_y - 1.0) * 0.5);
+  p.im_size = im_size; p.clip = clip_bbox; p.iou_aware = iou_aware;
+  p.e_obj = (float)(1.0 - factor); p.e_iou = (float)factor;   // python-float exponents of head.py:125
+  p.boxes = boxes; p.scores = scores; p.box_offset = box_offset; p.total_boxes = total_boxes;
+  long long warps = (long long)n * size * size * an_num;
+  yolo_decode_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, as_stream(s)>>>(p);
+  return check_launch();
+}
+
+int ppy_iou_aware_score(const float* x, int x_ld, float* y, int y_ld, long long pixels, int an_num, int num_classes,
+                        double factor, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(x && y && pixels > 0 && an_num > 0 && num_classes > 0);
+  PPY_REQUIRE(x_ld >= an_num * (num_classes + 6) && y_ld >= an_num * (num_classes + 5));
+  long long total = pixels * an_num * (5 + num_classes);
+  long long blocks = ceil_div(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  iou_aware_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(x, x_ld, y, y_ld, pixels, an_num, num_classes,
+                                                              (float)(1.0 - factor), (float)factor);
+  return check_launch();
+}
+
+}  // extern "C"

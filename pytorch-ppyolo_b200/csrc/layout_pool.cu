@@ -1,0 +1,284 @@
+// HBM-bound glue kernels on NHWC activations: layout conversion, pooling, SPP, nearest upsample,
+// channel-slice copies (concat), CoordConv channels.  All move 16-byte vectors along the channel
+// dimension (8 bf16 / 4 fp32) so every warp access is a run of full 32-byte sectors; grids are
+// grid-stride loops capped at a few waves of the 148 SMs.
+#include <float.h>
+#include "common.cuh"
+
+namespace ppy {
+namespace {
+
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float (&v)[Vec16<T>::N]) {
+  uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < Vec16<T>::N; ++i) v[i] = to_f<T>(e[i]);
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* p, const float (&v)[Vec16<T>::N]) {
+  uint4 raw;
+  T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < Vec16<T>::N; ++i) e[i] = from_f<T>(v[i]);
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+
+inline unsigned grid_for(long long work, int threads) {
+  long long b = ceil_div(work, threads);
+  long long cap = 148ll * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int n, int c, int h, int w, int ld) {
+  const long long pixels = (long long)n * h * w;
+  const long long hw = (long long)h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, rem = i % hw;
+    const float* src = x + img * c * hw + rem;
+    T* dst = y + i * ld;
+    for (int ch = 0; ch < ld; ++ch) dst[ch] = from_f<T>(ch < c ? __ldg(src + ch * hw) : 0.f);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ld, float* __restrict__ y, int n, int c, int h, int w) {
+  const long long total = (long long)n * c * h * w;
+  const long long hw = (long long)h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / (c * hw);
+    const int ch = (int)((i / hw) % c);
+    const long long rem = i % hw;
+    y[i] = to_f<T>(x[(img * hw + rem) * ld + ch]);
+  }
+}
+
+// generic window op: MODE 0 = max 3x3 s2 p1, 1 = avg 2x2 s2 p0
+template <typename T, int MODE>
+__global__ void pool_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int n, int h, int w, int c,
+                            int ho, int wo) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = c / V;
+  const long long total = (long long)n * ho * wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long p = i / cv;
+    const int ox = (int)(p % wo); p /= wo;
+    const int oy = (int)(p % ho);
+    const int img = (int)(p / ho);
+    float acc[V];
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = -FLT_MAX;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int iy = oy * 2 + dy;
+        if (iy < 0 || iy >= h) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int ix = ox * 2 + dx;
+          if (ix < 0 || ix >= w) continue;
+          float t[V];
+          load_vec<T>(x + (((long long)img * h + iy) * w + ix) * x_ld + v * V, t);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = fmaxf(acc[k], t[k]);
+        }
+      }
+    } else {
+      float a[V], b[V], cc[V], d[V];
+      const T* base = x + (((long long)img * h + oy * 2) * w + ox * 2) * x_ld + v * V;
+      load_vec<T>(base, a);
+      load_vec<T>(base + x_ld, b);
+      load_vec<T>(base + (long long)w * x_ld, cc);
+      load_vec<T>(base + (long long)w * x_ld + x_ld, d);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a[k], b[k]), cc[k]), d[k]), 4.f);
+    }
+    store_vec<T>(y + (((long long)img * ho + oy) * wo + ox) * y_ld + v * V, acc);
+  }
+}
+
+// SPP: one thread per (pixel, 16-byte channel vector); max over nested 5/9/13 windows in a single sweep
+// of the 13x13 neighbourhood (each tap is classified into the smallest window containing it).
+template <typename T>
+__global__ void spp_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int n, int h, int w, int c) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = c / V;
+  const long long total = (long long)n * h * w * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long p = i / cv;
+    const int ox = (int)(p % w); p /= w;
+    const int oy = (int)(p % h);
+    const int img = (int)(p / h);
+    float m5[V], m9[V], m13[V], ctr[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { m5[k] = -FLT_MAX; m9[k] = -FLT_MAX; m13[k] = -FLT_MAX; }
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int iy = oy + dy;
+      if (iy < 0 || iy >= h) continue;
+      const int ady = dy < 0 ? -dy : dy;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int ix = ox + dx;
+        if (ix < 0 || ix >= w) continue;
+        const int adx = dx < 0 ? -dx : dx;
+        const int r = ady > adx ? ady : adx;
+        float t[V];
+        load_vec<T>(x + (((long long)img * h + iy) * w + ix) * x_ld + v * V, t);
+        if (r <= 2) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) m5[k] = fmaxf(m5[k], t[k]);
+        } else if (r <= 4) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) m9[k] = fmaxf(m9[k], t[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) m13[k] = fmaxf(m13[k], t[k]);
+        }
+        if (r == 0) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) ctr[k] = t[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) { m9[k] = fmaxf(m9[k], m5[k]); m13[k] = fmaxf(m13[k], m9[k]); }
+    T* dst = y + (((long long)img * h + oy) * w + ox) * y_ld + v * V;
+    store_vec<T>(dst, ctr);
+    store_vec<T>(dst + c, m5);
+    store_vec<T>(dst + 2 * c, m9);
+    store_vec<T>(dst + 3 * c, m13);
+  }
+}
+
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int n, int h, int w, int c) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = c / V;
+  const int ho = 2 * h, wo = 2 * w;
+  const long long total = (long long)n * ho * wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long p = i / cv;
+    const int ox = (int)(p % wo); p /= wo;
+    const int oy = (int)(p % ho);
+    const int img = (int)(p / ho);
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (((long long)img * h + oy / 2) * w + ox / 2) * x_ld + v * V));
+    *reinterpret_cast<uint4*>(y + (((long long)img * ho + oy) * wo + ox) * y_ld + v * V) = raw;
+  }
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, long long rows, int c) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = c / V;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const long long r = i / cv;
+    *reinterpret_cast<uint4*>(y + r * y_ld + v * V) = __ldg(reinterpret_cast<const uint4*>(x + r * x_ld + v * V));
+  }
+}
+
+template <typename T>
+__global__ void coord_kernel(T* __restrict__ y, int ld, int h, int w) {
+  const int total = h * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ix = i % w, iy = i / w;
+    // arange / (w - 1) * 2.0 - 1 in fp32, custom_layers.py:267-268
+    float cx = __fsub_rn(__fmul_rn(__fdiv_rn((float)ix, (float)(w - 1)), 2.f), 1.f);
+    float cy = __fsub_rn(__fmul_rn(__fdiv_rn((float)iy, (float)(h - 1)), 2.f), 1.f);
+    T* dst = y + (long long)i * ld;
+    dst[0] = from_f<T>(cx);
+    dst[1] = from_f<T>(cy);
+    for (int k = 2; k < ld; ++k) dst[k] = from_f<T>(0.f);
+  }
+}
+
+template <typename T>
+__global__ void activation_kernel(T* __restrict__ x, long long count, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    x[i] = from_f<T>(apply_act(to_f<T>(x[i]), act));
+}
+
+inline bool vec_ok(const void* p, int ld, int c, int dtype) {
+  const int v = 16 / dtype_size(dtype);
+  return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % v == 0 && c % v == 0 && c > 0 && ld >= c;
+}
+
+}  // namespace
+}  // namespace ppy
+
+#define PPY_DISPATCH(dtype, ...)                                  \
+  if ((dtype) == PPY_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+  else if ((dtype) == PPY_F32) { using T = float; __VA_ARGS__ }     \
+  else return PPY_ERR_INVALID;
+
+extern "C" {
+using namespace ppy;
+
+int ppy_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int w, int y_ld, int y_dtype, ppy_stream_t s) {
+  PPY_REQUIRE(x && y && n > 0 && c > 0 && h > 0 && w > 0 && y_ld >= c);
+  const long long pixels = (long long)n * h * w;
+  PPY_DISPATCH(y_dtype, nchw_to_nhwc_kernel<T><<<grid_for(pixels, 256), 256, 0, as_stream(s)>>>(x, (T*)y, n, c, h, w, y_ld);)
+  return check_launch();
+}
+
+int ppy_nhwc_to_nchw(const void* x, int x_ld, int x_dtype, float* y, int n, int c, int h, int w, ppy_stream_t s) {
+  PPY_REQUIRE(x && y && n > 0 && c > 0 && h > 0 && w > 0 && x_ld >= c);
+  const long long total = (long long)n * c * h * w;
+  PPY_DISPATCH(x_dtype, nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, y, n, c, h, w);)
+  return check_launch();
+}
+
+int ppy_maxpool3x3s2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(n > 0 && h > 0 && w > 0 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype));
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  const long long total = (long long)n * ho * wo * (c / (16 / dtype_size(dtype)));
+  PPY_DISPATCH(dtype, pool_kernel<T, 0><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c, ho, wo);)
+  return check_launch();
+}
+
+int ppy_avgpool2x2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(n > 0 && h > 1 && w > 1 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype));
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * (c / (16 / dtype_size(dtype)));
+  PPY_DISPATCH(dtype, pool_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c, ho, wo);)
+  return check_launch();
+}
+
+int ppy_spp(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(n > 0 && h > 0 && w > 0 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype) && y_ld >= 4 * c);
+  const long long total = (long long)n * h * w * (c / (16 / dtype_size(dtype)));
+  PPY_DISPATCH(dtype, spp_kernel<T><<<grid_for(total, 128), 128, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c);)
+  return check_launch();
+}
+
+int ppy_upsample2x(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(n > 0 && h > 0 && w > 0 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype));
+  const long long total = (long long)n * h * w * 4 * (c / (16 / dtype_size(dtype)));
+  PPY_DISPATCH(dtype, upsample2x_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c);)
+  return check_launch();
+}
+
+int ppy_copy_channels(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(rows > 0 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype));
+  const long long total = rows * (c / (16 / dtype_size(dtype)));
+  PPY_DISPATCH(dtype, copy_channels_kernel<T><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, rows, c);)
+  return check_launch();
+}
+
+int ppy_coord_channels(void* y, int y_ld, int h, int w, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(y && y_ld >= 2 && h > 1 && w > 1);
+  PPY_DISPATCH(dtype, coord_kernel<T><<<grid_for((long long)h * w, 128), 128, 0, as_stream(s)>>>((T*)y, y_ld, h, w);)
+  return check_launch();
+}
+
+int ppy_activation(void* x, long long count, int act, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(x && count > 0 && act >= PPY_ACT_NONE && act <= PPY_ACT_MISH);
+  PPY_DISPATCH(dtype, activation_kernel<T><<<grid_for(count, 256), 256, 0, as_stream(s)>>>((T*)x, count, act);)
+  return check_launch();
+}
+
+}  // extern "C"

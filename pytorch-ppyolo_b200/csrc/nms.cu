@@ -1,0 +1,394 @@
+// Batched Matrix-NMS for sm_100a (reference model/matrix_nms.py:51-151, looped per image at
+// model/head.py:462-464).  Whole batch in three launches, no host sync:
+//
+//   1. nms_hist_kernel    (HBM-bound scan)  per-image histogram of candidate scores (> score_threshold),
+//                                           binned on (float_bits - bits(threshold)) >> shift
+//   2. nms_collect_kernel (HBM-bound scan)  every CTA re-derives the cutoff bin that holds the
+//                                           nms_top_k-th best score from the histogram, then appends all
+//                                           candidates in bins >= cutoff as 64-bit keys
+//                                           (score_bits << 32 | ~flat_index)
+//   3. nms_matrix_kernel  (one CTA / image) bitonic sort of the keys in shared memory -> top nms_top_k;
+//                                           boxes staged in shared memory; warp-cooperative upper-
+//                                           triangular IoU + same-label test (the n x n matrix is never
+//                                           materialised); column max -> compensate, column min -> decay;
+//                                           post-threshold; second sort; top keep_top_k rows written.
+//
+// Ordering: keys sort by score descending then (box, class) flat index ascending, i.e. exactly a stable
+// descending sort of the reference's row-major nonzero() order (matrix_nms.py:115-125).
+// NaN semantics follow torch: min/max/clamp propagate NaN, NaN*0 = NaN, comparisons with NaN are false.
+#include <math_constants.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace ppy {
+namespace {
+
+constexpr int kBins = 4096;           // histogram bins per image
+constexpr int kCap = 8192;            // max collected candidates per image (keys in shared memory)
+constexpr int kMaxN = 1024;           // max boxes entering the n x n stage
+constexpr int kScanThreads = 256;
+constexpr int kMatrixThreads = 1024;
+
+struct Workspace {
+  unsigned int* hist;     // [n][kBins]
+  unsigned int* count;    // [n] collected keys
+  unsigned long long* keys;  // [n][kCap]
+};
+
+__device__ __forceinline__ int score_bin(float s, unsigned int thr_bits, int shift) {
+  // s > threshold > 0 here, so the bit pattern is monotonic in s
+  unsigned int d = (__float_as_uint(s) - thr_bits) >> shift;
+  return d < (unsigned)kBins ? (int)d : kBins - 1;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_hist_kernel(const float* __restrict__ scores, long long per_image, long long chunk, float thr,
+                unsigned int thr_bits, int shift, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[kBins];
+  for (int i = threadIdx.x; i < kBins; i += kScanThreads) sh[i] = 0;
+  __syncthreads();
+  const int img = blockIdx.y;
+  const float* base = scores + (long long)img * per_image;
+  long long lo = (long long)blockIdx.x * chunk;
+  long long hi = lo + chunk < per_image ? lo + chunk : per_image;
+  const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (chunk % 4 == 0);
+  if (vec) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    long long hi4 = hi / 4;
+    for (long long i = lo / 4 + threadIdx.x; i < hi4; i += kScanThreads) {
+      float4 v = __ldg(b4 + i);
+      if (v.x > thr) atomicAdd(&sh[score_bin(v.x, thr_bits, shift)], 1u);
+      if (v.y > thr) atomicAdd(&sh[score_bin(v.y, thr_bits, shift)], 1u);
+      if (v.z > thr) atomicAdd(&sh[score_bin(v.z, thr_bits, shift)], 1u);
+      if (v.w > thr) atomicAdd(&sh[score_bin(v.w, thr_bits, shift)], 1u);
+    }
+    lo = hi4 * 4;  // scalar tail (only the last chunk can have one)
+  }
+  for (long long i = lo + threadIdx.x; i < hi; i += kScanThreads) {
+    float v = __ldg(base + i);
+    if (v > thr) atomicAdd(&sh[score_bin(v, thr_bits, shift)], 1u);
+  }
+  __syncthreads();
+  unsigned int* gh = hist + (long long)img * kBins;
+  for (int i = threadIdx.x; i < kBins; i += kScanThreads)
+    if (sh[i]) atomicAdd(&gh[i], sh[i]);
+}
+
+// Cutoff bin: the largest bin b such that count(bins >= b) >= want; 0 if fewer candidates than `want`.
+__device__ int find_cutoff_bin(const unsigned int* __restrict__ gh, int want, unsigned int* sh /*kBins*/,
+                               unsigned int* part /*blockDim/32 + 1*/) {
+  const int T = blockDim.x;
+  const int per = kBins / T;  // bins per thread, contiguous, thread 0 owns the TOP bins
+  unsigned int local = 0;
+  for (int k = 0; k < per; ++k) {
+    int bin = kBins - 1 - (threadIdx.x * per + k);
+    unsigned int v = gh[bin];
+    sh[bin] = v;
+    local += v;
+  }
+  // inclusive scan of `local` over threads (top bins first)
+  unsigned int incl = local;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) part[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned int v = lane < (T >> 5) ? part[lane] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    part[lane] = v;  // inclusive warp totals
+  }
+  __syncthreads();
+  unsigned int before = incl - local + (wid ? part[wid - 1] : 0);  // candidates in bins above this thread's
+  __shared__ int s_cut;
+  if (threadIdx.x == 0) s_cut = 0;
+  __syncthreads();
+  if (before < (unsigned)want && before + local >= (unsigned)want) {
+    unsigned int acc = before;
+    for (int k = 0; k < per; ++k) {
+      int bin = kBins - 1 - (threadIdx.x * per + k);
+      acc += sh[bin];
+      if (acc >= (unsigned)want) { s_cut = bin; break; }
+    }
+  }
+  __syncthreads();
+  return s_cut;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_collect_kernel(const float* __restrict__ scores, long long per_image, long long chunk, float thr,
+                   unsigned int thr_bits, int shift, int want, const unsigned int* __restrict__ hist, unsigned int* __restrict__ count,
+                   unsigned long long* __restrict__ keys) {
+  __shared__ unsigned int sh[kBins];
+  __shared__ unsigned int part[33];
+  const int img = blockIdx.y;
+  const int cut = find_cutoff_bin(hist + (long long)img * kBins, want, sh, part);
+  const float* base = scores + (long long)img * per_image;
+  unsigned long long* out = keys + (long long)img * kCap;
+  unsigned int* cnt = count + img;
+  long long lo = (long long)blockIdx.x * chunk;
+  long long hi = lo + chunk < per_image ? lo + chunk : per_image;
+  auto emit = [&](float v, long long idx) {
+    if (v > thr && score_bin(v, thr_bits, shift) >= cut) {
+      unsigned int slot = atomicAdd(cnt, 1u);
+      if (slot < (unsigned)kCap)
+        out[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)idx);
+    }
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (chunk % 4 == 0);
+  if (vec) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+    long long hi4 = hi / 4;
+    for (long long i = lo / 4 + threadIdx.x; i < hi4; i += kScanThreads) {
+      float4 v = __ldg(b4 + i);
+      emit(v.x, 4 * i); emit(v.y, 4 * i + 1); emit(v.z, 4 * i + 2); emit(v.w, 4 * i + 3);
+    }
+    lo = hi4 * 4;
+  }
+  for (long long i = lo + threadIdx.x; i < hi; i += kScanThreads) emit(__ldg(base + i), i);
+}
+
+// descending bitonic sort of `len` (power of two) 64-bit keys in shared memory
+__device__ void bitonic_sort_desc(unsigned long long* k, int len) {
+  for (int size = 2; size <= len; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        unsigned long long a = k[lo], b = k[hi];
+        if ((a < b) == desc) { k[lo] = b; k[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fminf(a, b); }
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fmaxf(a, b); }
+__device__ __forceinline__ float clamp_min0(float v) { return v < 0.f ? 0.f : v; }  // torch.clamp(min=0): NaN stays NaN
+
+// jaccard of two xyxy boxes with exactly the reference's fp32 operation order (matrix_nms.py:15-47)
+__device__ __forceinline__ float box_iou(const float4 a, const float4 b) {
+  float iw = clamp_min0(__fsub_rn(nan_min(a.z, b.z), nan_max(a.x, b.x)));
+  float ih = clamp_min0(__fsub_rn(nan_min(a.w, b.w), nan_max(a.y, b.y)));
+  float inter = __fmul_rn(iw, ih);
+  float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  return __fdiv_rn(inter, uni);
+}
+
+__global__ void __launch_bounds__(kMatrixThreads)
+nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classes, const unsigned int* __restrict__ count,
+                  const unsigned long long* __restrict__ keys, int nms_top_k, int keep_top_k, float post_thr,
+                  int use_gaussian, float sigma, float* __restrict__ out, int* __restrict__ counts) {
+  extern __shared__ unsigned long long s_keys[];           // kCap keys, later reused for the second sort
+  __shared__ float4 s_box[kMaxN];
+  __shared__ float s_score[kMaxN];
+  __shared__ int s_label[kMaxN];
+  __shared__ float s_comp[kMaxN];
+  __shared__ float s_new[kMaxN];
+  __shared__ int s_nan_from;   // largest i with NaN compensate (poisons every column j <= i), -1 if none
+  __shared__ int s_kept;
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMatrixThreads >> 5;
+  const unsigned int total = count[img];
+  float* my_out = out + (long long)img * keep_top_k * 6;
+  if (total > (unsigned)kCap) {   // cutoff bin too crowded (mass ties) -- flagged, see DESIGN.md
+    if (tid == 0) counts[img] = -2;
+    return;
+  }
+  const int m = (int)total;
+  if (m == 0) { if (tid == 0) counts[img] = 0; return; }
+  int len = 1; while (len < m) len <<= 1;
+  const unsigned long long* gk = keys + (long long)img * kCap;
+  for (int i = tid; i < len; i += kMatrixThreads) s_keys[i] = i < m ? gk[i] : 0ull;
+  bitonic_sort_desc(s_keys, len);
+  int n = m;
+  if (nms_top_k > 0 && n > nms_top_k) n = nms_top_k;
+  if (n > kMaxN) { if (tid == 0) counts[img] = -3; return; }
+  if (tid == 0) { s_nan_from = -1; s_kept = 0; }
+  const float4* gb = reinterpret_cast<const float4*>(boxes) + (long long)img * num_boxes;
+  for (int i = tid; i < n; i += kMatrixThreads) {
+    unsigned long long k = s_keys[i];
+    unsigned int flat = 0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull);
+    s_score[i] = __uint_as_float((unsigned int)(k >> 32));
+    s_label[i] = (int)(flat % (unsigned)num_classes);
+    s_box[i] = __ldg(gb + flat / (unsigned)num_classes);
+  }
+  __syncthreads();
+  // compensate[j] = max_i (iou*same)[i][j] over the strict upper triangle (matrix_nms.py:67-78); warp per column
+  for (int j = wid; j < n; j += nwarps) {
+    const float4 bj = s_box[j];
+    const int lj = s_label[j];
+    float mx = 0.f;
+    for (int i = lane; i < j; i += 32) {
+      float v = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
+      mx = nan_max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+      s_comp[j] = mx;
+      if (mx != mx) atomicMax(&s_nan_from, j);
+    }
+  }
+  __syncthreads();
+  // decay[j] = min_i f(d[i][j]) / f(compensate[i])  (:85-93).  Rows i >= j have d = 0 and contribute
+  // 1/f(comp_i) >= 1 >= row 0's term, so only their NaNs matter (s_nan_from); row i < j evaluated exactly.
+  const int nan_from = s_nan_from;
+  const float neg_sigma = -1.f * sigma;
+  for (int j = wid; j < n; j += nwarps) {
+    const float4 bj = s_box[j];
+    const int lj = s_label[j];
+    float mn = CUDART_INF_F;
+    for (int i = lane; i < j; i += 32) {
+      float d = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
+      float c = s_comp[i];
+      float e;
+      if (use_gaussian) e = __fdiv_rn(expf(__fmul_rn(neg_sigma, __fmul_rn(d, d))), expf(__fmul_rn(neg_sigma, __fmul_rn(c, c))));
+      else e = __fdiv_rn(__fsub_rn(1.f, d), __fsub_rn(1.f, c));
+      mn = nan_min(mn, e);
+    }
+    for (int o = 16; o > 0; o >>= 1) mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) {
+      // rows i >= j: term (f(0)/f(comp_i)); row j itself always exists
+      float cj = s_comp[j];
+      float self = use_gaussian ? __fdiv_rn(1.f, expf(__fmul_rn(neg_sigma, __fmul_rn(cj, cj)))) : __fdiv_rn(1.f, __fsub_rn(1.f, cj));
+      mn = nan_min(mn, self);   // j == 0: comp[0] == 0 -> exactly 1
+      if (nan_from >= j) mn = CUDART_NAN_F;
+      s_new[j] = __fmul_rn(s_score[j], mn);
+    }
+  }
+  __syncthreads();
+  // post threshold (>=, NaN fails; :132) then stable descending sort by decayed score (:140-145)
+  int len2 = 1; while (len2 < n) len2 <<= 1;
+  for (int i = tid; i < len2; i += kMatrixThreads) {
+    unsigned long long k = 0ull;
+    if (i < n) {
+      float v = s_new[i];
+      if (v >= post_thr) {
+        // sign-magnitude -> monotonic unsigned (scores are >= 0 in practice; this keeps negatives ordered too)
+        unsigned int b = __float_as_uint(v);
+        b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+        k = ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
+        atomicAdd(&s_kept, 1);
+      }
+    }
+    s_keys[i] = k;
+  }
+  bitonic_sort_desc(s_keys, len2);
+  int kept = s_kept;
+  if (kept > keep_top_k) kept = keep_top_k;
+  for (int r = tid; r < kept; r += kMatrixThreads) {
+    int i = (int)(0xFFFFFFFFu - (unsigned int)(s_keys[r] & 0xFFFFFFFFull));
+    float4 b = s_box[i];
+    float* row = my_out + r * 6;
+    row[0] = (float)s_label[i]; row[1] = s_new[i]; row[2] = b.x; row[3] = b.y; row[4] = b.z; row[5] = b.w;
+  }
+  if (tid == 0) counts[img] = kept;
+}
+
+__global__ void pairwise_iou_kernel(const float4* __restrict__ a, int na, const float4* __restrict__ b, int nb,
+                                    float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j < nb && i < na) out[(long long)i * nb + j] = box_iou(__ldg(a + i), __ldg(b + j));
+}
+
+Workspace carve(void* ws, int n) {
+  Workspace w;
+  char* p = reinterpret_cast<char*>(ws);
+  w.hist = reinterpret_cast<unsigned int*>(p);
+  p += sizeof(unsigned int) * (size_t)n * kBins;
+  w.count = reinterpret_cast<unsigned int*>(p);
+  p += ((sizeof(unsigned int) * (size_t)n + 255) / 256) * 256;
+  w.keys = reinterpret_cast<unsigned long long*>(p);
+  return w;
+}
+
+size_t workspace_bytes(int n) {
+  return sizeof(unsigned int) * (size_t)n * kBins + ((sizeof(unsigned int) * (size_t)n + 255) / 256) * 256 +
+         sizeof(unsigned long long) * (size_t)n * kCap;
+}
+
+}  // namespace
+}  // namespace ppy
+
+extern "C" {
+
+int ppy_matrix_nms_workspace_bytes(int n, int num_boxes, int num_classes, size_t* bytes) {
+  PPY_REQUIRE(bytes && n > 0 && num_boxes > 0 && num_classes > 0);
+  *bytes = ppy::workspace_bytes(n);
+  return PPY_OK;
+}
+
+int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
+                           float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
+                           int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
+                           size_t workspace_bytes, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(boxes && scores && out && counts && workspace);
+  PPY_REQUIRE(n > 0 && num_boxes > 0 && num_classes > 0 && keep_top_k > 0);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
+  PPY_REQUIRE(nms_top_k <= kMaxN);
+  PPY_REQUIRE((long long)num_boxes * num_classes < 0xFFFFFFFFll);
+  if (workspace_bytes < ppy::workspace_bytes(n)) return PPY_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(s);
+  Workspace w = carve(workspace, n);
+  // histogram + count live at the head of the workspace, contiguous
+  int rc = check_cuda(cudaMemsetAsync(w.hist, 0, reinterpret_cast<char*>(w.keys) - reinterpret_cast<char*>(w.hist), st));
+  if (rc) return rc;
+  // binning: candidates satisfy score > thr; bins cover (thr, 1] and everything above lands in the top bin
+  float thr_pos = score_threshold > 1e-30f ? score_threshold : 1e-30f;
+  unsigned int thr_bits, one_bits;
+  float one = 1.0f;
+  memcpy(&thr_bits, &thr_pos, 4);
+  memcpy(&one_bits, &one, 4);
+  int shift = 0;
+  if (one_bits > thr_bits) while (((one_bits - thr_bits) >> shift) >= (unsigned)kBins) ++shift;
+  const long long per_image = (long long)num_boxes * num_classes;
+  // enough CTAs to saturate HBM: ~4 per SM over the whole batch, each CTA >= 16K scores, chunk % 4 == 0
+  long long gx = ceil_div(148 * 4, n);
+  long long max_gx = ceil_div(per_image, 16384);
+  if (gx > max_gx) gx = max_gx;
+  if (gx < 1) gx = 1;
+  long long chunk = ceil_div(ceil_div(per_image, gx), 4) * 4;
+  gx = ceil_div(per_image, chunk);
+  dim3 grid((unsigned)gx, (unsigned)n);
+  int want = nms_top_k > 0 ? nms_top_k : kCap + 1;   // <=0: take everything (cutoff bin 0)
+  nms_hist_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.hist);
+  if ((rc = check_launch())) return rc;
+  nms_collect_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, want, w.hist,
+                                                    w.count, w.keys);
+  if ((rc = check_launch())) return rc;
+  static bool attr_set = false;
+  const int smem = kCap * (int)sizeof(unsigned long long);
+  if (!attr_set) {
+    rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (rc) return rc;
+    attr_set = true;
+  }
+  nms_matrix_kernel<<<n, kMatrixThreads, smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, nms_top_k,
+                                                     keep_top_k, post_threshold, use_gaussian, gaussian_sigma, out,
+                                                     counts);
+  return check_launch();
+}
+
+int ppy_pairwise_iou(const float* a, int na, const float* b, int nb, float* out, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(a && b && out && na > 0 && nb > 0);
+  PPY_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0);
+  dim3 grid((unsigned)ceil_div(nb, 128), (unsigned)na);
+  pairwise_iou_kernel<<<grid, 128, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(a), na,
+                                                      reinterpret_cast<const float4*>(b), nb, out);
+  return check_launch();
+}
+
+}  // extern "C"

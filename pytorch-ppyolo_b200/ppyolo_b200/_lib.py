@@ -1,0 +1,95 @@
+"""ctypes binding of libppyolo_b200.so (the C ABI declared in include/ppyolo_b200.h).
+
+The library must exist: there is no Python/torch fallback for any entry point.  If the shared object is
+missing and nvcc is available it is built in-tree once; otherwise import fails loudly.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
+                                                      ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
+
+PPY_F32, PPY_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
+
+
+class ConvParams(ctypes.Structure):
+    """Mirror of ``struct ppy_conv_params``."""
+    _fields_ = [
+        ('x', c_void_p), ('x_ld', c_int),
+        ('n', c_int), ('h', c_int), ('w', c_int), ('cin', c_int),
+        ('weight', c_void_p),
+        ('cout', c_int), ('kh', c_int), ('kw', c_int), ('stride', c_int), ('pad', c_int),
+        ('k_pad', c_int), ('cout_pad', c_int),
+        ('scale', c_void_p), ('shift', c_void_p), ('bias_map', c_void_p),
+        ('residual', c_void_p), ('res_ld', c_int),
+        ('act', c_int),
+        ('y', c_void_p), ('y_ld', c_int), ('out_dtype', c_int), ('upsample2x', c_int),
+        ('offset_mask', c_void_p), ('om_ld', c_int),
+    ]
+
+
+SIGNATURES = {
+    'ppy_abi_version': (c_int, []),
+    'ppy_status_string': (ctypes.c_char_p, [c_int]),
+    'ppy_last_cuda_error': (c_int, []),
+    'ppy_kernel_launch_count': (c_ll, []),
+    'ppy_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_nhwc_to_nchw': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_maxpool3x3s2': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_avgpool2x2': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_spp': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_upsample2x': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_copy_channels': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p]),
+    'ppy_coord_channels': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_activation': (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p]),
+    'ppy_pack_conv_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_void_p]),
+    'ppy_conv_f32': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
+    'ppy_conv_bf16': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
+    'ppy_conv_bf16_supported': (c_int, []),
+    'ppy_iou_aware_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_double, c_void_p]),
+    'ppy_yolo_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
+                                c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'ppy_pairwise_iou': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'ppy_matrix_nms_workspace_bytes': (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    'ppy_matrix_nms_batched': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                                       c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+
+def _load():
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc / compile error: fail loudly, never fall back
+            raise ImportError('libppyolo_b200.so is missing and could not be built (%s). Run '
+                              '`python -c "import __graft_entry__ as g; g.build()"` at the repo root.' % exc)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+LIB_PATH = _build.LIB_PATH
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib.ppy_status_string(status).decode()
+        raise KernelError('%s failed: %s (status %d, cudaError %d)' % (what or 'ppyolo_b200 call', msg, status,
+                                                                      lib.ppy_last_cuda_error()))
+
+
+def launch_count():
+    return int(lib.ppy_kernel_launch_count())

@@ -1,1 +1,352 @@
-# placeholder, replaced below
+"""Operator-level host API over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+These are the functions the module surface in ``model/`` calls (one reference operator each).  They take
+and return NCHW-shaped fp32 tensors like the reference's operators, convert to the kernels' NHWC layout
+with the library's own layout kernels, and launch on torch's current stream.  There is no CPU path: a
+non-CUDA tensor raises.  The whole-network fast path (``engine.InferenceEngine``) bypasses these
+wrappers and drives the same C entry points over pre-allocated NHWC buffers.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16
+
+_PRECISION = 'fp32'      # arithmetic of module-level convs: 'fp32' (SIMT) or 'bf16' (tcgen05)
+
+
+def set_precision(p):
+    global _PRECISION
+    if p not in ('fp32', 'bf16'):
+        raise ValueError(p)
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _cuda(t, name='tensor'):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError('ppyolo_b200: %s must be a CUDA tensor -- the kernels have no CPU fallback' % name)
+    return t
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def torch_dtype(code):
+    return torch.bfloat16 if code == PPY_BF16 else torch.float32
+
+
+def dtype_code(precision):
+    return PPY_BF16 if precision == 'bf16' else PPY_F32
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers (NCHW fp32 <-> NHWC)
+# ------------------------------------------------------------------------------------------------
+def to_nhwc(x, dtype_code_=PPY_F32, c_pad=None):
+    """NCHW fp32 tensor -> new NHWC buffer [N,H,W,c_pad] (channels zero padded)."""
+    _cuda(x, 'input')
+    x = x.detach().float().contiguous()
+    n, c, h, w = x.shape
+    c_pad = c_pad or round_up(c, 8)
+    y = torch.empty((n, h, w, c_pad), dtype=torch_dtype(dtype_code_), device=x.device)
+    check(lib.ppy_nchw_to_nhwc(ptr(x), ptr(y), n, c, h, w, c_pad, dtype_code_, stream_ptr()), 'nchw_to_nhwc')
+    return y
+
+
+def from_nhwc(y, c):
+    """NHWC buffer [N,H,W,ld] (fp32 or bf16) -> NCHW fp32 tensor with the first ``c`` channels."""
+    n, h, w, ld = y.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=y.device)
+    code = PPY_BF16 if y.dtype == torch.bfloat16 else PPY_F32
+    check(lib.ppy_nhwc_to_nchw(ptr(y), ld, code, ptr(out), n, c, h, w, stream_ptr()), 'nhwc_to_nchw')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# conv + folded norm + act (+residual), DCNv2
+# ------------------------------------------------------------------------------------------------
+_PACK_CACHE = {}
+
+
+def pack_weight(weight, code, c_begin=0, c_count=None):
+    """OIHW fp32 -> packed K-major [cout_pad, k_pad]; cached per (tensor, version, dtype, slice)."""
+    _cuda(weight, 'weight')
+    cout, cin_total, kh, kw = weight.shape
+    c_count = cin_total - c_begin if c_count is None else c_count
+    key = (weight.data_ptr(), weight._version, code, c_begin, c_count, tuple(weight.shape))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    cin_pad = round_up(c_count, 8)
+    k_pad = round_up(kh * kw * cin_pad, 64)
+    cout_pad = round_up(cout, 32)
+    w32 = weight.detach().float().contiguous()
+    packed = torch.empty((cout_pad, k_pad), dtype=torch_dtype(code), device=weight.device)
+    check(lib.ppy_pack_conv_weight(ptr(w32), cout, cin_total, kh, kw, c_begin, c_count, ptr(packed), cout_pad, cin_pad,
+                                   k_pad, code, stream_ptr()), 'pack_conv_weight')
+    if len(_PACK_CACHE) > 4096:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (packed, cin_pad, k_pad, cout_pad)
+    return _PACK_CACHE[key]
+
+
+def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, residual=None, bias_map=None,
+              out=None, out_code=None, upsample2x=False, offset_mask=None, x_ld=None):
+    """Launch one fused conv on NHWC buffers. ``x`` [N,H,W,ld]; returns ``out`` [N,Ho,Wo,ld_out]."""
+    w_packed, cin_pad, k_pad, cout_pad = packed
+    n, h, w, ld = x.shape
+    ho = (h + 2 * pad - k) // stride + 1
+    wo = (w + 2 * pad - k) // stride + 1
+    out_code = code if out_code is None else out_code
+    if out is None:
+        oh, ow = (2 * ho, 2 * wo) if upsample2x else (ho, wo)
+        out = torch.empty((n, oh, ow, round_up(cout, 8)), dtype=torch_dtype(out_code), device=x.device)
+    p = ConvParams()
+    p.x, p.x_ld = x.data_ptr(), (x_ld or ld)
+    p.n, p.h, p.w, p.cin = n, h, w, cin_pad
+    p.weight = w_packed.data_ptr()
+    p.cout, p.kh, p.kw, p.stride, p.pad = cout, k, k, stride, pad
+    p.k_pad, p.cout_pad = k_pad, cout_pad
+    p.scale, p.shift = scale.data_ptr(), shift.data_ptr()
+    p.bias_map = bias_map.data_ptr() if bias_map is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.res_ld = residual.shape[-1] if residual is not None else 0
+    p.act = act
+    p.y, p.y_ld, p.out_dtype = out.data_ptr(), out.shape[-1], out_code
+    p.upsample2x = 1 if upsample2x else 0
+    p.offset_mask = offset_mask.data_ptr() if offset_mask is not None else None
+    p.om_ld = offset_mask.shape[-1] if offset_mask is not None else 0
+    fn = lib.ppy_conv_bf16 if code == PPY_BF16 else lib.ppy_conv_f32
+    check(fn(ctypes.byref(p), stream_ptr()), 'conv_bf16' if code == PPY_BF16 else 'conv_f32')
+    return out
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def conv_bn_act(x, weight, scale, shift, stride=1, padding=0, act=0, residual=None, precision=None,
+                keep_nhwc=False):
+    """Conv2dUnit.forward (reference model/custom_layers.py:243-253) as one kernel; NCHW fp32 in/out."""
+    precision = precision or _PRECISION
+    code = dtype_code(precision)
+    cout, cin, k, _ = weight.shape
+    packed = pack_weight(weight, code)
+    xh = to_nhwc(x, code, packed[1])
+    res = to_nhwc(residual, code) if residual is not None else None
+    y = conv_nhwc(xh, packed, cin, cout, k, stride, padding, _f32(scale), _f32(shift), act, code, residual=res)
+    return y if keep_nhwc else from_nhwc(y, cout)
+
+
+def conv_unit_residual_relu(unit, x, shortcut):
+    """Last conv of a residual block with the block's `x + shortcut; relu` fused into its epilogue
+    (reference model/resnet_vd.py:54-56, :84-86, :264-266). The unit itself has act=None."""
+    scale, shift = unit.folded_scale_shift()
+    if unit.bn is not None and unit.bn.training:
+        raise NotImplementedError('train-mode BatchNorm is not built yet; call model.eval() first')
+    return conv_bn_act(x, unit.conv.weight, scale, shift, stride=unit.stride, padding=unit.padding,
+                       act=_lib.ACT_RELU, residual=shortcut)
+
+
+def dcnv2(x, offset_w, offset_b, dcn_w, dcn_b=None, stride=1, padding=1, scale=None, shift=None, act=0,
+          residual=None, precision=None):
+    """DCNv2.forward (reference model/custom_layers.py:551-677) + optional folded norm/act epilogue."""
+    precision = precision or _PRECISION
+    code = dtype_code(precision)
+    cout, cin, k, _ = dcn_w.shape
+    dev = x.device
+    xh = to_nhwc(x, code)
+    # offset/mask conv: plain conv with bias, fp32 output kept NHWC for the sampler
+    om_packed = pack_weight(offset_w, code)
+    n_om = offset_w.shape[0]
+    ones = torch.ones(n_om, dtype=torch.float32, device=dev)
+    om = conv_nhwc(xh, om_packed, cin, n_om, k, stride, padding, ones, _f32(offset_b), 0, code, out_code=PPY_F32)
+    packed = pack_weight(dcn_w, code)
+    if scale is None:
+        scale = torch.ones(cout, dtype=torch.float32, device=dev)
+    if shift is None:
+        shift = torch.zeros(cout, dtype=torch.float32, device=dev)
+    if dcn_b is not None:
+        shift = shift + _f32(dcn_b) * scale
+    res = to_nhwc(residual, code) if residual is not None else None
+    y = conv_nhwc(xh, packed, cin, cout, k, stride, padding, _f32(scale), _f32(shift), act, code, residual=res,
+                  offset_mask=om)
+    return from_nhwc(y, cout)
+
+
+# ------------------------------------------------------------------------------------------------
+# glue ops
+# ------------------------------------------------------------------------------------------------
+def _pool(fn, x, out_hw, name):
+    xh = to_nhwc(x)
+    n, h, w, ld = xh.shape
+    y = torch.empty((n, out_hw[0], out_hw[1], ld), dtype=torch.float32, device=x.device)
+    check(fn(ptr(xh), ld, ptr(y), ld, n, h, w, ld, PPY_F32, stream_ptr()), name)
+    return from_nhwc(y, x.shape[1])
+
+
+def max_pool3s2(x):
+    """MaxPool2d(3, 2, 1), reference model/resnet_vd.py:103."""
+    return _pool(lib.ppy_maxpool3x3s2, x, ((x.shape[2] + 1) // 2, (x.shape[3] + 1) // 2), 'maxpool3x3s2')
+
+
+def avg_pool2(x):
+    """AvgPool2d(2, 2, 0), reference model/resnet_vd.py:30."""
+    return _pool(lib.ppy_avgpool2x2, x, (x.shape[2] // 2, x.shape[3] // 2), 'avgpool2x2')
+
+
+def spp(x, descending=False):
+    """SPP (reference model/custom_layers.py:275-290)."""
+    xh = to_nhwc(x)
+    n, h, w, ld = xh.shape
+    c = x.shape[1]
+    if ld != c:
+        raise NotImplementedError('SPP needs a channel count that is a multiple of 8')
+    y = torch.empty((n, h, w, 4 * c), dtype=torch.float32, device=x.device)
+    check(lib.ppy_spp(ptr(xh), ld, ptr(y), 4 * c, n, h, w, c, PPY_F32, stream_ptr()), 'spp')
+    out = from_nhwc(y, 4 * c)
+    if descending:
+        out = torch.cat([out[:, 3 * c:], out[:, 2 * c:3 * c], out[:, c:2 * c], out[:, :c]], dim=1)
+    return out
+
+
+def coord_concat(x):
+    """CoordConv (reference model/custom_layers.py:256-272): cat([x, xs, ys], dim=1)."""
+    _cuda(x, 'input')
+    n, c, h, w = x.shape
+    coords = torch.empty((1, h, w, 8), dtype=torch.float32, device=x.device)
+    check(lib.ppy_coord_channels(ptr(coords), 8, h, w, PPY_F32, stream_ptr()), 'coord_channels')
+    cc = from_nhwc(coords, 2).expand(n, 2, h, w)
+    return torch.cat([x, cc], dim=1)
+
+
+def upsample2x_concat(route, feat):
+    """nearest x2 upsample of ``route`` then channel concat with ``feat`` (reference model/head.py:390-397)."""
+    rh, fh = to_nhwc(route), to_nhwc(feat)
+    n, h, w, rc = rh.shape
+    fc = fh.shape[-1]
+    if rc != route.shape[1] or fc != feat.shape[1]:
+        raise NotImplementedError('concat needs channel counts that are multiples of 8')
+    y = torch.empty((n, 2 * h, 2 * w, rc + fc), dtype=torch.float32, device=route.device)
+    check(lib.ppy_upsample2x(ptr(rh), rc, ptr(y), rc + fc, n, h, w, rc, PPY_F32, stream_ptr()), 'upsample2x')
+    ysl = ctypes.c_void_p(y.data_ptr() + 4 * rc)
+    check(lib.ppy_copy_channels(ptr(fh), fc, ysl, rc + fc, n * 4 * h * w, fc, PPY_F32, stream_ptr()), 'copy_channels')
+    return from_nhwc(y, rc + fc)
+
+
+def activation(x, act):
+    y = _cuda(x).detach().float().contiguous().clone()
+    check(lib.ppy_activation(ptr(y), y.numel(), act, PPY_F32, stream_ptr()), 'activation')
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# head post-processing
+# ------------------------------------------------------------------------------------------------
+def iou_aware_score(output, an_num, num_classes, factor):
+    xh = to_nhwc(output, PPY_F32, output.shape[1])
+    n, h, w, ld = xh.shape
+    oc = an_num * (5 + num_classes)
+    y = torch.empty((n, h, w, oc), dtype=torch.float32, device=output.device)
+    check(lib.ppy_iou_aware_score(ptr(xh), ld, ptr(y), oc, n * h * w, an_num, num_classes, float(factor), stream_ptr()),
+          'iou_aware_score')
+    return from_nhwc(y, oc)
+
+
+def yolo_decode_nhwc(head, ld, n, size, anchors, stride, num_classes, scale_x_y, im_size, clip_bbox, iou_aware,
+                     factor, boxes, scores, box_offset, total_boxes):
+    anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.float32).reshape(-1))
+    an = anchors.size // 2
+    check(lib.ppy_yolo_decode(ptr(head), ld, n, size, an, num_classes,
+                              anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(stride), float(scale_x_y),
+                              ptr(im_size), 1 if clip_bbox else 0, 1 if iou_aware else 0, float(factor), ptr(boxes),
+                              ptr(scores), box_offset, total_boxes, stream_ptr()), 'yolo_decode')
+
+
+def yolo_box(conv_output, anchors, stride, num_classes, scale_x_y, im_size, clip_bbox, iou_aware=False,
+             iou_aware_factor=0.0):
+    """(get_iou_aware_score +) yolo_box, reference model/head.py:21-141. NCHW head output in."""
+    xh = to_nhwc(conv_output, PPY_F32, conv_output.shape[1])
+    n, size, size_w, ld = xh.shape
+    if size != size_w:
+        raise ValueError('yolo_box assumes square feature maps, like the reference (head.py:25-27)')
+    an = len(np.asarray(anchors).reshape(-1)) // 2
+    total = size * size * an
+    boxes = torch.empty((n, total, 4), dtype=torch.float32, device=xh.device)
+    scores = torch.empty((n, total, num_classes), dtype=torch.float32, device=xh.device)
+    ims = _cuda(im_size, 'im_size').detach().float().contiguous()
+    yolo_decode_nhwc(xh, ld, n, size, anchors, stride, num_classes, scale_x_y, ims, clip_bbox, iou_aware,
+                     iou_aware_factor, boxes, scores, 0, total)
+    return boxes, scores
+
+
+def pairwise_iou(a, b):
+    a = _cuda(a).detach().float().contiguous()
+    b = _cuda(b).detach().float().contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    if out.numel():
+        check(lib.ppy_pairwise_iou(ptr(a), a.shape[0], ptr(b), b.shape[0], ptr(out), stream_ptr()), 'pairwise_iou')
+    return out
+
+
+_NMS_WS = {}
+
+
+def nms_workspace(n, num_boxes, num_classes, device):
+    need = ctypes.c_size_t(0)
+    check(lib.ppy_matrix_nms_workspace_bytes(n, num_boxes, num_classes, ctypes.byref(need)), 'nms_workspace_bytes')
+    key = (device, need.value)
+    ws = _NMS_WS.get(key)
+    if ws is None:
+        ws = torch.empty(need.value, dtype=torch.uint8, device=device)
+        _NMS_WS[key] = ws
+    return ws
+
+
+def matrix_nms_launch(boxes, scores, out, counts, workspace, score_threshold, post_threshold, nms_top_k, keep_top_k,
+                      use_gaussian, gaussian_sigma):
+    n, nb, nc = scores.shape
+    check(lib.ppy_matrix_nms_batched(ptr(boxes), ptr(scores), n, nb, nc, float(score_threshold), float(post_threshold),
+                                     int(nms_top_k), int(keep_top_k), 1 if use_gaussian else 0, float(gaussian_sigma),
+                                     ptr(out), ptr(counts), ptr(workspace), workspace.numel(), stream_ptr()),
+          'matrix_nms_batched')
+
+
+def split_predictions(out, counts_host):
+    """[N,keep,6] + per-image counts -> list of [M,6] tensors with the reference's -1 sentinel row."""
+    preds = []
+    for i, c in enumerate(counts_host):
+        if c < 0:
+            raise _lib.KernelError('matrix_nms: candidate overflow on image %d (code %d): more than 8192 scores tie '
+                                   'at the top-k cutoff, or nms_top_k<=0 with more than 1024 candidates' % (i, c))
+        preds.append(out[i, :c] if c > 0 else torch.full((1, 6), -1.0, device=out.device))
+    return preds
+
+
+def matrix_nms_batched(boxes, scores, score_threshold, post_threshold, nms_top_k, keep_top_k, use_gaussian=False,
+                       gaussian_sigma=2.):
+    """Reference model/matrix_nms.py:102-151 for every image of the batch; returns a list of [M,6] tensors."""
+    boxes = _cuda(boxes, 'boxes').detach().float().contiguous()
+    scores = _cuda(scores, 'scores').detach().float().contiguous()
+    n, nb, nc = scores.shape
+    out = torch.empty((n, keep_top_k, 6), dtype=torch.float32, device=boxes.device)
+    counts = torch.empty((n,), dtype=torch.int32, device=boxes.device)
+    ws = nms_workspace(n, nb, nc, boxes.device)
+    matrix_nms_launch(boxes, scores, out, counts, ws, score_threshold, post_threshold, nms_top_k, keep_top_k,
+                      use_gaussian, gaussian_sigma)
+    return split_predictions(out, counts.cpu().tolist())     # the single D2H sync of the post-processing

@@ -1,0 +1,287 @@
+"""GPU parity tests (B200): every kernel through the C ABI against the golden fixtures of the reference and
+against the CPU oracle on seeded inputs.
+
+Tolerances (stated per the north_star):
+  * Matrix-NMS: labels and row order bit-exact; linear-kernel scores exact to 1 ulp (rtol 2e-7); gaussian
+    kernel rtol 2e-6 (expf ulp).
+  * decode: boxes rtol 1e-5 + atol 1e-4 px, scores rtol 1e-5 (libm ulp of exp/log/pow).
+  * fp32 SIMT convs / DCN: 1e-4 relative to the output scale (fp32 re-association only).
+  * bf16 tcgen05 convs: compared with the oracle evaluated on the SAME bf16-rounded inputs/weights, fp32
+    output: 2e-3 relative to the output scale (fp32 accumulation order; bilinear blend rounded to bf16 for DCN).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppyolo_ref as ref
+from ppyolo_b200 import synth
+from tests.helpers import build_model, assert_preds_close
+
+pytestmark = pytest.mark.gpu
+NMS_CFG = dict(score_threshold=0.01, post_threshold=0.01, nms_top_k=500, keep_top_k=100)
+DEV = 'cuda'
+
+
+def ops():
+    from ppyolo_b200 import ops as _ops
+    return _ops
+
+
+def scale_of(t):
+    return float(np.abs(t).max()) + 1e-12
+
+
+# ------------------------------------------------------------------ Matrix-NMS
+@pytest.mark.parametrize('name', ['zeros', 'dups', 'chain', 'degenerate'])
+def test_nms_known_answers(golden, name):
+    from model.matrix_nms import matrix_nms
+    z = golden('nms')
+    for gauss in ((False,) if name == 'degenerate' else (False, True)):
+        tag = name if name == 'degenerate' else '%s_%s' % (name, 'g' if gauss else 'l')
+        out = matrix_nms(torch.from_numpy(z[tag + '_boxes']).to(DEV), torch.from_numpy(z[tag + '_scores']).to(DEV),
+                         use_gaussian=gauss, **NMS_CFG)
+        assert_preds_close(out.cpu().numpy(), z[tag + '_out'], rtol=2e-6 if gauss else 2e-7, atol=0)
+
+
+@pytest.mark.parametrize('nb,nc,seed,topk,keep', [(400, 80, 0, 500, 100), (400, 80, 1, 100, 20), (3000, 80, 2, 500, 100),
+                                                  (64, 3, 3, -1, 100), (1500, 20, 4, 300, 50)])
+@pytest.mark.parametrize('gauss', [False, True])
+def test_nms_golden_random(golden, nb, nc, seed, topk, keep, gauss):
+    from model.matrix_nms import matrix_nms
+    z = golden('nms')
+    b, s = synth.nms_inputs(nb, nc, seed=seed)
+    out = matrix_nms(b.to(DEV), s.to(DEV), 0.01, 0.01, topk, keep, use_gaussian=gauss, gaussian_sigma=2.0)
+    want = z['rand_b%d_c%d_s%d_t%d_k%d_%s_out' % (nb, nc, seed, topk, keep, 'g' if gauss else 'l')]
+    assert_preds_close(out.cpu().numpy(), want, rtol=2e-6 if gauss else 2e-7, atol=0)
+
+
+def test_nms_post_threshold(golden):
+    from model.matrix_nms import matrix_nms
+    z = golden('nms')
+    b, s = synth.nms_inputs(800, 80, seed=5)
+    out = matrix_nms(b.to(DEV), s.to(DEV), 0.05, 0.2, 200, 30)
+    assert_preds_close(out.cpu().numpy(), z['post05_out'], rtol=2e-7, atol=0)
+
+
+def test_nms_c5_batched_vs_oracle():
+    """BASELINE config C5 (10k boxes x 80 classes), batch of 4 different images in one launch sequence."""
+    o = ops()
+    pairs = [synth.nms_inputs(10000, 80, seed=100 + i) for i in range(4)]
+    boxes = torch.stack([p[0] for p in pairs]).to(DEV)
+    scores = torch.stack([p[1] for p in pairs]).to(DEV)
+    for gauss in (False, True):
+        got = o.matrix_nms_batched(boxes, scores, use_gaussian=gauss, **NMS_CFG)
+        for i in range(4):
+            want = ref.matrix_nms(pairs[i][0].numpy(), pairs[i][1].numpy(), use_gaussian=gauss, **NMS_CFG)
+            assert_preds_close(got[i].cpu().numpy(), want, rtol=2e-6 if gauss else 2e-7, atol=0)
+
+
+def test_nms_properties_full_size():
+    """Size-independent properties at the bench size (22743 boxes x 80, bs 8): sorted scores, idempotent
+    re-run, labels in range, all boxes are input boxes."""
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    n, nb = 8, 22743
+    cxy = torch.rand((n, nb, 2), generator=g) * 608
+    wh = torch.rand((n, nb, 2), generator=g) * 150 + 4
+    boxes = torch.cat([cxy - wh / 2, cxy + wh / 2], -1).to(DEV)
+    scores = (torch.sigmoid(torch.randn((n, nb, 1), generator=g) * 2 - 4) *
+              torch.sigmoid(torch.randn((n, nb, 80), generator=g) * 2 - 3)).to(DEV)
+    a = o.matrix_nms_batched(boxes, scores, **NMS_CFG)
+    b = o.matrix_nms_batched(boxes, scores, **NMS_CFG)
+    for i in range(n):
+        assert torch.equal(a[i], b[i])
+        p = a[i].cpu().numpy()
+        assert p.shape == (100, 6)
+        assert (np.diff(p[:, 1]) <= 0).all() and (p[:, 1] >= 0.01).all()
+        assert ((p[:, 0] >= 0) & (p[:, 0] < 80) & (p[:, 0] == np.round(p[:, 0]))).all()
+    # image 0 against the oracle as well
+    want = ref.matrix_nms(boxes[0].cpu().numpy(), scores[0].cpu().numpy(), **NMS_CFG)
+    assert_preds_close(a[0].cpu().numpy(), want, rtol=2e-7, atol=0)
+
+
+def test_jaccard(golden):
+    from model.matrix_nms import jaccard
+    z = golden('nms')
+    ba, _ = synth.nms_inputs(37, 1, seed=7)
+    bb, _ = synth.nms_inputs(53, 1, seed=8)
+    np.testing.assert_allclose(jaccard(ba.to(DEV), bb.to(DEV)).cpu().numpy(), z['jaccard_out'], rtol=2e-7, atol=0)
+
+
+# ------------------------------------------------------------------ decode
+@pytest.mark.parametrize('tag,stride,mask,iou_aware', [('s32', 32, [6, 7, 8], True), ('s8', 8, [0, 1, 2], True),
+                                                       ('plain', 16, [3, 4, 5], False)])
+def test_decode_golden(golden, tag, stride, mask, iou_aware):
+    from model import head as H
+    z = golden('decode')
+    anchors = np.array(build_model('r50vd')[1].head['anchors'], np.float32)[mask]
+    x = torch.from_numpy(z[tag + '_in']).to(DEV)
+    im_size = torch.from_numpy(z[tag + '_im_size']).to(DEV)
+    if iou_aware:
+        y = H.get_iou_aware_score(x, 3, 80, 0.4)
+        np.testing.assert_allclose(y.cpu().numpy(), z[tag + '_iouaware'], rtol=1e-5, atol=1e-5)
+    else:
+        y = x
+    for clip in (True, False):
+        boxes, scores = H.yolo_box(y, anchors, stride, 80, 1.05, im_size, clip, 0.01)
+        want = z['%s_boxes_clip%d' % (tag, int(clip))]
+        got = boxes.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(scores.cpu().numpy(), z[tag + '_scores'], rtol=1e-5, atol=1e-9)
+    if iou_aware:   # fused path: iou-aware inside the decode kernel
+        boxes, scores = ops().yolo_box(x, anchors, stride, 80, 1.05, im_size, True, iou_aware=True, iou_aware_factor=0.4)
+        np.testing.assert_allclose(boxes.cpu().numpy(), z[tag + '_boxes_clip1'], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(scores.cpu().numpy(), z[tag + '_scores'], rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------ glue layers
+def test_coord_spp_pool(golden):
+    from model.custom_layers import CoordConv, SPP
+    o = ops()
+    z = golden('layers')
+    np.testing.assert_allclose(CoordConv(True)(torch.zeros(1, 2, 3, 4, device=DEV)).cpu().numpy(), z['coord_out'], atol=1e-7)
+    x = torch.from_numpy(z['spp_in'])
+    x8 = torch.cat([x, x * 0.5], 1)                      # 8 channels (vector width)
+    got = SPP()(x8.to(DEV)).cpu()
+    np.testing.assert_array_equal(got.numpy(), ref.spp(x8).numpy())
+    g = torch.Generator().manual_seed(2)
+    t = torch.randn((2, 16, 13, 17), generator=g)
+    np.testing.assert_array_equal(o.max_pool3s2(t.to(DEV)).cpu().numpy(), torch.nn.functional.max_pool2d(t, 3, 2, 1).numpy())
+    t = torch.randn((2, 16, 12, 18), generator=g)
+    np.testing.assert_allclose(o.avg_pool2(t.to(DEV)).cpu().numpy(), torch.nn.functional.avg_pool2d(t, 2, 2).numpy(),
+                               rtol=1e-6, atol=1e-7)
+    r, f = torch.randn((2, 8, 5, 5), generator=g), torch.randn((2, 16, 10, 10), generator=g)
+    want = torch.cat([torch.nn.functional.interpolate(r, scale_factor=2, mode='nearest'), f], 1)
+    np.testing.assert_array_equal(o.upsample2x_concat(r.to(DEV), f.to(DEV)).cpu().numpy(), want.numpy())
+
+
+# ------------------------------------------------------------------ conv units (golden from the reference)
+UNIT_CASES = (('c3s1', 8, 16, 3, 1, 'leaky', False), ('c3s2', 8, 16, 3, 2, 'relu', False),
+              ('c1s1', 16, 24, 1, 1, None, True), ('c1s2', 8, 8, 1, 2, 'relu', False))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_conv_units_golden(golden, precision):
+    from model.custom_layers import Conv2dUnit
+    o = ops()
+    z = golden('layers')
+    o.set_precision(precision)
+    try:
+        for tag, cin, cout, k, stride, act, bias in UNIT_CASES:
+            u = Conv2dUnit(cin, cout, k, stride=stride, bias_attr=bias, bn=0 if bias else 1, act=act)
+            synth.randomize_(u, seed=30)
+            u = u.to(DEV).eval()
+            y = u(torch.from_numpy(z[tag + '_in']).to(DEV)).cpu().numpy()
+            want = z[tag + '_out']
+            tol = 1e-4 if precision == 'fp32' else 3e-2      # bf16: inputs, weights AND output rounded to bf16
+            np.testing.assert_allclose(y, want, rtol=0, atol=tol * scale_of(want), err_msg=tag)
+    finally:
+        o.set_precision('fp32')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('tag,stride', [('dcn_s1', 1), ('dcn_s2', 2)])
+def test_dcn_golden(golden, precision, tag, stride):
+    from model.custom_layers import Conv2dUnit
+    o = ops()
+    z = golden('layers')
+    u = Conv2dUnit(16, 24, 3, stride=stride, bn=1, act='relu', use_dcn=True)
+    synth.randomize_(u, seed=31, offset_scale=0.05)
+    u = u.to(DEV).eval()
+    x = torch.from_numpy(z[tag + '_in']).to(DEV)
+    if precision == 'fp32':
+        raw = u.conv(x).cpu().numpy()
+        np.testing.assert_allclose(raw, z[tag + '_raw'], rtol=0, atol=1e-4 * scale_of(z[tag + '_raw']))
+        y = u(x).cpu().numpy()
+        np.testing.assert_allclose(y, z[tag + '_out'], rtol=0, atol=1e-4 * scale_of(z[tag + '_out']))
+    else:
+        pytest.skip('bf16 DCN needs cin % 64 == 0; covered by test_umma_dcn')
+
+
+# ------------------------------------------------------------------ tcgen05 conv kernel, tight check
+def _umma_conv(x, w, scale, shift, stride, act, residual=None, bias_map=None, upsample=False, out_f32=True,
+               offset_mask=None):
+    """Run ppy_conv_bf16 on NHWC bf16 buffers; returns NCHW fp32."""
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16
+    o = ops()
+    cout, cin, k, _ = w.shape
+    packed = o.pack_weight(w.to(DEV), PPY_BF16)
+    xh = o.to_nhwc(x.to(DEV), PPY_BF16, packed[1])
+    out_code = PPY_F32 if out_f32 else PPY_BF16
+    res = o.to_nhwc(residual.to(DEV), out_code) if residual is not None else None
+    y = o.conv_nhwc(xh, packed, cin, cout, k, stride, (k - 1) // 2, scale.to(DEV), shift.to(DEV), act, PPY_BF16,
+                    residual=res, bias_map=bias_map.to(DEV) if bias_map is not None else None, out_code=out_code,
+                    upsample2x=upsample, offset_mask=offset_mask)
+    return o.from_nhwc(y, cout).cpu()
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+UMMA_SHAPES = [  # (n, cin, cout, k, stride, hw)
+    (2, 64, 64, 1, 1, 16), (2, 64, 128, 3, 1, 16), (1, 128, 256, 3, 2, 16), (2, 32, 32, 3, 1, 24),
+    (2, 3, 32, 3, 2, 32), (1, 256, 258, 1, 1, 12), (1, 512, 27, 3, 1, 10), (3, 64, 512, 1, 1, 9),
+    (1, 1024, 256, 1, 1, 19), (1, 256, 512, 3, 1, 19), (2, 64, 96, 3, 1, 7),
+]
+
+
+@pytest.mark.parametrize('n,cin,cout,k,stride,hw', UMMA_SHAPES)
+def test_umma_conv_shapes(n, cin, cout, k, stride, hw):
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    x = bf16_round(torch.randn((n, cin, hw, hw), generator=g))
+    w = bf16_round(torch.randn((cout, cin, k, k), generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    want = torch.nn.functional.conv2d(x, w, None, stride, (k - 1) // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    want = torch.nn.functional.leaky_relu(want, 0.1)
+    got = _umma_conv(x, w, scale, shift, stride, 2)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-4 * scale_of(want.numpy()))
+
+
+def test_umma_conv_epilogue_variants():
+    g = torch.Generator().manual_seed(9)
+    n, cin, cout, hw = 2, 64, 64, 10
+    x = bf16_round(torch.randn((n, cin, hw, hw), generator=g))
+    w = bf16_round(torch.randn((cout, cin, 3, 3), generator=g) * 0.05)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    base = torch.nn.functional.conv2d(x, w, None, 1, 1)
+    # residual + relu, bf16 output (the block epilogue of resnet_vd.py:54-56)
+    res = bf16_round(torch.randn((n, cout, hw, hw), generator=g))
+    want = torch.relu(base * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    got = _umma_conv(x, w, scale, shift, 1, 1, residual=res, out_f32=False)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
+    # CoordConv bias map + leaky, fp32 out
+    bm = torch.randn((hw * hw, cout), generator=g)
+    want = torch.nn.functional.leaky_relu((base + bm.t().reshape(1, cout, hw, hw)) * scale.view(1, -1, 1, 1) +
+                                          shift.view(1, -1, 1, 1), 0.1)
+    got = _umma_conv(x, w, scale, shift, 1, 2, bias_map=bm)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-4 * scale_of(want.numpy()))
+    # fused nearest x2 upsample
+    want = torch.nn.functional.interpolate(base * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), scale_factor=2)
+    got = _umma_conv(x, w, scale, shift, 1, 0, upsample=True)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-4 * scale_of(want.numpy()))
+
+
+@pytest.mark.parametrize('stride,hw', [(1, 19), (2, 20)])
+def test_umma_dcn(stride, hw):
+    """Fused DCNv2 on tensor cores (cin=cout=128) vs the oracle on bf16-rounded operands."""
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16
+    o = ops()
+    g = torch.Generator().manual_seed(77 + stride)
+    n, c, cout = 2, 128, 128
+    x = bf16_round(torch.randn((n, c, hw, hw), generator=g))
+    ow = bf16_round(torch.randn((27, c, 3, 3), generator=g) * 0.03)
+    ob = torch.randn(27, generator=g)
+    w = bf16_round(torch.randn((cout, c, 3, 3), generator=g) * 0.03)
+    want = ref.dcnv2(x, ow, ob, w, stride, 1)
+    # run the two kernels like ops.dcnv2 does, but with fp32 output of the main GEMM
+    xh = o.to_nhwc(x.to(DEV), PPY_BF16)
+    om = o.conv_nhwc(xh, o.pack_weight(ow.to(DEV), PPY_BF16), c, 27, 3, stride, 1, torch.ones(27, device=DEV),
+                     ob.to(DEV), 0, PPY_BF16, out_code=PPY_F32)
+    y = o.conv_nhwc(xh, o.pack_weight(w.to(DEV), PPY_BF16), c, cout, 3, stride, 1, torch.ones(cout, device=DEV),
+                    torch.zeros(cout, device=DEV), 0, PPY_BF16, out_code=PPY_F32, offset_mask=om)
+    got = o.from_nhwc(y, cout).cpu()
+    # A operand (modulated bilinear sample) is rounded to bf16 before the MMA: ~2^-9 relative per element
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=4e-3 * scale_of(want.numpy()))
