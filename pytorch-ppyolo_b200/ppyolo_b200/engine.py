@@ -1,0 +1,353 @@
+"""Whole-network inference engine: PPYOLO.forward(eval=True) as a static plan of fused sm_100a kernels.
+
+Built once per (batch, H, W, precision) from the module tree (so it sees the same parameters a loaded
+reference checkpoint provides), then replayed -- as a CUDA graph -- for every batch:
+
+  * activations live in pre-allocated NHWC buffers (bf16 on the tcgen05 path, fp32 on the parity path);
+    180 GB of HBM means no buffer reuse games are needed even at bs=32 x 608^2
+  * every Conv2dUnit is ONE kernel: implicit GEMM + folded BN/bias + activation, with the block's residual
+    add + ReLU, the head's nearest-x2 upsample and the concat placement (channel-slice writes) fused into
+    its epilogue; CoordConv is folded into a per-pixel bias map computed once at build time
+    (its two channels are constants of the feature-map shape), so no K padding and no concat at run time
+  * DCNv2 = offset/mask conv (fp32 out) + the fused deformable-gather GEMM
+  * decode = one kernel per scale writing straight into the batch-wide boxes/scores buffers;
+    Matrix-NMS = 3 launches for the whole batch; the only host sync is the final read of the counts.
+
+Reference path being replaced: model/ppyolo.py:19-22 -> model/resnet_vd.py:132-168 (or :302-330) ->
+model/head.py:424-469.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16
+
+
+class TensorRef(object):
+    """A channel slice [c_off, c_off+c) of an NHWC buffer [N,H,W,ld]."""
+
+    def __init__(self, t, c=None, c_off=0):
+        self.t, self.c_off = t, c_off
+        self.c = t.shape[-1] - c_off if c is None else c
+
+    n = property(lambda self: self.t.shape[0])
+    h = property(lambda self: self.t.shape[1])
+    w = property(lambda self: self.t.shape[2])
+    ld = property(lambda self: self.t.shape[3])
+    code = property(lambda self: PPY_BF16 if self.t.dtype == torch.bfloat16 else PPY_F32)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + self.c_off * self.t.element_size()
+
+    def slice(self, c_off, c):
+        return TensorRef(self.t, c, self.c_off + c_off)
+
+
+class InferenceEngine(object):
+    def __init__(self, model, batch, height, width, precision='bf16', use_graph=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError('InferenceEngine needs a CUDA device (no CPU fallback)')
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError(precision)
+        if precision == 'bf16' and not lib.ppy_conv_bf16_supported():
+            raise RuntimeError('the tcgen05 conv path needs an sm_100 device')
+        if height % 32 or width % 32 or height != width:
+            raise ValueError('input must be square with a side that is a multiple of 32 (reference yolo_box '
+                             'assumes square maps, model/head.py:25-27)')
+        self.model, self.n, self.h, self.w = model, batch, height, width
+        self.precision, self.code = precision, ops.dtype_code(precision)
+        self.dev = next(model.parameters()).device
+        if self.dev.type != 'cuda':
+            raise RuntimeError('model must be on a CUDA device')
+        self.act_dtype = ops.torch_dtype(self.code)
+        self.steps = []          # (name, callable)
+        self.keep = []           # tensors / ctypes structs referenced by raw pointer
+        self.conv_flops = 0      # algorithmic 2*MAC of all convs in the plan (per batch)
+        self.graph = None
+        self.launches_per_run = 0
+        with torch.no_grad():
+            self._build()
+        # one eager pass: first-use initialisation (func attributes, tensor maps) + launch count
+        before = _lib.launch_count()
+        self._run_steps()
+        torch.cuda.synchronize(self.dev)
+        self.launches_per_run = _lib.launch_count() - before
+        if use_graph:
+            self._capture()
+
+    # ------------------------------------------------------------------ buffers
+    def _new(self, n, h, w, c, dtype=None):
+        t = torch.zeros((n, h, w, c), dtype=dtype or self.act_dtype, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def _keep(self, t):
+        self.keep.append(t)
+        return t
+
+    # ------------------------------------------------------------------ op builders
+    def _add(self, name, fn):
+        self.steps.append((name, fn))
+
+    def _simple(self, name, cfn, x, out, *extra):
+        """pool-like op: cfn(x_ptr, x_ld, y_ptr, y_ld, n, h, w, c, dtype, stream)"""
+        args = (ctypes.c_void_p(x.ptr), x.ld, ctypes.c_void_p(out.ptr), out.ld, x.n, x.h, x.w, x.c, x.code)
+
+        def run():
+            check(cfn(*args, ops.stream_ptr()), name)
+        self._add(name, run)
+        return out
+
+    def _maxpool(self, x):
+        out = TensorRef(self._new(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c))
+        return self._simple('maxpool3x3s2', lib.ppy_maxpool3x3s2, x, out)
+
+    def _avgpool(self, x):
+        out = TensorRef(self._new(x.n, x.h // 2, x.w // 2, x.c))
+        return self._simple('avgpool2x2', lib.ppy_avgpool2x2, x, out)
+
+    def _spp(self, x):
+        out = TensorRef(self._new(x.n, x.h, x.w, 4 * x.c))
+        return self._simple('spp', lib.ppy_spp, x, out)
+
+    def _coord_bias_map(self, weight, c_main, h, w):
+        """Contribution of the two CoordConv channels for one image: [h*w, cout] fp32 (pre-BN)."""
+        cout, _, k, _ = weight.shape
+        coords = self._new(1, h, w, 8, torch.float32)
+        check(lib.ppy_coord_channels(ops.ptr(coords), 8, h, w, PPY_F32, ops.stream_ptr()), 'coord_channels')
+        packed = ops.pack_weight(weight, PPY_F32, c_begin=c_main, c_count=2)
+        one = self._keep(torch.ones(cout, dtype=torch.float32, device=self.dev))
+        zero = self._keep(torch.zeros(cout, dtype=torch.float32, device=self.dev))
+        out = self._new(1, h, w, cout, torch.float32)
+        ops.conv_nhwc(coords, packed, 2, cout, k, 1, (k - 1) // 2, one, zero, 0, PPY_F32, out=out, out_code=PPY_F32)
+        return out
+
+    def _conv(self, name, x, weight, scale, shift, stride, act, residual=None, dst=None, coord=False, upsample=False,
+              out_code=None, offset_mask=None):
+        cout, cin_total, k, _ = weight.shape
+        c_main = cin_total - (2 if coord else 0)
+        if c_main != x.c and not (c_main < x.c and x.c == ops.round_up(c_main, 8)):
+            raise ValueError('%s: weight expects %d input channels, buffer has %d' % (name, c_main, x.c))
+        pad = (k - 1) // 2
+        packed, cin_pad, k_pad, cout_pad = ops.pack_weight(weight, self.code, c_begin=0, c_count=c_main)
+        self._keep(packed)
+        ho = (x.h + 2 * pad - k) // stride + 1
+        wo = (x.w + 2 * pad - k) // stride + 1
+        out_code = self.code if out_code is None else out_code
+        if dst is None:
+            oh, ow = (2 * ho, 2 * wo) if upsample else (ho, wo)
+            dst = TensorRef(self._new(x.n, oh, ow, ops.round_up(cout, 8), ops.torch_dtype(out_code)), c=cout)
+        bias_map = self._coord_bias_map(weight, c_main, x.h, x.w) if coord else None
+        p = ConvParams()
+        p.x, p.x_ld = x.ptr, x.ld
+        p.n, p.h, p.w, p.cin = x.n, x.h, x.w, cin_pad
+        p.weight = packed.data_ptr()
+        p.cout, p.kh, p.kw, p.stride, p.pad = cout, k, k, stride, pad
+        p.k_pad, p.cout_pad = k_pad, cout_pad
+        p.scale, p.shift = self._keep(scale).data_ptr(), self._keep(shift).data_ptr()
+        p.bias_map = bias_map.data_ptr() if bias_map is not None else None
+        p.residual = residual.ptr if residual is not None else None
+        p.res_ld = residual.ld if residual is not None else 0
+        p.act = act
+        p.y, p.y_ld, p.out_dtype = dst.ptr, dst.ld, out_code
+        p.upsample2x = 1 if upsample else 0
+        p.offset_mask = offset_mask.ptr if offset_mask is not None else None
+        p.om_ld = offset_mask.ld if offset_mask is not None else 0
+        self._keep(p)
+        fn = lib.ppy_conv_bf16 if self.code == PPY_BF16 else lib.ppy_conv_f32
+        ref = ctypes.byref(p)
+
+        def run():
+            check(fn(ref, ops.stream_ptr()), name)
+        self._add(name, run)
+        self.conv_flops += 2 * x.n * ho * wo * cout * cin_total * k * k
+        return dst
+
+    def _unit(self, name, unit, x, residual=None, act=None, dst=None, coord=False, upsample=False, out_code=None):
+        """One Conv2dUnit (conv|DCNv2 -> folded norm -> act) as one (DCN: two) kernels."""
+        from model.custom_layers import DCNv2, ACT_CODES
+        scale, shift = unit.folded_scale_shift()
+        act = ACT_CODES[unit.act_name] if act is None else act
+        if isinstance(unit.conv, DCNv2):
+            d = unit.conv
+            n_om = d.conv_offset.weight.shape[0]
+            one = torch.ones(n_om, dtype=torch.float32, device=self.dev)
+            om = self._conv(name + '.offset', x, d.conv_offset.weight.detach(), one,
+                            d.conv_offset.bias.detach().float().contiguous(), unit.stride, 0, out_code=PPY_F32)
+            om = TensorRef(om.t)     # the sampler reads the padded row (ld) directly
+            if d.dcn_bias is not None:
+                shift = shift + d.dcn_bias.detach().float() * scale
+            return self._conv(name, x, d.dcn_weight.detach(), scale, shift, unit.stride, act, residual=residual,
+                              dst=dst, offset_mask=om)
+        return self._conv(name, x, unit.conv.weight.detach(), scale, shift, unit.stride, act, residual=residual,
+                          dst=dst, coord=coord, upsample=upsample, out_code=out_code)
+
+    # ------------------------------------------------------------------ network walk
+    def _block(self, name, blk, x, dst=None):
+        from model.resnet_vd import ConvBlock, IdentityBlock, BasicBlock
+        relu = _lib.ACT_RELU
+        if isinstance(blk, ConvBlock):
+            sc = self._unit(name + '.conv4', blk.conv4, x if blk.is_first else self._avgpool(x))
+            y = self._unit(name + '.conv1', blk.conv1, x)
+            y = self._unit(name + '.conv2', blk.conv2, y)
+            return self._unit(name + '.conv3', blk.conv3, y, residual=sc, act=relu, dst=dst)
+        if isinstance(blk, IdentityBlock):
+            y = self._unit(name + '.conv1', blk.conv1, x)
+            y = self._unit(name + '.conv2', blk.conv2, y)
+            return self._unit(name + '.conv3', blk.conv3, y, residual=x, act=relu, dst=dst)
+        if isinstance(blk, BasicBlock):
+            sc = x
+            if blk.conv3 is not None:
+                sc = self._unit(name + '.conv3', blk.conv3, x if blk.is_first else self._avgpool(x))
+            y = self._unit(name + '.conv1', blk.conv1, x)
+            return self._unit(name + '.conv2', blk.conv2, y, residual=sc, act=relu, dst=dst)
+        raise TypeError(type(blk))
+
+    def _build(self):
+        m, n = self.model, self.n
+        bb, head = m.backbone, m.head
+        n_out = len(head.anchor_masks)
+        # static input: NCHW fp32 exactly as Decode.predict uploads it (model/decode_np.py:142-147)
+        self.x_in = torch.zeros((n, 3, self.h, self.w), dtype=torch.float32, device=self.dev)
+        self.im_size = torch.zeros((n, 2), dtype=torch.float32, device=self.dev)
+        x0 = TensorRef(self._new(n, self.h, self.w, 8))
+        args = (ops.ptr(self.x_in), ctypes.c_void_p(x0.ptr), n, 3, self.h, self.w, 8, self.code)
+        self._add('nchw_to_nhwc', lambda: check(lib.ppy_nchw_to_nhwc(*args, ops.stream_ptr()), 'nchw_to_nhwc'))
+
+        # head level i > 0 consumes cat([upsampled route, backbone feature]); give the backbone stage that
+        # produces the feature a destination inside that concat buffer (no copy at run time)
+        fmaps = list(bb.feature_maps)
+        head_feats = fmaps[-1:-n_out - 1:-1]              # stages in head order (deepest first)
+        route_c = [0] + [head.upsample_layers[2 * (i - 1)].filters for i in range(1, n_out)]
+        stage_dst = {}
+        self.concat = {}
+        for i, stage in enumerate(head_feats):
+            if i == 0:
+                continue
+            side = self.h // (2 ** stage)
+            feat_c = self._stage_channels(bb, stage)
+            buf = self._new(n, side, side, route_c[i] + feat_c)
+            self.concat[i] = TensorRef(buf)
+            stage_dst[stage] = TensorRef(buf, feat_c, route_c[i])
+
+        x = x0
+        for u, nm in zip(bb._stem_units(), ('conv1_1', 'conv1_2', 'conv1_3')):
+            x = self._unit('stem.' + nm, u, x)
+        x = self._maxpool(x)
+        feats = {}
+        for stage in (2, 3, 4, 5):
+            names = bb.stage_names(stage)
+            for j, nm in enumerate(names):
+                dst = stage_dst.get(stage) if j == len(names) - 1 else None
+                x = self._block(nm, getattr(bb, nm), x, dst=dst)
+            feats[stage] = x
+
+        # ---- head
+        from model.custom_layers import Conv2dUnit, CoordConv, SPP, DropBlock
+        self.head_outs = []
+        route = None
+        for i, stage in enumerate(head_feats):
+            x = feats[stage] if i == 0 else self.concat[i]
+            blk = head.detection_blocks[i]
+            coord = False
+
+            def walk(layers, x, prefix):
+                nonlocal coord
+                for j, ly in enumerate(layers):
+                    if isinstance(ly, CoordConv):
+                        coord = coord or ly.coord_conv
+                    elif isinstance(ly, Conv2dUnit):
+                        x = self._unit('%s.%d' % (prefix, j), ly, x, coord=coord)
+                        coord = False
+                    elif isinstance(ly, SPP):
+                        x = self._spp(x)
+                    elif isinstance(ly, DropBlock):
+                        if not ly.is_test:
+                            raise RuntimeError('DropBlock must be in test mode for inference (head.set_dropblock(True))')
+                    else:
+                        raise TypeError(type(ly))
+                return x
+            route = walk(blk.layers, x, 'head.block%d.layers' % i)
+            tip = walk(blk.tip_layers, route, 'head.block%d.tip' % i)
+            out = self._unit('head.out%d' % i, head.yolo_output_convs[i], tip, out_code=PPY_F32)
+            self.head_outs.append(out)
+            if i < n_out - 1:
+                nxt = self.concat[i + 1]
+                self._unit('head.transition%d' % i, head.upsample_layers[2 * i], route, upsample=True,
+                           dst=nxt.slice(0, route_c[i + 1]))
+
+        # ---- decode + NMS
+        an_per = [len(mk) for mk in head.anchor_masks]
+        sizes = [o.h for o in self.head_outs]
+        self.total_boxes = sum(s * s * a for s, a in zip(sizes, an_per))
+        nc = head.num_classes
+        self.boxes = torch.zeros((n, self.total_boxes, 4), dtype=torch.float32, device=self.dev)
+        self.scores = torch.zeros((n, self.total_boxes, nc), dtype=torch.float32, device=self.dev)
+        off = 0
+        for i, o in enumerate(self.head_outs):
+            anchors = head._anchors[head.anchor_masks[i]].reshape(-1)
+
+            def run(o=o, anchors=anchors, off=off, i=i):
+                ops.yolo_decode_nhwc(o.t, o.ld, n, o.h, anchors, head.downsample[i], nc, head.scale_x_y, self.im_size,
+                                     head.clip_bbox, head.iou_aware, head.iou_aware_factor, self.boxes, self.scores,
+                                     off, self.total_boxes)
+            self._add('decode%d' % i, run)
+            off += o.h * o.h * an_per[i]
+        cfg = dict(head.nms_cfg)
+        if cfg.pop('nms_type') != 'matrix_nms':
+            raise NotImplementedError('only matrix_nms is on the PP-YOLO path')
+        self.keep_top_k = cfg['keep_top_k']
+        self.nms_out = torch.zeros((n, self.keep_top_k, 6), dtype=torch.float32, device=self.dev)
+        self.nms_counts = torch.zeros((n,), dtype=torch.int32, device=self.dev)
+        ws = ops.nms_workspace(n, self.total_boxes, nc, self.dev)
+        self._add('matrix_nms', lambda: ops.matrix_nms_launch(
+            self.boxes, self.scores, self.nms_out, self.nms_counts, ws, cfg['score_threshold'], cfg['post_threshold'],
+            cfg['nms_top_k'], cfg['keep_top_k'], cfg.get('use_gaussian', False), cfg.get('gaussian_sigma', 2.0)))
+
+    @staticmethod
+    def _stage_channels(bb, stage):
+        last = getattr(bb, bb.stage_names(stage)[-1])
+        unit = last.conv3 if hasattr(last, 'conv4') or type(last).__name__ == 'IdentityBlock' else last.conv2
+        return unit.filters
+
+    # ------------------------------------------------------------------ execution
+    def _run_steps(self):
+        for _, fn in self.steps:
+            fn()
+
+    def _capture(self):
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self._run_steps()                     # warm-up on the capture stream
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        with torch.cuda.graph(g, stream=s):
+            self._run_steps()
+        self.graph = g
+
+    def launch(self):
+        """Enqueue one forward over the static input buffers on the current stream (no sync)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._run_steps()
+
+    def run(self, x, im_size):
+        """PPYOLO.forward(x, im_size) -> list of [M,6] tensors (reference model/ppyolo.py:19-22)."""
+        if tuple(x.shape) != tuple(self.x_in.shape):
+            raise ValueError('engine built for input %s, got %s' % (tuple(self.x_in.shape), tuple(x.shape)))
+        self.x_in.copy_(x, non_blocking=True)
+        self.im_size.copy_(im_size.reshape(self.n, 2), non_blocking=True)
+        self.launch()
+        counts = self.nms_counts.cpu().tolist()          # the one host sync
+        out = self.nms_out.clone()
+        return ops.split_predictions(out, counts)
+
+    def head_outputs_nchw(self):
+        """Raw head outputs of the last run as NCHW fp32 tensors (parity tests)."""
+        return [ops.from_nhwc(o.t, o.c) for o in self.head_outs]

@@ -7,6 +7,7 @@ non-CUDA tensor raises.  The whole-network fast path (``engine.InferenceEngine``
 wrappers and drives the same C entry points over pre-allocated NHWC buffers.
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -84,14 +85,18 @@ _PACK_CACHE = {}
 
 
 def pack_weight(weight, code, c_begin=0, c_count=None):
-    """OIHW fp32 -> packed K-major [cout_pad, k_pad]; cached per (tensor, version, dtype, slice)."""
+    """OIHW fp32 -> packed K-major [cout_pad, k_pad].
+
+    Cached per live tensor object (weak reference + in-place version counter), so module parameters are
+    packed once while temporaries can never alias a stale entry.
+    """
     _cuda(weight, 'weight')
     cout, cin_total, kh, kw = weight.shape
     c_count = cin_total - c_begin if c_count is None else c_count
-    key = (weight.data_ptr(), weight._version, code, c_begin, c_count, tuple(weight.shape))
+    key = (id(weight), code, c_begin, c_count)
     hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
+        return hit[3]
     cin_pad = round_up(c_count, 8)
     k_pad = round_up(kh * kw * cin_pad, 64)
     cout_pad = round_up(cout, 32)
@@ -101,8 +106,9 @@ def pack_weight(weight, code, c_begin=0, c_count=None):
                                    k_pad, code, stream_ptr()), 'pack_conv_weight')
     if len(_PACK_CACHE) > 4096:
         _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (packed, cin_pad, k_pad, cout_pad)
-    return _PACK_CACHE[key]
+    result = (packed, cin_pad, k_pad, cout_pad)
+    _PACK_CACHE[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), result)
+    return result
 
 
 def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, residual=None, bias_map=None,
