@@ -6,15 +6,21 @@
 // model/custom_layers.py:571-676 materialises ~1.3 GB of them per layer at bs=32).
 //
 //   GEMM view: D[M x N] = A[M x K] * B[N x K]^T,  M = n*ho*wo pixels, N = cout, K = kh*kw*cin,
-//   K index = (ky*kw + kx)*cin + c.  CTA tile 128 x BLOCK_N x 64, one tile per CTA.
+//   K index = (ky*kw + kx)*cin + c.  CTA tile 128 x BLOCK_N x 64.
 //
-//   warps 0-3  A producers: thread r owns tile row r; per 64-wide K block it issues eight 16-byte
-//              cp.async (zero-fill outside the image) into the 128B-swizzled K-major stage; later the
-//              epilogue: tcgen05.ld 32 columns at a time -> scale/shift/residual/act -> 64/128-byte stores
-//   warp 4     B producer: one thread issues TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) of the packed
-//              weight tile [BLOCK_N x 64] with mbarrier complete_tx
-//   warp 5     TMEM allocator + MMA issuer: one thread issues 4 x tcgen05.mma (K=16 each) per stage and
-//              tcgen05.commit's the stage back to the producers
+// PERSISTENT, warp-specialised: one CTA per SM walks tiles (n fastest) with stride gridDim.x; the TMEM
+// accumulator is double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+//   warps 0-3  epilogue: warp w owns TMEM lanes 32w..32w+31; per 32-column sub-tile: tcgen05.ld -> padded
+//              warp-private smem slab -> coalesced pass (lane = 8 channels of a row): CoordConv bias map,
+//              scale/shift, residual (16-byte loads, all issued before use), activation, 16-byte stores
+//   warps 4-7  A producers (MODE gather): per 64-wide K block each thread issues eight 16-byte cp.async
+//              (zero-fill outside the image) into the 128B-swizzled K-major stage, eight consecutive lanes
+//              covering one pixel's contiguous 128-byte channel run.  (MODE dcn): thread = tile row,
+//              bilinear sample x mask in fp32 -> bf16 st.shared.  (MODE tma_a, 1x1 stride-1): idle, the
+//              A tile is a plain [128 x 64] box of the NHWC matrix and comes in by TMA.
+//   warp 8     TMA producer: weight tile [BLOCK_N x 64] (SWIZZLE_128B) per stage, + the A tile in tma_a mode
+//   warp 9     TMEM allocator + MMA issuer: one thread, 4 x tcgen05.mma (K=16) per stage, tcgen05.commit
 //
 // Shared-memory operand layout is the canonical K-major SWIZZLE_128B one: row r of a stage lives at
 // r*128 bytes, its 16-byte chunk j at ((j ^ (r & 7)) << 4); 8-row groups are 1024 bytes apart (SBO).
@@ -30,14 +36,19 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                  // 4 epilogue + 4 producer + 1 TMA + 1 MMA warps
 constexpr int CP_LAG = 2;                         // cp.async groups in flight per producer thread
+constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2;
+constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
+constexpr int ST_LD = SUB + 4;                    // floats per staged row (+4: conflict-free v4 access)
+constexpr int STAGING_BYTES = BLOCK_M * ST_LD * 4;
 
 template <int BN> struct TileCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kBStageBytes = BN * BLOCK_K * 2;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;      // power of two for BN in {32,64,128,256}
-  static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
+  static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + STAGING_BYTES + 1024 /*align slack*/ +
+                                    512 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -132,241 +143,345 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Generic (unaligned / partial-vector / upsampling / fp32-residual) epilogue for 8 channels of one output row.
+// Kept out of line so the hot path of the kernel stays small enough for the instruction cache.
+__device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, const float* acc8, int m, int co, int ho, int wo, float slope) {
+  const int ncol = (p.cout - co) < 8 ? (p.cout - co) : 8;
+  const int hw_out = ho * wo;
+  const int pix = m % hw_out, img = m / hw_out;
+  const int oy = pix / wo, ox = pix % wo;
+  for (int e = 0; e < ncol; ++e) {
+    float f = acc8[e];
+    if (p.bias_map) f += __ldg(p.bias_map + (size_t)pix * p.cout + co + e);
+    f = f * __ldg(p.scale + co + e) + __ldg(p.shift + co + e);
+    if (p.residual) {
+      if (p.out_dtype == PPY_BF16) f += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)m * p.res_ld + co + e]);
+      else f += reinterpret_cast<const float*>(p.residual)[(size_t)m * p.res_ld + co + e];
+    }
+    f = f > 0.f ? f : f * slope;
+    const int reps = p.upsample2x ? 4 : 1;
+    for (int q = 0; q < reps; ++q) {
+      size_t drow = (size_t)m;
+      if (p.upsample2x) drow = ((size_t)img * 2 * ho + 2 * oy + (q >> 1)) * 2 * wo + 2 * ox + (q & 1);
+      if (p.out_dtype == PPY_BF16) reinterpret_cast<__nv_bfloat16*>(p.y)[drow * p.y_ld + co + e] = __float2bfloat16_rn(f);
+      else reinterpret_cast<float*>(p.y)[drow * p.y_ld + co + e] = f;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool DCN>
-__global__ void __launch_bounds__(NUM_THREADS)
-conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb,
-                 const __grid_constant__ CUtensorMap tmap_b) {
+template <int BN, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
+                 const int num_n_tiles, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_a) {
   using Cfg = TileCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + S * A_STAGE_BYTES;
-  const uint32_t bars = smem_b + S * Cfg::kBStageBytes;      // full[S], empty[S], tmem_full, tmem_ptr
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + S * (A_STAGE_BYTES + Cfg::kBStageBytes) + (2 * S + 1) * 8);
+  const uint32_t stg_off = S * (A_STAGE_BYTES + Cfg::kBStageBytes);
+  const uint32_t bars = smem_base + stg_off + STAGING_BYTES;   // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_ptr
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + STAGING_BYTES + (2 * S + 4) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * S);
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long M = (long long)p.n * ho * wo;
-  const long long m0 = (long long)blockIdx.y * BLOCK_M;
-  const int n0 = blockIdx.x * BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), BLOCK_M + 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    const uint32_t full_count = (MODE == MODE_TMA_A) ? 1u : (uint32_t)(BLOCK_M + 1);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
+  if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
-  if (warp < 4) {
-    // ======================= A producer (thread = tile row) =======================
-    const int r = tid;
-    const long long m = m0 + r;
-    const bool valid = m < M;
-    int img = 0, oy = 0, ox = 0;
-    if (valid) { ox = (int)(m % wo); oy = (int)((m / wo) % ho); img = (int)(m / ((long long)wo * ho)); }
+  if (warp >= 4 && warp < 8) {
+    // =====================================================================================
+    // A producers
+    // =====================================================================================
+    const int ptid = tid - 128;
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
     const int taps = p.kh * p.kw;
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    if (!DCN) {
-      int tap = 0, c = 0, ky = 0, kx = 0;
-      const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
-        const uint32_t dst_row = smem_a + s * A_STAGE_BYTES + row_off;
+    if (MODE == MODE_GATHER) {
+      const int j = ptid & 7, rg = ptid >> 3;
+      const uint32_t dst0 = (uint32_t)rg * 128u + (((uint32_t)j ^ (uint32_t)(rg & 7)) << 4);
+      int g = 0;                                   // global K-block counter (ring position)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long m0 = (long long)(tile / num_n_tiles) * BLOCK_M;
+        int iy0[8], ix0[8];
+        long long pbase[8];                        // element offset of pixel (img, 0, 0); < 0 = row beyond M
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int iy = iy0 + ky, ix = ix0 + kx;
-          const bool ok = valid && tap < taps && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-          const __nv_bfloat16* src = ok ? x + (((long long)img * p.h + iy) * p.w + ix) * p.x_ld + c : x;
-          cp_async16(dst_row + (((uint32_t)j ^ sw) << 4), src, ok ? 16u : 0u);
-          c += 8;
-          if (c >= p.cin) { c = 0; ++tap; if (++kx == p.kw) { kx = 0; ++ky; } }
+        for (int i = 0; i < 8; ++i) {
+          const long long m = m0 + rg + 16 * i;
+          if (m < M) {
+            const unsigned mu = (unsigned)m, pix = mu % (unsigned)(wo * ho), img = mu / (unsigned)(wo * ho);
+            const int oy = (int)(pix / (unsigned)wo), ox = (int)(pix % (unsigned)wo);
+            iy0[i] = oy * p.stride - p.pad; ix0[i] = ox * p.stride - p.pad;
+            pbase[i] = (long long)img * p.h * p.w;
+          } else { iy0[i] = 0; ix0[i] = 0; pbase[i] = -1; }
         }
-        cp_async_commit();
-        if (kb >= CP_LAG) {
-          cp_async_wait<CP_LAG>();
-          fence_proxy_async();
-          mbar_arrive(full_bar((kb - CP_LAG) % S));
+        int tap = 0, c = j * 8, ky = 0, kx = 0;
+        while (c >= p.cin) { c -= p.cin; ++tap; if (++kx == p.kw) { kx = 0; ++ky; } }
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % S;
+          mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
+          const uint32_t dst = smem_a + s * A_STAGE_BYTES + dst0;
+          const bool tap_ok = tap < taps;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int iy = iy0[i] + ky, ix = ix0[i] + kx;
+            const bool ok = tap_ok && pbase[i] >= 0 && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+            const __nv_bfloat16* src = ok ? x + (pbase[i] + (long long)iy * p.w + ix) * p.x_ld + c : x;
+            cp_async16(dst + (uint32_t)i * (16u * 128u), src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          c += BLOCK_K;
+          while (c >= p.cin) { c -= p.cin; ++tap; if (++kx == p.kw) { kx = 0; ++ky; } }
+          if (g >= CP_LAG) {
+            cp_async_wait<CP_LAG>();
+            fence_proxy_async();
+            mbar_arrive(full_bar((g - CP_LAG) % S));
+          }
         }
       }
-      // drain the last CP_LAG groups
       cp_async_wait<0>();
       fence_proxy_async();
-      for (int kb = (num_kb > CP_LAG ? num_kb - CP_LAG : 0); kb < num_kb; ++kb) mbar_arrive(full_bar(kb % S));
-    } else {
-      // DCNv2: one tap per K block (cin % 64 == 0); bilinear sample + modulation, fp32 math, bf16 store
-      const float* om = valid ? p.offset_mask + m * p.om_ld : nullptr;
+      for (int q = (g > CP_LAG ? g - CP_LAG : 0); q < g; ++q) mbar_arrive(full_bar(q % S));
+    } else if (MODE == MODE_DCN) {
+      // thread = tile row; one tap per K block (cin % 64 == 0)
+      const int r = ptid;
+      const uint32_t row_off = (uint32_t)r * 128u;
+      const uint32_t sw = (uint32_t)(r & 7);
       const int kb_per_tap = p.cin / BLOCK_K;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long m = (long long)(tile / num_n_tiles) * BLOCK_M + r;
+        const bool valid = m < M;
+        int img = 0, oy = 0, ox = 0;
+        if (valid) { ox = (int)(m % wo); oy = (int)((m / wo) % ho); img = (int)(m / ((long long)wo * ho)); }
+        const float* om = valid ? p.offset_mask + m * p.om_ld : nullptr;
         float w4[4] = {0.f, 0.f, 0.f, 0.f};
         const __nv_bfloat16* src4[4] = {nullptr, nullptr, nullptr, nullptr};
-        if (valid && tap < taps) {
-          const int ky = tap / p.kw, kx = tap % p.kw;
-          const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1), ml = __ldg(om + 2 * taps + tap);
-          const float mask = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-ml)));
-          const float py = (float)(oy * p.stride - p.pad + ky) + dy, px = (float)(ox * p.stride - p.pad + kx) + dx;
-          const float fy = floorf(py), fx = floorf(px);
-          const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-          const int y0 = (int)fy, x0 = (int)fx;
-          const float wq[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % S;
+          const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
+          if (c0 == 0) {                          // new tap: sampling position, corner pointers and weights
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int yy = y0 + (q >> 1), xx = x0 + (q & 1);
-            if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
-              src4[q] = x + (((long long)img * p.h + yy) * p.w + xx) * p.x_ld + c0;
-              w4[q] = wq[q] * mask;
+            for (int q = 0; q < 4; ++q) { src4[q] = nullptr; w4[q] = 0.f; }
+            if (valid && tap < taps) {
+              const int ky = tap / p.kw, kx = tap % p.kw;
+              const float dy = __ldg(om + 2 * tap), dx = __ldg(om + 2 * tap + 1), ml = __ldg(om + 2 * taps + tap);
+              const float mask = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-ml)));
+              const float py = (float)(oy * p.stride - p.pad + ky) + dy, px = (float)(ox * p.stride - p.pad + kx) + dx;
+              const float fy = floorf(py), fx = floorf(px);
+              const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+              const int y0 = (int)fy, x0 = (int)fx;
+              const float wq[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int yy = y0 + (q >> 1), xx = x0 + (q & 1);
+                if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w) {
+                  src4[q] = x + (((long long)img * p.h + yy) * p.w + xx) * p.x_ld;
+                  w4[q] = wq[q] * mask;
+                }
+              }
             }
           }
-        }
-        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
-        const uint32_t dst_row = smem_a + s * A_STAGE_BYTES + row_off;
+          mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
+          const uint32_t dst_row = smem_a + s * A_STAGE_BYTES + row_off;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (src4[q]) {
-              const uint4 v = __ldg(reinterpret_cast<const uint4*>(src4[q] + 8 * j));
-              const float wq = w4[q];
-              acc[0] += wq * bf_lo(v.x); acc[1] += wq * bf_hi(v.x); acc[2] += wq * bf_lo(v.y); acc[3] += wq * bf_hi(v.y);
-              acc[4] += wq * bf_lo(v.z); acc[5] += wq * bf_hi(v.z); acc[6] += wq * bf_lo(v.w); acc[7] += wq * bf_hi(v.w);
-            }
-          }
-          const uint32_t d = dst_row + (((uint32_t)j ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(pack_bf16(acc[0], acc[1])),
-                       "r"(pack_bf16(acc[2], acc[3])), "r"(pack_bf16(acc[4], acc[5])), "r"(pack_bf16(acc[6], acc[7])) : "memory");
-        }
-        fence_proxy_async();
-        mbar_arrive(full_bar(s));
-      }
-    }
-
-    // ======================= epilogue (same 4 warps; warp w owns TMEM lanes 32w..32w+31) ==========
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const long long pix = (long long)oy * wo + ox;
-    const float* bm_row = p.bias_map ? p.bias_map + pix * p.cout : nullptr;
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), v);
-      const int co0 = n0 + cc * 32;
-      if (!valid || co0 >= p.cout) continue;
-      const int ncol = (p.cout - co0) < 32 ? (p.cout - co0) : 32;
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a = __uint_as_float(v[j]);
-        if (j < ncol) {
-          if (bm_row) a += __ldg(bm_row + co0 + j);
-          a = a * __ldg(p.scale + co0 + j) + __ldg(p.shift + co0 + j);
-        }
-        f[j] = a;
-      }
-      if (p.out_dtype == PPY_BF16) {
-        const bool vec = (ncol == 32) && ((p.y_ld & 7) == 0) && ((co0 & 7) == 0);
-        if (p.residual) {
-          const __nv_bfloat16* rr = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.res_ld + co0;
-          if (vec && (p.res_ld & 7) == 0) {
+          for (int j = 0; j < 8; ++j) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 t = __ldg(reinterpret_cast<const uint4*>(rr) + q);
-              f[8 * q + 0] += bf_lo(t.x); f[8 * q + 1] += bf_hi(t.x); f[8 * q + 2] += bf_lo(t.y); f[8 * q + 3] += bf_hi(t.y);
-              f[8 * q + 4] += bf_lo(t.z); f[8 * q + 5] += bf_hi(t.z); f[8 * q + 6] += bf_lo(t.w); f[8 * q + 7] += bf_hi(t.w);
+              if (src4[q]) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src4[q] + c0 + 8 * j));
+                const float wq = w4[q];
+                acc[0] += wq * bf_lo(v.x); acc[1] += wq * bf_hi(v.x); acc[2] += wq * bf_lo(v.y); acc[3] += wq * bf_hi(v.y);
+                acc[4] += wq * bf_lo(v.z); acc[5] += wq * bf_hi(v.z); acc[6] += wq * bf_lo(v.w); acc[7] += wq * bf_hi(v.w);
+              }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) f[j] += __bfloat162float(rr[j]);
+            const uint32_t d = dst_row + (((uint32_t)j ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(pack_bf16(acc[0], acc[1])),
+                         "r"(pack_bf16(acc[2], acc[3])), "r"(pack_bf16(acc[4], acc[5])), "r"(pack_bf16(acc[6], acc[7])) : "memory");
           }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y);
-        const int reps = p.upsample2x ? 4 : 1;
-        for (int q4 = 0; q4 < reps; ++q4) {
-          long long drow = m;
-          if (p.upsample2x) drow = ((long long)img * 2 * ho + 2 * oy + (q4 >> 1)) * 2 * wo + 2 * ox + (q4 & 1);
-          __nv_bfloat16* dst = yb + drow * p.y_ld + co0;
-          if (vec && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<uint4*>(dst)[q] = make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
-                                                            pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) dst[j] = __float2bfloat16_rn(f[j]);
-          }
-        }
-      } else {
-        if (p.residual) {
-          const float* rr = reinterpret_cast<const float*>(p.residual) + m * p.res_ld + co0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncol) f[j] += __ldg(rr + j);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        float* yf = reinterpret_cast<float*>(p.y);
-        const int reps = p.upsample2x ? 4 : 1;
-        for (int q4 = 0; q4 < reps; ++q4) {
-          long long drow = m;
-          if (p.upsample2x) drow = ((long long)img * 2 * ho + 2 * oy + (q4 >> 1)) * 2 * wo + 2 * ox + (q4 & 1);
-          float* dst = yf + drow * p.y_ld + co0;
-          if (ncol == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncol) dst[j] = f[j];
-          }
+          fence_proxy_async();
+          mbar_arrive(full_bar(s));
         }
       }
     }
-  } else if (warp == 4) {
-    // ======================= B producer: TMA of the packed weight tile =======================
+    // MODE_TMA_A: producers have nothing to do
+  } else if (warp == 8) {
+    // =====================================================================================
+    // TMA producer (weights; + activations in tma_a mode)
+    // =====================================================================================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
-        mbar_arrive_expect_tx(full_bar(s), Cfg::kBStageBytes);
-        tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K, n0);
+      constexpr uint32_t tx_bytes = Cfg::kBStageBytes + (MODE == MODE_TMA_A ? A_STAGE_BYTES : 0);
+      int g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % num_n_tiles) * BN;
+        const int m0 = (tile / num_n_tiles) * BLOCK_M;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % S;
+          mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
+          mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+          if (MODE == MODE_TMA_A) tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
+          tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K, n0);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =====================================================================================
+    // MMA issuer
+    // =====================================================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tmem_empty_bar(acc), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % S;
+          mbar_wait(full_bar(s), (g / S) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_a + s * A_STAGE_BYTES, b_addr = smem_b + s * Cfg::kBStageBytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));             // frees the stage once these MMAs have read it
+        }
+        umma_commit(tmem_full_bar(acc));         // accumulator complete -> epilogue
       }
     }
   } else {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(full_bar(s), (kb / S) & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_a + s * A_STAGE_BYTES, b_addr = smem_b + s * Cfg::kBStageBytes;
+    // =====================================================================================
+    // epilogue warps 0-3
+    // =====================================================================================
+    float* slab = reinterpret_cast<float*>(gen_base + stg_off) + (size_t)warp * 32 * ST_LD;   // warp-private 32 rows
+    const uint32_t slab_u32 = smem_base + stg_off + (uint32_t)(warp * 32 * ST_LD * 4);
+    const bool out_bf16 = p.out_dtype == PPY_BF16;
+    const int esz = out_bf16 ? 2 : 4;
+    const unsigned hw_out = (unsigned)(ho * wo);
+    const int colv = (lane & 3) * 8;             // 4 lanes cover a 32-column row segment, 8 rows per pass
+    const int rsub = lane >> 2;
+    const float slope = p.act == PPY_ACT_RELU ? 0.f : (p.act == PPY_ACT_LEAKY ? 0.1f : 1.f);
+    // the fast path needs 16-byte aligned full vectors everywhere; anything else goes through epilogue_slow
+    const bool aligned = ((p.y_ld * esz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && !p.upsample2x &&
+                         (!p.residual || (out_bf16 && ((p.res_ld * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
+                         (!p.bias_map || (p.cout & 7) == 0);
+    const bool has_res = p.residual != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int n0 = (tile % num_n_tiles) * BN;
+      const int m0 = (tile / num_n_tiles) * BLOCK_M;
+      int mrow[4];
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k)
-          umma_bf16(tmem_base, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(empty_bar(s));          // frees the stage once these MMAs have read it
+      for (int ps = 0; ps < 4; ++ps) {
+        const long long m = (long long)m0 + warp * 32 + ps * 8 + rsub;
+        mrow[ps] = m < M ? (int)m : -1;
       }
-      umma_commit(tmem_full_bar);           // accumulator complete -> epilogue
+      // residual of sub-tile 0 is requested before the accumulator is even ready
+      uint4 rv[4];
+      auto load_res = [&](int cc, uint4 (&dst)[4]) {
+        const int co = n0 + cc * SUB + colv;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          dst[ps] = make_uint4(0u, 0u, 0u, 0u);
+          if (has_res && aligned && mrow[ps] >= 0 && co + 8 <= p.cout)
+            dst[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                           (size_t)mrow[ps] * p.res_ld + co));
+        }
+      };
+      load_res(0, rv);
+      mbar_wait(tmem_full_bar(acc), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / SUB; ++cc) {
+        uint4 rn[4];
+        if (cc + 1 < BN / SUB) load_res(cc + 1, rn);
+        // phase 1: TMEM -> warp-private slab (lane = row)
+        {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + cc * SUB), v);
+          const uint32_t st_row = slab_u32 + (uint32_t)lane * (ST_LD * 4);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (uint32_t)(q * 16)),
+                         "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3]) : "memory");
+        }
+        if (cc == BN / SUB - 1) {                // all TMEM reads of this tile are done: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        } else {
+          __syncwarp();
+        }
+        // phase 2: coalesced (lane = 8 channels of one row; 8 rows per pass, 4 passes)
+        const int co = n0 + cc * SUB + colv;
+        if (co < p.cout) {
+          if (aligned && co + 8 <= p.cout) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + co)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + co) + 1);
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + co)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + co) + 1);
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+              const int m = mrow[ps];
+              if (m < 0) continue;
+              const float* sp = slab + (ps * 8 + rsub) * ST_LD + colv;
+              float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+              if (p.bias_map) {
+                const float4* bm = reinterpret_cast<const float4*>(p.bias_map + (size_t)((unsigned)m % hw_out) * p.cout + co);
+                const float4 b0 = __ldg(bm), b1 = __ldg(bm + 1);
+                a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w; b.x += b1.x; b.y += b1.y; b.z += b1.z; b.w += b1.w;
+              }
+              a.x = a.x * s0.x + h0.x; a.y = a.y * s0.y + h0.y; a.z = a.z * s0.z + h0.z; a.w = a.w * s0.w + h0.w;
+              b.x = b.x * s1.x + h1.x; b.y = b.y * s1.y + h1.y; b.z = b.z * s1.z + h1.z; b.w = b.w * s1.w + h1.w;
+              const uint4 t = rv[ps];            // zeros when there is no residual
+              a.x += bf_lo(t.x); a.y += bf_hi(t.x); a.z += bf_lo(t.y); a.w += bf_hi(t.y);
+              b.x += bf_lo(t.z); b.y += bf_hi(t.z); b.z += bf_lo(t.w); b.w += bf_hi(t.w);
+              a.x = a.x > 0.f ? a.x : a.x * slope; a.y = a.y > 0.f ? a.y : a.y * slope;
+              a.z = a.z > 0.f ? a.z : a.z * slope; a.w = a.w > 0.f ? a.w : a.w * slope;
+              b.x = b.x > 0.f ? b.x : b.x * slope; b.y = b.y > 0.f ? b.y : b.y * slope;
+              b.z = b.z > 0.f ? b.z : b.z * slope; b.w = b.w > 0.f ? b.w : b.w * slope;
+              if (out_bf16) {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)m * p.y_ld + co) =
+                    make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+              } else {
+                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + (size_t)m * p.y_ld + co);
+                dst[0] = a; dst[1] = b;
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int ps = 0; ps < 4; ++ps)
+              if (mrow[ps] >= 0) epilogue_slow(p, slab + (ps * 8 + rsub) * ST_LD + colv, mrow[ps], co, ho, wo, slope);
+          }
+        }
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) rv[ps] = rn[ps];
+        __syncwarp();                            // slab is rewritten by the next sub-tile
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 9) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -390,39 +505,67 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool DCN>
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int encode_2d(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
+              uint32_t box_inner, uint32_t box_outer) {
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+  return PPY_OK;
+}
+
+template <int BN, int MODE>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PPY_ERR_UNSUPPORTED;
-  CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)p->k_pad, (cuuint64_t)p->cout_pad};
-  const cuuint64_t strides[1] = {(cuuint64_t)p->k_pad * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BN};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p->weight), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+  CUtensorMap tmap_b, tmap_a;
+  int rc = encode_2d(enc, &tmap_b, p->weight, (uint64_t)p->k_pad, (uint64_t)p->cout_pad, (uint64_t)p->k_pad * 2, BLOCK_K, BN);
+  if (rc) return rc;
+  const long long M = (long long)p->n * ho * wo;
+  if (MODE == MODE_TMA_A) {
+    // 1x1 stride-1: the A operand is the NHWC activation itself, [M rows][cin] with row pitch x_ld
+    rc = encode_2d(enc, &tmap_a, p->x, (uint64_t)p->cin, (uint64_t)M, (uint64_t)p->x_ld * 2, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+  } else {
+    tmap_a = tmap_b;
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    int rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, DCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (rc) return rc;
     attr_done = true;
   }
-  const long long M = (long long)p->n * ho * wo;
-  dim3 grid((unsigned)ceil_div(p->cout, BN), (unsigned)ceil_div(M, BLOCK_M));
-  conv_umma_kernel<BN, DCN><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, p->k_pad / BLOCK_K, tmap);
+  const int num_m_tiles = (int)ceil_div(M, BLOCK_M), num_n_tiles = (int)ceil_div(p->cout, BN);
+  const long long tiles = (long long)num_m_tiles * num_n_tiles;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  conv_umma_kernel<BN, MODE><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, p->k_pad / BLOCK_K, num_m_tiles,
+                                                                        num_n_tiles, tmap_b, tmap_a);
   return check_launch();
 }
 
-template <bool DCN>
+template <int MODE>
 int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int c = p->cout;
-  if (c <= 32) return launch<32, DCN>(p, ho, wo, st);
-  if (c <= 64) return launch<64, DCN>(p, ho, wo, st);
-  if (c % 256 == 0) return launch<256, DCN>(p, ho, wo, st);
-  return launch<128, DCN>(p, ho, wo, st);
+  if (c <= 32) return launch<32, MODE>(p, ho, wo, st);
+  if (c <= 64) return launch<64, MODE>(p, ho, wo, st);
+  if (c % 256 == 0) return launch<256, MODE>(p, ho, wo, st);
+  return launch<128, MODE>(p, ho, wo, st);
 }
 
 }  // namespace
@@ -444,9 +587,15 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   if (rc) return rc;
   PPY_REQUIRE(p->k_pad * 2 % 16 == 0);
   if (p->offset_mask) PPY_REQUIRE(p->cin % BLOCK_K == 0);
+  PPY_REQUIRE((long long)p->n * ho * wo < 0x7FFFFFFFll);
+  if (p->act == PPY_ACT_MISH) return PPY_ERR_UNSUPPORTED;   // no config uses it; ppy_activation covers module-level Mish
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->shift) & 15) == 0);
   if (!ppy_conv_bf16_supported()) return PPY_ERR_UNSUPPORTED;
-  if (p->offset_mask) return dispatch<true>(p, ho, wo, as_stream(s));
-  return dispatch<false>(p, ho, wo, as_stream(s));
+  if (p->offset_mask) return dispatch<MODE_DCN>(p, ho, wo, as_stream(s));
+  const bool plain_1x1 = p->kh == 1 && p->stride == 1 && p->pad == 0 && p->cin % BLOCK_K == 0 &&
+                         p->k_pad == p->cin;
+  if (plain_1x1) return dispatch<MODE_TMA_A>(p, ho, wo, as_stream(s));
+  return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }
 
 }  // extern "C"

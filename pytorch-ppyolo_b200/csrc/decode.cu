@@ -51,10 +51,14 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(DecodeArgs p) {
   const int gx = pix % p.size, gy = pix / p.size;
   const float* px = p.head + ((long long)img * p.size * p.size + pix) * p.ld;
   const int base = (p.iou_aware ? p.an : 0) + a * (5 + p.nc);
-  float t_obj = __ldg(px + base + 4);
-  float conf;
-  if (p.iou_aware) conf = sigmoidf_ref(fused_obj_logit(t_obj, __ldg(px + a), p.e_obj, p.e_iou));
-  else conf = sigmoidf_ref(t_obj);
+  // objectness (pow/log heavy when IoU-aware) once per warp, broadcast to the class lanes
+  float conf = 0.f;
+  if (lane == 0) {
+    const float t_obj = __ldg(px + base + 4);
+    if (p.iou_aware) conf = sigmoidf_ref(fused_obj_logit(t_obj, __ldg(px + a), p.e_obj, p.e_iou));
+    else conf = sigmoidf_ref(t_obj);
+  }
+  conf = __shfl_sync(0xffffffffu, conf, 0);
   const long long row = (long long)img * p.total_boxes + p.box_offset + r;
   float* srow = p.scores + row * p.nc;
   for (int c = lane; c < p.nc; c += 32) srow[c] = __fmul_rn(conf, sigmoidf_ref(__ldg(px + base + 5 + c)));

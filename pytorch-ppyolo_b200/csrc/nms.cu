@@ -195,6 +195,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   __shared__ int s_label[kMaxN];
   __shared__ float s_comp[kMaxN];
   __shared__ float s_new[kMaxN];
+  __shared__ unsigned char s_odd[kMaxN];   // box whose IoU can be NaN/inf (area not a positive finite number)
   __shared__ int s_nan_from;   // largest i with NaN compensate (poisons every column j <= i), -1 if none
   __shared__ int s_kept;
   const int img = blockIdx.x;
@@ -221,15 +222,21 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     unsigned int flat = 0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull);
     s_score[i] = __uint_as_float((unsigned int)(k >> 32));
     s_label[i] = (int)(flat % (unsigned)num_classes);
-    s_box[i] = __ldg(gb + flat / (unsigned)num_classes);
+    const float4 bx = __ldg(gb + flat / (unsigned)num_classes);
+    s_box[i] = bx;
+    const float area = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    s_odd[i] = !(area > 0.f && area < CUDART_INF_F);
   }
   __syncthreads();
   // compensate[j] = max_i (iou*same)[i][j] over the strict upper triangle (matrix_nms.py:67-78); warp per column
   for (int j = wid; j < n; j += nwarps) {
     const float4 bj = s_box[j];
     const int lj = s_label[j];
+    const bool oddj = s_odd[j];
     float mx = 0.f;
     for (int i = lane; i < j; i += 32) {
+      // different labels contribute iou*0 = 0 exactly unless the IoU itself is NaN, which needs an odd box
+      if (s_label[i] != lj && !oddj && !s_odd[i]) continue;
       float v = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
       mx = nan_max(mx, v);
     }
@@ -247,9 +254,11 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   for (int j = wid; j < n; j += nwarps) {
     const float4 bj = s_box[j];
     const int lj = s_label[j];
+    const bool oddj = s_odd[j];
     float mn = CUDART_INF_F;
     for (int i = lane; i < j; i += 32) {
-      float d = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
+      float d = 0.f;
+      if (s_label[i] == lj || oddj || s_odd[i]) d = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
       float c = s_comp[i];
       float e;
       if (use_gaussian) e = __fdiv_rn(expf(__fmul_rn(neg_sigma, __fmul_rn(d, d))), expf(__fmul_rn(neg_sigma, __fmul_rn(c, c))));
