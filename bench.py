@@ -127,6 +127,11 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def is_glue(name):
+    return (name.startswith(('nchw', 'maxpool', 'avgpool', 'spp', 'decode', 'matrix_nms')) or name.endswith('.gather')
+            or name == 'stem.conv1_1')
+
+
 def per_op_times(eng, iters=3):
     """CUDA-event duration of every plan step (eager, on the launching stream), averaged over `iters`."""
     stream = torch.cuda.current_stream()
@@ -238,9 +243,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), rank 0 ----------
     peaks, peak_src = measured_peaks()
     ops_t = per_op_times(eng, iters=3)
-    conv_ms = sum(t for name, t in ops_t if not name.startswith(('nchw', 'maxpool', 'avgpool', 'spp', 'decode', 'matrix_nms')))
+    conv_ms = sum(t for name, t in ops_t if not is_glue(name))
     total_ms = sum(t for _, t in ops_t)
-    conv_launches = sum(1 for name, _ in ops_t if not name.startswith(('nchw', 'maxpool', 'avgpool', 'spp', 'decode', 'matrix_nms')))
+    conv_launches = sum(1 for name, _ in ops_t if not is_glue(name))
     achieved = eng.conv_flops / (conv_ms * 1e-3) / 1e12
     peak = peaks['bf16_tflops_sustained'] if args.precision == 'bf16' else 75.0
     roofline = {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all %d conv launches of one step)' % conv_launches,

@@ -96,6 +96,18 @@ typedef struct ppy_conv_params {
   int om_ld;
 } ppy_conv_params;
 
+/* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)
+ * + folded BN + act -> NHWC.  weight (OIHW [32,3,3,3]), scale, shift are HOST pointers (they travel in the kernel
+ * parameter / constant bank). */
+int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, const float* weight_oihw_host, const float* scale_host,
+                       const float* shift_host, int cout, int act, void* y, int y_ld, int y_dtype, ppy_stream_t s);
+
+/* Stage 1 of the two-kernel DCNv2 (model/custom_layers.py:551-674): bilinear sample x sigmoid(mask) for every
+ * (output pixel, tap) -> out[m][tap*c + ch], the K-major A matrix a 1x1 ppy_conv_* over [n,ho,wo,k*k*c] consumes with
+ * the SAME packed 3x3 weight.  offset_mask as in ppy_conv_params. */
+int ppy_dcn_gather(const void* x, int x_ld, int n, int h, int w, int c, const float* offset_mask, int om_ld, int k,
+                   int stride, int pad, void* out, int dtype, ppy_stream_t s);
+
 /* fp32 SIMT implicit GEMM (the 1e-4 parity path).  x/weight/residual fp32. */
 int ppy_conv_f32(const ppy_conv_params* p, ppy_stream_t s);
 /* bf16 tcgen05 implicit GEMM, fp32 accumulate in TMEM, TMA-fed weights (the throughput path). */

@@ -11,16 +11,17 @@
 // PERSISTENT, warp-specialised: one CTA per SM walks tiles (n fastest) with stride gridDim.x; the TMEM
 // accumulator is double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-//   warps 0-3  epilogue: warp w owns TMEM lanes 32w..32w+31; per 32-column sub-tile: tcgen05.ld -> padded
-//              warp-private smem slab -> coalesced pass (lane = 8 channels of a row): CoordConv bias map,
-//              scale/shift, residual (16-byte loads, all issued before use), activation, 16-byte stores
-//   warps 4-7  A producers (MODE gather): per 64-wide K block each thread issues eight 16-byte cp.async
+//   warps 0-7  epilogue: warp w owns TMEM lanes 32(w&3)..+31 and every other 32-column sub-tile; per sub-tile:
+//              tcgen05.ld (next sub-tile prefetched) -> XOR-swizzled warp-private smem slab -> coalesced pass
+//              (lane = 8 channels of a row): CoordConv bias map, scale/shift, residual (16-byte loads issued one
+//              sub-tile ahead), activation, 16-byte stores
+//   warps 8-11 A producers (MODE gather): per 64-wide K block each thread issues eight 16-byte cp.async
 //              (zero-fill outside the image) into the 128B-swizzled K-major stage, eight consecutive lanes
 //              covering one pixel's contiguous 128-byte channel run.  (MODE dcn): thread = tile row,
 //              bilinear sample x mask in fp32 -> bf16 st.shared.  (MODE tma_a, 1x1 stride-1): idle, the
 //              A tile is a plain [128 x 64] box of the NHWC matrix and comes in by TMA.
-//   warp 8     TMA producer: weight tile [BLOCK_N x 64] (SWIZZLE_128B) per stage, + the A tile in tma_a mode
-//   warp 9     TMEM allocator + MMA issuer: one thread, 4 x tcgen05.mma (K=16) per stage, tcgen05.commit
+//   warp 12    TMA producer: weight tile [BLOCK_N x 64] (SWIZZLE_128B) per stage, + the A tile in tma_a mode
+//   warp 13    TMEM allocator + MMA issuer: one thread, 4 x tcgen05.mma (K=16) per stage, tcgen05.commit
 //
 // Shared-memory operand layout is the canonical K-major SWIZZLE_128B one: row r of a stage lives at
 // r*128 bytes, its 16-byte chunk j at ((j ^ (r & 7)) << 4); 8-row groups are 1024 bytes apart (SBO).
@@ -36,15 +37,17 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 320;                  // 4 epilogue + 4 producer + 1 TMA + 1 MMA warps
-constexpr int CP_LAG = 2;                         // cp.async groups in flight per producer thread
+constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating sub-tiles
+constexpr int NUM_THREADS = 448;                  // 8 epilogue + 4 producer + 1 TMA + 1 MMA warps
+constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5;
 constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2;
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
-constexpr int ST_LD = SUB + 4;                    // floats per staged row (+4: conflict-free v4 access)
-constexpr int STAGING_BYTES = BLOCK_M * ST_LD * 4;
+constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
+constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
 
 template <int BN> struct TileCfg {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
   static constexpr int kBStageBytes = BN * BLOCK_K * 2;
   static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
   static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + STAGING_BYTES + 1024 /*align slack*/ +
@@ -110,7 +113,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -120,7 +124,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -141,6 +144,26 @@ __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// nearest x2 upsample fused into the store: one output pixel -> its 2x2 block (aligned 8-channel vectors)
+__device__ __noinline__ void store_upsampled(const ppy_conv_params& p, int m, int co, int ho, int wo, float4 a, float4 b) {
+  const unsigned hw_out = (unsigned)(ho * wo);
+  const unsigned pix = (unsigned)m % hw_out, img = (unsigned)m / hw_out;
+  const unsigned oy = pix / (unsigned)wo, ox = pix % (unsigned)wo;
+  const size_t r0 = ((size_t)img * 2 * ho + 2 * oy) * 2 * wo + 2 * ox;
+  const size_t rows[4] = {r0, r0 + 1, r0 + 2 * (size_t)wo, r0 + 2 * (size_t)wo + 1};
+  if (p.out_dtype == PPY_BF16) {
+    const uint4 v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + rows[q] * p.y_ld + co) = v;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + rows[q] * p.y_ld + co);
+      dst[0] = a; dst[1] = b;
+    }
+  }
 }
 
 // Generic (unaligned / partial-vector / upsampling / fp32-residual) epilogue for 8 channels of one output row.
@@ -179,6 +202,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
                  const __grid_constant__ CUtensorMap tmap_a) {
   using Cfg = TileCfg<BN>;
   constexpr int S = Cfg::kStages;
+  constexpr int CP_LAG = Cfg::kCpLag;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -199,20 +223,20 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   if (tid == 0) {
     const uint32_t full_count = (MODE == MODE_TMA_A) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= PRODUCER_WARP0 && warp < PRODUCER_WARP0 + 4) {
     // =====================================================================================
     // A producers
     // =====================================================================================
-    const int ptid = tid - 128;
+    const int ptid = tid - PRODUCER_WARP0 * 32;
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
     const int taps = p.kh * p.kw;
     if (MODE == MODE_GATHER) {
@@ -324,7 +348,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       }
     }
     // MODE_TMA_A: producers have nothing to do
-  } else if (warp == 8) {
+  } else if (warp == TMA_WARP) {
     // =====================================================================================
     // TMA producer (weights; + activations in tma_a mode)
     // =====================================================================================
@@ -343,7 +367,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     // =====================================================================================
     // MMA issuer
     // =====================================================================================
@@ -370,21 +394,25 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     }
   } else {
     // =====================================================================================
-    // epilogue warps 0-3
+    // epilogue warps 0-7: warp w reads TMEM lanes 32*(w&3).. and handles sub-tiles cc = (w>>2), (w>>2)+2, ...
     // =====================================================================================
-    float* slab = reinterpret_cast<float*>(gen_base + stg_off) + (size_t)warp * 32 * ST_LD;   // warp-private 32 rows
+    const int quarter = warp & 3, half = warp >> 2;
+    float* slab = reinterpret_cast<float*>(gen_base + stg_off) + (size_t)warp * 32 * ST_LD;   // warp-private 32 x 32 fp32
     const uint32_t slab_u32 = smem_base + stg_off + (uint32_t)(warp * 32 * ST_LD * 4);
     const bool out_bf16 = p.out_dtype == PPY_BF16;
     const int esz = out_bf16 ? 2 : 4;
     const unsigned hw_out = (unsigned)(ho * wo);
-    const int colv = (lane & 3) * 8;             // 4 lanes cover a 32-column row segment, 8 rows per pass
-    const int rsub = lane >> 2;
+    const int cpair = (lane & 3) * 2;            // this lane's two 16-byte chunks (8 channels) of a 32-column row
+    const int colv = cpair * 4;
+    const int rsub = lane >> 2;                  // 8 rows per pass, 4 passes
     const float slope = p.act == PPY_ACT_RELU ? 0.f : (p.act == PPY_ACT_LEAKY ? 0.1f : 1.f);
     // the fast path needs 16-byte aligned full vectors everywhere; anything else goes through epilogue_slow
-    const bool aligned = ((p.y_ld * esz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && !p.upsample2x &&
+    const bool aligned = ((p.y_ld * esz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
                          (!p.residual || (out_bf16 && ((p.res_ld * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
                          (!p.bias_map || (p.cout & 7) == 0);
     const bool has_res = p.residual != nullptr;
+    constexpr int NSUB = BN / SUB;               // sub-tiles per tile
+    constexpr int MY_SUBS = (NSUB + 1) / 2;      // upper bound of sub-tiles per warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -393,44 +421,50 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       int mrow[4];
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
-        const long long m = (long long)m0 + warp * 32 + ps * 8 + rsub;
+        const long long m = (long long)m0 + quarter * 32 + ps * 8 + rsub;
         mrow[ps] = m < M ? (int)m : -1;
       }
-      // residual of sub-tile 0 is requested before the accumulator is even ready
-      uint4 rv[4];
       auto load_res = [&](int cc, uint4 (&dst)[4]) {
         const int co = n0 + cc * SUB + colv;
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
           dst[ps] = make_uint4(0u, 0u, 0u, 0u);
-          if (has_res && aligned && mrow[ps] >= 0 && co + 8 <= p.cout)
+          if (has_res && aligned && cc < NSUB && mrow[ps] >= 0 && co + 8 <= p.cout)
             dst[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
                                                            (size_t)mrow[ps] * p.res_ld + co));
         }
       };
-      load_res(0, rv);
+      // residual of the first sub-tile is requested before the accumulator is even ready
+      uint4 rv[4];
+      load_res(half, rv);
       mbar_wait(tmem_full_bar(acc), (it >> 1) & 1);
       tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      uint32_t v[32];
+      if (half < NSUB) tmem_ld32_nowait(t_row + (uint32_t)(half * SUB), v);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / SUB; ++cc) {
+      for (int k = 0; k < MY_SUBS; ++k) {
+        const int cc = half + 2 * k;
+        if (cc >= NSUB) break;
         uint4 rn[4];
-        if (cc + 1 < BN / SUB) load_res(cc + 1, rn);
-        // phase 1: TMEM -> warp-private slab (lane = row)
+        load_res(cc + 2, rn);
+        // phase 1: accumulator registers (lane = row) -> swizzled warp-private slab
+        tmem_wait_ld();
         {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + cc * SUB), v);
           const uint32_t st_row = slab_u32 + (uint32_t)lane * (ST_LD * 4);
+          const uint32_t sw = (uint32_t)(lane & 7);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + (uint32_t)(q * 16)),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((((uint32_t)q) ^ sw) << 4)),
                          "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3]) : "memory");
         }
-        if (cc == BN / SUB - 1) {                // all TMEM reads of this tile are done: hand the accumulator back
+        if (cc + 2 < NSUB) {
+          tmem_ld32_nowait(t_row + (uint32_t)((cc + 2) * SUB), v);     // next sub-tile streams in during phase 2
+          __syncwarp();
+        } else {                                   // this warp's TMEM reads of the tile are done: release the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-        } else {
-          __syncwarp();
         }
         // phase 2: coalesced (lane = 8 channels of one row; 8 rows per pass, 4 passes)
         const int co = n0 + cc * SUB + colv;
@@ -442,8 +476,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             for (int ps = 0; ps < 4; ++ps) {
               const int m = mrow[ps];
               if (m < 0) continue;
-              const float* sp = slab + (ps * 8 + rsub) * ST_LD + colv;
-              float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+              const int row = ps * 8 + rsub;
+              const float* sp = slab + row * ST_LD;
+              float4 a = *reinterpret_cast<const float4*>(sp + ((cpair ^ (row & 7)) << 2));
+              float4 b = *reinterpret_cast<const float4*>(sp + (((cpair + 1) ^ (row & 7)) << 2));
               if (p.bias_map) {
                 const float4* bm = reinterpret_cast<const float4*>(p.bias_map + (size_t)((unsigned)m % hw_out) * p.cout + co);
                 const float4 b0 = __ldg(bm), b1 = __ldg(bm + 1);
@@ -458,7 +494,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               a.z = a.z > 0.f ? a.z : a.z * slope; a.w = a.w > 0.f ? a.w : a.w * slope;
               b.x = b.x > 0.f ? b.x : b.x * slope; b.y = b.y > 0.f ? b.y : b.y * slope;
               b.z = b.z > 0.f ? b.z : b.z * slope; b.w = b.w > 0.f ? b.w : b.w * slope;
-              if (out_bf16) {
+              if (p.upsample2x) {
+                store_upsampled(p, m, co, ho, wo, a, b);
+              } else if (out_bf16) {
                 *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)m * p.y_ld + co) =
                     make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
               } else {
@@ -468,20 +506,31 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             }
           } else {
 #pragma unroll 1
-            for (int ps = 0; ps < 4; ++ps)
-              if (mrow[ps] >= 0) epilogue_slow(p, slab + (ps * 8 + rsub) * ST_LD + colv, mrow[ps], co, ho, wo, slope);
+            for (int ps = 0; ps < 4; ++ps) {
+              if (mrow[ps] < 0) continue;
+              const int row = ps * 8 + rsub;
+              float tmp[8];
+              const float4 a = *reinterpret_cast<const float4*>(slab + row * ST_LD + ((cpair ^ (row & 7)) << 2));
+              const float4 b = *reinterpret_cast<const float4*>(slab + row * ST_LD + (((cpair + 1) ^ (row & 7)) << 2));
+              tmp[0] = a.x; tmp[1] = a.y; tmp[2] = a.z; tmp[3] = a.w; tmp[4] = b.x; tmp[5] = b.y; tmp[6] = b.z; tmp[7] = b.w;
+              epilogue_slow(p, tmp, mrow[ps], co, ho, wo, slope);
+            }
           }
         }
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) rv[ps] = rn[ps];
         __syncwarp();                            // slab is rewritten by the next sub-tile
       }
+      if (half >= NSUB) {                        // BN == 32: the second warp of a quarter has no sub-tile, still releases
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -586,7 +635,7 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   int rc = validate_conv(p, 2, &ho, &wo);
   if (rc) return rc;
   PPY_REQUIRE(p->k_pad * 2 % 16 == 0);
-  if (p->offset_mask) PPY_REQUIRE(p->cin % BLOCK_K == 0);
+  if (p->offset_mask) PPY_REQUIRE(p->cin % BLOCK_K == 0 && (long long)p->n * p->h * p->w * p->x_ld < 0x7FFFFFFFll);
   PPY_REQUIRE((long long)p->n * ho * wo < 0x7FFFFFFFll);
   if (p->act == PPY_ACT_MISH) return PPY_ERR_UNSUPPORTED;   // no config uses it; ppy_activation covers module-level Mish
   PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->shift) & 15) == 0);

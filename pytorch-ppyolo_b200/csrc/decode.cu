@@ -39,51 +39,65 @@ struct DecodeArgs {
   float* boxes; float* scores; int box_offset; int total_boxes;
 };
 
-__global__ void __launch_bounds__(256) yolo_decode_kernel(DecodeArgs p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long per_img = (long long)p.size * p.size * p.an;
-  if (warp >= per_img * p.n) return;
-  const int img = (int)(warp / per_img);
-  const int r = (int)(warp % per_img);
-  const int a = r % p.an;
-  const int pix = r / p.an;
-  const int gx = pix % p.size, gy = pix / p.size;
-  const float* px = p.head + ((long long)img * p.size * p.size + pix) * p.ld;
-  const int base = (p.iou_aware ? p.an : 0) + a * (5 + p.nc);
-  // objectness (pow/log heavy when IoU-aware) once per warp, broadcast to the class lanes
-  float conf = 0.f;
-  if (lane == 0) {
-    const float t_obj = __ldg(px + base + 4);
-    if (p.iou_aware) conf = sigmoidf_ref(fused_obj_logit(t_obj, __ldg(px + a), p.e_obj, p.e_iou));
-    else conf = sigmoidf_ref(t_obj);
-  }
-  conf = __shfl_sync(0xffffffffu, conf, 0);
-  const long long row = (long long)img * p.total_boxes + p.box_offset + r;
-  float* srow = p.scores + row * p.nc;
-  for (int c = lane; c < p.nc; c += 32) srow[c] = __fmul_rn(conf, sigmoidf_ref(__ldg(px + base + 5 + c)));
-  if (lane == 0) {
-    float tx = __ldg(px + base), ty = __ldg(px + base + 1), tw = __ldg(px + base + 2), th = __ldg(px + base + 3);
-    // (scale_x_y * sigmoid(t) + grid - (scale_x_y - 1) * 0.5) * stride      head.py:40
-    float cx = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(tx)), (float)gx), p.sxy_off), p.stride);
-    float cy = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(ty)), (float)gy), p.sxy_off), p.stride);
-    float bw = __fmul_rn(expf(tw), p.aw[a]);                                 // head.py:44
-    float bh = __fmul_rn(expf(th), p.ah[a]);
-    float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
-    float x0 = __fsub_rn(cx, hw), y0 = __fsub_rn(cy, hh), x1 = __fadd_rn(cx, hw), y1 = __fadd_rn(cy, hh);
-    const float im_h = __ldg(p.im_size + 2 * img), im_w = __ldg(p.im_size + 2 * img + 1);
-    const float fs = (float)p.size;
-    x0 = __fmul_rn(__fdiv_rn(__fdiv_rn(x0, fs), p.stride), im_w);            // head.py:66-67
-    y0 = __fmul_rn(__fdiv_rn(__fdiv_rn(y0, fs), p.stride), im_h);
-    x1 = __fmul_rn(__fdiv_rn(__fdiv_rn(x1, fs), p.stride), im_w);
-    y1 = __fmul_rn(__fdiv_rn(__fdiv_rn(y1, fs), p.stride), im_h);
-    if (p.clip) {                                                            // head.py:73-76
-      x0 = x0 < 0.f ? __fmul_rn(x0, 0.f) : x0;
-      y0 = y0 < 0.f ? __fmul_rn(y0, 0.f) : y0;
-      x1 = x1 > im_w ? im_w : x1;
-      y1 = y1 > im_h ? im_h : y1;
+constexpr int kDecodeWarps = 8;
+constexpr int kMaxPixelFloats = 4 * 96;    // an <= 4, nc + 6 <= 96 channels per anchor staged per warp
+
+// One warp per pixel: the pixel's A*(5|6+C) logits are staged once in shared memory with coalesced loads
+// (all in flight together), every lane then sigmoids its share of the A*C class logits; the A score rows of a
+// pixel are contiguous in the output (box index = pixel*A + a), so the warp writes one contiguous run.
+__global__ void __launch_bounds__(kDecodeWarps * 32) yolo_decode_kernel(DecodeArgs p) {
+  __shared__ float stage[kDecodeWarps][kMaxPixelFloats];
+  __shared__ float conf_s[kDecodeWarps][4];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long npix = (long long)p.n * p.size * p.size;
+  const int per = 5 + p.nc;
+  const int chans = p.an * (per + (p.iou_aware ? 1 : 0));
+  const int first = p.iou_aware ? p.an : 0;
+  float* st = stage[wib];
+  for (long long pixg = (long long)blockIdx.x * kDecodeWarps + wib; pixg < npix; pixg += (long long)gridDim.x * kDecodeWarps) {
+    const int img = (int)(pixg / (p.size * p.size));
+    const int pix = (int)(pixg % (p.size * p.size));
+    const int gx = pix % p.size, gy = pix / p.size;
+    const float* px = p.head + pixg * p.ld;
+    for (int i = lane; i < chans; i += 32) st[i] = __ldg(px + i);
+    __syncwarp();
+    if (lane < p.an) {            // one lane per anchor: objectness (+IoU-aware fusion) and the box
+      const int a = lane;
+      const float* t = st + first + a * per;
+      float conf;
+      if (p.iou_aware) conf = sigmoidf_ref(fused_obj_logit(t[4], st[a], p.e_obj, p.e_iou));
+      else conf = sigmoidf_ref(t[4]);
+      conf_s[wib][a] = conf;
+      // (scale_x_y * sigmoid(t) + grid - (scale_x_y - 1) * 0.5) * stride      head.py:40
+      float cx = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(t[0])), (float)gx), p.sxy_off), p.stride);
+      float cy = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(t[1])), (float)gy), p.sxy_off), p.stride);
+      float bw = __fmul_rn(expf(t[2]), p.aw[a]);                               // head.py:44
+      float bh = __fmul_rn(expf(t[3]), p.ah[a]);
+      float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
+      float x0 = __fsub_rn(cx, hw), y0 = __fsub_rn(cy, hh), x1 = __fadd_rn(cx, hw), y1 = __fadd_rn(cy, hh);
+      const float im_h = __ldg(p.im_size + 2 * img), im_w = __ldg(p.im_size + 2 * img + 1);
+      const float fs = (float)p.size;
+      x0 = __fmul_rn(__fdiv_rn(__fdiv_rn(x0, fs), p.stride), im_w);            // head.py:66-67
+      y0 = __fmul_rn(__fdiv_rn(__fdiv_rn(y0, fs), p.stride), im_h);
+      x1 = __fmul_rn(__fdiv_rn(__fdiv_rn(x1, fs), p.stride), im_w);
+      y1 = __fmul_rn(__fdiv_rn(__fdiv_rn(y1, fs), p.stride), im_h);
+      if (p.clip) {                                                            // head.py:73-76
+        x0 = x0 < 0.f ? __fmul_rn(x0, 0.f) : x0;
+        y0 = y0 < 0.f ? __fmul_rn(y0, 0.f) : y0;
+        x1 = x1 > im_w ? im_w : x1;
+        y1 = y1 > im_h ? im_h : y1;
+      }
+      const long long row = (long long)img * p.total_boxes + p.box_offset + (long long)pix * p.an + a;
+      reinterpret_cast<float4*>(p.boxes)[row] = make_float4(x0, y0, x1, y1);
     }
-    reinterpret_cast<float4*>(p.boxes)[row] = make_float4(x0, y0, x1, y1);
+    __syncwarp();
+    float* srow = p.scores + ((long long)img * p.total_boxes + p.box_offset + (long long)pix * p.an) * p.nc;
+    const int total = p.an * p.nc;
+    for (int i = lane; i < total; i += 32) {
+      const int a = i / p.nc, c = i - a * p.nc;
+      srow[i] = __fmul_rn(conf_s[wib][a], sigmoidf_ref(st[first + a * per + 5 + c]));
+    }
+    __syncwarp();
   }
 }
 
@@ -124,8 +138,11 @@ int ppy_yolo_decode(const float* head, int ld, int n, int size, int an_num, int 
   p.im_size = im_size; p.clip = clip_bbox; p.iou_aware = iou_aware;
   p.e_obj = (float)(1.0 - factor); p.e_iou = (float)factor;   // python-float exponents of head.py:125
   p.boxes = boxes; p.scores = scores; p.box_offset = box_offset; p.total_boxes = total_boxes;
-  long long warps = (long long)n * size * size * an_num;
-  yolo_decode_kernel<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, as_stream(s)>>>(p);
+  PPY_REQUIRE(num_classes + 6 <= 96);
+  long long pixels = (long long)n * size * size;
+  long long blocks = ceil_div(pixels, kDecodeWarps);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  yolo_decode_kernel<<<(unsigned)blocks, kDecodeWarps * 32, 0, as_stream(s)>>>(p);
   return check_launch();
 }
 

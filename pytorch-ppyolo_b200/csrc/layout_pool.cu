@@ -282,3 +282,74 @@ int ppy_activation(void* x, long long count, int act, int dtype, ppy_stream_t s)
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// DCNv2 "gather" stage of the two-kernel deformable conv: one warp per (output pixel, tap) bilinearly samples
+// the NHWC input at the learned offset, applies sigmoid(mask) and writes the C-channel run of
+// A[m][tap*C + c] (bf16/fp32).  The matrix (M x 9C, e.g. 106 MB at bs=32 608^2) is consumed immediately by the
+// TMA-fed 1x1 tcgen05 GEMM and stays L2-resident; the sampling math is identical to the fused kernel's.
+// ------------------------------------------------------------------------------------------------
+namespace ppy {
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) dcn_gather_kernel(const T* __restrict__ x, int x_ld, int n, int h, int w, int c,
+                                                         const float* __restrict__ om, int om_ld, int k, int stride, int pad,
+                                                         int ho, int wo, T* __restrict__ out) {
+  constexpr int V = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int taps = k * k;
+  const long long total = (long long)n * ho * wo * taps;
+  const int cv = c / V;
+  for (long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < total; wi += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int tap = (int)(wi % taps);
+    const long long m = wi / taps;
+    const int ox = (int)(m % wo), oy = (int)((m / wo) % ho), img = (int)(m / ((long long)wo * ho));
+    const float* o = om + m * om_ld;
+    const float dy = __ldg(o + 2 * tap), dx = __ldg(o + 2 * tap + 1), ml = __ldg(o + 2 * taps + tap);
+    const float mask = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-ml)));
+    const float py = (float)(oy * stride - pad + tap / k) + dy, px = (float)(ox * stride - pad + tap % k) + dx;
+    const float fy = floorf(py), fx = floorf(px);
+    const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+    const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)h), x0 = (int)fminf(fmaxf(fx, -2.f), (float)w);
+    const float wq[4] = {hy * hx * mask, hy * lx * mask, ly * hx * mask, ly * lx * mask};
+    const T* src[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = y0 + (q >> 1), xx = x0 + (q & 1);
+      src[q] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? x + (((long long)img * h + yy) * w + xx) * x_ld : nullptr;
+    }
+    T* dst = out + (m * taps + tap) * c;
+    for (int v = lane; v < cv; v += 32) {
+      float acc[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (src[q]) {
+          float t[V];
+          load_vec<T>(src[q] + v * V, t);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] += wq[q] * t[e];
+        }
+      }
+      store_vec<T>(dst + v * V, acc);
+    }
+  }
+}
+}  // namespace
+}  // namespace ppy
+
+extern "C" int ppy_dcn_gather(const void* x, int x_ld, int n, int h, int w, int c, const float* offset_mask, int om_ld, int k,
+                              int stride, int pad, void* out, int dtype, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(x && offset_mask && out && n > 0 && h > 0 && w > 0 && k > 0 && stride > 0 && pad >= 0);
+  PPY_REQUIRE(vec_ok(x, x_ld, c, dtype) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && om_ld >= 3 * k * k);
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  PPY_REQUIRE(ho > 0 && wo > 0);
+  const long long warps = (long long)n * ho * wo * k * k;
+  long long blocks = ceil_div(warps, 8);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  PPY_DISPATCH(dtype, dcn_gather_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(s)>>>((const T*)x, x_ld, n, h, w, c, offset_mask,
+                                                                                     om_ld, k, stride, pad, ho, wo, (T*)out);)
+  return check_launch();
+}

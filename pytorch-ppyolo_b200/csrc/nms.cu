@@ -255,11 +255,16 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     const float4 bj = s_box[j];
     const int lj = s_label[j];
     const bool oddj = s_odd[j];
-    float mn = CUDART_INF_F;
+    // row 0 (comp_0 == 0) contributes (1 - d_0j) <= 1, exactly 1 when skipped below: start the min at 1 for j > 0
+    float mn = j > 0 ? 1.f : CUDART_INF_F;
     for (int i = lane; i < j; i += 32) {
-      float d = 0.f;
-      if (s_label[i] == lj || oddj || s_odd[i]) d = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
+      // d == 0 rows contribute 1/f(comp_i) >= 1 >= row 0's term: only their NaNs matter, and a NaN compensate of
+      // row i < j is covered by s_nan_from >= i only for columns <= i, so keep the exact path when comp_i is not 0
       float c = s_comp[i];
+      const bool same = s_label[i] == lj;
+      if (!same && !oddj && !s_odd[i] && c == 0.f) continue;
+      float d = 0.f;
+      if (same || oddj || s_odd[i]) d = __fmul_rn(box_iou(s_box[i], bj), same ? 1.f : 0.f);
       float e;
       if (use_gaussian) e = __fdiv_rn(expf(__fmul_rn(neg_sigma, __fmul_rn(d, d))), expf(__fmul_rn(neg_sigma, __fmul_rn(c, c))));
       else e = __fdiv_rn(__fsub_rn(1.f, d), __fsub_rn(1.f, c));

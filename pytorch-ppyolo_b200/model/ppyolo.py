@@ -15,15 +15,16 @@ class PPYOLO(torch.nn.Module):
         self.backbone = backbone
         self.head = head
         self.precision = 'bf16'
+        self.dcn_impl = None          # None = engine default; 'fused' | 'gather_gemm'
         self.use_engine = True
         self._engines = {}
 
     def engine(self, batch, height, width):
         from ppyolo_b200.engine import InferenceEngine
-        key = (batch, height, width, self.precision)
+        key = (batch, height, width, self.precision, self.dcn_impl)
         eng = self._engines.get(key)
         if eng is None:
-            eng = InferenceEngine(self, batch, height, width, precision=self.precision)
+            eng = InferenceEngine(self, batch, height, width, precision=self.precision, dcn_impl=self.dcn_impl)
             self._engines[key] = eng
         return eng
 

@@ -47,6 +47,10 @@ SIGNATURES = {
     'ppy_activation': (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p]),
     'ppy_pack_conv_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                      c_int, c_void_p]),
+    'ppy_stem_conv3x3s2': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float),
+                                   ctypes.POINTER(c_float), c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    'ppy_dcn_gather': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                               c_int, c_void_p]),
     'ppy_conv_f32': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_conv_bf16': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_conv_bf16_supported': (c_int, []),

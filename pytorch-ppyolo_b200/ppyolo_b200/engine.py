@@ -47,7 +47,7 @@ class TensorRef(object):
 
 
 class InferenceEngine(object):
-    def __init__(self, model, batch, height, width, precision='bf16', use_graph=True):
+    def __init__(self, model, batch, height, width, precision='bf16', use_graph=True, dcn_impl=None):
         if not torch.cuda.is_available():
             raise RuntimeError('InferenceEngine needs a CUDA device (no CPU fallback)')
         if precision not in ('bf16', 'fp32'):
@@ -63,6 +63,9 @@ class InferenceEngine(object):
         if self.dev.type != 'cuda':
             raise RuntimeError('model must be on a CUDA device')
         self.act_dtype = ops.torch_dtype(self.code)
+        # DCNv2 on the bf16 path: 'gather_gemm' = sampling kernel -> L2-resident A matrix -> TMA-fed 1x1 tcgen05 GEMM
+        # (fastest today); 'fused' = the single im2col-free kernel with the bilinear producer
+        self.dcn_impl = dcn_impl or getattr(model, 'dcn_impl', None) or ('gather_gemm' if precision == 'bf16' else 'fused')
         self.steps = []          # (name, callable)
         self.keep = []           # tensors / ctypes structs referenced by raw pointer
         self.conv_flops = 0      # algorithmic 2*MAC of all convs in the plan (per batch)
@@ -113,6 +116,25 @@ class InferenceEngine(object):
         out = TensorRef(self._new(x.n, x.h, x.w, 4 * x.c))
         return self._simple('spp', lib.ppy_spp, x, out)
 
+    def _stem(self, unit):
+        from model.custom_layers import ACT_CODES
+        scale, shift = unit.folded_scale_shift()
+        w_host = np.ascontiguousarray(unit.conv.weight.detach().float().cpu().numpy())
+        sc_host = np.ascontiguousarray(scale.cpu().numpy())
+        sh_host = np.ascontiguousarray(shift.cpu().numpy())
+        self.keep += [w_host, sc_host, sh_host]
+        ho, wo = (self.h - 1) // 2 + 1, (self.w - 1) // 2 + 1
+        out = TensorRef(self._new(self.n, ho, wo, 32))
+        fp = ctypes.POINTER(ctypes.c_float)
+        args = (ops.ptr(self.x_in), self.n, self.h, self.w, w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp),
+                sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name], ctypes.c_void_p(out.ptr), out.ld, self.code)
+
+        def run():
+            check(lib.ppy_stem_conv3x3s2(*args, ops.stream_ptr()), 'stem.conv1_1')
+        self._add('stem.conv1_1', run)
+        self.conv_flops += 2 * self.n * ho * wo * 32 * 27
+        return out
+
     def _coord_bias_map(self, weight, c_main, h, w):
         """Contribution of the two CoordConv channels for one image: [h*w, cout] fp32 (pre-BN)."""
         cout, _, k, _ = weight.shape
@@ -126,8 +148,12 @@ class InferenceEngine(object):
         return out
 
     def _conv(self, name, x, weight, scale, shift, stride, act, residual=None, dst=None, coord=False, upsample=False,
-              out_code=None, offset_mask=None):
+              out_code=None, offset_mask=None, gemm_taps=False):
+        """``gemm_taps``: ``x`` already is the sampled [n,ho,wo,k*k*cin] matrix of a DCN gather; run the k x k
+        weight as a 1x1 GEMM over it (same packed K order (tap, c))."""
         cout, cin_total, k, _ = weight.shape
+        if gemm_taps:
+            return self._conv_over_taps(name, x, weight, scale, shift, act, residual, dst)
         c_main = cin_total - (2 if coord else 0)
         if c_main != x.c and not (c_main < x.c and x.c == ops.round_up(c_main, 8)):
             raise ValueError('%s: weight expects %d input channels, buffer has %d' % (name, c_main, x.c))
@@ -166,6 +192,50 @@ class InferenceEngine(object):
         self.conv_flops += 2 * x.n * ho * wo * cout * cin_total * k * k
         return dst
 
+    def _conv_over_taps(self, name, xcol, weight, scale, shift, act, residual, dst):
+        cout, cin, k, _ = weight.shape
+        packed, cin_pad, k_pad, cout_pad = ops.pack_weight(weight, self.code)
+        if cin_pad != cin or k_pad != k * k * cin or xcol.c != k * k * cin:
+            raise ValueError('%s: gather_gemm needs cin %% 64 == 0' % name)
+        self._keep(packed)
+        if dst is None:
+            dst = TensorRef(self._new(xcol.n, xcol.h, xcol.w, ops.round_up(cout, 8)), c=cout)
+        p = ConvParams()
+        p.x, p.x_ld = xcol.ptr, xcol.ld
+        p.n, p.h, p.w, p.cin = xcol.n, xcol.h, xcol.w, k * k * cin
+        p.weight = packed.data_ptr()
+        p.cout, p.kh, p.kw, p.stride, p.pad = cout, 1, 1, 1, 0
+        p.k_pad, p.cout_pad = k_pad, cout_pad
+        p.scale, p.shift = self._keep(scale).data_ptr(), self._keep(shift).data_ptr()
+        p.bias_map = None
+        p.residual = residual.ptr if residual is not None else None
+        p.res_ld = residual.ld if residual is not None else 0
+        p.act = act
+        p.y, p.y_ld, p.out_dtype = dst.ptr, dst.ld, self.code
+        p.upsample2x, p.offset_mask, p.om_ld = 0, None, 0
+        self._keep(p)
+        fn = lib.ppy_conv_bf16 if self.code == PPY_BF16 else lib.ppy_conv_f32
+        ref = ctypes.byref(p)
+
+        def run():
+            check(fn(ref, ops.stream_ptr()), name)
+        self._add(name, run)
+        self.conv_flops += 2 * xcol.n * xcol.h * xcol.w * cout * cin * k * k
+        return dst
+
+    def _dcn_gather(self, name, x, om, k, stride):
+        pad = (k - 1) // 2
+        ho = (x.h + 2 * pad - k) // stride + 1
+        wo = (x.w + 2 * pad - k) // stride + 1
+        out = TensorRef(self._new(x.n, ho, wo, k * k * x.c))
+        args = (ctypes.c_void_p(x.ptr), x.ld, x.n, x.h, x.w, x.c, ctypes.c_void_p(om.ptr), om.ld, k, stride, pad,
+                ctypes.c_void_p(out.ptr), x.code)
+
+        def run():
+            check(lib.ppy_dcn_gather(*args, ops.stream_ptr()), name)
+        self._add(name, run)
+        return out
+
     def _unit(self, name, unit, x, residual=None, act=None, dst=None, coord=False, upsample=False, out_code=None):
         """One Conv2dUnit (conv|DCNv2 -> folded norm -> act) as one (DCN: two) kernels."""
         from model.custom_layers import DCNv2, ACT_CODES
@@ -180,6 +250,10 @@ class InferenceEngine(object):
             om = TensorRef(om.t)     # the sampler reads the padded row (ld) directly
             if d.dcn_bias is not None:
                 shift = shift + d.dcn_bias.detach().float() * scale
+            if self.dcn_impl == 'gather_gemm' and x.c % 64 == 0:
+                xcol = self._dcn_gather(name + '.gather', x, om, d.dcn_weight.shape[-1], unit.stride)
+                return self._conv(name, xcol, d.dcn_weight.detach(), scale, shift, 1, act, residual=residual, dst=dst,
+                                  gemm_taps=True)
             return self._conv(name, x, d.dcn_weight.detach(), scale, shift, unit.stride, act, residual=residual,
                               dst=dst, offset_mask=om)
         return self._conv(name, x, unit.conv.weight.detach(), scale, shift, unit.stride, act, residual=residual,
@@ -213,9 +287,16 @@ class InferenceEngine(object):
         # static input: NCHW fp32 exactly as Decode.predict uploads it (model/decode_np.py:142-147)
         self.x_in = torch.zeros((n, 3, self.h, self.w), dtype=torch.float32, device=self.dev)
         self.im_size = torch.zeros((n, 2), dtype=torch.float32, device=self.dev)
-        x0 = TensorRef(self._new(n, self.h, self.w, 8))
-        args = (ops.ptr(self.x_in), ctypes.c_void_p(x0.ptr), n, 3, self.h, self.w, 8, self.code)
-        self._add('nchw_to_nhwc', lambda: check(lib.ppy_nchw_to_nhwc(*args, ops.stream_ptr()), 'nchw_to_nhwc'))
+        stem_units = list(zip(bb._stem_units(), ('conv1_1', 'conv1_2', 'conv1_3')))
+        u0 = stem_units[0][0]
+        if tuple(u0.conv.weight.shape) == (32, 3, 3, 3) and u0.stride == 2 and u0.act_name in (None, 'relu', 'leaky'):
+            # conv1_1 fused with the NCHW->NHWC change (K = 27: HBM-bound, fp32 SIMT, weights in the constant bank)
+            x0 = self._stem(u0)
+            stem_units = stem_units[1:]
+        else:
+            x0 = TensorRef(self._new(n, self.h, self.w, 8))
+            args = (ops.ptr(self.x_in), ctypes.c_void_p(x0.ptr), n, 3, self.h, self.w, 8, self.code)
+            self._add('nchw_to_nhwc', lambda: check(lib.ppy_nchw_to_nhwc(*args, ops.stream_ptr()), 'nchw_to_nhwc'))
 
         # head level i > 0 consumes cat([upsampled route, backbone feature]); give the backbone stage that
         # produces the feature a destination inside that concat buffer (no copy at run time)
@@ -234,7 +315,7 @@ class InferenceEngine(object):
             stage_dst[stage] = TensorRef(buf, feat_c, route_c[i])
 
         x = x0
-        for u, nm in zip(bb._stem_units(), ('conv1_1', 'conv1_2', 'conv1_3')):
+        for u, nm in stem_units:
             x = self._unit('stem.' + nm, u, x)
         x = self._maxpool(x)
         feats = {}
