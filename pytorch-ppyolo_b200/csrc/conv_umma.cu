@@ -20,7 +20,9 @@
 //              covering one pixel's contiguous 128-byte channel run.  (MODE dcn): thread = tile row,
 //              bilinear sample x mask in fp32 -> bf16 st.shared.  (MODE tma_a, 1x1 stride-1): idle, the
 //              A tile is a plain [128 x 64] box of the NHWC matrix and comes in by TMA.
-//   warp 12    TMA producer: weight tile [BLOCK_N x 64] (SWIZZLE_128B) per stage, + the A tile in tma_a mode
+//   warp 12    TMA producer: weight tile [BLOCK_N x 64] (SWIZZLE_128B) per stage, + the A tile in tma_a mode, or
+//              (MODE tma_patch, 3x3 stride-1) one 4-D box {64 ch, 16, 8, 1} per (tap, channel block) at pixel offset
+//              (kx-1, ky-1): the zero halo comes from TMA's out-of-bounds fill, the 128 tile rows are a 16x8 patch
 //   warp 13    TMEM allocator + MMA issuer: one thread, 4 x tcgen05.mma (K=16) per stage, tcgen05.commit
 //
 // Shared-memory operand layout is the canonical K-major SWIZZLE_128B one: row r of a stage lives at
@@ -40,7 +42,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating sub-tiles
 constexpr int NUM_THREADS = 448;                  // 8 epilogue + 4 producer + 1 TMA + 1 MMA warps
 constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5;
-constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2;
+constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3;
+constexpr int PATCH_W = 16, PATCH_H = 8;          // 3x3 stride-1 convs: the 128 tile rows are a 16x8 pixel patch of one image
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
@@ -93,6 +96,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
@@ -198,7 +206,7 @@ __device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, const float
 template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
-                 const int num_n_tiles, const __grid_constant__ CUtensorMap tmap_b,
+                 const int num_n_tiles, const int pw_tiles, const int ph_tiles, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a) {
   using Cfg = TileCfg<BN>;
   constexpr int S = Cfg::kStages;
@@ -221,7 +229,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const int num_tiles = num_m_tiles * num_n_tiles;
 
   if (tid == 0) {
-    const uint32_t full_count = (MODE == MODE_TMA_A) ? 1u : (uint32_t)(BLOCK_M + 1);
+    const uint32_t full_count = (MODE == MODE_TMA_A || MODE == MODE_TMA_PATCH) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS); }
     fence_barrier_init();
@@ -353,16 +361,27 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // TMA producer (weights; + activations in tma_a mode)
     // =====================================================================================
     if (lane == 0) {
-      constexpr uint32_t tx_bytes = Cfg::kBStageBytes + (MODE == MODE_TMA_A ? A_STAGE_BYTES : 0);
+      constexpr uint32_t tx_bytes = Cfg::kBStageBytes + ((MODE == MODE_TMA_A || MODE == MODE_TMA_PATCH) ? A_STAGE_BYTES : 0);
+      const int kb_per_tap = p.cin / BLOCK_K;
       int g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n0 = (tile % num_n_tiles) * BN;
-        const int m0 = (tile / num_n_tiles) * BLOCK_M;
+        const int mt = tile / num_n_tiles;
+        const int m0 = mt * BLOCK_M;
+        int px0 = 0, py0 = 0, img = 0;
+        if (MODE == MODE_TMA_PATCH) {
+          px0 = (mt % pw_tiles) * PATCH_W; py0 = ((mt / pw_tiles) % ph_tiles) * PATCH_H; img = mt / (pw_tiles * ph_tiles);
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
           if (MODE == MODE_TMA_A) tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
+          if (MODE == MODE_TMA_PATCH) {
+            // one tap x 64 channels of the 16x8 patch; the halo (negative / beyond-edge coordinates) is zero-filled by TMA
+            const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
+            tma_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+          }
           tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K, n0);
         }
       }
@@ -417,12 +436,19 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int n0 = (tile % num_n_tiles) * BN;
-      const int m0 = (tile / num_n_tiles) * BLOCK_M;
+      const int mt = tile / num_n_tiles;
       int mrow[4];
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
-        const long long m = (long long)m0 + quarter * 32 + ps * 8 + rsub;
-        mrow[ps] = m < M ? (int)m : -1;
+        const int r = quarter * 32 + ps * 8 + rsub;
+        if (MODE == MODE_TMA_PATCH) {
+          const int y = ((mt / pw_tiles) % ph_tiles) * PATCH_H + r / PATCH_W, xq = (mt % pw_tiles) * PATCH_W + r % PATCH_W;
+          const int img = mt / (pw_tiles * ph_tiles);
+          mrow[ps] = (y < ho && xq < wo) ? (img * ho + y) * wo + xq : -1;
+        } else {
+          const long long m = (long long)mt * BLOCK_M + r;
+          mrow[ps] = m < M ? (int)m : -1;
+        }
       }
       auto load_res = [&](int cc, uint4 (&dst)[4]) {
         const int co = n0 + cc * SUB + colv;
@@ -578,6 +604,19 @@ int encode_2d(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t in
   return PPY_OK;
 }
 
+int encode_patch_4d(EncodeTiledFn enc, CUtensorMap* map, const ppy_conv_params* p) {
+  // NHWC activation as (C, W, H, N); box = 64 channels x 16 x 8 pixels of one image
+  const cuuint64_t dims[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
+  const cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->w * p->x_ld * 2, (cuuint64_t)p->h * p->w * p->x_ld * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)PATCH_W, (cuuint32_t)PATCH_H, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+  return PPY_OK;
+}
+
 template <int BN, int MODE>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
@@ -591,6 +630,9 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     // 1x1 stride-1: the A operand is the NHWC activation itself, [M rows][cin] with row pitch x_ld
     rc = encode_2d(enc, &tmap_a, p->x, (uint64_t)p->cin, (uint64_t)M, (uint64_t)p->x_ld * 2, BLOCK_K, BLOCK_M);
     if (rc) return rc;
+  } else if (MODE == MODE_TMA_PATCH) {
+    rc = encode_patch_4d(enc, &tmap_a, p);
+    if (rc) return rc;
   } else {
     tmap_a = tmap_b;
   }
@@ -600,11 +642,13 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     if (rc) return rc;
     attr_done = true;
   }
-  const int num_m_tiles = (int)ceil_div(M, BLOCK_M), num_n_tiles = (int)ceil_div(p->cout, BN);
+  const int pw_tiles = (int)ceil_div(wo, PATCH_W), ph_tiles = (int)ceil_div(ho, PATCH_H);
+  const int num_m_tiles = MODE == MODE_TMA_PATCH ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);
+  const int num_n_tiles = (int)ceil_div(p->cout, BN);
   const long long tiles = (long long)num_m_tiles * num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   conv_umma_kernel<BN, MODE><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, p->k_pad / BLOCK_K, num_m_tiles,
-                                                                        num_n_tiles, tmap_b, tmap_a);
+                                                                        num_n_tiles, pw_tiles, ph_tiles, tmap_b, tmap_a);
   return check_launch();
 }
 
@@ -644,6 +688,13 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   const bool plain_1x1 = p->kh == 1 && p->stride == 1 && p->pad == 0 && p->cin % BLOCK_K == 0 &&
                          p->k_pad == p->cin;
   if (plain_1x1) return dispatch<MODE_TMA_A>(p, ho, wo, as_stream(s));
+  // 3x3 stride-1: A tiles as 16x8 pixel patches fetched by 4-D TMA, when the patch grid wastes < 15% of the tiles
+  const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&
+                         (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
+  if (patchable) {
+    const double eff = (double)ho * wo / ((double)ceil_div(ho, PATCH_H) * PATCH_H * ceil_div(wo, PATCH_W) * PATCH_W);
+    if (eff >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
+  }
   return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }
 

@@ -235,10 +235,17 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     const bool oddj = s_odd[j];
     float mx = 0.f;
     for (int i = lane; i < j; i += 32) {
-      // different labels contribute iou*0 = 0 exactly unless the IoU itself is NaN, which needs an odd box
-      if (s_label[i] != lj && !oddj && !s_odd[i]) continue;
-      float v = __fmul_rn(box_iou(s_box[i], bj), s_label[i] == lj ? 1.f : 0.f);
-      mx = nan_max(mx, v);
+      const bool same = s_label[i] == lj;
+      if (!oddj && !s_odd[i]) {
+        // both areas positive and finite: no NaN possible; different labels or disjoint boxes give exactly +0
+        if (!same) continue;
+        const float4 bi = s_box[i];
+        const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+        if (iw <= 0.f || ih <= 0.f) continue;
+        mx = fmaxf(mx, box_iou(bi, bj));
+      } else {
+        mx = nan_max(mx, __fmul_rn(box_iou(s_box[i], bj), same ? 1.f : 0.f));
+      }
     }
     for (int o = 16; o > 0; o >>= 1) mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) {
@@ -255,16 +262,23 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     const float4 bj = s_box[j];
     const int lj = s_label[j];
     const bool oddj = s_odd[j];
-    // row 0 (comp_0 == 0) contributes (1 - d_0j) <= 1, exactly 1 when skipped below: start the min at 1 for j > 0
+    // row 0 (comp_0 == 0) contributes (1 - d_0j) <= 1, exactly 1 when skipped below: start the min at 1 for j > 0.
+    // Rows with d == 0 contribute 1/f(comp_i) >= 1 and can be skipped; a NaN compensate anywhere makes EVERY
+    // column NaN (it sits in a full row of the decay matrix), which s_nan_from handles globally below.
     float mn = j > 0 ? 1.f : CUDART_INF_F;
     for (int i = lane; i < j; i += 32) {
-      // d == 0 rows contribute 1/f(comp_i) >= 1 >= row 0's term: only their NaNs matter, and a NaN compensate of
-      // row i < j is covered by s_nan_from >= i only for columns <= i, so keep the exact path when comp_i is not 0
-      float c = s_comp[i];
       const bool same = s_label[i] == lj;
-      if (!same && !oddj && !s_odd[i] && c == 0.f) continue;
-      float d = 0.f;
-      if (same || oddj || s_odd[i]) d = __fmul_rn(box_iou(s_box[i], bj), same ? 1.f : 0.f);
+      float d;
+      if (!oddj && !s_odd[i]) {
+        if (!same) continue;
+        const float4 bi = s_box[i];
+        const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+        if (iw <= 0.f || ih <= 0.f) continue;
+        d = box_iou(bi, bj);
+      } else {
+        d = __fmul_rn(box_iou(s_box[i], bj), same ? 1.f : 0.f);
+      }
+      const float c = s_comp[i];
       float e;
       if (use_gaussian) e = __fdiv_rn(expf(__fmul_rn(neg_sigma, __fmul_rn(d, d))), expf(__fmul_rn(neg_sigma, __fmul_rn(c, c))));
       else e = __fdiv_rn(__fsub_rn(1.f, d), __fsub_rn(1.f, c));
@@ -276,7 +290,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
       float cj = s_comp[j];
       float self = use_gaussian ? __fdiv_rn(1.f, expf(__fmul_rn(neg_sigma, __fmul_rn(cj, cj)))) : __fdiv_rn(1.f, __fsub_rn(1.f, cj));
       mn = nan_min(mn, self);   // j == 0: comp[0] == 0 -> exactly 1
-      if (nan_from >= j) mn = CUDART_NAN_F;
+      if (nan_from >= 0) mn = CUDART_NAN_F;
       s_new[j] = __fmul_rn(s_score[j], mn);
     }
   }

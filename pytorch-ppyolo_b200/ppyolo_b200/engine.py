@@ -236,6 +236,31 @@ class InferenceEngine(object):
         self._add(name, run)
         return out
 
+    def _unit_pixel_pairs(self, name, unit, x):
+        """3x3 stride-1 conv with 32 input channels run on the free reinterpretation [N,H,W,32] == [N,H,W/2,64]:
+        two horizontally adjacent pixels form one 64-channel "pixel", so every K block is a full 128-byte row and
+        the 4-D TMA patch loader applies.  The 3x3 weight becomes a 3x3 weight over pixel pairs
+        (W2[(px,co),(qx,ci),ky,d+1] = W[co,ci,ky,2d+qx-px+1], zero where that tap does not exist); the output
+        [N,H,W/2,2*cout] is bit-for-bit the [N,H,W,cout] tensor.  Half of the issued MACs multiply structural
+        zeros -- the layer is HBM/L2-bound, the tensor pipe has the headroom -- and conv_flops counts the original."""
+        from model.custom_layers import ACT_CODES
+        w = unit.conv.weight.detach().float()
+        cout, cin, k, _ = w.shape
+        w2 = torch.zeros((2 * cout, 2 * cin, 3, 3), dtype=torch.float32, device=w.device)
+        for px in range(2):
+            for qx in range(2):
+                for d in (-1, 0, 1):
+                    kx = 2 * d + qx - px + 1
+                    if 0 <= kx <= 2:
+                        w2[px * cout:(px + 1) * cout, qx * cin:(qx + 1) * cin, :, d + 1] = w[:, :, :, kx]
+        scale, shift = unit.folded_scale_shift()
+        scale2, shift2 = torch.cat([scale, scale]).contiguous(), torch.cat([shift, shift]).contiguous()
+        xp = TensorRef(x.t.view(x.n, x.h, x.w // 2, 2 * x.c))
+        flops_before = self.conv_flops
+        out = self._conv(name, xp, self._keep(w2), scale2, shift2, 1, ACT_CODES[unit.act_name])
+        self.conv_flops = flops_before + 2 * x.n * x.h * x.w * cout * cin * 9
+        return TensorRef(out.t.view(x.n, x.h, x.w, cout))
+
     def _unit(self, name, unit, x, residual=None, act=None, dst=None, coord=False, upsample=False, out_code=None):
         """One Conv2dUnit (conv|DCNv2 -> folded norm -> act) as one (DCN: two) kernels."""
         from model.custom_layers import DCNv2, ACT_CODES
@@ -316,7 +341,10 @@ class InferenceEngine(object):
 
         x = x0
         for u, nm in stem_units:
-            x = self._unit('stem.' + nm, u, x)
+            pairable = (self.code == PPY_BF16 and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
+                        tuple(u.conv.weight.shape[1:]) == (32, 3, 3) and x.c == 32 and x.ld == 32 and x.c_off == 0 and
+                        x.w % 2 == 0 and u.conv.weight.shape[0] % 8 == 0 and u.conv.bias is None)
+            x = self._unit_pixel_pairs('stem.' + nm, u, x) if pairable else self._unit('stem.' + nm, u, x)
         x = self._maxpool(x)
         feats = {}
         for stage in (2, 3, 4, 5):

@@ -224,6 +224,7 @@ UMMA_SHAPES = [  # (n, cin, cout, k, stride, hw)
     (2, 64, 64, 1, 1, 16), (2, 64, 128, 3, 1, 16), (1, 128, 256, 3, 2, 16), (2, 32, 32, 3, 1, 24),
     (2, 3, 32, 3, 2, 32), (1, 256, 258, 1, 1, 12), (1, 512, 27, 3, 1, 10), (3, 64, 512, 1, 1, 9),
     (1, 1024, 256, 1, 1, 19), (1, 256, 512, 3, 1, 19), (2, 64, 96, 3, 1, 7),
+    (2, 64, 64, 3, 1, 30), (1, 128, 128, 3, 1, 46), (3, 64, 32, 3, 1, 16),      # 4-D TMA patch mode (16x8 pixel tiles)
 ]
 
 
