@@ -432,24 +432,40 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     const bool has_res = p.residual != nullptr;
     constexpr int NSUB = BN / SUB;               // sub-tiles per tile
     constexpr int MY_SUBS = (NSUB + 1) / 2;      // upper bound of sub-tiles per warp
+    auto row_to_m = [&](int mt, int r) -> int {  // output pixel index of tile row r, -1 if outside
+      if (MODE == MODE_TMA_PATCH) {
+        const int y = ((mt / pw_tiles) % ph_tiles) * PATCH_H + r / PATCH_W, xq = (mt % pw_tiles) * PATCH_W + r % PATCH_W;
+        const int img = mt / (pw_tiles * ph_tiles);
+        return (y < ho && xq < wo) ? (img * ho + y) * wo + xq : -1;
+      }
+      const long long m = (long long)mt * BLOCK_M + r;
+      return m < M ? (int)m : -1;
+    };
+    // The residual tile (128 rows x BN bf16) is pulled into L2 one whole tile ahead with prefetch.global.L2, so the
+    // register loads below (issued one sub-tile ahead) hit L2 instead of paying DRAM latency with little in flight.
+    constexpr int LINES_PER_ROW = (BN * 2 + 127) / 128;
+    auto prefetch_residual = [&](int tile_) {
+      if (!has_res || tile_ >= num_tiles) return;
+      const int n0_ = (tile_ % num_n_tiles) * BN, mt_ = tile_ / num_n_tiles;
+      for (int e = tid; e < BLOCK_M * LINES_PER_ROW; e += EPI_WARPS * 32) {
+        const int m = row_to_m(mt_, e / LINES_PER_ROW);
+        const int col = n0_ + (e % LINES_PER_ROW) * 64;
+        if (m >= 0 && col < p.cout) {
+          const char* a = reinterpret_cast<const char*>(p.residual) + ((size_t)m * p.res_ld + col) * esz;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+      }
+    };
+    prefetch_residual(blockIdx.x);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int n0 = (tile % num_n_tiles) * BN;
       const int mt = tile / num_n_tiles;
+      prefetch_residual(tile + gridDim.x);
       int mrow[4];
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int r = quarter * 32 + ps * 8 + rsub;
-        if (MODE == MODE_TMA_PATCH) {
-          const int y = ((mt / pw_tiles) % ph_tiles) * PATCH_H + r / PATCH_W, xq = (mt % pw_tiles) * PATCH_W + r % PATCH_W;
-          const int img = mt / (pw_tiles * ph_tiles);
-          mrow[ps] = (y < ho && xq < wo) ? (img * ho + y) * wo + xq : -1;
-        } else {
-          const long long m = (long long)mt * BLOCK_M + r;
-          mrow[ps] = m < M ? (int)m : -1;
-        }
-      }
+      for (int ps = 0; ps < 4; ++ps) mrow[ps] = row_to_m(mt, quarter * 32 + ps * 8 + rsub);
       auto load_res = [&](int cc, uint4 (&dst)[4]) {
         const int co = n0 + cc * SUB + colv;
 #pragma unroll

@@ -152,6 +152,72 @@ __global__ void spp_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y,
   }
 }
 
+// SPP, separable + cascaded: maxpool9 = maxpool5(maxpool5(x)), maxpool13 = maxpool5(maxpool9) (exact for max with
+// -inf padding), each 5x5 as a row pass and a column pass in shared memory.  One CTA = one image x 4 channel vectors.
+template <typename T> __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b);
+template <> __device__ __forceinline__ uint4 vmax<float>(uint4 a, uint4 b) {
+  return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))), __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                    __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))), __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+template <> __device__ __forceinline__ uint4 vmax<__nv_bfloat16>(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+constexpr int SPP_VECS = 4;   // 16-byte channel vectors per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(256) spp_separable_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int h,
+                                                            int w, int c) {
+  constexpr int V = Vec16<T>::N;
+  extern __shared__ uint4 spp_smem[];
+  const int hw = h * w;
+  uint4* cur = spp_smem;                 // [hw][SPP_VECS]
+  uint4* tmp = spp_smem + hw * SPP_VECS;
+  const int img = blockIdx.y;
+  const int c0 = blockIdx.x * SPP_VECS * V;
+  const T* xi = x + (long long)img * hw * x_ld + c0;
+  T* yo = y + (long long)img * hw * y_ld + c0;
+  const int items = hw * SPP_VECS;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int pix = i / SPP_VECS, v = i % SPP_VECS;
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(xi + (long long)pix * x_ld + v * V));
+    cur[i] = val;
+    *reinterpret_cast<uint4*>(yo + (long long)pix * y_ld + v * V) = val;
+  }
+  __syncthreads();
+  for (int round = 1; round <= 3; ++round) {
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {      // row pass
+      const int pix = i / SPP_VECS, v = i % SPP_VECS;
+      const int px = pix % w, row0 = pix - px;
+      uint4 m = cur[i];
+      for (int d = -2; d <= 2; ++d) {
+        const int xx = px + d;
+        if (d != 0 && xx >= 0 && xx < w) m = vmax<T>(m, cur[(row0 + xx) * SPP_VECS + v]);
+      }
+      tmp[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {      // column pass
+      const int pix = i / SPP_VECS, v = i % SPP_VECS;
+      const int py = pix / w;
+      uint4 m = tmp[i];
+      for (int d = -2; d <= 2; ++d) {
+        const int yy = py + d;
+        if (d != 0 && yy >= 0 && yy < h) m = vmax<T>(m, tmp[(pix + d * w) * SPP_VECS + v]);
+      }
+      cur[i] = m;
+      *reinterpret_cast<uint4*>(yo + (long long)pix * y_ld + round * c + v * V) = m;
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 __global__ void upsample2x_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int n, int h, int w, int c) {
   constexpr int V = Vec16<T>::N;
@@ -250,7 +316,20 @@ int ppy_avgpool2x2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int
 
 int ppy_spp(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s) {
   PPY_REQUIRE(n > 0 && h > 0 && w > 0 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype) && y_ld >= 4 * c);
-  const long long total = (long long)n * h * w * (c / (16 / dtype_size(dtype)));
+  const int vec = 16 / dtype_size(dtype);
+  const size_t smem = (size_t)2 * h * w * SPP_VECS * 16;
+  if (c % (SPP_VECS * vec) == 0 && smem <= 200 * 1024) {
+    dim3 grid((unsigned)(c / (SPP_VECS * vec)), (unsigned)n);
+    if (dtype == PPY_BF16) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(spp_separable_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      spp_separable_kernel<__nv_bfloat16><<<grid, 256, smem, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, h, w, c);
+    } else if (dtype == PPY_F32) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(spp_separable_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      spp_separable_kernel<float><<<grid, 256, smem, as_stream(s)>>>((const float*)x, x_ld, (float*)y, y_ld, h, w, c);
+    } else return PPY_ERR_INVALID;
+    return check_launch();
+  }
+  const long long total = (long long)n * h * w * (c / vec);
   PPY_DISPATCH(dtype, spp_kernel<T><<<grid_for(total, 128), 128, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c);)
   return check_launch();
 }

@@ -145,6 +145,13 @@ def test_coord_spp_pool(golden):
     x8 = torch.cat([x, x * 0.5], 1)                      # 8 channels (vector width)
     got = SPP()(x8.to(DEV)).cpu()
     np.testing.assert_array_equal(got.numpy(), ref.spp(x8).numpy())
+    x64 = torch.randn((3, 64, 19, 19), generator=torch.Generator().manual_seed(4))      # separable shared-memory kernel
+    np.testing.assert_array_equal(SPP()(x64.to(DEV)).cpu().numpy(), ref.spp(x64).numpy())
+    from ppyolo_b200._lib import PPY_BF16, lib, check
+    xb = o.to_nhwc(x64.to(DEV), PPY_BF16)
+    yb = torch.empty((3, 19, 19, 256), dtype=torch.bfloat16, device=DEV)
+    check(lib.ppy_spp(o.ptr(xb), 64, o.ptr(yb), 256, 3, 19, 19, 64, PPY_BF16, o.stream_ptr()), 'spp')
+    np.testing.assert_array_equal(o.from_nhwc(yb, 256).cpu().numpy(), ref.spp(x64.to(torch.bfloat16).float()).numpy())
     g = torch.Generator().manual_seed(2)
     t = torch.randn((2, 16, 13, 17), generator=g)
     np.testing.assert_array_equal(o.max_pool3s2(t.to(DEV)).cpu().numpy(), torch.nn.functional.max_pool2d(t, 3, 2, 1).numpy())
