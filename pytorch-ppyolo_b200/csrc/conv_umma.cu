@@ -532,10 +532,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               const uint4 t = rv[ps];            // zeros when there is no residual
               a.x += bf_lo(t.x); a.y += bf_hi(t.x); a.z += bf_lo(t.y); a.w += bf_hi(t.y);
               b.x += bf_lo(t.z); b.y += bf_hi(t.z); b.z += bf_lo(t.w); b.w += bf_hi(t.w);
-              a.x = a.x > 0.f ? a.x : a.x * slope; a.y = a.y > 0.f ? a.y : a.y * slope;
-              a.z = a.z > 0.f ? a.z : a.z * slope; a.w = a.w > 0.f ? a.w : a.w * slope;
-              b.x = b.x > 0.f ? b.x : b.x * slope; b.y = b.y > 0.f ? b.y : b.y * slope;
-              b.z = b.z > 0.f ? b.z : b.z * slope; b.w = b.w > 0.f ? b.w : b.w * slope;
+              if (slope != 1.f) {                // relu / leaky(0.1): max(v, slope*v) is exact for 0 <= slope < 1
+                a.x = fmaxf(a.x, a.x * slope); a.y = fmaxf(a.y, a.y * slope); a.z = fmaxf(a.z, a.z * slope); a.w = fmaxf(a.w, a.w * slope);
+                b.x = fmaxf(b.x, b.x * slope); b.y = fmaxf(b.y, b.y * slope); b.z = fmaxf(b.z, b.z * slope); b.w = fmaxf(b.w, b.w * slope);
+              }
               if (p.upsample2x) {
                 store_upsampled(p, m, co, ho, wo, a, b);
               } else if (out_bf16) {
