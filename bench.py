@@ -117,6 +117,10 @@ def run_reference(args, rank):
     if rank != 0:
         return
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    try:      # torchrun pins OMP_NUM_THREADS=1; the reference arm may use every host core it is allowed
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     rate, ms, cores = cpu_reference_rate(steps, warmup)
     sample = '%d forward(s) of 1 image 608x608 (of the 32-image batch), torch CPU fp32, %d threads' % (steps, cores)
     line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
@@ -235,8 +239,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
     e2e_value = world * BATCH / (e2e_ms * 1e-3)
-    h2d = x_host[0].numel() * 4 + im_host[0].numel() * 4
-    d2h = out_host[0].numel() * 4 + cnt_host[0].numel() * 4
+    h2d = world * (x_host[0].numel() * 4 + im_host[0].numel() * 4)          # whole job, like `value`
+    d2h = world * (out_host[0].numel() * 4 + cnt_host[0].numel() * 4)
 
     if rank != 0:
         return
@@ -269,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
             'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'l2_policy': 'inputs_exceed_l2 '
                        '(141.9 MB batch, multi-GB activations per step vs 126 MB L2)', 'cuda_graph': True,
                        'sharding': 'batch-sharded replicas, no collective'},
-            'clocks': clocks, 'gpu_launches': eng.launches_per_run * args.steps,
+            'clocks': clocks, 'gpu_launches': eng.launches_per_run * args.steps * world,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
             'roofline': roofline, 'cpu_baseline': cpu,

@@ -190,7 +190,50 @@ def gen_net(name, cfg, size, batch=2):
                                                                       [tuple(p.shape) for p in preds]))
 
 
+def gen_losses():
+    """Training losses (model/losses.py, model/iou_losses.py) and targets (tools/transform.py:1318-1421) of the reference."""
+    from config import select_loss
+    from tools.transform import Gt2YoloTargetSingle
+    spec = importlib.util.spec_from_file_location('targets', os.path.join(REPO, 'pytorch-ppyolo_b200', 'ppyolo_b200', 'targets.py'))
+    tg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tg)
+    arrays = {}
+    for tag, cfg in (('r50vd', PPYOLO_2x_Config()), ('r18vd', PPYOLO_r18vd_Config())):
+        size, batch = 128, 2
+        gt_bbox, gt_class, gt_score = tg.synthetic_ground_truth(batch, seed=3)
+        op = Gt2YoloTargetSingle(**cfg.gt2YoloTarget)
+        per_image = []
+        for b in range(batch):
+            sample = {'image': np.zeros((3, size, size), np.float32), 'gt_bbox': gt_bbox[b], 'gt_class': gt_class[b],
+                      'gt_score': gt_score[b]}
+            per_image.append(op(sample))
+        n_scale = len(cfg.head['anchor_masks'])
+        targets = [np.stack([s['target%d' % i] for s in per_image]) for i in range(n_scale)]
+        iou_loss = select_loss(cfg.iou_loss_type)(**cfg.iou_loss)
+        iou_aware = select_loss(cfg.iou_aware_loss_type)(**cfg.iou_aware_loss) if cfg.head['iou_aware'] else None
+        yolo = select_loss(cfg.yolo_loss_type)(iou_loss=iou_loss, iou_aware_loss=iou_aware, **cfg.yolo_loss)
+        g = torch.Generator().manual_seed(41)
+        per = 86 if cfg.head['iou_aware'] else 85
+        outs = [(torch.randn((batch, 3 * per, size // s, size // s), generator=g) * 1.2).requires_grad_(True)
+                for s in cfg.head['downsample']]
+        anchors, masks = cfg.head['anchors'], cfg.head['anchor_masks']
+        mask_anchors = [[v for aid in m for v in anchors[aid]] for m in masks]
+        losses = yolo(outs, torch.from_numpy(gt_bbox), torch.from_numpy(gt_class), torch.from_numpy(gt_score),
+                      [torch.from_numpy(t) for t in targets], anchors, masks, mask_anchors, 80)
+        total = sum(losses.values())
+        total.backward()
+        for k, v in losses.items():
+            arrays['%s_%s' % (tag, k)] = v.detach()
+        for i, (o, t) in enumerate(zip(outs, targets)):
+            arrays['%s_target%d' % (tag, i)] = t
+            arrays['%s_grad%d' % (tag, i)] = o.grad if i < n_scale - 1 or n_scale == 2 else np.zeros(1, np.float32)
+            arrays['%s_gradsum%d' % (tag, i)] = np.array([float(o.grad.double().sum()), float(o.grad.double().abs().sum())])
+        print('   losses %s:' % tag, {k: round(float(v), 4) for k, v in losses.items()})
+    save('losses', **arrays)
+
+
 if __name__ == '__main__':
+    gen_losses()
     gen_nms()
     gen_decode()
     gen_layers()
