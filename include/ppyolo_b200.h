@@ -116,6 +116,21 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s);
 int ppy_conv_bf16_supported(void);
 
 /* ------------------------------------------------------------------------------------------------
+ * training side (train.py:427-442; frozen-backbone BNs run on BATCH statistics, custom_layers.py:122)
+ * ---------------------------------------------------------------------------------------------- */
+/* Per-channel batch statistics of an NHWC tensor -> folded scale = gamma/sqrt(var+eps), shift = beta - mean*scale;
+ * running_mean/var (optional) updated in place with torch's momentum / unbiased-variance rule. workspace: 2*c doubles. */
+int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
+                       float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                       double* workspace, ppy_stream_t s);
+/* y = act(x*scale[c] + shift[c] (+ residual)) on NHWC rows. */
+int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* scale,
+                        const float* shift, const void* residual, int res_ld, int act, ppy_stream_t s);
+/* torch.optim.SGD(momentum, weight_decay) update of one fp32 tensor, gradient pre-scaled by grad_scale (1/world). */
+int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                     float weight_decay, float grad_scale, int first_step, ppy_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
  * head post-processing
  * ---------------------------------------------------------------------------------------------- */
 /* get_iou_aware_score, model/head.py:138-141, on an NHWC fp32 head output: [.., A*(6+C)] -> [.., A*(5+C)]. */

@@ -1,0 +1,178 @@
+// Training-side kernels: train-mode BatchNorm for the (frozen) backbone -- the reference leaves its frozen BNs in train
+// mode, so they normalise with BATCH statistics and keep updating the running ones (reference
+// model/custom_layers.py:122, train.py:264) -- and the fused SGD-momentum update (reference train.py:437-442 with
+// torch.optim.SGD semantics: weight decay folded into the gradient, dampening 0, no Nesterov).
+//
+//   bn_stats      per-channel sum / sum of squares over all pixels of an NHWC tensor (fp32 partials, fp64 atomics)
+//   bn_finalize   mean / biased var -> folded scale, shift; running stats <- (1-m)*running + m*(mean, unbiased var)
+//   scale_shift   y = act(x*scale[c] + shift[c] (+ residual)), 16-byte channel vectors
+//   sgd_momentum  g' = g*grad_scale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
+#include "common.cuh"
+
+namespace ppy {
+namespace {
+
+template <typename T> struct VecT { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void ldv(const T* p, float (&v)[VecT<T>::N]) {
+  uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < VecT<T>::N; ++i) v[i] = to_f<T>(e[i]);
+}
+
+// block = 32 channel-vectors x 8 row lanes; grid.x tiles the channel vectors, grid.y strides the rows
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, int ld, long long rows, int c,
+                                                       double* __restrict__ sums) {
+  constexpr int V = VecT<T>::N;
+  __shared__ float red[2][8][32][V];
+  const int vl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int vec = blockIdx.x * 32 + vl;
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  if (vec * V < c) {
+    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+      float v[V];
+      ldv<T>(x + r * ld + vec * V, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { s[k] += v[k]; q[k] += v[k] * v[k]; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red[0][rl][vl][k] = s[k]; red[1][rl][vl][k] = q[k]; }
+  __syncthreads();
+  if (rl == 0 && vec * V < c) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      double ds = 0.0, dq = 0.0;
+      for (int j = 0; j < 8; ++j) { ds += red[0][j][vl][k]; dq += red[1][j][vl][k]; }
+      atomicAdd(&sums[vec * V + k], ds);
+      atomicAdd(&sums[c + vec * V + k], dq);
+    }
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long rows, int c, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double mean = sums[ch] / (double)rows;
+  double var = sums[c + ch] / (double)rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float inv = rsqrtf((float)var + eps) * (gamma ? gamma[ch] : 1.f);
+  scale[ch] = inv;
+  shift[ch] = (beta ? beta[ch] : 0.f) - (float)mean * inv;
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_shift_act_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld,
+                                                              long long rows, int c, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, const T* __restrict__ res,
+                                                              int res_ld, int act) {
+  constexpr int V = VecT<T>::N;
+  const int cv = c / V;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const long long r = i / cv;
+    float a[V];
+    ldv<T>(x + r * x_ld + v * V, a);
+    if (res) {
+      float b[V];
+      ldv<T>(res + r * res_ld + v * V, b);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] = a[k] * __ldg(scale + v * V + k) + __ldg(shift + v * V + k) + b[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] = a[k] * __ldg(scale + v * V + k) + __ldg(shift + v * V + k);
+    }
+    uint4 raw;
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < V; ++k) e[k] = from_f<T>(apply_act(a[k], act));
+    *reinterpret_cast<uint4*>(y + r * y_ld + v * V) = raw;
+  }
+}
+
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                                    float lr, float momentum, float wd, float grad_scale, int first_step) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    const float d = g[i] * grad_scale + wd * w;
+    const float b = first_step ? d : momentum * buf[i] + d;
+    buf[i] = b;
+    p[i] = w - lr * b;
+  }
+}
+
+inline unsigned blocks_for(long long work, int threads, long long cap = 148ll * 16) {
+  long long b = ceil_div(work, threads);
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+}  // namespace ppy
+
+extern "C" {
+using namespace ppy;
+
+int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
+                       float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                       double* workspace /* 2*c doubles */, ppy_stream_t s) {
+  PPY_REQUIRE(x && scale && shift && workspace && rows > 0 && c > 0 && x_ld >= c);
+  const int v = 16 / dtype_size(dtype);
+  PPY_REQUIRE(c % v == 0 && x_ld % v == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  cudaStream_t st = as_stream(s);
+  int rc = check_cuda(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * (size_t)c, st));
+  if (rc) return rc;
+  const int gx = (int)ceil_div(c / v, 32);
+  long long gy = ceil_div(rows, 8 * 16);            // >= 16 rows per row-lane
+  const long long cap = ceil_div(148ll * 8, gx);
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (dtype == PPY_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, x_ld, rows, c, workspace);
+  else if (dtype == PPY_F32) bn_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_ld, rows, c, workspace);
+  else return PPY_ERR_INVALID;
+  if ((rc = check_launch())) return rc;
+  bn_finalize_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, st>>>(workspace, rows, c, gamma, beta, eps, momentum, running_mean,
+                                                                running_var, scale, shift);
+  return check_launch();
+}
+
+int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* scale,
+                        const float* shift, const void* residual, int res_ld, int act, ppy_stream_t s) {
+  PPY_REQUIRE(x && y && scale && shift && rows > 0 && c > 0 && x_ld >= c && y_ld >= c);
+  const int v = 16 / dtype_size(dtype);
+  PPY_REQUIRE(c % v == 0 && x_ld % v == 0 && y_ld % v == 0 && (!residual || res_ld % v == 0));
+  PPY_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0);
+  PPY_REQUIRE(act >= PPY_ACT_NONE && act <= PPY_ACT_MISH);
+  const long long total = rows * (c / v);
+  if (dtype == PPY_BF16)
+    scale_shift_act_kernel<__nv_bfloat16><<<blocks_for(total, 256, 148ll * 32), 256, 0, as_stream(s)>>>(
+        (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, rows, c, scale, shift, (const __nv_bfloat16*)residual, res_ld, act);
+  else if (dtype == PPY_F32)
+    scale_shift_act_kernel<float><<<blocks_for(total, 256, 148ll * 32), 256, 0, as_stream(s)>>>(
+        (const float*)x, x_ld, (float*)y, y_ld, rows, c, scale, shift, (const float*)residual, res_ld, act);
+  else return PPY_ERR_INVALID;
+  return check_launch();
+}
+
+int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                     float weight_decay, float grad_scale, int first_step, ppy_stream_t s) {
+  PPY_REQUIRE(param && grad && momentum_buf && n > 0);
+  sgd_momentum_kernel<<<blocks_for(n, 256), 256, 0, as_stream(s)>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
+                                                                    grad_scale, first_step);
+  return check_launch();
+}
+
+}  // extern "C"

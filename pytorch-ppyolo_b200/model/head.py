@@ -153,6 +153,15 @@ class YOLOv3Head(torch.nn.Module):
         return self.yolo_loss(outputs, gt_box, gt_label, gt_score, targets, self.anchors, self.anchor_masks,
                               self.mask_anchors, self.num_classes)
 
+    def get_loss_autograd(self, body_feats, gt_box, gt_label, gt_score, targets):
+        """get_loss (reference :400-422) with the head evaluated as differentiable tensor code."""
+        from ppyolo_b200 import autograd_head
+        if self.yolo_loss is None:
+            raise RuntimeError('YOLOv3Head was built without yolo_loss; pass the YOLOv3Loss object like train.py:246-252')
+        outputs = autograd_head.head_outputs(self, body_feats)
+        return self.yolo_loss(outputs, gt_box, gt_label, gt_score, targets, self.anchors, self.anchor_masks,
+                              self.mask_anchors, self.num_classes)
+
     def decode_outputs(self, outputs, im_size):
         """Fused IoU-aware + yolo_box over all scales -> (boxes [N,B,4], scores [N,B,C])."""
         boxes, scores = [], []

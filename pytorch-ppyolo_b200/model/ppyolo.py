@@ -15,6 +15,7 @@ class PPYOLO(torch.nn.Module):
         self.backbone = backbone
         self.head = head
         self.precision = 'bf16'
+        self.train_precision = 'fp32'     # arithmetic of the frozen-backbone forward inside a training step
         self.dcn_impl = None          # None = engine default; 'fused' | 'gather_gemm'
         self.use_engine = True
         self._engines = {}
@@ -32,6 +33,11 @@ class PPYOLO(torch.nn.Module):
         """Drop compiled plans (call after mutating weights, e.g. load_state_dict)."""
         self._engines = {}
 
+    def invalidate_engines_for_weights(self):
+        """After an optimizer step only the (eval) inference plans hold stale folded head weights; the frozen-backbone
+        training engine reads BN statistics and conv weights that did not change."""
+        self._engines = {k: v for k, v in self._engines.items() if k[-1] == 'train'}
+
     def load_state_dict(self, *args, **kwargs):
         self.invalidate_engines()
         return super().load_state_dict(*args, **kwargs)
@@ -40,10 +46,38 @@ class PPYOLO(torch.nn.Module):
         if eval and self.use_engine and not self.training and x.is_cuda:
             n, _, h, w = x.shape
             return self.engine(n, h, w).run(x, im_size)
+        if not eval:
+            return self.forward_train(x, gt_box, gt_label, gt_score, targets)
         body_feats = self.backbone(x)
-        if eval:
-            return self.head.get_prediction(body_feats, im_size)
-        return self.head.get_loss(body_feats, gt_box, gt_label, gt_score, targets)
+        return self.head.get_prediction(body_feats, im_size)
+
+    def forward_train(self, x, gt_box, gt_label, gt_score, targets):
+        """Training forward (reference train.py:427 -> model/head.py:400-422): dict of scalar losses.
+
+        The frozen backbone (``freeze_at=5`` in both configs) runs under no_grad on the kernel engine with BATCH-statistic
+        BatchNorm, exactly like the reference's train-mode frozen BNs; the trainable head runs as differentiable tensor code
+        (``ppyolo_b200.autograd_head``) so torch autograd provides its backward, and the losses are ``model/losses.py``."""
+        from ppyolo_b200 import autograd_head
+        if any(p.requires_grad for p in self.backbone.parameters()):
+            raise NotImplementedError('training with an unfrozen backbone (freeze_at < 5) is not built yet: the conv/DCN '
+                                      'backward kernels are a later row of the scope table')
+        if not x.is_cuda:
+            raise RuntimeError('ppyolo_b200: training needs CUDA tensors -- the backbone kernels have no CPU fallback')
+        n, _, h, w = x.shape
+        with torch.no_grad():
+            feats = self.backbone_train_engine(n, h, w).run_backbone(x)
+        return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
+
+    def backbone_train_engine(self, batch, height, width):
+        from ppyolo_b200.engine import InferenceEngine
+        key = (batch, height, width, self.train_precision, bool(self.backbone.training), 'train')
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = InferenceEngine(self, batch, height, width, precision=self.train_precision, dcn_impl=self.dcn_impl,
+                                  train_bn=self.backbone.stage1_conv1_1.bn is not None and self.backbone.training,
+                                  backbone_only=True, use_graph=False)
+            self._engines[key] = eng
+        return eng
 
     def add_param_group(self, param_groups, base_lr, base_wd):
         self.backbone.add_param_group(param_groups, base_lr, base_wd)

@@ -54,6 +54,11 @@ SIGNATURES = {
     'ppy_conv_f32': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_conv_bf16': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_conv_bf16_supported': (c_int, []),
+    'ppy_bn_batch_stats': (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ppy_scale_shift_act': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                    c_int, c_void_p]),
+    'ppy_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     'ppy_iou_aware_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_double, c_void_p]),
     'ppy_yolo_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -47,7 +47,8 @@ class TensorRef(object):
 
 
 class InferenceEngine(object):
-    def __init__(self, model, batch, height, width, precision='bf16', use_graph=True, dcn_impl=None):
+    def __init__(self, model, batch, height, width, precision='bf16', use_graph=True, dcn_impl=None, train_bn=False,
+                 backbone_only=False):
         if not torch.cuda.is_available():
             raise RuntimeError('InferenceEngine needs a CUDA device (no CPU fallback)')
         if precision not in ('bf16', 'fp32'):
@@ -66,18 +67,27 @@ class InferenceEngine(object):
         # DCNv2 on the bf16 path: 'gather_gemm' = sampling kernel -> L2-resident A matrix -> TMA-fed 1x1 tcgen05 GEMM
         # (fastest today); 'fused' = the single im2col-free kernel with the bilinear producer
         self.dcn_impl = dcn_impl or getattr(model, 'dcn_impl', None) or ('gather_gemm' if precision == 'bf16' else 'fused')
+        # train_bn: BatchNorm layers normalise with BATCH statistics and update their running stats, as the reference's
+        # frozen backbone does during training; backbone_only: stop at the C3/C4/C5 feature maps
+        self.train_bn, self.backbone_only = train_bn, backbone_only
         self.steps = []          # (name, callable)
         self.keep = []           # tensors / ctypes structs referenced by raw pointer
         self.conv_flops = 0      # algorithmic 2*MAC of all convs in the plan (per batch)
         self.graph = None
         self.launches_per_run = 0
+        self.bn_modules = []
         with torch.no_grad():
             self._build()
         # one eager pass: first-use initialisation (func attributes, tensor maps) + launch count
+        # (train_bn engines update BatchNorm running statistics: this dry run on a zero batch must leave them untouched)
+        saved = [(bn, bn.running_mean.clone(), bn.running_var.clone()) for bn in self.bn_modules]
         before = _lib.launch_count()
         self._run_steps()
         torch.cuda.synchronize(self.dev)
         self.launches_per_run = _lib.launch_count() - before
+        for bn, mean, var in saved:
+            bn.running_mean.copy_(mean)
+            bn.running_var.copy_(var)
         if use_graph:
             self._capture()
 
@@ -261,11 +271,52 @@ class InferenceEngine(object):
         self.conv_flops = flops_before + 2 * x.n * x.h * x.w * cout * cin * 9
         return TensorRef(out.t.view(x.n, x.h, x.w, cout))
 
+    def _unit_batch_stats(self, name, unit, x, residual, act, dst, coord):
+        """conv (raw) -> per-channel batch statistics (+ running-stat update) -> normalise + residual + act."""
+        from model.custom_layers import DCNv2
+        bn = unit.bn
+        cout = bn.num_features
+        one = torch.ones(cout, dtype=torch.float32, device=self.dev)
+        zero = torch.zeros(cout, dtype=torch.float32, device=self.dev)
+        if isinstance(unit.conv, DCNv2):
+            d = unit.conv
+            n_om = d.conv_offset.weight.shape[0]
+            om = self._conv(name + '.offset', x, d.conv_offset.weight.detach(), torch.ones(n_om, dtype=torch.float32, device=self.dev),
+                            d.conv_offset.bias.detach().float().contiguous(), unit.stride, 0, out_code=PPY_F32)
+            om = TensorRef(om.t)
+            bias = d.dcn_bias.detach().float() if d.dcn_bias is not None else zero
+            if self.dcn_impl == 'gather_gemm' and x.c % 64 == 0:
+                xcol = self._dcn_gather(name + '.gather', x, om, d.dcn_weight.shape[-1], unit.stride)
+                raw = self._conv(name + '.raw', xcol, d.dcn_weight.detach(), one, bias, 1, 0, gemm_taps=True)
+            else:
+                raw = self._conv(name + '.raw', x, d.dcn_weight.detach(), one, bias, unit.stride, 0, offset_mask=om)
+        else:
+            bias = unit.conv.bias.detach().float() if unit.conv.bias is not None else zero
+            raw = self._conv(name + '.raw', x, unit.conv.weight.detach(), one, bias, unit.stride, 0, coord=coord)
+        if dst is None:
+            dst = TensorRef(self._new(raw.n, raw.h, raw.w, ops.round_up(cout, 8)), c=cout)
+        scale = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
+        shift = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
+        ws = self._keep(torch.empty(2 * cout, dtype=torch.float64, device=self.dev))
+        rows = raw.n * raw.h * raw.w
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        a1 = (ctypes.c_void_p(raw.ptr), raw.ld, rows, cout, raw.code, ops.ptr(bn.weight.data), ops.ptr(bn.bias.data), float(bn.eps),
+              momentum, ops.ptr(bn.running_mean), ops.ptr(bn.running_var), ops.ptr(scale), ops.ptr(shift), ops.ptr(ws))
+        a2 = (ctypes.c_void_p(raw.ptr), raw.ld, ctypes.c_void_p(dst.ptr), dst.ld, rows, cout, raw.code, ops.ptr(scale), ops.ptr(shift),
+              ctypes.c_void_p(residual.ptr) if residual is not None else ctypes.c_void_p(0),
+              residual.ld if residual is not None else 0, act)
+        self._add(name + '.bn_stats', lambda: check(lib.ppy_bn_batch_stats(*a1, ops.stream_ptr()), name + '.bn_stats'))
+        self._add(name + '.bn_apply', lambda: check(lib.ppy_scale_shift_act(*a2, ops.stream_ptr()), name + '.bn_apply'))
+        self.bn_modules.append(bn)
+        return dst
+
     def _unit(self, name, unit, x, residual=None, act=None, dst=None, coord=False, upsample=False, out_code=None):
         """One Conv2dUnit (conv|DCNv2 -> folded norm -> act) as one (DCN: two) kernels."""
         from model.custom_layers import DCNv2, ACT_CODES
-        scale, shift = unit.folded_scale_shift()
         act = ACT_CODES[unit.act_name] if act is None else act
+        if self.train_bn and unit.bn is not None:
+            return self._unit_batch_stats(name, unit, x, residual, act, dst, coord)
+        scale, shift = unit.folded_scale_shift()
         if isinstance(unit.conv, DCNv2):
             d = unit.conv
             n_om = d.conv_offset.weight.shape[0]
@@ -314,7 +365,8 @@ class InferenceEngine(object):
         self.im_size = torch.zeros((n, 2), dtype=torch.float32, device=self.dev)
         stem_units = list(zip(bb._stem_units(), ('conv1_1', 'conv1_2', 'conv1_3')))
         u0 = stem_units[0][0]
-        if tuple(u0.conv.weight.shape) == (32, 3, 3, 3) and u0.stride == 2 and u0.act_name in (None, 'relu', 'leaky'):
+        if (not self.train_bn and tuple(u0.conv.weight.shape) == (32, 3, 3, 3) and u0.stride == 2 and
+                u0.act_name in (None, 'relu', 'leaky')):
             # conv1_1 fused with the NCHW->NHWC change (K = 27: HBM-bound, fp32 SIMT, weights in the constant bank)
             x0 = self._stem(u0)
             stem_units = stem_units[1:]
@@ -331,7 +383,7 @@ class InferenceEngine(object):
         stage_dst = {}
         self.concat = {}
         for i, stage in enumerate(head_feats):
-            if i == 0:
+            if i == 0 or self.backbone_only:
                 continue
             side = self.h // (2 ** stage)
             feat_c = self._stage_channels(bb, stage)
@@ -341,7 +393,7 @@ class InferenceEngine(object):
 
         x = x0
         for u, nm in stem_units:
-            pairable = (self.code == PPY_BF16 and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
+            pairable = (self.code == PPY_BF16 and not self.train_bn and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
                         tuple(u.conv.weight.shape[1:]) == (32, 3, 3) and x.c == 32 and x.ld == 32 and x.c_off == 0 and
                         x.w % 2 == 0 and u.conv.weight.shape[0] % 8 == 0 and u.conv.bias is None)
             x = self._unit_pixel_pairs('stem.' + nm, u, x) if pairable else self._unit('stem.' + nm, u, x)
@@ -354,6 +406,9 @@ class InferenceEngine(object):
                 x = self._block(nm, getattr(bb, nm), x, dst=dst)
             feats[stage] = x
 
+        self.feats = [feats[stage] for stage in fmaps]
+        if self.backbone_only:
+            return
         # ---- head
         from model.custom_layers import Conv2dUnit, CoordConv, SPP, DropBlock
         self.head_outs = []
@@ -460,3 +515,12 @@ class InferenceEngine(object):
     def head_outputs_nchw(self):
         """Raw head outputs of the last run as NCHW fp32 tensors (parity tests)."""
         return [ops.from_nhwc(o.t, o.c) for o in self.head_outs]
+
+    def run_backbone(self, x):
+        """Backbone forward only (``backbone_only`` engines): list of NCHW fp32 feature maps (fresh tensors)."""
+        self.x_in.copy_(x, non_blocking=True)
+        self.launch()
+        if self.train_bn:
+            for bn in self.bn_modules:
+                bn.num_batches_tracked += 1
+        return [ops.from_nhwc(f.t[..., f.c_off:f.c_off + f.c].contiguous() if f.c_off else f.t, f.c) for f in self.feats]

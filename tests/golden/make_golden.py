@@ -232,7 +232,49 @@ def gen_losses():
     save('losses', **arrays)
 
 
+def gen_train():
+    """One training forward+backward of the reference (train.py:427-441) with its default frozen backbone in TRAIN mode
+    (batch-statistic BN), DropBlock disabled for determinism."""
+    from config import select_loss
+    spec = importlib.util.spec_from_file_location('targets', os.path.join(REPO, 'pytorch-ppyolo_b200', 'ppyolo_b200', 'targets.py'))
+    tg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tg)
+    arrays = {}
+    for tag, cfg in (('r50vd', PPYOLO_2x_Config()), ('r18vd', PPYOLO_r18vd_Config())):
+        size, batch = 128, 2
+        iou_loss = select_loss(cfg.iou_loss_type)(**cfg.iou_loss)
+        iou_aware = select_loss(cfg.iou_aware_loss_type)(**cfg.iou_aware_loss) if cfg.head['iou_aware'] else None
+        yolo = select_loss(cfg.yolo_loss_type)(iou_loss=iou_loss, iou_aware_loss=iou_aware, **cfg.yolo_loss)
+        head_kw = dict(cfg.head); head_kw['drop_block'] = False
+        backbone = select_backbone(cfg.backbone_type)(**cfg.backbone)
+        head = select_head(cfg.head_type)(yolo_loss=yolo, is_train=True, nms_cfg=cfg.nms_cfg, **head_kw)
+        model = PPYOLO(backbone, head)
+        synth.randomize_(model, seed=0)
+        model.train()
+        backbone.freeze()
+        x = synth.images(batch, size, seed=1)
+        gt_bbox, gt_class, gt_score = tg.synthetic_ground_truth(batch, seed=3)
+        targets = tg.gt2yolo_target(gt_bbox, gt_class, gt_score, h=size, w=size, **cfg.gt2YoloTarget)
+        losses = model(x, None, False, torch.from_numpy(gt_bbox), torch.from_numpy(gt_class), torch.from_numpy(gt_score),
+                       [torch.from_numpy(t) for t in targets])
+        sum(losses.values()).backward()
+        for k, v in losses.items():
+            arrays['%s_%s' % (tag, k)] = v.detach()
+        sd = model.state_dict()
+        arrays[tag + '_stem_running_mean'] = sd['backbone.stage1_conv1_1.bn.running_mean']
+        arrays[tag + '_stem_running_var'] = sd['backbone.stage1_conv1_1.bn.running_var']
+        last = 'backbone.stage5_%d.conv%d.bn.running_var' % ((2, 3) if tag == 'r50vd' else (1, 2))
+        arrays[tag + '_last_running_var'] = sd[last]
+        g = head.yolo_output_convs[0].conv.bias.grad
+        arrays[tag + '_out0_bias_grad'] = g
+        w = head.detection_blocks[0].layers[1].conv.weight.grad
+        arrays[tag + '_blk0_w_gradsum'] = np.array([float(w.double().sum()), float(w.double().abs().sum())])
+        print('   train %s:' % tag, {k: round(float(v.detach()), 4) for k, v in losses.items()})
+    save('train', **arrays)
+
+
 if __name__ == '__main__':
+    gen_train()
     gen_losses()
     gen_nms()
     gen_decode()

@@ -1,0 +1,121 @@
+"""GPU parity of the training step (BASELINE config C4 path at test size): losses, a head gradient and the backbone's
+BatchNorm running statistics after one forward+backward against the unmodified reference (tests/golden/train.npz);
+fused SGD against torch.optim.SGD; batch-statistic BN kernels against torch."""
+import numpy as np
+import pytest
+import torch
+
+import config as cfgs
+from ppyolo_b200 import synth, targets as tg
+from tests.helpers import CONFIGS
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def build_train_model(tag):
+    from model.ppyolo import PPYOLO
+    cfg = CONFIGS[tag]()
+    iou_loss = cfgs.select_loss(cfg.iou_loss_type)(**cfg.iou_loss)
+    iou_aware = cfgs.select_loss(cfg.iou_aware_loss_type)(**cfg.iou_aware_loss) if cfg.head['iou_aware'] else None
+    yolo = cfgs.select_loss(cfg.yolo_loss_type)(iou_loss=iou_loss, iou_aware_loss=iou_aware, **cfg.yolo_loss)
+    head_kw = dict(cfg.head)
+    head_kw['drop_block'] = False
+    backbone = cfgs.select_backbone(cfg.backbone_type)(**cfg.backbone)
+    head = cfgs.select_head(cfg.head_type)(yolo_loss=yolo, is_train=True, nms_cfg=cfg.nms_cfg, **head_kw)
+    model = PPYOLO(backbone, head)
+    synth.randomize_(model, seed=0)
+    model.train()
+    backbone.freeze()
+    return model.to(DEV), cfg
+
+
+def train_inputs(cfg, size=128, batch=2):
+    x = synth.images(batch, size, seed=1).to(DEV)
+    gt_bbox, gt_class, gt_score = tg.synthetic_ground_truth(batch, seed=3)
+    targets = tg.gt2yolo_target(gt_bbox, gt_class, gt_score, h=size, w=size, **cfg.gt2YoloTarget)
+    to = lambda a: torch.from_numpy(a).to(DEV)
+    return x, to(gt_bbox), to(gt_class), to(gt_score), [to(t) for t in targets]
+
+
+@pytest.mark.parametrize('tag', ['r50vd', 'r18vd'])
+def test_train_forward_backward_vs_reference(golden, tag):
+    z = golden('train')
+    model, cfg = build_train_model(tag)
+    x, gb, gc, gs, targets = train_inputs(cfg)
+    losses = model(x, None, False, gb, gc, gs, targets)
+    sum(losses.values()).backward()
+    for k, v in losses.items():
+        np.testing.assert_allclose(float(v.detach()), float(z['%s_%s' % (tag, k)]), rtol=5e-3, err_msg=k)   # head convs: ATen TF32
+    sd = model.state_dict()
+    np.testing.assert_allclose(sd['backbone.stage1_conv1_1.bn.running_mean'].cpu().numpy(), z[tag + '_stem_running_mean'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(sd['backbone.stage1_conv1_1.bn.running_var'].cpu().numpy(), z[tag + '_stem_running_var'], rtol=1e-4, atol=1e-6)
+    last = 'backbone.stage5_%d.conv%d.bn.running_var' % ((2, 3) if tag == 'r50vd' else (1, 2))
+    np.testing.assert_allclose(sd[last].cpu().numpy(), z[tag + '_last_running_var'], rtol=2e-3, atol=1e-6)
+    g = model.head.yolo_output_convs[0].conv.bias.grad.cpu().numpy()
+    want = z[tag + '_out0_bias_grad']
+    np.testing.assert_allclose(g, want, rtol=0, atol=1e-2 * np.abs(want).max())
+    w = model.head.detection_blocks[0].layers[1].conv.weight.grad
+    # (the signed sum cancels to ~0.1% of the absolute sum, i.e. below the TF32 noise of ATen's convs: compare magnitudes)
+    np.testing.assert_allclose(float(w.double().abs().sum()), z[tag + '_blk0_w_gradsum'][1], rtol=3e-2)
+
+
+def test_bn_batch_stats_kernels():
+    from ppyolo_b200 import ops
+    from ppyolo_b200._lib import lib, check, PPY_F32, PPY_BF16
+    g = torch.Generator().manual_seed(0)
+    for code, tol in ((PPY_F32, 1e-5), (PPY_BF16, 1e-2)):
+        x = torch.randn((3, 24, 17, 19), generator=g) * 2 + 0.5
+        res = torch.randn((3, 24, 17, 19), generator=g)
+        bn = torch.nn.BatchNorm2d(24)
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1); bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 1.5)
+        xr = x if code == PPY_F32 else x.to(torch.bfloat16).float()
+        rr = res if code == PPY_F32 else res.to(torch.bfloat16).float()
+        want = torch.relu(bn.train()(xr) + rr)
+        xh, rh = ops.to_nhwc(x.to(DEV), code), ops.to_nhwc(res.to(DEV), code)
+        rm, rv = torch.zeros(24, device=DEV), torch.ones(24, device=DEV)
+        with torch.no_grad():
+            bn2 = torch.nn.BatchNorm2d(24)
+            bn2.load_state_dict({k: v for k, v in bn.state_dict().items()})
+        # start from the same running stats as the torch module had BEFORE its forward
+        sc, sh = torch.empty(24, device=DEV), torch.empty(24, device=DEV)
+        ws = torch.empty(48, dtype=torch.float64, device=DEV)
+        rm0 = torch.zeros(24, device=DEV); rv0 = torch.ones(24, device=DEV)
+        gam, bet = bn.weight.detach().to(DEV), bn.bias.detach().to(DEV)
+        n, h, w, ld = xh.shape
+        check(lib.ppy_bn_batch_stats(ops.ptr(xh), ld, n * h * w, 24, code, ops.ptr(gam), ops.ptr(bet), 1e-5, 0.1, ops.ptr(rm0), ops.ptr(rv0),
+                                     ops.ptr(sc), ops.ptr(sh), ops.ptr(ws), ops.stream_ptr()), 'bn_stats')
+        y = torch.empty_like(xh)
+        check(lib.ppy_scale_shift_act(ops.ptr(xh), ld, ops.ptr(y), ld, n * h * w, 24, code, ops.ptr(sc), ops.ptr(sh), ops.ptr(rh), ld, 1,
+                                      ops.stream_ptr()), 'scale_shift_act')
+        got = ops.from_nhwc(y, 24).cpu()
+        np.testing.assert_allclose(got.numpy(), want.detach().numpy(), rtol=0, atol=tol * float(want.abs().max()))
+        ref_bn = torch.nn.BatchNorm2d(24).train()
+        ref_bn(xr)
+        np.testing.assert_allclose(rm0.cpu().numpy(), ref_bn.running_mean.numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(rv0.cpu().numpy(), ref_bn.running_var.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_trainer_step_matches_torch_sgd():
+    """Two Trainer.step()s (fused SGD kernel on the flat gradient bucket) vs torch.optim.SGD fed with the same gradients."""
+    from ppyolo_b200.trainer import Trainer, calc_lr
+    model, cfg = build_train_model('r18vd')
+    x, gb, gc, gs, targets = train_inputs(cfg)
+    trainer = Trainer(model, cfg)
+    assert len(trainer.groups) == 19                       # frozen-backbone param groups of r18vd (reference: 19)
+    shadow = [p.detach().clone().requires_grad_(True) for p in trainer.params]
+    opt = torch.optim.SGD([{'params': [s], 'lr': g['lr'], 'weight_decay': g['weight_decay']} for s, g in zip(shadow, trainer.groups)],
+                          lr=trainer.base_lr, momentum=trainer.momentum)
+    for it in range(2):
+        losses = trainer.step(x, gb, gc, gs, targets)
+        assert all(torch.isfinite(v) for v in losses.values())
+        lr = calc_lr(it, cfg)
+        for s, g, pg, i in zip(shadow, trainer.groups, opt.param_groups, range(len(shadow))):
+            pg['lr'] = lr * g['base_lr'] / trainer.base_lr
+            s.grad = trainer.bucket.view(i).reshape(s.shape).clone()
+        opt.step()
+        if it == 0:      # iteration 0 has lr 0 (linear warm-up from 0): parameters must not move
+            pass
+    for s, p in zip(shadow, trainer.params):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), s.detach().cpu().numpy(), rtol=1e-6, atol=1e-8)

@@ -52,3 +52,35 @@ def test_two_rank_gloo(tmp_path):
         assert r['slow'] == 11.0
         assert [int(p[0, 0]) for p in r['merged']] == list(range(total))
         assert [p.shape[0] for p in r['merged']] == [i % 3 + 1 for i in range(total)]
+
+
+def _grad_worker(rank, ws, port, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=ws)
+    try:
+        from ppyolo_b200.trainer import GradientBucket
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2, 2))]
+        for i, p in enumerate(params):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        params[1].grad = None if rank == 1 else params[1].grad      # a rank without a gradient contributes zeros
+        bucket = GradientBucket(params)
+        bucket.pack()
+        scale = bucket.all_reduce()
+        bucket.unpack_mean(scale)
+        torch.save({'grads': [p.grad.clone() for p in params], 'scale': scale}, os.path.join(out_dir, 'g%d.pt' % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_gloo(tmp_path):
+    """The one exchange step of training: flat-bucket all-reduce(sum)/world, world_size 2 on gloo."""
+    ws = 2
+    mp.spawn(_grad_worker, args=(ws, _free_port(), str(tmp_path)), nprocs=ws, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), 'g%d.pt' % r)) for r in range(ws)]
+    for r in res:
+        assert r['scale'] == 0.5
+        assert torch.allclose(r['grads'][0], torch.full((3, 4), 1.5))       # (1 + 2) / 2
+        assert torch.allclose(r['grads'][1], torch.full((5,), 1.0))         # (2 + 0) / 2
+        assert torch.allclose(r['grads'][2], torch.full((2, 2, 2), 4.5))    # (3 + 6) / 2
