@@ -258,7 +258,7 @@ def run_ours(args, rank, world, local_rank):
                 'flops_per_step': eng.conv_flops, 'kernel_ms_per_step': conv_ms, 'share_of_step': conv_ms / total_ms}
     os.makedirs(os.path.join(REPO, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(REPO, 'gpurun_out', 'per_op_ms.json'), 'w') as f:
-        json.dump({'ops': ops_t, 'total_ms': total_ms, 'graph_ms_per_step': ms_step}, f, indent=1)
+        json.dump({'ops': ops_t, 'total_ms': total_ms, 'graph_ms_per_step': ms_step, 'info': eng.step_info}, f, indent=1)
 
     # ---- CPU baseline (oracle port), bounded sample -------------------------------------------
     cpu = None

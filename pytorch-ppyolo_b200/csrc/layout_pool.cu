@@ -62,13 +62,13 @@ __global__ void pool_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y
                             int ho, int wo) {
   constexpr int V = Vec16<T>::N;
   const int cv = c / V;
-  const long long total = (long long)n * ho * wo * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cv);
-    long long p = i / cv;
-    const int ox = (int)(p % wo); p /= wo;
-    const int oy = (int)(p % ho);
-    const int img = (int)(p / ho);
+  const unsigned total = (unsigned)(n * ho * wo * cv);          // host guarantees < 2^31: 32-bit index math
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = (int)(i % (unsigned)cv);
+    unsigned p = i / (unsigned)cv;
+    const int ox = (int)(p % (unsigned)wo); p /= (unsigned)wo;
+    const int oy = (int)(p % (unsigned)ho);
+    const int img = (int)(p / (unsigned)ho);
     float acc[V];
     if (MODE == 0) {
 #pragma unroll
@@ -302,6 +302,7 @@ int ppy_maxpool3x3s2(const void* x, int x_ld, void* y, int y_ld, int n, int h, i
   PPY_REQUIRE(n > 0 && h > 0 && w > 0 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype));
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   const long long total = (long long)n * ho * wo * (c / (16 / dtype_size(dtype)));
+  PPY_REQUIRE(total < 0x7FFFFFFFll);
   PPY_DISPATCH(dtype, pool_kernel<T, 0><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c, ho, wo);)
   return check_launch();
 }
@@ -310,6 +311,7 @@ int ppy_avgpool2x2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int
   PPY_REQUIRE(n > 0 && h > 1 && w > 1 && vec_ok(x, x_ld, c, dtype) && vec_ok(y, y_ld, c, dtype));
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * (c / (16 / dtype_size(dtype)));
+  PPY_REQUIRE(total < 0x7FFFFFFFll);
   PPY_DISPATCH(dtype, pool_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c, ho, wo);)
   return check_launch();
 }

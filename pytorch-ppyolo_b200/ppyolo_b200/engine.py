@@ -76,6 +76,7 @@ class InferenceEngine(object):
         self.graph = None
         self.launches_per_run = 0
         self.bn_modules = []
+        self.step_info = {}      # per conv step: algorithmic flops / minimum HBM bytes / GEMM shape
         with torch.no_grad():
             self._build()
         # one eager pass: first-use initialisation (func attributes, tensor maps) + launch count
@@ -199,7 +200,12 @@ class InferenceEngine(object):
         def run():
             check(fn(ref, ops.stream_ptr()), name)
         self._add(name, run)
-        self.conv_flops += 2 * x.n * ho * wo * cout * cin_total * k * k
+        flops = 2 * x.n * ho * wo * cout * cin_total * k * k
+        self.conv_flops += flops
+        esz_in, esz_out = x.t.element_size(), dst.t.element_size()
+        nbytes = (x.n * x.h * x.w * c_main * esz_in + packed.numel() * packed.element_size() +
+                  x.n * ho * wo * cout * esz_out * (4 if upsample else 1) + (x.n * ho * wo * cout * esz_out if residual is not None else 0))
+        self.step_info[name] = {'flops': flops, 'bytes': nbytes, 'm': x.n * ho * wo, 'n': cout, 'k': cin_total * k * k}
         return dst
 
     def _conv_over_taps(self, name, xcol, weight, scale, shift, act, residual, dst):
@@ -230,7 +236,11 @@ class InferenceEngine(object):
         def run():
             check(fn(ref, ops.stream_ptr()), name)
         self._add(name, run)
-        self.conv_flops += 2 * xcol.n * xcol.h * xcol.w * cout * cin * k * k
+        flops = 2 * xcol.n * xcol.h * xcol.w * cout * cin * k * k
+        self.conv_flops += flops
+        m = xcol.n * xcol.h * xcol.w
+        self.step_info[name] = {'flops': flops, 'bytes': (m * k * k * cin + packed.numel() + m * cout * (2 if residual is not None else 1)) * 2,
+                                'm': m, 'n': cout, 'k': cin * k * k}
         return dst
 
     def _dcn_gather(self, name, x, om, k, stride):
@@ -244,6 +254,25 @@ class InferenceEngine(object):
         def run():
             check(lib.ppy_dcn_gather(*args, ops.stream_ptr()), name)
         self._add(name, run)
+        return out
+
+    def _head_output_conv(self, name, unit, x):
+        """1x1 output conv to A*(5|6+C) channels, fp32 out.  258 channels would need a third, almost empty 128-wide N
+        tile (re-reading the whole input for 2 columns); instead the first 256 channels run as full 256-wide tiles and
+        the 2 leftover channels as a 32-wide launch into the same buffer."""
+        cout = unit.filters
+        if self.code != PPY_BF16 or cout <= 256 or cout % 256 > 32 or unit.bn is not None:
+            return self._unit(name, unit, x, out_code=PPY_F32)
+        from model.custom_layers import ACT_CODES
+        scale, shift = unit.folded_scale_shift()
+        w = unit.conv.weight.detach()
+        out = TensorRef(self._new(x.n, x.h, x.w, ops.round_up(cout, 8), torch.float32), c=cout)
+        act = ACT_CODES[unit.act_name]
+        main = (cout // 256) * 256
+        self._conv(name, x, w[:main].contiguous(), scale[:main].contiguous(), shift[:main].contiguous(), 1, act,
+                   dst=out.slice(0, main), out_code=PPY_F32)
+        self._conv(name + '.tail', x, w[main:].contiguous(), scale[main:].contiguous(), shift[main:].contiguous(), 1, act,
+                   dst=out.slice(main, cout - main), out_code=PPY_F32)
         return out
 
     def _unit_pixel_pairs(self, name, unit, x):
@@ -436,7 +465,7 @@ class InferenceEngine(object):
                 return x
             route = walk(blk.layers, x, 'head.block%d.layers' % i)
             tip = walk(blk.tip_layers, route, 'head.block%d.tip' % i)
-            out = self._unit('head.out%d' % i, head.yolo_output_convs[i], tip, out_code=PPY_F32)
+            out = self._head_output_conv('head.out%d' % i, head.yolo_output_convs[i], tip)
             self.head_outs.append(out)
             if i < n_out - 1:
                 nxt = self.concat[i + 1]

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""BASELINE config C4: ppyolo_2x 608x608, bs=8/GPU, train.py step (frozen-backbone forward with batch-stat BN, head
+forward+backward, 6 losses, NCCL gradient all-reduce, fused SGD) on synthetic data.  Prints one JSON line on rank 0.
+
+    python tools/train_bench.py [--steps 10] [--warmup 3] [--precision fp32|bf16] [--size 608] [--batch 8]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py ...
+"""
+import argparse, json, os, sys, time
+REPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+sys.path.insert(0, os.path.join(REPO, 'pytorch-ppyolo_b200')); sys.path.insert(0, REPO)
+import torch
+import torch.distributed as dist
+import config as cfgs
+from model.ppyolo import PPYOLO
+from ppyolo_b200 import synth, targets as tg, parallel
+from ppyolo_b200.trainer import Trainer
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--steps', type=int, default=10); ap.add_argument('--warmup', type=int, default=3)
+ap.add_argument('--precision', default='fp32'); ap.add_argument('--size', type=int, default=608)
+ap.add_argument('--batch', type=int, default=8); ap.add_argument('--arch', default='r50vd')
+a = ap.parse_args()
+rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+cfg = {'r50vd': cfgs.PPYOLO_2x_Config, 'r18vd': cfgs.PPYOLO_r18vd_Config}[a.arch]()
+iou_loss = cfgs.select_loss(cfg.iou_loss_type)(**cfg.iou_loss)
+iou_aware = cfgs.select_loss(cfg.iou_aware_loss_type)(**cfg.iou_aware_loss) if cfg.head['iou_aware'] else None
+yolo = cfgs.select_loss(cfg.yolo_loss_type)(iou_loss=iou_loss, iou_aware_loss=iou_aware, **cfg.yolo_loss)
+backbone = cfgs.select_backbone(cfg.backbone_type)(**cfg.backbone)
+head = cfgs.select_head(cfg.head_type)(yolo_loss=yolo, is_train=True, nms_cfg=cfg.nms_cfg, **cfg.head)
+model = PPYOLO(backbone, head)
+synth.randomize_(model, seed=0)
+model.train(); backbone.freeze()
+model = model.to(dev)
+model.train_precision = a.precision
+trainer = Trainer(model, cfg)
+x = synth.images(a.batch, a.size, seed=20 + rank).to(dev)
+gb, gc, gs = tg.synthetic_ground_truth(a.batch, seed=30 + rank)
+targets = [torch.from_numpy(t).to(dev) for t in tg.gt2yolo_target(gb, gc, gs, h=a.size, w=a.size, **cfg.gt2YoloTarget)]
+gb, gc, gs = (torch.from_numpy(v).to(dev) for v in (gb, gc, gs))
+for _ in range(a.warmup):
+    losses = trainer.step(x, gb, gc, gs, targets)
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
+    losses = trainer.step(x, gb, gc, gs, targets)
+e1.record()
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
+if rank == 0:
+    print(json.dumps({'metric': 'train_images_per_sec', 'value': world * a.batch / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
+                      'ms_per_step': ms, 'steps': a.steps, 'warmup': a.warmup, 'scaling': 'weak',
+                      'config': {'workload': 'ppyolo_2x %dx%d bs=%d/GPU train step (freeze_at=5)' % (a.size, a.size, a.batch),
+                                 'backbone_precision': a.precision, 'trainable_params': int(sum(p.numel() for p in trainer.params)),
+                                 'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'head_backward': 'torch autograd (ATen)'},
+                      'losses': {k: float(v) for k, v in losses.items()}}), flush=True)
+if world > 1:
+    dist.destroy_process_group()
