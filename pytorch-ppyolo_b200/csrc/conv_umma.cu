@@ -15,6 +15,9 @@
 //              tcgen05.ld (next sub-tile prefetched) -> XOR-swizzled warp-private smem slab -> coalesced pass
 //              (lane = 8 channels of a row): CoordConv bias map, scale/shift, residual (16-byte loads issued one
 //              sub-tile ahead), activation, 16-byte stores
+//              (EPI_TMA variant, bf16 layers with K <= 512, i.e. the HBM-bound ones: residual boxes arrive by TMA into
+//              smem, lane = tile row does the math straight from the TMEM registers, output boxes leave by TMA store;
+//              warp 14 is the residual loader)
 //   warps 8-11 A producers (MODE gather): per 64-wide K block each thread issues eight 16-byte cp.async
 //              (zero-fill outside the image) into the 128B-swizzled K-major stage, eight consecutive lanes
 //              covering one pixel's contiguous 128-byte channel run.  (MODE dcn): thread = tile row,
@@ -40,21 +43,26 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating sub-tiles
-constexpr int NUM_THREADS = 448;                  // 8 epilogue + 4 producer + 1 TMA + 1 MMA warps
-constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5;
+constexpr int NUM_THREADS = 480;                  // 8 epilogue + 4 producer + TMA + MMA + residual-TMA warps
+constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5, RES_WARP = EPI_WARPS + 6;
+constexpr int EPI_SLAB = 0, EPI_TMA = 1;          // epilogue variants (see the kernel header)
+constexpr int GROUP_COLS = 64;                    // EPI_TMA: residual / output move as [128 rows x 64 ch] bf16 boxes (16 KB)
+constexpr int GROUP_BYTES = BLOCK_M * GROUP_COLS * 2;
 constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3;
 constexpr int PATCH_W = 16, PATCH_H = 8;          // 3x3 stride-1 convs: the 128 tile rows are a 16x8 pixel patch of one image
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
 
-template <int BN> struct TileCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+template <int BN, int EPI> struct TileCfg {
+  // EPI_TMA is only dispatched for K <= 512, so 3 stages are plenty there and free smem for the tile buffers
+  static constexpr int kStages = EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
   static constexpr int kBStageBytes = BN * BLOCK_K * 2;
   static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
-  static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + STAGING_BYTES + 1024 /*align slack*/ +
-                                    512 /*barriers*/;
+  // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: 2 residual + 2 output boxes and the scale/shift table of the N tile
+  static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 2 * BN * 4 : STAGING_BYTES;
+  static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -102,6 +110,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -203,12 +223,13 @@ __device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, const float
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MODE>
+template <int BN, int MODE, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
                  const int num_n_tiles, const int pw_tiles, const int ph_tiles, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_a) {
-  using Cfg = TileCfg<BN>;
+                 const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
+                 const __grid_constant__ CUtensorMap tmap_r) {
+  using Cfg = TileCfg<BN, EPI>;
   constexpr int S = Cfg::kStages;
   constexpr int CP_LAG = Cfg::kCpLag;
   extern __shared__ uint8_t smem_raw[];
@@ -217,12 +238,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + S * A_STAGE_BYTES;
   const uint32_t stg_off = S * (A_STAGE_BYTES + Cfg::kBStageBytes);
-  const uint32_t bars = smem_base + stg_off + STAGING_BYTES;   // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_ptr
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + STAGING_BYTES + (2 * S + 4) * 8);
+  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2], then the TMEM base slot
+  const uint32_t bars = smem_base + stg_off + Cfg::kEpiBytes;
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + Cfg::kEpiBytes + (2 * S + 8) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto res_full_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
+  auto res_empty_bar = [&](int b) { return bars + 8u * (2 * S + 6 + b); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long M = (long long)p.n * ho * wo;
@@ -231,7 +255,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   if (tid == 0) {
     const uint32_t full_count = (MODE == MODE_TMA_A || MODE == MODE_TMA_PATCH) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS);
+      mbar_init(res_full_bar(a), 1); mbar_init(res_empty_bar(a), 1);
+    }
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
@@ -411,6 +438,119 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         umma_commit(tmem_full_bar(acc));         // accumulator complete -> epilogue
       }
     }
+  } else if (warp == RES_WARP) {
+    // =====================================================================================
+    // EPI_TMA: residual tile loader -- one [128 x 64] bf16 box per column group, double buffered
+    // =====================================================================================
+    if (EPI == EPI_TMA && lane == 0 && p.residual != nullptr) {
+      constexpr int G = BN / GROUP_COLS;
+      const uint32_t res_smem = smem_base + stg_off;
+      int gg = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % num_n_tiles) * BN, mt = tile / num_n_tiles;
+        for (int g = 0; g < G; ++g) {
+          if (n0 + g * GROUP_COLS >= p.cout) continue;             // group beyond cout: skipped by the epilogue too
+          const int b = gg & 1;
+          mbar_wait(res_empty_bar(b), ((gg >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(res_full_bar(b), GROUP_BYTES);
+          if (MODE == MODE_TMA_PATCH)
+            tma_load_4d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, (mt % pw_tiles) * PATCH_W,
+                        ((mt / pw_tiles) % ph_tiles) * PATCH_H, mt / (pw_tiles * ph_tiles));
+          else
+            tma_load_2d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, mt * BLOCK_M);
+          ++gg;
+        }
+      }
+    }
+  } else if (EPI == EPI_TMA) {
+    // =====================================================================================
+    // EPI_TMA epilogue, warps 0-7: no global-memory instruction at all.  Per 64-column group: the residual box arrives
+    // by TMA, every lane (= one tile row) turns 32 accumulator columns from TMEM into bf16 with scale/shift (smem
+    // table), residual and activation, writes them into the swizzled output box, and one thread hands the box to a
+    // TMA store (rows beyond M / columns beyond cout are clipped by the copy engine, so there are no masks here).
+    // =====================================================================================
+    constexpr int G = BN / GROUP_COLS;
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t res_smem = smem_base + stg_off, out_smem = res_smem + 2 * GROUP_BYTES;
+    float* ss = reinterpret_cast<float*>(gen_base + stg_off + 4 * GROUP_BYTES);      // scale[BN] | shift[BN] of this N tile
+    const float slope = p.act == PPY_ACT_RELU ? 0.f : (p.act == PPY_ACT_LEAKY ? 0.1f : 1.f);
+    const bool has_res = p.residual != nullptr;
+    const int row = quarter * 32 + lane;                    // tile row of this lane
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    int it = 0, gg = 0, cur_n0 = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int n0 = (tile % num_n_tiles) * BN, mt = tile / num_n_tiles;
+      if (n0 != cur_n0) {                                   // (re)load the folded-norm table of this N tile
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // nobody still reads the previous table
+        for (int e = tid; e < 2 * BN; e += EPI_WARPS * 32) {
+          const int col = n0 + (e % BN);
+          ss[e] = col < p.cout ? __ldg((e < BN ? p.scale : p.shift) + col) : 0.f;
+        }
+        cur_n0 = n0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      mbar_wait(tmem_full_bar(acc), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const int cc = 2 * g + half;                        // this warp's 32-column sub-tile inside the group
+        const bool live = n0 + g * GROUP_COLS < p.cout;     // whole group beyond cout: only the TMEM bookkeeping
+        uint32_t v[32];
+        tmem_ld32_nowait(t_row + (uint32_t)(cc * SUB), v);
+        if (live) {
+          const int b = gg & 1;
+          if (tid == 0) bulk_wait_read<1>();                // the store that last used out[b] has drained its smem reads
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (has_res) mbar_wait(res_full_bar(b), (gg >> 1) & 1);
+          tmem_wait_ld();
+          const uint32_t rbase = res_smem + b * GROUP_BYTES + row_off, obase = out_smem + b * GROUP_BYTES + row_off;
+          const float* sc = ss + cc * SUB;
+          const float* sh = ss + BN + cc * SUB;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {                      // 8 channels (one 16-byte chunk) at a time
+            const uint32_t chunk = ((uint32_t)(half * 4 + q) ^ sw) << 4;
+            uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+            if (has_res) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(rbase + chunk));
+            const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8), s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8), h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
+            float f[8];
+            f[0] = __uint_as_float(v[8 * q + 0]) * s0.x + h0.x + bf_lo(r0); f[1] = __uint_as_float(v[8 * q + 1]) * s0.y + h0.y + bf_hi(r0);
+            f[2] = __uint_as_float(v[8 * q + 2]) * s0.z + h0.z + bf_lo(r1); f[3] = __uint_as_float(v[8 * q + 3]) * s0.w + h0.w + bf_hi(r1);
+            f[4] = __uint_as_float(v[8 * q + 4]) * s1.x + h1.x + bf_lo(r2); f[5] = __uint_as_float(v[8 * q + 5]) * s1.y + h1.y + bf_hi(r2);
+            f[6] = __uint_as_float(v[8 * q + 6]) * s1.z + h1.z + bf_lo(r3); f[7] = __uint_as_float(v[8 * q + 7]) * s1.w + h1.w + bf_hi(r3);
+            if (slope != 1.f) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], f[e] * slope);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + chunk), "r"(pack_bf16(f[0], f[1])),
+                         "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+          }
+          fence_proxy_async();                              // generic-proxy writes of the box -> visible to the TMA store
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (tid == 0) {
+            if (MODE == MODE_TMA_PATCH)
+              tma_store_4d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, (mt % pw_tiles) * PATCH_W,
+                           ((mt / pw_tiles) % ph_tiles) * PATCH_H, mt / (pw_tiles * ph_tiles));
+            else
+              tma_store_2d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, mt * BLOCK_M);
+            bulk_commit();
+            if (has_res) mbar_arrive(res_empty_bar(b));     // everybody is past bar 2: res[b] may be refilled
+          }
+          ++gg;
+        } else {
+          tmem_wait_ld();
+        }
+        if (g == G - 1) {                                   // this warp's TMEM reads of the tile are done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+      }
+    }
+    if (tid == 0) bulk_wait<0>();                           // all output boxes are in global memory before the CTA exits
   } else {
     // =====================================================================================
     // epilogue warps 0-7: warp w reads TMEM lanes 32*(w&3).. and handles sub-tiles cc = (w>>2), (w>>2)+2, ...
@@ -633,12 +773,27 @@ int encode_patch_4d(EncodeTiledFn enc, CUtensorMap* map, const ppy_conv_params* 
   return PPY_OK;
 }
 
-template <int BN, int MODE>
+int encode_tile_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int ld, int cols, const ppy_conv_params* p, int ho,
+                    int wo, bool patch) {
+  // output / residual tensors: channels innermost; 2-D [M rows][cols] or 4-D (C, W, H, N) for patch tiles
+  if (!patch) return encode_2d(enc, map, base, (uint64_t)cols, (uint64_t)p->n * ho * wo, (uint64_t)ld * 2, GROUP_COLS, BLOCK_M);
+  const cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)p->n};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)wo * ld * 2, (cuuint64_t)ho * wo * ld * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)GROUP_COLS, (cuuint32_t)PATCH_W, (cuuint32_t)PATCH_H, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+  return PPY_OK;
+}
+
+template <int BN, int MODE, int EPI>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, EPI>;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PPY_ERR_UNSUPPORTED;
-  CUtensorMap tmap_b, tmap_a;
+  CUtensorMap tmap_b, tmap_a, tmap_y, tmap_r;
   int rc = encode_2d(enc, &tmap_b, p->weight, (uint64_t)p->k_pad, (uint64_t)p->cout_pad, (uint64_t)p->k_pad * 2, BLOCK_K, BN);
   if (rc) return rc;
   const long long M = (long long)p->n * ho * wo;
@@ -652,9 +807,19 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   } else {
     tmap_a = tmap_b;
   }
+  tmap_y = tmap_b;
+  tmap_r = tmap_b;
+  if (EPI == EPI_TMA) {
+    rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, MODE == MODE_TMA_PATCH);
+    if (rc) return rc;
+    if (p->residual) {
+      rc = encode_tile_map(enc, &tmap_r, p->residual, p->res_ld, p->cout, p, ho, wo, MODE == MODE_TMA_PATCH);
+      if (rc) return rc;
+    }
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (rc) return rc;
     attr_done = true;
   }
@@ -663,18 +828,28 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int num_n_tiles = (int)ceil_div(p->cout, BN);
   const long long tiles = (long long)num_m_tiles * num_n_tiles;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_umma_kernel<BN, MODE><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, p->k_pad / BLOCK_K, num_m_tiles,
-                                                                        num_n_tiles, pw_tiles, ph_tiles, tmap_b, tmap_a);
+  conv_umma_kernel<BN, MODE, EPI><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, p->k_pad / BLOCK_K, num_m_tiles, num_n_tiles,
+                                                                             pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r);
   return check_launch();
+}
+
+// The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
+// 64-column group; it is used for K <= 512 (the HBM-bound layers), the slab epilogue with its deeper operand ring elsewhere.
+bool tma_epilogue_ok(const ppy_conv_params* p) {
+  if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS || p->k_pad > 512) return false;
+  if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * 2) % 16) return false;
+  if (p->residual && ((reinterpret_cast<uintptr_t>(p->residual) & 15) || (p->res_ld * 2) % 16)) return false;
+  return true;
 }
 
 template <int MODE>
 int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int c = p->cout;
-  if (c <= 32) return launch<32, MODE>(p, ho, wo, st);
-  if (c <= 64) return launch<64, MODE>(p, ho, wo, st);
-  if (c % 256 == 0) return launch<256, MODE>(p, ho, wo, st);
-  return launch<128, MODE>(p, ho, wo, st);
+  if (c <= 32) return launch<32, MODE, EPI_SLAB>(p, ho, wo, st);
+  const bool tma_epi = MODE != MODE_DCN && tma_epilogue_ok(p);
+  if (c <= 64) return tma_epi ? launch<64, MODE, EPI_TMA>(p, ho, wo, st) : launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
+  if (c % 256 == 0) return tma_epi ? launch<256, MODE, EPI_TMA>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB>(p, ho, wo, st);
+  return tma_epi ? launch<128, MODE, EPI_TMA>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB>(p, ho, wo, st);
 }
 
 }  // namespace

@@ -293,3 +293,19 @@ def test_umma_dcn(stride, hw):
     got = o.from_nhwc(y, cout).cpu()
     # A operand (modulated bilinear sample) is rounded to bf16 before the MMA: ~2^-9 relative per element
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=4e-3 * scale_of(want.numpy()))
+
+
+@pytest.mark.parametrize('n,cin,cout,k,hw', [(2, 64, 256, 1, 19), (1, 128, 512, 1, 30), (3, 64, 96, 1, 11), (2, 64, 64, 3, 32),
+                                             (1, 256, 128, 1, 24), (2, 64, 128, 3, 46)])
+def test_umma_conv_tma_epilogue(n, cin, cout, k, hw):
+    """bf16-output layers with K <= 512 take the TMA epilogue (residual boxes in by TMA, output boxes out by TMA store):
+    residual + ReLU against the oracle on bf16-rounded operands; covers M tails, N tails (cout 96) and 16x8 patch tiles."""
+    g = torch.Generator().manual_seed(cin + cout + hw)
+    x = bf16_round(torch.randn((n, cin, hw, hw), generator=g))
+    w = bf16_round(torch.randn((cout, cin, k, k), generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    res = bf16_round(torch.randn((n, cout, hw, hw), generator=g))
+    base = torch.nn.functional.conv2d(x, w, None, 1, (k - 1) // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    for residual, act, want in ((res, 1, torch.relu(base + res)), (None, 2, torch.nn.functional.leaky_relu(base, 0.1))):
+        got = _umma_conv(x, w, scale, shift, 1, act, residual=residual, out_f32=False)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
