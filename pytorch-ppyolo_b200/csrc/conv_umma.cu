@@ -55,7 +55,8 @@ constexpr int ST_LD = SUB;                        // floats per staged row; 16-b
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
 
 template <int BN, int EPI> struct TileCfg {
-  // EPI_TMA is only dispatched for K <= 512, so 3 stages are plenty there and free smem for the tile buffers
+  // EPI_TMA is only dispatched for small K (<= 512 at BLOCK_N 256, <= 1152 below), so fewer stages suffice there and
+  // free shared memory for the tile buffers
   static constexpr int kStages = EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
   static constexpr int kBStageBytes = BN * BLOCK_K * 2;
@@ -836,7 +837,8 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 // The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
 // 64-column group; it is used for K <= 512 (the HBM-bound layers), the slab epilogue with its deeper operand ring elsewhere.
 bool tma_epilogue_ok(const ppy_conv_params* p) {
-  if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS || p->k_pad > 512) return false;
+  if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
+  if (p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;     // 3 operand stages at BLOCK_N 256, 4-6 below
   if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * 2) % 16) return false;
   if (p->residual && ((reinterpret_cast<uintptr_t>(p->residual) & 15) || (p->res_ld * 2) % 16)) return false;
   return true;
