@@ -49,6 +49,7 @@ constexpr int kMaxPixelFloats = 4 * 96;    // an <= 4, nc + 6 <= 96 channels per
 __global__ void __launch_bounds__(kDecodeWarps * 32) yolo_decode_kernel(DecodeArgs p) {
   __shared__ float stage[kDecodeWarps][kMaxPixelFloats];
   __shared__ float conf_s[kDecodeWarps][4];
+  __shared__ float tmp_s[kDecodeWarps][32];      // [0,24): step-1 results (a*6+f), [24,32): step-2 powers
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long npix = (long long)p.n * p.size * p.size;
   const int per = 5 + p.nc;
@@ -62,18 +63,41 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) yolo_decode_kernel(DecodeAr
     const float* px = p.head + pixg * p.ld;
     for (int i = lane; i < chans; i += 32) st[i] = __ldg(px + i);
     __syncwarp();
-    if (lane < p.an) {            // one lane per anchor: objectness (+IoU-aware fusion) and the box
+    // anchor-level math spread over lanes in lock-step (same instruction stream for every active lane):
+    //   step 1, lanes 0..6A-1: item (a, f) -> f<2: sigmoid(t_xy), f in {2,3}: exp(t_wh), f=4: sigmoid(obj), f=5: sigmoid(ioup)
+    //   step 2, lanes 0..2A-1: pow(sigmoid(obj), 1-f) and pow(sigmoid(ioup), f)            (IoU-aware only)
+    //   step 3, lanes 0..A-1 : clamp / de-sigmoid / re-sigmoid of the fused objectness, box assembly and clip
+    if (lane < 6 * p.an) {
+      const int a = lane / 6, f = lane - 6 * a;
+      const float t = (f == 5) ? (p.iou_aware ? st[a] : 0.f) : st[first + a * per + f];
+      const bool is_exp = (f == 2 || f == 3);
+      const float e = expf(is_exp ? t : -t);
+      tmp_s[wib][lane] = is_exp ? e : __frcp_rn(__fadd_rn(1.f, e));
+    }
+    __syncwarp();
+    if (p.iou_aware && lane < 2 * p.an) {
+      const int a = lane >> 1, j = lane & 1;
+      tmp_s[wib][24 + lane] = powf(tmp_s[wib][6 * a + 4 + j], j ? p.e_iou : p.e_obj);
+    }
+    __syncwarp();
+    if (lane < p.an) {
       const int a = lane;
-      const float* t = st + first + a * per;
-      float conf;
-      if (p.iou_aware) conf = sigmoidf_ref(fused_obj_logit(t[4], st[a], p.e_obj, p.e_iou));
-      else conf = sigmoidf_ref(t[4]);
+      const float* r = tmp_s[wib] + 6 * a;
+      float conf = r[4];
+      if (p.iou_aware) {                                                       // _de_sigmoid, head.py:97-109, then sigmoid again (:47)
+        const float eps = 1e-7f, inv_eps = 1.f / 1e-7f;
+        float v = __fmul_rn(tmp_s[wib][24 + 2 * a], tmp_s[wib][24 + 2 * a + 1]);
+        v = clampf_ref(v, eps, inv_eps);
+        v = __fsub_rn(__fdiv_rn(1.f, v), 1.f);
+        v = clampf_ref(v, eps, inv_eps);
+        conf = sigmoidf_ref(-logf(v));
+      }
       conf_s[wib][a] = conf;
       // (scale_x_y * sigmoid(t) + grid - (scale_x_y - 1) * 0.5) * stride      head.py:40
-      float cx = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(t[0])), (float)gx), p.sxy_off), p.stride);
-      float cy = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, sigmoidf_ref(t[1])), (float)gy), p.sxy_off), p.stride);
-      float bw = __fmul_rn(expf(t[2]), p.aw[a]);                               // head.py:44
-      float bh = __fmul_rn(expf(t[3]), p.ah[a]);
+      float cx = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, r[0]), (float)gx), p.sxy_off), p.stride);
+      float cy = __fmul_rn(__fsub_rn(__fadd_rn(__fmul_rn(p.sxy, r[1]), (float)gy), p.sxy_off), p.stride);
+      float bw = __fmul_rn(r[2], p.aw[a]);                                     // head.py:44
+      float bh = __fmul_rn(r[3], p.ah[a]);
       float hw = __fdiv_rn(bw, 2.f), hh = __fdiv_rn(bh, 2.f);
       float x0 = __fsub_rn(cx, hw), y0 = __fsub_rn(cy, hh), x1 = __fadd_rn(cx, hw), y1 = __fadd_rn(cy, hh);
       const float im_h = __ldg(p.im_size + 2 * img), im_w = __ldg(p.im_size + 2 * img + 1);
