@@ -198,6 +198,7 @@ def run_ours(args, rank, world, local_rank):
     value = world * BATCH / (ms_step * 1e-3)
     counts = eng.nms_counts.cpu()
     assert int(counts.min()) >= 0, 'matrix_nms overflow flag'
+    cand_mean = float(eng.candidate_counts().float().mean()) if eng.scores is None else None
 
     # ---- end to end through the public API with host buffers ----------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -271,7 +272,8 @@ def run_ours(args, rank, world, local_rank):
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'l2_policy': 'inputs_exceed_l2 '
-                       '(141.9 MB batch, multi-GB activations per step vs 126 MB L2)', 'cuda_graph': True,
+                       '(141.9 MB batch, multi-GB activations per step vs 126 MB L2)', 'cuda_graph': True, 'postprocess': eng.postprocess_impl,
+                       'nms_candidates_per_image': cand_mean, 'detections_per_image': float(counts.float().mean()),
                        'sharding': 'batch-sharded replicas, no collective'},
             'clocks': clocks, 'gpu_launches': eng.launches_per_run * args.steps * world,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,

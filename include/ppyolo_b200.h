@@ -94,6 +94,18 @@ typedef struct ppy_conv_params {
   int upsample2x;           /* 1: write every output pixel to its 2x2 block of an [n,2ho,2wo,*] buffer */
   const float* offset_mask; /* non-null => DCNv2: [n,ho,wo,om_ld] fp32, ch 2t=dy 2t+1=dx, 18+t=mask logit */
   int om_ld;
+  /* --- bf16 path only: partial-sum launches (K splits; the weight-gradient GEMM of the training step) ---------------
+   * accumulate=1: results are ADDED (fp32 atomics) into y, which the caller zeroed; act none, no residual/bias_map,
+   * shift applied once.  split_k: K splits per output tile (0 = enough to fill the SMs).
+   * Weight gradient of a kxk stride-1 conv as ONE such launch (see ppy_conv_wgrad_bf16): a 1x1 "conv" whose rows are the
+   * conv's output channels (x = dY transposed, [cout][pixels]), whose packed "weight" is the transposed zero-bordered
+   * input ([cin][pixels]) and whose K runs over the pixels; wgrad_taps=9 repeats the GEMM per tap with the B operand
+   * read at flat pixel offset (ky-1)*wgrad_pitch + (kx-1) and the result written to columns [tap*wgrad_tap_stride, ..). */
+  int accumulate;
+  int split_k;
+  int wgrad_taps;
+  int wgrad_pitch;
+  int wgrad_tap_stride;
 } ppy_conv_params;
 
 /* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)
@@ -142,6 +154,13 @@ int ppy_iou_aware_score(const float* x, int x_ld, float* y, int y_ld, long long 
 int ppy_yolo_decode(const float* head, int ld, int n, int size, int an_num, int num_classes, const float* anchors,
                     int stride, double scale_x_y, const float* im_size, int clip_bbox, int iou_aware, double factor,
                     float* boxes, float* scores, int box_offset, int total_boxes, ppy_stream_t s);
+/* Same, and every score > score_threshold is also counted in the per-image score histogram at the head of a Matrix-NMS
+ * workspace (ppy_matrix_nms_workspace_bytes; zero it once per batch with ppy_nms_candidates_reset(ws, n, 1) before the
+ * first scale), so that ppy_matrix_nms_batched_hist can skip its own histogram pass over the scores. */
+int ppy_yolo_decode_hist(const float* head, int ld, int n, int size, int an_num, int num_classes, const float* anchors,
+                         int stride, double scale_x_y, const float* im_size, int clip_bbox, int iou_aware, double factor,
+                         float* boxes, float* scores, int box_offset, int total_boxes, float score_threshold,
+                         void* nms_workspace, ppy_stream_t s);
 /* jaccard, model/matrix_nms.py:33-47. */
 int ppy_pairwise_iou(const float* a, int na, const float* b, int nb, float* out, ppy_stream_t s);
 
@@ -153,6 +172,27 @@ int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int n
                            float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
                            int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
                            size_t workspace_bytes, ppy_stream_t s);
+/* ppy_matrix_nms_batched with the score histogram already in the workspace (ppy_yolo_decode_hist). */
+int ppy_matrix_nms_batched_hist(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
+                                float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
+                                int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
+                                size_t workspace_bytes, ppy_stream_t s);
+
+/* Sparse post-processing for the whole-network path (no dense score tensor): ppy_yolo_decode_candidates writes the boxes
+ * of one scale and appends every (box, class) score > score_threshold to a per-image candidate list + score histogram
+ * in `workspace` (ppy_nms_candidate_workspace_bytes; zero the counters once per batch with ppy_nms_candidates_reset
+ * before the first scale); ppy_matrix_nms_candidates then runs Matrix-NMS for the whole batch from those lists.
+ * Results are bit-identical to ppy_yolo_decode + ppy_matrix_nms_batched.  `cap` = list capacity per image; an image
+ * with more candidates is flagged counts[i] = -2. */
+int ppy_nms_candidate_workspace_bytes(int n, int cap, size_t* bytes);
+int ppy_nms_candidates_reset(void* workspace, int n, int cap, ppy_stream_t s);
+int ppy_yolo_decode_candidates(const float* head, int ld, int n, int size, int an_num, int num_classes,
+                               const float* anchors, int stride, double scale_x_y, const float* im_size, int clip_bbox,
+                               int iou_aware, double factor, float* boxes, int box_offset, int total_boxes,
+                               float score_threshold, void* workspace, int cap, ppy_stream_t s);
+int ppy_matrix_nms_candidates(const float* boxes, int n, int num_boxes, int num_classes, float score_threshold,
+                              float post_threshold, int nms_top_k, int keep_top_k, int use_gaussian, float gaussian_sigma,
+                              float* out, int* counts, void* workspace, int cap, ppy_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -221,13 +221,44 @@ __device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, const float
   }
 }
 
+// Work unit of the persistent loop: (tap, M tile, N tile, K split); N tile fastest among the tiles that share an A tile,
+// K splits of one tile adjacent.  Plain convs have one tap and one split, so unit == tile (n fastest) as before.
+struct Unit { int mt, nt, tap, sp, kb0, kb1; };
+template <bool ACC>
+__device__ __forceinline__ Unit decode_unit(int u, int num_m_tiles, int num_n_tiles, int num_splits, int num_kb) {
+  Unit r;
+  if (!ACC) { r.sp = 0; r.tap = 0; r.nt = u % num_n_tiles; r.mt = u / num_n_tiles; r.kb0 = 0; r.kb1 = num_kb; return r; }
+  r.sp = u % num_splits;
+  int t = u / num_splits;
+  r.nt = t % num_n_tiles; t /= num_n_tiles;
+  r.mt = t % num_m_tiles;
+  r.tap = t / num_m_tiles;
+  const int per = (num_kb + num_splits - 1) / num_splits;
+  r.kb0 = r.sp * per;
+  r.kb1 = r.kb0 + per < num_kb ? r.kb0 + per : num_kb;
+  return r;
+}
+
+// Partial-sum epilogue (K splits / weight-gradient taps): 8 channels of one output row are ADDED to the caller-zeroed fp32
+// output with red.global; y_col = first output column of this tap, the shift is contributed by the first split only.
+__device__ __noinline__ void epilogue_acc(const ppy_conv_params& p, const float* acc8, int m, int co, int y_col, bool first_split) {
+  const int ncol = (p.cout - co) < 8 ? (p.cout - co) : 8;
+  float* dst = reinterpret_cast<float*>(p.y) + (size_t)m * p.y_ld + y_col + co;
+  const unsigned long long g = (unsigned long long)__cvta_generic_to_global(dst);
+  for (int e = 0; e < ncol; ++e) {
+    const float f = acc8[e] * __ldg(p.scale + co + e) + (first_split ? __ldg(p.shift + co + e) : 0.f);
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g + 4ull * e), "f"(f) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MODE, int EPI>
+template <int BN, int MODE, int EPI, bool ACC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
-                 const int num_n_tiles, const int pw_tiles, const int ph_tiles, const __grid_constant__ CUtensorMap tmap_b,
+                 const int num_n_tiles, const int num_splits, const int num_taps, const int pw_tiles, const int ph_tiles,
+                 const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                  const __grid_constant__ CUtensorMap tmap_r) {
   using Cfg = TileCfg<BN, EPI>;
@@ -251,7 +282,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long M = (long long)p.n * ho * wo;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_tiles = ACC ? num_m_tiles * num_n_tiles * num_splits * num_taps : num_m_tiles * num_n_tiles;
 
   if (tid == 0) {
     const uint32_t full_count = (MODE == MODE_TMA_A || MODE == MODE_TMA_PATCH) ? 1u : (uint32_t)(BLOCK_M + 1);
@@ -280,7 +311,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       const uint32_t dst0 = (uint32_t)rg * 128u + (((uint32_t)j ^ (uint32_t)(rg & 7)) << 4);
       int g = 0;                                   // global K-block counter (ring position)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long m0 = (long long)(tile / num_n_tiles) * BLOCK_M;
+        const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
+        const long long m0 = (long long)u.mt * BLOCK_M;
         int iy0[8], ix0[8];
         long long pbase[8];                        // element offset of pixel (img, 0, 0); < 0 = row beyond M
 #pragma unroll
@@ -293,9 +325,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             pbase[i] = (long long)img * p.h * p.w;
           } else { iy0[i] = 0; ix0[i] = 0; pbase[i] = -1; }
         }
-        int tap = 0, c = j * 8, ky = 0, kx = 0;
+        int tap = 0, c = j * 8 + u.kb0 * BLOCK_K, ky = 0, kx = 0;
         while (c >= p.cin) { c -= p.cin; ++tap; if (++kx == p.kw) { kx = 0; ++ky; } }
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
           const uint32_t dst = smem_a + s * A_STAGE_BYTES + dst0;
@@ -393,14 +425,18 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       const int kb_per_tap = p.cin / BLOCK_K;
       int g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % num_n_tiles) * BN;
-        const int mt = tile / num_n_tiles;
+        const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
+        const int n0 = u.nt * BN;
+        const int mt = u.mt;
         const int m0 = mt * BLOCK_M;
+        // weight-gradient GEMM (p.wgrad_pitch > 0): the B operand is the transposed, zero-bordered activation read at the
+        // flat pixel offset of this tap -- (ky-1)*pitch + (kx-1)
+        const int b_shift = (ACC && num_taps == 9) ? (u.tap / 3 - 1) * p.wgrad_pitch + (u.tap % 3 - 1) : 0;
         int px0 = 0, py0 = 0, img = 0;
         if (MODE == MODE_TMA_PATCH) {
           px0 = (mt % pw_tiles) * PATCH_W; py0 = ((mt / pw_tiles) % ph_tiles) * PATCH_H; img = mt / (pw_tiles * ph_tiles);
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
@@ -410,7 +446,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
             tma_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
           }
-          tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K, n0);
+          tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K + b_shift, n0);
         }
       }
     }
@@ -426,14 +462,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         mbar_wait(tmem_empty_bar(acc), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
+        for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(full_bar(s), (g / S) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_a + s * A_STAGE_BYTES, b_addr = smem_b + s * Cfg::kBStageBytes;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, ((ACC ? kb - u.kb0 : kb) | k) ? 1u : 0u);
           umma_commit(empty_bar(s));             // frees the stage once these MMAs have read it
         }
         umma_commit(tmem_full_bar(acc));         // accumulator complete -> epilogue
@@ -569,7 +606,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // the fast path needs 16-byte aligned full vectors everywhere; anything else goes through epilogue_slow
     const bool aligned = ((p.y_ld * esz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
                          (!p.residual || (out_bf16 && ((p.res_ld * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
-                         (!p.bias_map || (p.cout & 7) == 0);
+                         (!p.bias_map || (p.cout & 7) == 0) && !ACC;            // partial-sum launches: atomics, out of line
     const bool has_res = p.residual != nullptr;
     constexpr int NSUB = BN / SUB;               // sub-tiles per tile
     constexpr int MY_SUBS = (NSUB + 1) / 2;      // upper bound of sub-tiles per warp
@@ -601,8 +638,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int n0 = (tile % num_n_tiles) * BN;
-      const int mt = tile / num_n_tiles;
+      const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
+      const int n0 = u.nt * BN;
+      const int mt = u.mt;
       prefetch_residual(tile + gridDim.x);
       int mrow[4];
 #pragma unroll
@@ -696,7 +734,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               const float4 a = *reinterpret_cast<const float4*>(slab + row * ST_LD + ((cpair ^ (row & 7)) << 2));
               const float4 b = *reinterpret_cast<const float4*>(slab + row * ST_LD + (((cpair + 1) ^ (row & 7)) << 2));
               tmp[0] = a.x; tmp[1] = a.y; tmp[2] = a.z; tmp[3] = a.w; tmp[4] = b.x; tmp[5] = b.y; tmp[6] = b.z; tmp[7] = b.w;
-              epilogue_slow(p, tmp, mrow[ps], co, ho, wo, slope);
+              if (ACC) epilogue_acc(p, tmp, mrow[ps], co, u.tap * p.wgrad_tap_stride, u.sp == 0);
+              else epilogue_slow(p, tmp, mrow[ps], co, ho, wo, slope);
             }
           }
         }
@@ -789,7 +828,29 @@ int encode_tile_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int l
   return PPY_OK;
 }
 
-template <int BN, int MODE, int EPI>
+// K splits for accumulate launches (fp32 atomics into a zeroed output): minimise rounds x (k-blocks per unit + fixed
+// per-unit cost of the pipeline ramp and epilogue, ~6 k-blocks) over the split counts that leave no unit empty.
+int pick_splits(const ppy_conv_params* p, long long tiles, int num_kb) {
+  if (!p->accumulate) return 1;
+  auto normalise = [&](int want) {
+    if (want < 1) want = 1;
+    if (want > num_kb) want = num_kb;
+    const int per = (num_kb + want - 1) / want;
+    return (num_kb + per - 1) / per;
+  };
+  if (p->split_k > 0) return normalise(p->split_k);
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= 32 && s <= num_kb; ++s) {
+    const int sn = normalise(s);
+    const long long rounds = ceil_div(tiles * sn, num_sms());
+    const long long cost = rounds * (ceil_div(num_kb, sn) + 6);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sn; }
+  }
+  return best;
+}
+
+template <int BN, int MODE, int EPI, bool ACC = false>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   using Cfg = TileCfg<BN, EPI>;
   EncodeTiledFn enc = get_encode_fn();
@@ -820,23 +881,28 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (rc) return rc;
     attr_done = true;
   }
   const int pw_tiles = (int)ceil_div(wo, PATCH_W), ph_tiles = (int)ceil_div(ho, PATCH_H);
   const int num_m_tiles = MODE == MODE_TMA_PATCH ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);
   const int num_n_tiles = (int)ceil_div(p->cout, BN);
-  const long long tiles = (long long)num_m_tiles * num_n_tiles;
+  const int num_kb = p->k_pad / BLOCK_K;
+  const int num_taps = p->wgrad_taps > 0 ? p->wgrad_taps : 1;
+  const int num_splits = pick_splits(p, (long long)num_m_tiles * num_n_tiles * num_taps, num_kb);
+  const long long tiles = (long long)num_m_tiles * num_n_tiles * num_taps * num_splits;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_umma_kernel<BN, MODE, EPI><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, p->k_pad / BLOCK_K, num_m_tiles, num_n_tiles,
-                                                                             pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r);
+  conv_umma_kernel<BN, MODE, EPI, ACC><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, num_kb, num_m_tiles, num_n_tiles, num_splits,
+                                                                             num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y,
+                                                                             tmap_r);
   return check_launch();
 }
 
 // The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
 // 64-column group; it is used for K <= 512 (the HBM-bound layers), the slab epilogue with its deeper operand ring elsewhere.
 bool tma_epilogue_ok(const ppy_conv_params* p) {
+  if (p->accumulate) return false;
   if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
   if (p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;     // 3 operand stages at BLOCK_N 256, 4-6 below
   if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * 2) % 16) return false;
@@ -847,6 +913,14 @@ bool tma_epilogue_ok(const ppy_conv_params* p) {
 template <int MODE>
 int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int c = p->cout;
+  if (p->accumulate) {       // partial-sum launches (split-K, weight gradients): slab epilogue with fp32 atomics
+    if (MODE == MODE_DCN || MODE == MODE_TMA_PATCH) return PPY_ERR_UNSUPPORTED;
+    constexpr int M2 = (MODE == MODE_TMA_A) ? MODE_TMA_A : MODE_GATHER;
+    if (c <= 32) return launch<32, M2, EPI_SLAB, true>(p, ho, wo, st);
+    if (c <= 64) return launch<64, M2, EPI_SLAB, true>(p, ho, wo, st);
+    if (c <= 128) return launch<128, M2, EPI_SLAB, true>(p, ho, wo, st);
+    return launch<256, M2, EPI_SLAB, true>(p, ho, wo, st);
+  }
   if (c <= 32) return launch<32, MODE, EPI_SLAB>(p, ho, wo, st);
   const bool tma_epi = MODE != MODE_DCN && tma_epilogue_ok(p);
   if (c <= 64) return tma_epi ? launch<64, MODE, EPI_TMA>(p, ho, wo, st) : launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
@@ -875,6 +949,14 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   if (p->offset_mask) PPY_REQUIRE(p->cin % BLOCK_K == 0 && (long long)p->n * p->h * p->w * p->x_ld < 0x7FFFFFFFll);
   PPY_REQUIRE((long long)p->n * ho * wo < 0x7FFFFFFFll);
   if (p->act == PPY_ACT_MISH) return PPY_ERR_UNSUPPORTED;   // no config uses it; ppy_activation covers module-level Mish
+  if (p->accumulate) {
+    // partial sums (K splits and/or the taps of a weight-gradient GEMM) are added atomically into a caller-zeroed fp32 output
+    PPY_REQUIRE(p->out_dtype == PPY_F32 && p->act == PPY_ACT_NONE && !p->residual && !p->bias_map && !p->upsample2x && !p->offset_mask);
+    PPY_REQUIRE(p->wgrad_taps == 0 || p->wgrad_taps == 1 || p->wgrad_taps == 9);
+    PPY_REQUIRE(p->wgrad_taps <= 1 || (p->kh == 1 && p->stride == 1 && p->wgrad_pitch > 0 && p->wgrad_tap_stride >= p->cout));
+  } else {
+    PPY_REQUIRE(p->split_k <= 1 && p->wgrad_taps <= 1);
+  }
   PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->shift) & 15) == 0);
   if (!ppy_conv_bf16_supported()) return PPY_ERR_UNSUPPORTED;
   if (p->offset_mask) return dispatch<MODE_DCN>(p, ho, wo, as_stream(s));
@@ -884,7 +966,7 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   // 3x3 stride-1: A tiles as 16x8 pixel patches fetched by 4-D TMA, when the patch grid wastes < 15% of the tiles
   const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&
                          (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
-  if (patchable) {
+  if (patchable && !p->accumulate) {
     const double eff = (double)ho * wo / ((double)ceil_div(ho, PATCH_H) * PATCH_H * ceil_div(wo, PATCH_W) * PATCH_W);
     if (eff >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
   }

@@ -19,11 +19,11 @@
 #include <math_constants.h>
 #include <string.h>
 #include "common.cuh"
+#include "nms_common.cuh"
 
 namespace ppy {
 namespace {
 
-constexpr int kBins = 4096;           // histogram bins per image
 constexpr int kCap = 8192;            // max collected candidates per image (keys in shared memory)
 constexpr int kMaxN = 1024;           // max boxes entering the n x n stage
 constexpr int kScanThreads = 256;
@@ -34,12 +34,6 @@ struct Workspace {
   unsigned int* count;    // [n] collected keys
   unsigned long long* keys;  // [n][kCap]
 };
-
-__device__ __forceinline__ int score_bin(float s, unsigned int thr_bits, int shift) {
-  // s > threshold > 0 here, so the bit pattern is monotonic in s
-  unsigned int d = (__float_as_uint(s) - thr_bits) >> shift;
-  return d < (unsigned)kBins ? (int)d : kBins - 1;
-}
 
 __global__ void __launch_bounds__(kScanThreads)
 nms_hist_kernel(const float* __restrict__ scores, long long per_image, long long chunk, float thr,
@@ -185,37 +179,69 @@ __device__ __forceinline__ float box_iou(const float4 a, const float4 b) {
   return __fdiv_rn(inter, uni);
 }
 
+// One CTA per image.  `hist` == nullptr: `keys` already holds only the candidates at/above the cutoff bin
+// (nms_collect_kernel).  Otherwise `keys` holds EVERY candidate (sparse decode, decode.cu) and the CTA first derives the
+// cutoff bin from the histogram and filters the list into shared memory.
 __global__ void __launch_bounds__(kMatrixThreads)
 nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classes, const unsigned int* __restrict__ count,
-                  const unsigned long long* __restrict__ keys, int nms_top_k, int keep_top_k, float post_thr,
+                  const unsigned long long* __restrict__ keys, int key_stride, const unsigned int* __restrict__ hist,
+                  unsigned int thr_bits, int shift, int nms_top_k, int keep_top_k, float post_thr,
                   int use_gaussian, float sigma, float* __restrict__ out, int* __restrict__ counts) {
-  extern __shared__ unsigned long long s_keys[];           // kCap keys, later reused for the second sort
+  extern __shared__ unsigned long long s_keys[];           // kCap keys, later reused for the other sorts
   __shared__ float4 s_box[kMaxN];
   __shared__ float s_score[kMaxN];
   __shared__ int s_label[kMaxN];
   __shared__ float s_comp[kMaxN];
   __shared__ float s_new[kMaxN];
-  __shared__ unsigned char s_odd[kMaxN];   // box whose IoU can be NaN/inf (area not a positive finite number)
+  __shared__ unsigned short s_order[kMaxN];   // box indices grouped by label (ascending index inside a label)
+  __shared__ unsigned short s_gstart[kMaxN];  // first position of the label group a position belongs to
+  __shared__ unsigned char s_odd[kMaxN];      // box whose IoU can be NaN/inf (area not a positive finite number)
+  __shared__ unsigned int s_part[33];
   __shared__ int s_nan_from;   // largest i with NaN compensate (poisons every column j <= i), -1 if none
   __shared__ int s_kept;
+  __shared__ int s_any_odd;
+  __shared__ unsigned int s_m;
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMatrixThreads >> 5;
   const unsigned int total = count[img];
   float* my_out = out + (long long)img * keep_top_k * 6;
-  if (total > (unsigned)kCap) {   // cutoff bin too crowded (mass ties) -- flagged, see DESIGN.md
+  if (total > (unsigned)key_stride) {   // candidate list overflowed -- flagged, see DESIGN.md
     if (tid == 0) counts[img] = -2;
     return;
   }
-  const int m = (int)total;
-  if (m == 0) { if (tid == 0) counts[img] = 0; return; }
+  if (total == 0) { if (tid == 0) counts[img] = 0; return; }
+  const unsigned long long* gk = keys + (long long)img * key_stride;
+  int m;
+  if (hist != nullptr) {
+    const int want = nms_top_k > 0 ? nms_top_k : kCap + 1;
+    const int cut = find_cutoff_bin(hist + (long long)img * kBins, want, reinterpret_cast<unsigned int*>(s_keys), s_part);
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (unsigned int i = tid; i < total; i += kMatrixThreads) {
+      const unsigned long long k = gk[i];
+      if (score_bin(__uint_as_float((unsigned int)(k >> 32)), thr_bits, shift) >= cut) {
+        const unsigned int slot = atomicAdd(&s_m, 1u);
+        if (slot < (unsigned)kCap) s_keys[slot] = k;
+      }
+    }
+    __syncthreads();
+    if (s_m > (unsigned)kCap) {         // cutoff bin too crowded (mass ties)
+      if (tid == 0) counts[img] = -2;
+      return;
+    }
+    m = (int)s_m;
+  } else {
+    m = (int)total;
+    for (int i = tid; i < m; i += kMatrixThreads) s_keys[i] = gk[i];
+  }
   int len = 1; while (len < m) len <<= 1;
-  const unsigned long long* gk = keys + (long long)img * kCap;
-  for (int i = tid; i < len; i += kMatrixThreads) s_keys[i] = i < m ? gk[i] : 0ull;
+  for (int i = m + tid; i < len; i += kMatrixThreads) s_keys[i] = 0ull;
   bitonic_sort_desc(s_keys, len);
   int n = m;
   if (nms_top_k > 0 && n > nms_top_k) n = nms_top_k;
   if (n > kMaxN) { if (tid == 0) counts[img] = -3; return; }
-  if (tid == 0) { s_nan_from = -1; s_kept = 0; }
+  if (tid == 0) { s_nan_from = -1; s_kept = 0; s_any_odd = 0; }
+  __syncthreads();
   const float4* gb = reinterpret_cast<const float4*>(boxes) + (long long)img * num_boxes;
   for (int i = tid; i < n; i += kMatrixThreads) {
     unsigned long long k = s_keys[i];
@@ -225,9 +251,68 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     const float4 bx = __ldg(gb + flat / (unsigned)num_classes);
     s_box[i] = bx;
     const float area = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-    s_odd[i] = !(area > 0.f && area < CUDART_INF_F);
+    const bool odd = !(area > 0.f && area < CUDART_INF_F);
+    s_odd[i] = odd;
+    if (odd) s_any_odd = 1;
   }
   __syncthreads();
+  const float neg_sigma = -1.f * sigma;
+  if (!s_any_odd) {
+    // ---- every area is positive and finite: IoU is never NaN and pairs with different labels (or disjoint boxes)
+    // contribute exactly +0 to compensate and a factor >= 1 to the decay min, so only same-label pairs matter.
+    // Group the boxes by label (sort of (label, index)) and let each warp walk just its column's group prefix.
+    int len2 = 1; while (len2 < n) len2 <<= 1;
+    for (int i = tid; i < len2; i += kMatrixThreads)
+      s_keys[i] = i < n ? (((unsigned long long)(0xFFFFFFFFu - (unsigned int)s_label[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i)) : 0ull;
+    bitonic_sort_desc(s_keys, len2);
+    for (int p = tid; p < n; p += kMatrixThreads) s_order[p] = (unsigned short)(0xFFFFFFFFu - (unsigned int)(s_keys[p] & 0xFFFFFFFFull));
+    __syncthreads();
+    for (int p = tid; p < n; p += kMatrixThreads) {
+      const int lp = s_label[s_order[p]];
+      int q = p;
+      while (q > 0 && s_label[s_order[q - 1]] == lp) --q;
+      s_gstart[p] = (unsigned short)q;
+    }
+    __syncthreads();
+    for (int p = wid; p < n; p += nwarps) {
+      const int j = s_order[p];
+      const float4 bj = s_box[j];
+      float mx = 0.f;
+      for (int q = s_gstart[p] + lane; q < p; q += 32) {
+        const float4 bi = s_box[s_order[q]];
+        const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+        if (iw <= 0.f || ih <= 0.f) continue;
+        mx = fmaxf(mx, box_iou(bi, bj));
+      }
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) s_comp[j] = mx;
+    }
+    __syncthreads();
+    for (int p = wid; p < n; p += nwarps) {
+      const int j = s_order[p];
+      const float4 bj = s_box[j];
+      float mn = j > 0 ? 1.f : CUDART_INF_F;
+      for (int q = s_gstart[p] + lane; q < p; q += 32) {
+        const int i = s_order[q];
+        const float4 bi = s_box[i];
+        const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+        if (iw <= 0.f || ih <= 0.f) continue;
+        const float d = box_iou(bi, bj);
+        const float c = s_comp[i];
+        float e;
+        if (use_gaussian) e = __fdiv_rn(expf(__fmul_rn(neg_sigma, __fmul_rn(d, d))), expf(__fmul_rn(neg_sigma, __fmul_rn(c, c))));
+        else e = __fdiv_rn(__fsub_rn(1.f, d), __fsub_rn(1.f, c));
+        mn = nan_min(mn, e);
+      }
+      for (int o = 16; o > 0; o >>= 1) mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if (lane == 0) {
+        const float cj = s_comp[j];
+        const float self = use_gaussian ? __fdiv_rn(1.f, expf(__fmul_rn(neg_sigma, __fmul_rn(cj, cj)))) : __fdiv_rn(1.f, __fsub_rn(1.f, cj));
+        mn = nan_min(mn, self);
+        s_new[j] = __fmul_rn(s_score[j], mn);
+      }
+    }
+  } else {
   // compensate[j] = max_i (iou*same)[i][j] over the strict upper triangle (matrix_nms.py:67-78); warp per column
   for (int j = wid; j < n; j += nwarps) {
     const float4 bj = s_box[j];
@@ -257,7 +342,6 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   // decay[j] = min_i f(d[i][j]) / f(compensate[i])  (:85-93).  Rows i >= j have d = 0 and contribute
   // 1/f(comp_i) >= 1 >= row 0's term, so only their NaNs matter (s_nan_from); row i < j evaluated exactly.
   const int nan_from = s_nan_from;
-  const float neg_sigma = -1.f * sigma;
   for (int j = wid; j < n; j += nwarps) {
     const float4 bj = s_box[j];
     const int lj = s_label[j];
@@ -294,10 +378,11 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
       s_new[j] = __fmul_rn(s_score[j], mn);
     }
   }
+  }
   __syncthreads();
   // post threshold (>=, NaN fails; :132) then stable descending sort by decayed score (:140-145)
-  int len2 = 1; while (len2 < n) len2 <<= 1;
-  for (int i = tid; i < len2; i += kMatrixThreads) {
+  int len3 = 1; while (len3 < n) len3 <<= 1;
+  for (int i = tid; i < len3; i += kMatrixThreads) {
     unsigned long long k = 0ull;
     if (i < n) {
       float v = s_new[i];
@@ -311,7 +396,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     }
     s_keys[i] = k;
   }
-  bitonic_sort_desc(s_keys, len2);
+  bitonic_sort_desc(s_keys, len3);
   int kept = s_kept;
   if (kept > keep_top_k) kept = keep_top_k;
   for (int r = tid; r < kept; r += kMatrixThreads) {
@@ -357,10 +442,10 @@ int ppy_matrix_nms_workspace_bytes(int n, int num_boxes, int num_classes, size_t
   return PPY_OK;
 }
 
-int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
-                           float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
-                           int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
-                           size_t workspace_bytes, ppy_stream_t s) {
+static int matrix_nms_dense(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
+                            float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
+                            int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
+                            size_t workspace_bytes, ppy_stream_t s, bool have_hist) {
   using namespace ppy;
   PPY_REQUIRE(boxes && scores && out && counts && workspace);
   PPY_REQUIRE(n > 0 && num_boxes > 0 && num_classes > 0 && keep_top_k > 0);
@@ -371,16 +456,14 @@ int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int n
   cudaStream_t st = as_stream(s);
   Workspace w = carve(workspace, n);
   // histogram + count live at the head of the workspace, contiguous
-  int rc = check_cuda(cudaMemsetAsync(w.hist, 0, reinterpret_cast<char*>(w.keys) - reinterpret_cast<char*>(w.hist), st));
-  if (rc) return rc;
-  // binning: candidates satisfy score > thr; bins cover (thr, 1] and everything above lands in the top bin
-  float thr_pos = score_threshold > 1e-30f ? score_threshold : 1e-30f;
-  unsigned int thr_bits, one_bits;
-  float one = 1.0f;
-  memcpy(&thr_bits, &thr_pos, 4);
-  memcpy(&one_bits, &one, 4);
-  int shift = 0;
-  if (one_bits > thr_bits) while (((one_bits - thr_bits) >> shift) >= (unsigned)kBins) ++shift;
+  int rc = PPY_OK;
+  if (!have_hist) {
+    rc = check_cuda(cudaMemsetAsync(w.hist, 0, reinterpret_cast<char*>(w.keys) - reinterpret_cast<char*>(w.hist), st));
+    if (rc) return rc;
+  }
+  unsigned int thr_bits;
+  int shift;
+  score_binning(score_threshold, &thr_bits, &shift);
   const long long per_image = (long long)num_boxes * num_classes;
   // enough CTAs to saturate HBM: ~4 per SM over the whole batch, each CTA >= 16K scores, chunk % 4 == 0
   long long gx = ceil_div(148 * 4, n);
@@ -391,8 +474,10 @@ int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int n
   gx = ceil_div(per_image, chunk);
   dim3 grid((unsigned)gx, (unsigned)n);
   int want = nms_top_k > 0 ? nms_top_k : kCap + 1;   // <=0: take everything (cutoff bin 0)
-  nms_hist_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.hist);
-  if ((rc = check_launch())) return rc;
+  if (!have_hist) {
+    nms_hist_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.hist);
+    if ((rc = check_launch())) return rc;
+  }
   nms_collect_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, want, w.hist,
                                                     w.count, w.keys);
   if ((rc = check_launch())) return rc;
@@ -403,9 +488,48 @@ int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int n
     if (rc) return rc;
     attr_set = true;
   }
-  nms_matrix_kernel<<<n, kMatrixThreads, smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, nms_top_k,
-                                                     keep_top_k, post_threshold, use_gaussian, gaussian_sigma, out,
-                                                     counts);
+  nms_matrix_kernel<<<n, kMatrixThreads, smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, kCap, nullptr, 0u, 0,
+                                                     nms_top_k, keep_top_k, post_threshold, use_gaussian, gaussian_sigma,
+                                                     out, counts);
+  return check_launch();
+}
+
+int ppy_matrix_nms_batched(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
+                           float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
+                           int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
+                           size_t workspace_bytes, ppy_stream_t s) {
+  return matrix_nms_dense(boxes, scores, n, num_boxes, num_classes, score_threshold, post_threshold, nms_top_k, keep_top_k,
+                          use_gaussian, gaussian_sigma, out, counts, workspace, workspace_bytes, s, false);
+}
+
+int ppy_matrix_nms_batched_hist(const float* boxes, const float* scores, int n, int num_boxes, int num_classes,
+                                float score_threshold, float post_threshold, int nms_top_k, int keep_top_k,
+                                int use_gaussian, float gaussian_sigma, float* out, int* counts, void* workspace,
+                                size_t workspace_bytes, ppy_stream_t s) {
+  return matrix_nms_dense(boxes, scores, n, num_boxes, num_classes, score_threshold, post_threshold, nms_top_k, keep_top_k,
+                          use_gaussian, gaussian_sigma, out, counts, workspace, workspace_bytes, s, true);
+}
+
+int ppy_matrix_nms_candidates(const float* boxes, int n, int num_boxes, int num_classes, float score_threshold,
+                              float post_threshold, int nms_top_k, int keep_top_k, int use_gaussian, float gaussian_sigma,
+                              float* out, int* counts, void* workspace, int cap, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(boxes && out && counts && workspace);
+  PPY_REQUIRE(n > 0 && num_boxes > 0 && num_classes > 0 && keep_top_k > 0 && cap > 0 && score_threshold > 0.f);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
+  PPY_REQUIRE(nms_top_k <= kMaxN);
+  PPY_REQUIRE((long long)num_boxes * num_classes < 0xFFFFFFFFll);
+  const CandSink c = cand_carve(workspace, n, cap, score_threshold);
+  static bool attr_set = false;
+  const int smem = kCap * (int)sizeof(unsigned long long);
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (rc) return rc;
+    attr_set = true;
+  }
+  nms_matrix_kernel<<<n, kMatrixThreads, smem, as_stream(s)>>>(boxes, num_boxes, num_classes, c.count, c.keys, cap, c.hist,
+                                                               c.thr_bits, c.shift, nms_top_k, keep_top_k, post_threshold,
+                                                               use_gaussian, gaussian_sigma, out, counts);
   return check_launch();
 }
 

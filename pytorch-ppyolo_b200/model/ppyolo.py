@@ -17,12 +17,13 @@ class PPYOLO(torch.nn.Module):
         self.precision = 'bf16'
         self.train_precision = 'fp32'     # arithmetic of the frozen-backbone forward inside a training step
         self.dcn_impl = None          # None = engine default; 'fused' | 'gather_gemm'
+        self.postprocess_impl = None  # None = engine default ('sparse'); 'sparse' | 'dense' (see engine.py)
         self.use_engine = True
         self._engines = {}
 
     def engine(self, batch, height, width):
         from ppyolo_b200.engine import InferenceEngine
-        key = (batch, height, width, self.precision, self.dcn_impl)
+        key = (batch, height, width, self.precision, self.dcn_impl, self.postprocess_impl)
         eng = self._engines.get(key)
         if eng is None:
             eng = InferenceEngine(self, batch, height, width, precision=self.precision, dcn_impl=self.dcn_impl)

@@ -28,6 +28,7 @@ class ConvParams(ctypes.Structure):
         ('act', c_int),
         ('y', c_void_p), ('y_ld', c_int), ('out_dtype', c_int), ('upsample2x', c_int),
         ('offset_mask', c_void_p), ('om_ld', c_int),
+        ('accumulate', c_int), ('split_k', c_int), ('wgrad_taps', c_int), ('wgrad_pitch', c_int), ('wgrad_tap_stride', c_int),
     ]
 
 
@@ -62,8 +63,20 @@ SIGNATURES = {
     'ppy_iou_aware_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_double, c_void_p]),
     'ppy_yolo_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'ppy_yolo_decode_hist': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
+                                     c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
+                                     c_void_p]),
+    'ppy_matrix_nms_batched_hist': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
+                                            c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ppy_pairwise_iou': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'ppy_matrix_nms_workspace_bytes': (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    'ppy_nms_candidate_workspace_bytes': (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
+    'ppy_nms_candidates_reset': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    'ppy_yolo_decode_candidates': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
+                                           c_void_p, c_int, c_int, c_double, c_void_p, c_int, c_int, c_float, c_void_p, c_int,
+                                           c_void_p]),
+    'ppy_matrix_nms_candidates': (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int, c_float,
+                                          c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'ppy_matrix_nms_batched': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                        c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }

@@ -70,6 +70,9 @@ class InferenceEngine(object):
         # train_bn: BatchNorm layers normalise with BATCH statistics and update their running stats, as the reference's
         # frozen backbone does during training; backbone_only: stop at the C3/C4/C5 feature maps
         self.train_bn, self.backbone_only = train_bn, backbone_only
+        self.postprocess_impl = getattr(model, 'postprocess_impl', None) or 'dense'
+        if self.postprocess_impl not in ('sparse', 'dense'):
+            raise ValueError(self.postprocess_impl)
         self.steps = []          # (name, callable)
         self.keep = []           # tensors / ctypes structs referenced by raw pointer
         self.conv_flops = 0      # algorithmic 2*MAC of all convs in the plan (per batch)
@@ -159,7 +162,7 @@ class InferenceEngine(object):
         return out
 
     def _conv(self, name, x, weight, scale, shift, stride, act, residual=None, dst=None, coord=False, upsample=False,
-              out_code=None, offset_mask=None, gemm_taps=False):
+              out_code=None, offset_mask=None, gemm_taps=False, split_k=False):
         """``gemm_taps``: ``x`` already is the sampled [n,ho,wo,k*k*cin] matrix of a DCN gather; run the k x k
         weight as a 1x1 GEMM over it (same packed K order (tap, c))."""
         cout, cin_total, k, _ = weight.shape
@@ -193,11 +196,17 @@ class InferenceEngine(object):
         p.upsample2x = 1 if upsample else 0
         p.offset_mask = offset_mask.ptr if offset_mask is not None else None
         p.om_ld = offset_mask.ld if offset_mask is not None else 0
+        # split_k: few output tiles and a long K (the DCN offset conv): K splits added atomically into the zeroed fp32 output
+        split_k = split_k and self.code == PPY_BF16 and out_code == PPY_F32 and act == 0 and residual is None and not coord
+        p.accumulate = 1 if split_k else 0
         self._keep(p)
         fn = lib.ppy_conv_bf16 if self.code == PPY_BF16 else lib.ppy_conv_f32
         ref = ctypes.byref(p)
+        zero_t = dst.t
 
         def run():
+            if split_k:
+                zero_t.zero_()
             check(fn(ref, ops.stream_ptr()), name)
         self._add(name, run)
         flops = 2 * x.n * ho * wo * cout * cin_total * k * k
@@ -478,27 +487,56 @@ class InferenceEngine(object):
         self.total_boxes = sum(s * s * a for s, a in zip(sizes, an_per))
         nc = head.num_classes
         self.boxes = torch.zeros((n, self.total_boxes, 4), dtype=torch.float32, device=self.dev)
-        self.scores = torch.zeros((n, self.total_boxes, nc), dtype=torch.float32, device=self.dev)
-        off = 0
-        for i, o in enumerate(self.head_outs):
-            anchors = head._anchors[head.anchor_masks[i]].reshape(-1)
-
-            def run(o=o, anchors=anchors, off=off, i=i):
-                ops.yolo_decode_nhwc(o.t, o.ld, n, o.h, anchors, head.downsample[i], nc, head.scale_x_y, self.im_size,
-                                     head.clip_bbox, head.iou_aware, head.iou_aware_factor, self.boxes, self.scores,
-                                     off, self.total_boxes)
-            self._add('decode%d' % i, run)
-            off += o.h * o.h * an_per[i]
         cfg = dict(head.nms_cfg)
         if cfg.pop('nms_type') != 'matrix_nms':
             raise NotImplementedError('only matrix_nms is on the PP-YOLO path')
         self.keep_top_k = cfg['keep_top_k']
         self.nms_out = torch.zeros((n, self.keep_top_k, 6), dtype=torch.float32, device=self.dev)
         self.nms_counts = torch.zeros((n,), dtype=torch.int32, device=self.dev)
-        ws = ops.nms_workspace(n, self.total_boxes, nc, self.dev)
-        self._add('matrix_nms', lambda: ops.matrix_nms_launch(
-            self.boxes, self.scores, self.nms_out, self.nms_counts, ws, cfg['score_threshold'], cfg['post_threshold'],
-            cfg['nms_top_k'], cfg['keep_top_k'], cfg.get('use_gaussian', False), cfg.get('gaussian_sigma', 2.0)))
+        nms_args = (cfg['score_threshold'], cfg['post_threshold'], cfg['nms_top_k'], cfg['keep_top_k'],
+                    cfg.get('use_gaussian', False), cfg.get('gaussian_sigma', 2.0))
+        # 'dense' (default): yolo_box's dense scores; the decode kernels also fill the per-image score histogram, so the
+        # NMS front end needs one pass over the scores (collect) instead of two.  Cost independent of the data.
+        # 'sparse': the decode kernels emit Matrix-NMS candidates (score > score_threshold) directly and skip the class
+        # scores of anchors whose objectness is already below the threshold; no dense [boxes x C] score tensor.  Wins when
+        # few scores pass the threshold (a trained detector), loses when most do (atomics per candidate).
+        sparse = self.postprocess_impl == 'sparse' and cfg['score_threshold'] > 0
+        if sparse:
+            self.scores = None
+            self.cand_cap = self.total_boxes * nc      # every score could pass: the list can never overflow (8 B/key of HBM)
+            ws = self._keep(ops.nms_candidate_workspace(n, self.cand_cap, self.dev))
+            self.cand_ws = ws
+        else:
+            self.scores = torch.zeros((n, self.total_boxes, nc), dtype=torch.float32, device=self.dev)
+            ws = self._keep(torch.empty_like(ops.nms_workspace(n, self.total_boxes, nc, self.dev)))   # private: holds the histogram
+        dense_hist = not sparse and cfg['score_threshold'] > 0
+        off = 0
+        for i, o in enumerate(self.head_outs):
+            anchors = head._anchors[head.anchor_masks[i]].reshape(-1)
+
+            def run(o=o, anchors=anchors, off=off, i=i):
+                if sparse:
+                    if i == 0:
+                        ops.nms_candidates_reset(ws, n, self.cand_cap)
+                    ops.yolo_decode_candidates_nhwc(o.t, o.ld, n, o.h, anchors, head.downsample[i], nc, head.scale_x_y,
+                                                    self.im_size, head.clip_bbox, head.iou_aware, head.iou_aware_factor,
+                                                    self.boxes, off, self.total_boxes, cfg['score_threshold'], ws,
+                                                    self.cand_cap)
+                else:
+                    if i == 0 and dense_hist:
+                        ops.nms_candidates_reset(ws, n, 1)
+                    ops.yolo_decode_nhwc(o.t, o.ld, n, o.h, anchors, head.downsample[i], nc, head.scale_x_y, self.im_size,
+                                         head.clip_bbox, head.iou_aware, head.iou_aware_factor, self.boxes, self.scores,
+                                         off, self.total_boxes, hist_threshold=cfg['score_threshold'] if dense_hist else None,
+                                         nms_workspace=ws if dense_hist else None)
+            self._add('decode%d' % i, run)
+            off += o.h * o.h * an_per[i]
+        if sparse:
+            self._add('matrix_nms', lambda: ops.matrix_nms_candidates_launch(self.boxes, nc, self.nms_out, self.nms_counts, ws,
+                                                                             self.cand_cap, *nms_args))
+        else:
+            self._add('matrix_nms', lambda: ops.matrix_nms_launch(self.boxes, self.scores, self.nms_out, self.nms_counts, ws,
+                                                                  *nms_args, have_hist=dense_hist))
 
     @staticmethod
     def _stage_channels(bb, stage):
@@ -540,6 +578,13 @@ class InferenceEngine(object):
         counts = self.nms_counts.cpu().tolist()          # the one host sync
         out = self.nms_out.clone()
         return ops.split_predictions(out, counts)
+
+    def candidate_counts(self):
+        """Scores above score_threshold per image in the last run (sparse post-processing only): int32 [n] tensor."""
+        if self.scores is not None:
+            raise RuntimeError('dense post-processing keeps no candidate list')
+        off = 4 * 4096 * self.n                   # workspace layout: hist[n][4096] u32 | count[n] u32 | keys (nms_common.cuh)
+        return self.cand_ws[off:off + 4 * self.n].view(torch.int32).clone()
 
     def head_outputs_nchw(self):
         """Raw head outputs of the last run as NCHW fp32 tensors (parity tests)."""

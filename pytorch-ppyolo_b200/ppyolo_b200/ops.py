@@ -275,9 +275,18 @@ def iou_aware_score(output, an_num, num_classes, factor):
 
 
 def yolo_decode_nhwc(head, ld, n, size, anchors, stride, num_classes, scale_x_y, im_size, clip_bbox, iou_aware,
-                     factor, boxes, scores, box_offset, total_boxes):
+                     factor, boxes, scores, box_offset, total_boxes, hist_threshold=None, nms_workspace=None):
+    """``nms_workspace`` + ``hist_threshold``: also count every score > threshold in the workspace's score histogram
+    (consumed by ``matrix_nms_launch(..., have_hist=True)``)."""
     anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.float32).reshape(-1))
     an = anchors.size // 2
+    if nms_workspace is not None:
+        check(lib.ppy_yolo_decode_hist(ptr(head), ld, n, size, an, num_classes,
+                                       anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(stride), float(scale_x_y),
+                                       ptr(im_size), 1 if clip_bbox else 0, 1 if iou_aware else 0, float(factor), ptr(boxes),
+                                       ptr(scores), box_offset, total_boxes, float(hist_threshold), ptr(nms_workspace),
+                                       stream_ptr()), 'yolo_decode_hist')
+        return
     check(lib.ppy_yolo_decode(ptr(head), ld, n, size, an, num_classes,
                               anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(stride), float(scale_x_y),
                               ptr(im_size), 1 if clip_bbox else 0, 1 if iou_aware else 0, float(factor), ptr(boxes),
@@ -325,12 +334,43 @@ def nms_workspace(n, num_boxes, num_classes, device):
 
 
 def matrix_nms_launch(boxes, scores, out, counts, workspace, score_threshold, post_threshold, nms_top_k, keep_top_k,
-                      use_gaussian, gaussian_sigma):
+                      use_gaussian, gaussian_sigma, have_hist=False):
     n, nb, nc = scores.shape
-    check(lib.ppy_matrix_nms_batched(ptr(boxes), ptr(scores), n, nb, nc, float(score_threshold), float(post_threshold),
+    fn = lib.ppy_matrix_nms_batched_hist if have_hist else lib.ppy_matrix_nms_batched
+    check(fn(ptr(boxes), ptr(scores), n, nb, nc, float(score_threshold), float(post_threshold),
                                      int(nms_top_k), int(keep_top_k), 1 if use_gaussian else 0, float(gaussian_sigma),
                                      ptr(out), ptr(counts), ptr(workspace), workspace.numel(), stream_ptr()),
           'matrix_nms_batched')
+
+
+# ---- sparse post-processing (whole-network path): candidates straight from the decode kernel, no dense score tensor
+def nms_candidate_workspace(n, cap, device):
+    need = ctypes.c_size_t(0)
+    check(lib.ppy_nms_candidate_workspace_bytes(n, cap, ctypes.byref(need)), 'nms_candidate_workspace_bytes')
+    return torch.empty(need.value, dtype=torch.uint8, device=device)
+
+
+def nms_candidates_reset(workspace, n, cap):
+    check(lib.ppy_nms_candidates_reset(ptr(workspace), n, cap, stream_ptr()), 'nms_candidates_reset')
+
+
+def yolo_decode_candidates_nhwc(head, ld, n, size, anchors, stride, num_classes, scale_x_y, im_size, clip_bbox, iou_aware,
+                                factor, boxes, box_offset, total_boxes, score_threshold, workspace, cap):
+    anchors = np.ascontiguousarray(np.asarray(anchors, dtype=np.float32).reshape(-1))
+    an = anchors.size // 2
+    check(lib.ppy_yolo_decode_candidates(ptr(head), ld, n, size, an, num_classes,
+                                         anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(stride),
+                                         float(scale_x_y), ptr(im_size), 1 if clip_bbox else 0, 1 if iou_aware else 0,
+                                         float(factor), ptr(boxes), box_offset, total_boxes, float(score_threshold),
+                                         ptr(workspace), cap, stream_ptr()), 'yolo_decode_candidates')
+
+
+def matrix_nms_candidates_launch(boxes, num_classes, out, counts, workspace, cap, score_threshold, post_threshold, nms_top_k,
+                                 keep_top_k, use_gaussian, gaussian_sigma):
+    n, nb, _ = boxes.shape
+    check(lib.ppy_matrix_nms_candidates(ptr(boxes), n, nb, num_classes, float(score_threshold), float(post_threshold),
+                                        int(nms_top_k), int(keep_top_k), 1 if use_gaussian else 0, float(gaussian_sigma),
+                                        ptr(out), ptr(counts), ptr(workspace), cap, stream_ptr()), 'matrix_nms_candidates')
 
 
 def split_predictions(out, counts_host):
@@ -339,7 +379,9 @@ def split_predictions(out, counts_host):
     for i, c in enumerate(counts_host):
         if c < 0:
             raise _lib.KernelError('matrix_nms: candidate overflow on image %d (code %d): more than 8192 scores tie '
-                                   'at the top-k cutoff, or nms_top_k<=0 with more than 1024 candidates' % (i, c))
+                                   'at the top-k cutoff, nms_top_k<=0 with more than 1024 candidates, or (sparse '
+                                   'post-processing) more scores above score_threshold than the candidate list holds -- '
+                                   "set model.postprocess_impl = 'dense'" % (i, c))
         preds.append(out[i, :c] if c > 0 else torch.full((1, 6), -1.0, device=out.device))
     return preds
 

@@ -135,6 +135,57 @@ def test_decode_golden(golden, tag, stride, mask, iou_aware):
         np.testing.assert_allclose(scores.cpu().numpy(), z[tag + '_scores'], rtol=1e-5, atol=1e-9)
 
 
+@pytest.mark.parametrize('obj_bias,gauss', [(-4.0, False), (0.5, False), (-2.0, True)])
+def test_sparse_decode_nms_equals_dense(obj_bias, gauss):
+    """ppy_yolo_decode_candidates + ppy_matrix_nms_candidates == ppy_yolo_decode + ppy_matrix_nms_batched, bit for bit,
+    at the three ppyolo_2x scales of a 320x320 input (sparse objectness, and a dense-objectness stress case where most
+    anchors pass the threshold)."""
+    o = ops()
+    from ppyolo_b200._lib import PPY_F32
+    n, nc = 3, 80
+    anchors = np.array(build_model('r50vd')[1].head['anchors'], np.float32)
+    g = torch.Generator().manual_seed(11)
+    sizes, strides, masks = (10, 20, 40), (32, 16, 8), ([6, 7, 8], [3, 4, 5], [0, 1, 2])
+    total = sum(s * s * 3 for s in sizes)
+    im_size = synth.im_sizes(n).to(DEV)
+    boxes_d = torch.zeros((n, total, 4), device=DEV)
+    scores_d = torch.zeros((n, total, nc), device=DEV)
+    boxes_s = torch.zeros((n, total, 4), device=DEV)
+    cap = total * nc
+    ws = o.nms_candidate_workspace(n, cap, torch.device(DEV))
+    o.nms_candidates_reset(ws, n, cap)
+    off = 0
+    for s, st, mk in zip(sizes, strides, masks):
+        x = torch.randn((n, 258, s, s), generator=g) * 1.5
+        x[:, 3:] += -3.0
+        for a in range(3):
+            x[:, 3 + a * 85 + 4] += obj_bias + 2.0
+        xh = o.to_nhwc(x.to(DEV), PPY_F32, 264)
+        o.yolo_decode_nhwc(xh, 264, n, s, anchors[mk], st, nc, 1.05, im_size, True, True, 0.4, boxes_d, scores_d, off, total)
+        o.yolo_decode_candidates_nhwc(xh, 264, n, s, anchors[mk], st, nc, 1.05, im_size, True, True, 0.4, boxes_s, off, total,
+                                      0.01, ws, cap)
+        off += s * s * 3
+    np.testing.assert_array_equal(boxes_d.cpu().numpy(), boxes_s.cpu().numpy())
+    n_cand = int((scores_d > 0.01).sum())
+    assert n_cand > 100
+    out_d = torch.zeros((n, 100, 6), device=DEV); cnt_d = torch.zeros((n,), dtype=torch.int32, device=DEV)
+    out_s = torch.zeros((n, 100, 6), device=DEV); cnt_s = torch.zeros((n,), dtype=torch.int32, device=DEV)
+    o.matrix_nms_launch(boxes_d, scores_d, out_d, cnt_d, o.nms_workspace(n, total, nc, torch.device(DEV)), 0.01, 0.01, 500, 100,
+                        gauss, 2.0)
+    o.matrix_nms_candidates_launch(boxes_s, nc, out_s, cnt_s, ws, cap, 0.01, 0.01, 500, 100, gauss, 2.0)
+    cd, cs = cnt_d.cpu().numpy(), cnt_s.cpu().numpy()
+    print('candidates > 0.01: %d, kept per image: %s' % (n_cand, cd.tolist()))
+    np.testing.assert_array_equal(cd, cs)
+    assert cd.min() > 0
+    for i in range(n):
+        np.testing.assert_array_equal(out_d[i, :cd[i]].cpu().numpy(), out_s[i, :cs[i]].cpu().numpy())
+    # and against the CPU oracle for one image (dense scores -> reference matrix_nms)
+    want = ref.matrix_nms(boxes_d[0].cpu().numpy(), scores_d[0].cpu().numpy(), 0.01, 0.01, 500, 100, use_gaussian=gauss)
+    got = out_s[0, :cs[0]].cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got[:, 0], want[:, 0])
+    np.testing.assert_allclose(got, want, rtol=2e-6 if gauss else 2e-7, atol=0)
+
+
 # ------------------------------------------------------------------ glue layers
 def test_coord_spp_pool(golden):
     from model.custom_layers import CoordConv, SPP
