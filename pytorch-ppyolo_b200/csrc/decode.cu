@@ -142,6 +142,67 @@ __global__ void __launch_bounds__(kDecThreads) yolo_decode_kernel(DecodeArgs p, 
   }
 }
 
+// Two-kernel dense decode of the whole-network path (ppy_yolo_decode_hist).
+//   yolo_anchor_kernel: one THREAD per (pixel, anchor): objectness + box with every lane busy (the transcendental-heavy
+//                       part); writes the box and the objectness conf[img][box] (4 B per anchor of scratch).
+//   yolo_scores_kernel: pure streaming pass, one thread per 4 consecutive classes of a box: 4 logits in, one 16-byte
+//                       score store out, + the per-image score histogram in shared memory (flushed once per CTA).
+// conf also lets the NMS front end skip whole boxes (score = conf * sigmoid(cls) <= conf).
+__global__ void __launch_bounds__(256) yolo_anchor_kernel(DecodeArgs p, float* __restrict__ conf_out) {
+  const long long total = (long long)p.n * p.size * p.size * p.an;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int per = 5 + p.nc;
+  const int first = p.iou_aware ? p.an : 0;
+  const long long pixg = gid / p.an;
+  const int a = (int)(gid - pixg * p.an);
+  const int img = (int)(pixg / (p.size * p.size)), pix = (int)(pixg - (long long)img * (p.size * p.size));
+  const float* px = p.head + pixg * p.ld;
+  const float* tp = px + first + a * per;
+  const float t[5] = {__ldg(tp), __ldg(tp + 1), __ldg(tp + 2), __ldg(tp + 3), __ldg(tp + 4)};
+  float4 box;
+  const float conf = decode_anchor(p, t, p.iou_aware ? __ldg(px + a) : 0.f, a, pix % p.size, pix / p.size, img, &box);
+  const long long row = (long long)img * p.total_boxes + p.box_offset + (long long)pix * p.an + a;
+  reinterpret_cast<float4*>(p.boxes)[row] = box;
+  conf_out[row] = conf;
+}
+
+template <int AN, int NC>
+__global__ void __launch_bounds__(256) yolo_scores_kernel(DecodeArgs p, const float* __restrict__ conf_in, CandSink sink) {
+  __shared__ unsigned int hist_s[kBins];
+  const int an = AN ? AN : p.an, nc = NC ? NC : p.nc;
+  const int per = 5 + nc, first = p.iou_aware ? an : 0, qpb = nc / 4;      // nc % 4 == 0 (checked by the host)
+  const int img = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < kBins; i += 256) hist_s[i] = 0u;
+  __syncthreads();
+  const int boxes_here = p.size * p.size * an;
+  const int quads = boxes_here * qpb;
+  const float* head = p.head + (long long)img * p.size * p.size * p.ld;
+  const float* conf = conf_in + (long long)img * p.total_boxes + p.box_offset;
+  float4* out = reinterpret_cast<float4*>(p.scores + ((long long)img * p.total_boxes + p.box_offset) * nc);
+  for (int q = blockIdx.x * 256 + tid; q < quads; q += gridDim.x * 256) {
+    const int b = q / qpb, c4 = (q - b * qpb) * 4;
+    const int pix = b / an, a = b - pix * an;
+    const float* lg = head + (long long)pix * p.ld + first + a * per + 5 + c4;
+    const float l0 = __ldg(lg), l1 = __ldg(lg + 1), l2 = __ldg(lg + 2), l3 = __ldg(lg + 3);
+    const float cf = __ldg(conf + b);
+    float4 sc;
+    sc.x = __fmul_rn(cf, sigmoidf_ref(l0)); sc.y = __fmul_rn(cf, sigmoidf_ref(l1));
+    sc.z = __fmul_rn(cf, sigmoidf_ref(l2)); sc.w = __fmul_rn(cf, sigmoidf_ref(l3));
+    out[q] = sc;
+    if (cf > sink.thr) {                              // score <= conf: nothing to count otherwise
+      if (sc.x > sink.thr) atomicAdd(&hist_s[score_bin(sc.x, sink.thr_bits, sink.shift)], 1u);
+      if (sc.y > sink.thr) atomicAdd(&hist_s[score_bin(sc.y, sink.thr_bits, sink.shift)], 1u);
+      if (sc.z > sink.thr) atomicAdd(&hist_s[score_bin(sc.z, sink.thr_bits, sink.shift)], 1u);
+      if (sc.w > sink.thr) atomicAdd(&hist_s[score_bin(sc.w, sink.thr_bits, sink.shift)], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned int* gh = sink.hist + (long long)img * kBins;
+  for (int i = tid; i < kBins; i += 256)
+    if (hist_s[i]) atomicAdd(&gh[i], hist_s[i]);
+}
+
 // Sparse variant for the whole-network path: one THREAD per (pixel, anchor) does the anchor-level math (IoU-aware
 // objectness, box) with every lane busy, writes the box, and only anchors whose objectness exceeds the NMS score
 // threshold get their C class scores evaluated (score = conf * sigmoid(cls) <= conf, so nothing is lost) -- by the
@@ -275,11 +336,23 @@ int ppy_yolo_decode_hist(const float* head, int ld, int n, int size, int an_num,
                          void* nms_workspace, ppy_stream_t s) {
   using namespace ppy;
   PPY_REQUIRE(scores && nms_workspace && score_threshold > 0.f);
+  PPY_REQUIRE(num_classes % 4 == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0);
   DecodeArgs p;
   int rc = fill_decode_args(p, head, ld, n, size, an_num, num_classes, anchors, stride, scale_x_y, im_size, clip_bbox,
                             iou_aware, factor, boxes, scores, box_offset, total_boxes);
   if (rc) return rc;
-  return launch_dense_decode(p, cand_carve(nms_workspace, n, 1, score_threshold), s);   // only the histogram is touched
+  const CandSink sink = cand_carve(nms_workspace, n, kNmsKeyCap, score_threshold);   // the dense NMS workspace layout
+  float* conf = reinterpret_cast<float*>(sink.keys + (size_t)n * kNmsKeyCap);         // conf[n][total_boxes] after the keys
+  const long long total = (long long)n * size * size * an_num;
+  yolo_anchor_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(s)>>>(p, conf);
+  if ((rc = check_launch())) return rc;
+  const long long quads = (long long)size * size * an_num * (num_classes / 4);
+  long long gx = ceil_div(148 * 8, n);
+  if (gx > ceil_div(quads, 256)) gx = ceil_div(quads, 256);
+  dim3 grid((unsigned)gx, (unsigned)n);
+  if (an_num == 3 && num_classes == 80) yolo_scores_kernel<3, 80><<<grid, 256, 0, as_stream(s)>>>(p, conf, sink);
+  else yolo_scores_kernel<0, 0><<<grid, 256, 0, as_stream(s)>>>(p, conf, sink);
+  return check_launch();
 }
 
 int ppy_nms_candidate_workspace_bytes(int n, int cap, size_t* bytes) {

@@ -24,7 +24,7 @@
 namespace ppy {
 namespace {
 
-constexpr int kCap = 8192;            // max collected candidates per image (keys in shared memory)
+constexpr int kCap = kNmsKeyCap;      // max collected candidates per image (keys in shared memory)
 constexpr int kMaxN = 1024;           // max boxes entering the n x n stage
 constexpr int kScanThreads = 256;
 constexpr int kMatrixThreads = 1024;
@@ -145,6 +145,40 @@ nms_collect_kernel(const float* __restrict__ scores, long long per_image, long l
     lo = hi4 * 4;
   }
   for (long long i = lo + threadIdx.x; i < hi; i += kScanThreads) emit(__ldg(base + i), i);
+}
+
+// Collect with box pruning (whole-network path): conf[img][box] is the objectness the scores were multiplied by, so a box
+// whose conf falls below the cutoff bin cannot hold a candidate.  One thread per (box, 4 consecutive classes): the conf
+// test is an L1-resident load shared by the box's threads, and only surviving boxes have their scores read (one 16-byte
+// load per thread).  Same keys as nms_collect_kernel.  Needs num_classes % 4 == 0.
+__global__ void __launch_bounds__(kScanThreads)
+nms_collect_pruned_kernel(const float* __restrict__ scores, const float* __restrict__ conf, int num_boxes, int num_classes,
+                          float thr, unsigned int thr_bits, int shift, int want,
+                          const unsigned int* __restrict__ hist, unsigned int* __restrict__ count, unsigned long long* __restrict__ keys) {
+  __shared__ unsigned int sh[kBins];
+  __shared__ unsigned int part[33];
+  const int img = blockIdx.y;
+  const int cut = find_cutoff_bin(hist + (long long)img * kBins, want, sh, part);
+  const float4* sc = reinterpret_cast<const float4*>(scores + (long long)img * num_boxes * num_classes);
+  const float* cf = conf + (long long)img * num_boxes;
+  unsigned long long* out = keys + (long long)img * kCap;
+  unsigned int* cnt = count + img;
+  const int qpb = num_classes / 4;
+  const int quads = num_boxes * qpb;
+  auto emit = [&](float v, unsigned int idx) {
+    if (v > thr && score_bin(v, thr_bits, shift) >= cut) {
+      const unsigned int slot = atomicAdd(cnt, 1u);
+      if (slot < (unsigned)kCap) out[slot] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+    }
+  };
+  for (int q = blockIdx.x * kScanThreads + threadIdx.x; q < quads; q += gridDim.x * kScanThreads) {
+    const int b = q / qpb;
+    const float c = __ldg(cf + b);
+    if (!(c > thr) || score_bin(c, thr_bits, shift) < cut) continue;
+    const float4 v = __ldg(sc + q);
+    const unsigned int idx = 4u * (unsigned int)q;          // = b * num_classes + 4 * (q % qpb)
+    emit(v.x, idx); emit(v.y, idx + 1); emit(v.z, idx + 2); emit(v.w, idx + 3);
+  }
 }
 
 // descending bitonic sort of `len` (power of two) 64-bit keys in shared memory
@@ -426,9 +460,9 @@ Workspace carve(void* ws, int n) {
   return w;
 }
 
-size_t workspace_bytes(int n) {
+size_t workspace_bytes(int n, int num_boxes) {
   return sizeof(unsigned int) * (size_t)n * kBins + ((sizeof(unsigned int) * (size_t)n + 255) / 256) * 256 +
-         sizeof(unsigned long long) * (size_t)n * kCap;
+         sizeof(unsigned long long) * (size_t)n * kCap + sizeof(float) * (size_t)n * num_boxes;
 }
 
 }  // namespace
@@ -438,7 +472,7 @@ extern "C" {
 
 int ppy_matrix_nms_workspace_bytes(int n, int num_boxes, int num_classes, size_t* bytes) {
   PPY_REQUIRE(bytes && n > 0 && num_boxes > 0 && num_classes > 0);
-  *bytes = ppy::workspace_bytes(n);
+  *bytes = ppy::workspace_bytes(n, num_boxes);
   return PPY_OK;
 }
 
@@ -452,7 +486,7 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
   PPY_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
   PPY_REQUIRE(nms_top_k <= kMaxN);
   PPY_REQUIRE((long long)num_boxes * num_classes < 0xFFFFFFFFll);
-  if (workspace_bytes < ppy::workspace_bytes(n)) return PPY_ERR_WORKSPACE;
+  if (workspace_bytes < ppy::workspace_bytes(n, num_boxes)) return PPY_ERR_WORKSPACE;
   cudaStream_t st = as_stream(s);
   Workspace w = carve(workspace, n);
   // histogram + count live at the head of the workspace, contiguous
@@ -478,8 +512,20 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
     nms_hist_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.hist);
     if ((rc = check_launch())) return rc;
   }
-  nms_collect_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, want, w.hist,
-                                                    w.count, w.keys);
+  if (have_hist && num_classes % 4 == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0) {
+    // decode left the objectness per box behind the keys: prune whole boxes (score <= conf)
+    const float* conf = reinterpret_cast<const float*>(w.keys + (size_t)n * kCap);
+    const long long quads = (long long)num_boxes * (num_classes / 4);
+    long long cx = ceil_div(148 * 6, n);
+    if (cx > ceil_div(quads, kScanThreads)) cx = ceil_div(quads, kScanThreads);
+    if (cx < 1) cx = 1;
+    dim3 cgrid((unsigned)cx, (unsigned)n);
+    nms_collect_pruned_kernel<<<cgrid, kScanThreads, 0, st>>>(scores, conf, num_boxes, num_classes, score_threshold, thr_bits, shift,
+                                                              want, w.hist, w.count, w.keys);
+  } else {
+    nms_collect_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, want, w.hist,
+                                                      w.count, w.keys);
+  }
   if ((rc = check_launch())) return rc;
   static bool attr_set = false;
   const int smem = kCap * (int)sizeof(unsigned long long);

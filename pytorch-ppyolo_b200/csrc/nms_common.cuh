@@ -7,6 +7,7 @@
 // (float_bits - bits(threshold)) >> shift, from which the NMS kernel derives the bin holding the nms_top_k-th score.
 //
 // Workspace layout (n images): hist[n][kBins] u32 | count[n] u32 (padded to 256 B) | keys[n][cap] u64
+// (dense Matrix-NMS workspace: cap = kNmsKeyCap, followed by conf[n][num_boxes] fp32 = objectness per box)
 #pragma once
 #include <string.h>
 #include "common.cuh"
@@ -14,6 +15,7 @@
 namespace ppy {
 
 constexpr int kBins = 4096;           // histogram bins per image
+constexpr int kNmsKeyCap = 8192;      // keys per image of the dense Matrix-NMS workspace (collected candidates)
 
 struct CandSink {
   float thr; unsigned int thr_bits; int shift;
