@@ -31,6 +31,7 @@
 // Shared-memory operand layout is the canonical K-major SWIZZLE_128B one: row r of a stage lives at
 // r*128 bytes, its 16-byte chunk j at ((j ^ (r & 7)) << 4); 8-row groups are 1024 bytes apart (SBO).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ppy {
@@ -48,7 +49,8 @@ constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = E
 constexpr int EPI_SLAB = 0, EPI_TMA = 1;          // epilogue variants (see the kernel header)
 constexpr int GROUP_COLS = 64;                    // EPI_TMA: residual / output move as [128 rows x 64 ch] bf16 boxes (16 KB)
 constexpr int GROUP_BYTES = BLOCK_M * GROUP_COLS * 2;
-constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3;
+constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3, MODE_TMA_IM2COL = 4;
+__host__ __device__ constexpr bool mode_is_tma(int mode) { return mode == MODE_TMA_A || mode == MODE_TMA_PATCH || mode == MODE_TMA_IM2COL; }
 constexpr int PATCH_W = 16, PATCH_H = 8;          // 3x3 stride-1 convs: the 128 tile rows are a 16x8 pixel patch of one image
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
@@ -110,6 +112,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// im2col-mode load (tensor map from cuTensorMapEncodeIm2col): BLOCK_M pixels starting at base pixel (w, h, n) -- the top-left
+// input pixel of the first output pixel's receptive field -- walked along W, H, N with the map's traversal stride inside its
+// bounding box, each sampled at filter offset (off_w, off_h); out-of-image samples are zero-filled
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -285,7 +296,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const int num_tiles = ACC ? num_m_tiles * num_n_tiles * num_splits * num_taps : num_m_tiles * num_n_tiles;
 
   if (tid == 0) {
-    const uint32_t full_count = (MODE == MODE_TMA_A || MODE == MODE_TMA_PATCH) ? 1u : (uint32_t)(BLOCK_M + 1);
+    const uint32_t full_count = mode_is_tma(MODE) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS);
@@ -421,7 +432,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // TMA producer (weights; + activations in tma_a mode)
     // =====================================================================================
     if (lane == 0) {
-      constexpr uint32_t tx_bytes = Cfg::kBStageBytes + ((MODE == MODE_TMA_A || MODE == MODE_TMA_PATCH) ? A_STAGE_BYTES : 0);
+      constexpr uint32_t tx_bytes = Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE_BYTES : 0);
       const int kb_per_tap = p.cin / BLOCK_K;
       int g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -436,6 +447,11 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         if (MODE == MODE_TMA_PATCH) {
           px0 = (mt % pw_tiles) * PATCH_W; py0 = ((mt / pw_tiles) % ph_tiles) * PATCH_H; img = mt / (pw_tiles * ph_tiles);
         }
+        if (MODE == MODE_TMA_IM2COL) {           // base pixel of the tile's first output pixel
+          const unsigned hw_out = (unsigned)(ho * wo), pix = (unsigned)m0 % hw_out;
+          img = (int)((unsigned)m0 / hw_out);
+          px0 = (int)(pix % (unsigned)wo) * p.stride - p.pad; py0 = (int)(pix / (unsigned)wo) * p.stride - p.pad;
+        }
         for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
@@ -445,6 +461,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             // one tap x 64 channels of the 16x8 patch; the halo (negative / beyond-edge coordinates) is zero-filled by TMA
             const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
             tma_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+          }
+          if (MODE == MODE_TMA_IM2COL) {
+            const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
+            tma_load_im2col(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
           }
           tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K + b_shift, n0);
         }
@@ -776,6 +796,24 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  return fn;
+}
+
 int num_sms() {
   static int sms = 0;
   if (!sms) {
@@ -810,6 +848,27 @@ int encode_patch_4d(EncodeTiledFn enc, CUtensorMap* map, const ppy_conv_params* 
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+  return PPY_OK;
+}
+
+int encode_im2col_4d(CUtensorMap* map, const ppy_conv_params* p) {
+  // NHWC activation as (C, W, H, N) in im2col mode: a box is 64 channels x BLOCK_M pixels walked from a base pixel with the
+  // conv stride; the base pixel's bounding box is [-pad, dim - 1 + pad - (k - 1)] so the walk wraps exactly at wo / ho
+  EncodeIm2colFn enc = get_encode_im2col_fn();
+  if (!enc) return PPY_ERR_UNSUPPORTED;
+  const cuuint64_t dims[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
+  const cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->w * p->x_ld * 2, (cuuint64_t)p->h * p->w * p->x_ld * 2};
+  const int lower[2] = {-p->pad, -p->pad};
+  const int upper[2] = {p->pad - (p->kw - 1), p->pad - (p->kh - 1)};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
+  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, lower, upper, (cuuint32_t)BLOCK_K,
+                    (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+  // drivers up to CUDA 13.1 set a descriptor bit for tensors under 128 KB that im2col loads then mishandle (same fix-up as CUTLASS)
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (long long)p->n * p->h * p->w * p->x_ld * 2 < 131072)
+    reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
   return PPY_OK;
 }
 
@@ -865,6 +924,9 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     if (rc) return rc;
   } else if (MODE == MODE_TMA_PATCH) {
     rc = encode_patch_4d(enc, &tmap_a, p);
+    if (rc) return rc;
+  } else if (MODE == MODE_TMA_IM2COL) {
+    rc = encode_im2col_4d(&tmap_a, p);
     if (rc) return rc;
   } else {
     tmap_a = tmap_b;
@@ -970,6 +1032,11 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
     const double eff = (double)ho * wo / ((double)ceil_div(ho, PATCH_H) * PATCH_H * ceil_div(wo, PATCH_W) * PATCH_W);
     if (eff >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
   }
+  // any other k x k conv over whole 64-channel blocks: im2col-mode TMA (stride and zero padding done by the copy engine)
+  const bool im2col_ok = p->cin % BLOCK_K == 0 && p->k_pad == p->kh * p->kw * p->cin && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
+                         (p->x_ld * 2) % 16 == 0 && p->pad <= 8 && p->kh <= 8 && p->kw <= 8 && p->stride <= 8 &&
+                         !p->accumulate && get_encode_im2col_fn() != nullptr && !getenv("PPY_NO_IM2COL");
+  if (im2col_ok) return dispatch<MODE_TMA_IM2COL>(p, ho, wo, as_stream(s));
   return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }
 

@@ -283,6 +283,8 @@ UMMA_SHAPES = [  # (n, cin, cout, k, stride, hw)
     (2, 3, 32, 3, 2, 32), (1, 256, 258, 1, 1, 12), (1, 512, 27, 3, 1, 10), (3, 64, 512, 1, 1, 9),
     (1, 1024, 256, 1, 1, 19), (1, 256, 512, 3, 1, 19), (2, 64, 96, 3, 1, 7),
     (2, 64, 64, 3, 1, 30), (1, 128, 128, 3, 1, 46), (3, 64, 32, 3, 1, 16),      # 4-D TMA patch mode (16x8 pixel tiles)
+    (2, 128, 128, 3, 2, 19), (3, 64, 64, 3, 2, 38), (2, 256, 256, 3, 1, 38), (5, 64, 64, 3, 1, 5),   # im2col-mode TMA (tile walks rows/images)
+    (1, 64, 64, 3, 2, 11), (2, 128, 320, 3, 1, 13),
 ]
 
 
@@ -347,7 +349,7 @@ def test_umma_dcn(stride, hw):
 
 
 @pytest.mark.parametrize('n,cin,cout,k,hw', [(2, 64, 256, 1, 19), (1, 128, 512, 1, 30), (3, 64, 96, 1, 11), (2, 64, 64, 3, 32),
-                                             (1, 256, 128, 1, 24), (2, 64, 128, 3, 46)])
+                                             (1, 256, 128, 1, 24), (2, 64, 128, 3, 46), (3, 64, 128, 3, 19), (2, 128, 64, 3, 13)])
 def test_umma_conv_tma_epilogue(n, cin, cout, k, hw):
     """bf16-output layers with K <= 512 take the TMA epilogue (residual boxes in by TMA, output boxes out by TMA store):
     residual + ReLU against the oracle on bf16-rounded operands; covers M tails, N tails (cout 96) and 16x8 patch tiles."""
