@@ -56,16 +56,19 @@ constexpr int SUB = 32;                           // epilogue sub-tile columns (
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
 
-template <int BN, int EPI> struct TileCfg {
-  // EPI_TMA is only dispatched for small K (<= 512 at BLOCK_N 256, <= 1152 below), so fewer stages suffice there and
-  // free shared memory for the tile buffers
-  static constexpr int kStages = EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+template <int BN, int EPI, bool CTA2 = false> struct TileCfg {
+  // CTA2 (cta_group::2 pair, 256 x BN tile): each CTA stages its own 128 rows of A and HALF of the B tile, so stages are smaller
+  // and the ring deeper.  EPI_TMA is only dispatched for small K (<= 512 at BLOCK_N 256, <= 1152 below), so fewer stages suffice
+  // there and free shared memory for the tile buffers
+  static constexpr int kBStageBytes = BN * BLOCK_K * 2 / (CTA2 ? 2 : 1);
+  static constexpr int kStages = CTA2 ? (EPI == EPI_TMA ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
+                                      : (EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
-  static constexpr int kBStageBytes = BN * BLOCK_K * 2;
   static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
   // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: 2 residual + 2 output boxes and the scale/shift table of the N tile
   static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 2 * BN * 4 : STAGING_BYTES;
   static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -121,6 +124,51 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
                                                 uint16_t off_w, uint16_t off_h) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) variants: the load lands in the executing CTA's shared memory, its bytes are counted on an mbarrier
+// of the pair's leader (bar = shared::cluster address of rank 0's barrier)
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                 uint16_t off_w, uint16_t off_h) {
+  asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {      // shared::cta -> shared::cluster address in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {    // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -265,16 +313,24 @@ __device__ __noinline__ void epilogue_acc(const ppy_conv_params& p, const float*
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MODE, int EPI, bool ACC>
+template <int BN, int MODE, int EPI, bool ACC, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
                  const int num_n_tiles, const int num_splits, const int num_taps, const int pw_tiles, const int ph_tiles,
                  const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_y,
                  const __grid_constant__ CUtensorMap tmap_r) {
-  using Cfg = TileCfg<BN, EPI>;
+  // CTA2: the kernel runs as clusters of two CTAs (one TPC); the pair shares a 256 x BN tile -- CTA `cta_rank` stages and drains
+  // M tile 2*unit + cta_rank and stages B rows [rank*BN/2, +BN/2); the leader (rank 0) issues tcgen05.mma.cta_group::2 over both
+  // CTAs' shared memory, its commits multicast to both CTAs' barriers.  num_m_tiles then counts PAIRS of M tiles.
+  static_assert(!CTA2 || (mode_is_tma(MODE) && !ACC), "the CTA-pair kernel is TMA-fed only");
+  using Cfg = TileCfg<BN, EPI, CTA2>;
   constexpr int S = Cfg::kStages;
   constexpr int CP_LAG = Cfg::kCpLag;
+  const int cta_rank = CTA2 ? (int)(blockIdx.x & 1) : 0;
+  const int tile_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_mt = [&](int tile) { return CTA2 ? 2 * (tile / num_n_tiles) + cta_rank : tile / num_n_tiles; };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -299,14 +355,17 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     const uint32_t full_count = mode_is_tma(MODE) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), EPI_WARPS);
+      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), CTA2 ? 2 * EPI_WARPS : EPI_WARPS);
       mbar_init(res_full_bar(a), 1); mbar_init(res_empty_bar(a), 1);
     }
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
+  if (warp == MMA_WARP) {
+    if (CTA2) tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();      // pair: the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
@@ -432,13 +491,13 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // TMA producer (weights; + activations in tma_a mode)
     // =====================================================================================
     if (lane == 0) {
-      constexpr uint32_t tx_bytes = Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE_BYTES : 0);
+      constexpr uint32_t tx_bytes = (Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE_BYTES : 0)) * (CTA2 ? 2 : 1);
       const int kb_per_tap = p.cin / BLOCK_K;
       int g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
-        const int n0 = u.nt * BN;
-        const int mt = u.mt;
+        const int n0 = u.nt * BN + (CTA2 ? cta_rank * (BN / 2) : 0);
+        const int mt = CTA2 ? 2 * u.mt + cta_rank : u.mt;
         const int m0 = mt * BLOCK_M;
         // weight-gradient GEMM (p.wgrad_pitch > 0): the B operand is the transposed, zero-bordered activation read at the
         // flat pixel offset of this tap -- (ky-1)*pitch + (kx-1)
@@ -455,6 +514,18 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
+          if (CTA2) {
+            // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the whole pair
+            const uint32_t lead_full = map_to_cta(full_bar(s), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+            const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
+            if (MODE == MODE_TMA_A) tma2_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, kb * BLOCK_K, m0);
+            if (MODE == MODE_TMA_PATCH) tma2_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+            if (MODE == MODE_TMA_IM2COL)
+              tma2_load_im2col(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+            tma2_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, lead_full, kb * BLOCK_K, n0);
+            continue;
+          }
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
           if (MODE == MODE_TMA_A) tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
           if (MODE == MODE_TMA_PATCH) {
@@ -474,10 +545,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // =====================================================================================
     // MMA issuer
     // =====================================================================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BN);
       int g = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         mbar_wait(tmem_empty_bar(acc), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -489,11 +560,13 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           tc_fence_after();
           const uint32_t a_addr = smem_a + s * A_STAGE_BYTES, b_addr = smem_b + s * Cfg::kBStageBytes;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, ((ACC ? kb - u.kb0 : kb) | k) ? 1u : 0u);
-          umma_commit(empty_bar(s));             // frees the stage once these MMAs have read it
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            if (CTA2) umma2_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, ((ACC ? kb - u.kb0 : kb) | k) ? 1u : 0u);
+          }
+          if (CTA2) umma_commit2(empty_bar(s)); else umma_commit(empty_bar(s));   // frees the stage (in both CTAs) once read
         }
-        umma_commit(tmem_full_bar(acc));         // accumulator complete -> epilogue
+        if (CTA2) umma_commit2(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue(s)
       }
     }
   } else if (warp == RES_WARP) {
@@ -504,8 +577,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       constexpr int G = BN / GROUP_COLS;
       const uint32_t res_smem = smem_base + stg_off;
       int gg = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % num_n_tiles) * BN, mt = tile / num_n_tiles;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const int n0 = (tile % num_n_tiles) * BN, mt = tile_mt(tile);
         for (int g = 0; g < G; ++g) {
           if (n0 + g * GROUP_COLS >= p.cout) continue;             // group beyond cout: skipped by the epilogue too
           const int b = gg & 1;
@@ -537,9 +610,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
     int it = 0, gg = 0, cur_n0 = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t empty_rank0 = CTA2 ? map_to_cta(tmem_empty_bar(0), 0) : 0u;      // the leader's MMA thread waits for both epilogues
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
-      const int n0 = (tile % num_n_tiles) * BN, mt = tile / num_n_tiles;
+      const int n0 = (tile % num_n_tiles) * BN, mt = tile_mt(tile);
       if (n0 != cur_n0) {                                   // (re)load the folded-norm table of this N tile
         asm volatile("bar.sync 1, 256;" ::: "memory");     // nobody still reads the previous table
         for (int e = tid; e < 2 * BN; e += EPI_WARPS * 32) {
@@ -604,7 +678,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         if (g == G - 1) {                                   // this warp's TMEM reads of the tile are done
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
         }
       }
     }
@@ -634,7 +708,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       if (MODE == MODE_TMA_PATCH) {
         const int y = ((mt / pw_tiles) % ph_tiles) * PATCH_H + r / PATCH_W, xq = (mt % pw_tiles) * PATCH_W + r % PATCH_W;
         const int img = mt / (pw_tiles * ph_tiles);
-        return (y < ho && xq < wo) ? (img * ho + y) * wo + xq : -1;
+        return (y < ho && xq < wo && img < p.n) ? (img * ho + y) * wo + xq : -1;
       }
       const long long m = (long long)mt * BLOCK_M + r;
       return m < M ? (int)m : -1;
@@ -644,7 +718,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     constexpr int LINES_PER_ROW = (BN * 2 + 127) / 128;
     auto prefetch_residual = [&](int tile_) {
       if (!has_res || tile_ >= num_tiles) return;
-      const int n0_ = (tile_ % num_n_tiles) * BN, mt_ = tile_ / num_n_tiles;
+      const int n0_ = (tile_ % num_n_tiles) * BN, mt_ = tile_mt(tile_);
       for (int e = tid; e < BLOCK_M * LINES_PER_ROW; e += EPI_WARPS * 32) {
         const int m = row_to_m(mt_, e / LINES_PER_ROW);
         const int col = n0_ + (e % LINES_PER_ROW) * 64;
@@ -654,14 +728,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         }
       }
     };
-    prefetch_residual(blockIdx.x);
+    prefetch_residual(tile_first);
+    const uint32_t empty_rank0 = CTA2 ? map_to_cta(tmem_empty_bar(0), 0) : 0u;      // the leader's MMA thread waits for both epilogues
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
       const int n0 = u.nt * BN;
-      const int mt = u.mt;
-      prefetch_residual(tile + gridDim.x);
+      const int mt = CTA2 ? 2 * u.mt + cta_rank : u.mt;
+      prefetch_residual(tile + tile_step);
       int mrow[4];
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) mrow[ps] = row_to_m(mt, quarter * 32 + ps * 8 + rsub);
@@ -705,7 +780,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         } else {                                   // this warp's TMEM reads of the tile are done: release the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
         }
         // phase 2: coalesced (lane = 8 channels of one row; 8 rows per pass, 4 passes)
         const int co = n0 + cc * SUB + colv;
@@ -765,14 +840,17 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       }
       if (half >= NSUB) {                        // BN == 32: the second warp of a quarter has no sub-tile, still releases
         tc_fence_before();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (CTA2) cluster_sync_all(); else __syncthreads();       // pair: nobody leaves while the peer may still touch its smem / TMEM
+  if (warp == MMA_WARP) {
+    if (CTA2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -909,13 +987,13 @@ int pick_splits(const ppy_conv_params* p, long long tiles, int num_kb) {
   return best;
 }
 
-template <int BN, int MODE, int EPI, bool ACC = false>
+template <int BN, int MODE, int EPI, bool ACC = false, bool CTA2 = false>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
-  using Cfg = TileCfg<BN, EPI>;
+  using Cfg = TileCfg<BN, EPI, CTA2>;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PPY_ERR_UNSUPPORTED;
   CUtensorMap tmap_b, tmap_a, tmap_y, tmap_r;
-  int rc = encode_2d(enc, &tmap_b, p->weight, (uint64_t)p->k_pad, (uint64_t)p->cout_pad, (uint64_t)p->k_pad * 2, BLOCK_K, BN);
+  int rc = encode_2d(enc, &tmap_b, p->weight, (uint64_t)p->k_pad, (uint64_t)p->cout_pad, (uint64_t)p->k_pad * 2, BLOCK_K, CTA2 ? BN / 2 : BN);
   if (rc) return rc;
   const long long M = (long long)p->n * ho * wo;
   if (MODE == MODE_TMA_A) {
@@ -943,21 +1021,39 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI, ACC, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (rc) return rc;
     attr_done = true;
   }
   const int pw_tiles = (int)ceil_div(wo, PATCH_W), ph_tiles = (int)ceil_div(ho, PATCH_H);
-  const int num_m_tiles = MODE == MODE_TMA_PATCH ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);
+  int num_m_tiles = MODE == MODE_TMA_PATCH ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);
+  if (CTA2) num_m_tiles = (num_m_tiles + 1) / 2;            // scheduler units are pairs of M tiles
   const int num_n_tiles = (int)ceil_div(p->cout, BN);
   const int num_kb = p->k_pad / BLOCK_K;
   const int num_taps = p->wgrad_taps > 0 ? p->wgrad_taps : 1;
   const int num_splits = pick_splits(p, (long long)num_m_tiles * num_n_tiles * num_taps, num_kb);
   const long long tiles = (long long)num_m_tiles * num_n_tiles * num_taps * num_splits;
+  if (CTA2) {
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MODE, EPI, ACC, CTA2>, *p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
+                                       num_splits, num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r));
+    if (rc) return rc;
+    return check_launch();
+  }
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_umma_kernel<BN, MODE, EPI, ACC><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, num_kb, num_m_tiles, num_n_tiles, num_splits,
-                                                                             num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y,
-                                                                             tmap_r);
+  conv_umma_kernel<BN, MODE, EPI, ACC, false><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
+                                                                                    num_splits, num_taps, pw_tiles, ph_tiles, tmap_b,
+                                                                                    tmap_a, tmap_y, tmap_r);
   return check_launch();
 }
 
@@ -986,6 +1082,14 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   if (c <= 32) return launch<32, MODE, EPI_SLAB>(p, ho, wo, st);
   const bool tma_epi = MODE != MODE_DCN && tma_epilogue_ok(p);
   if (c <= 64) return tma_epi ? launch<64, MODE, EPI_TMA>(p, ho, wo, st) : launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
+  if constexpr (mode_is_tma(MODE)) {
+    // CTA pairs (cta_group::2, 256 x BN tiles, B split across the pair) for every TMA-fed layer with at least two M tiles
+    static const bool no_pair = getenv("PPY_NO_CTA2") != nullptr;
+    if (!no_pair && (long long)p->n * ho * wo > BLOCK_M) {
+      if (c % 256 == 0) return tma_epi ? launch<256, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
+      return tma_epi ? launch<128, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
+    }
+  }
   if (c % 256 == 0) return tma_epi ? launch<256, MODE, EPI_TMA>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB>(p, ho, wo, st);
   return tma_epi ? launch<128, MODE, EPI_TMA>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB>(p, ho, wo, st);
 }
