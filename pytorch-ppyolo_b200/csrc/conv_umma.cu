@@ -96,6 +96,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// one lane of the (fully active) warp; the same lane every time, and -- unlike `lane == 0` -- the compiler keeps everything
+// around the elected block warp-uniform (descriptors and barrier addresses stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -347,7 +359,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   auto res_full_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
   auto res_empty_bar = [&](int b) { return bars + 8u * (2 * S + 6 + b); };
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler: role branches are not divergent
   const long long M = (long long)p.n * ho * wo;
   const int num_tiles = ACC ? num_m_tiles * num_n_tiles * num_splits * num_taps : num_m_tiles * num_n_tiles;
 
@@ -490,7 +503,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // =====================================================================================
     // TMA producer (weights; + activations in tma_a mode)
     // =====================================================================================
-    if (lane == 0) {
+    {
       constexpr uint32_t tx_bytes = (Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE_BYTES : 0)) * (CTA2 ? 2 : 1);
       const int kb_per_tap = p.cin / BLOCK_K;
       int g = 0;
@@ -514,6 +527,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
+          if (elect_one()) {                     // the whole warp walks the ring (uniform control flow), one lane issues
           if (CTA2) {
             // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the whole pair
             const uint32_t lead_full = map_to_cta(full_bar(s), 0);
@@ -524,8 +538,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             if (MODE == MODE_TMA_IM2COL)
               tma2_load_im2col(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
             tma2_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, lead_full, kb * BLOCK_K, n0);
-            continue;
-          }
+          } else {
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
           if (MODE == MODE_TMA_A) tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
           if (MODE == MODE_TMA_PATCH) {
@@ -538,6 +551,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             tma_load_im2col(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
           }
           tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K + b_shift, n0);
+          }
+          }
+          __syncwarp();
         }
       }
     }
@@ -545,7 +561,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // =====================================================================================
     // MMA issuer
     // =====================================================================================
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BN);
       int g = 0, it = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
@@ -559,14 +575,20 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           mbar_wait(full_bar(s), (g / S) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_a + s * A_STAGE_BYTES, b_addr = smem_b + s * Cfg::kBStageBytes;
+          if (elect_one()) {                     // warp-uniform loop, one lane issues the MMAs and their commit
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             if (CTA2) umma2_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
             else umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, ((ACC ? kb - u.kb0 : kb) | k) ? 1u : 0u);
           }
           if (CTA2) umma_commit2(empty_bar(s)); else umma_commit(empty_bar(s));   // frees the stage (in both CTAs) once read
+          }
+          __syncwarp();
         }
-        if (CTA2) umma_commit2(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue(s)
+        if (elect_one()) {
+          if (CTA2) umma_commit2(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue(s)
+        }
+        __syncwarp();
       }
     }
   } else if (warp == RES_WARP) {
@@ -1060,7 +1082,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 // The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
 // 64-column group; it is used for K <= 512 (the HBM-bound layers), the slab epilogue with its deeper operand ring elsewhere.
 bool tma_epilogue_ok(const ppy_conv_params* p) {
-  if (p->accumulate) return false;
+  if (p->accumulate || getenv("PPY_NO_TMA_EPI")) return false;
   if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
   if (p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;     // 3 operand stages at BLOCK_N 256, 4-6 below
   if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * 2) % 16) return false;
@@ -1132,7 +1154,7 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   // 3x3 stride-1: A tiles as 16x8 pixel patches fetched by 4-D TMA, when the patch grid wastes < 15% of the tiles
   const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&
                          (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
-  if (patchable && !p->accumulate) {
+  if (patchable && !p->accumulate && !getenv("PPY_NO_PATCH")) {
     const double eff = (double)ho * wo / ((double)ceil_div(ho, PATCH_H) * PATCH_H * ceil_div(wo, PATCH_W) * PATCH_W);
     if (eff >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
   }
