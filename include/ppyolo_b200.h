@@ -106,6 +106,11 @@ typedef struct ppy_conv_params {
   int wgrad_taps;
   int wgrad_pitch;
   int wgrad_tap_stride;
+  /* CoordConv fold for 1x1 stride-1 convs (model/custom_layers.py:256-272 feeding a 1x1 Conv2dUnit): the two coordinate
+   * channels contribute wx[co]*xc(ox) + wy[co]*yc(oy) with xc = ox/(wo-1)*2-1, yc = oy/(ho-1)*2-1 -- a rank-2 term the
+   * epilogue adds to the accumulator (before scale/shift) from coord_w = [wx[cout] | wy[cout]] fp32, instead of reading a
+   * per-pixel bias_map.  NULL = off; mutually exclusive with bias_map; requires kh == kw == 1. */
+  const float* coord_w;
 } ppy_conv_params;
 
 /* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)

@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(ppy_conv_params p, i
       if (co >= p.cout) continue;
       float v = acc[i][j];
       if (p.bias_map) v += __ldg(p.bias_map + pix * p.cout + co);
+      if (p.coord_w) v += __ldg(p.coord_w + co) * (__fdiv_rn((float)ox, (float)(wo - 1)) * 2.f - 1.f) +
+                          __ldg(p.coord_w + p.cout + co) * (__fdiv_rn((float)oy, (float)(ho - 1)) * 2.f - 1.f);
       v = v * __ldg(p.scale + co) + __ldg(p.shift + co);
       if (p.residual) {
         if (p.out_dtype == PPY_BF16) v += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[m * p.res_ld + co]);
@@ -158,6 +160,7 @@ int validate_conv(const ppy_conv_params* p, int elem_bytes, int* ho, int* wo) {
   *wo = (p->w + 2 * p->pad - (p->kw - 1) - 1) / p->stride + 1;
   PPY_REQUIRE(*ho > 0 && *wo > 0);
   if (p->offset_mask) PPY_REQUIRE(p->om_ld >= 3 * p->kh * p->kw);
+  if (p->coord_w) PPY_REQUIRE(p->kh == 1 && p->stride == 1 && p->pad == 0 && !p->bias_map && !p->accumulate && !p->upsample2x && *ho > 1 && *wo > 1);
   return PPY_OK;
 }
 

@@ -66,7 +66,7 @@ template <int BN, int EPI, bool CTA2 = false> struct TileCfg {
   static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
   static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
   // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: 2 residual + 2 output boxes and the scale/shift table of the N tile
-  static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 2 * BN * 4 : STAGING_BYTES;
+  static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 4 * BN * 4 : STAGING_BYTES;   // + scale|shift|wx|wy table
   static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -276,6 +276,8 @@ __device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, const float
   for (int e = 0; e < ncol; ++e) {
     float f = acc8[e];
     if (p.bias_map) f += __ldg(p.bias_map + (size_t)pix * p.cout + co + e);
+    if (p.coord_w) f += __ldg(p.coord_w + co + e) * (__fdiv_rn((float)ox, (float)(wo - 1)) * 2.f - 1.f) +
+                        __ldg(p.coord_w + p.cout + co + e) * (__fdiv_rn((float)oy, (float)(ho - 1)) * 2.f - 1.f);
     f = f * __ldg(p.scale + co + e) + __ldg(p.shift + co + e);
     if (p.residual) {
       if (p.out_dtype == PPY_BF16) f += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)m * p.res_ld + co + e]);
@@ -625,7 +627,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     constexpr int G = BN / GROUP_COLS;
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t res_smem = smem_base + stg_off, out_smem = res_smem + 2 * GROUP_BYTES;
-    float* ss = reinterpret_cast<float*>(gen_base + stg_off + 4 * GROUP_BYTES);      // scale[BN] | shift[BN] of this N tile
+    float* ss = reinterpret_cast<float*>(gen_base + stg_off + 4 * GROUP_BYTES);      // scale[BN] | shift[BN] | wx[BN] | wy[BN] of this N tile
+    const bool has_coord = p.coord_w != nullptr;
+    const unsigned hw_out = (unsigned)(ho * wo);
     const float slope = p.act == PPY_ACT_RELU ? 0.f : (p.act == PPY_ACT_LEAKY ? 0.1f : 1.f);
     const bool has_res = p.residual != nullptr;
     const int row = quarter * 32 + lane;                    // tile row of this lane
@@ -638,12 +642,19 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       const int n0 = (tile % num_n_tiles) * BN, mt = tile_mt(tile);
       if (n0 != cur_n0) {                                   // (re)load the folded-norm table of this N tile
         asm volatile("bar.sync 1, 256;" ::: "memory");     // nobody still reads the previous table
-        for (int e = tid; e < 2 * BN; e += EPI_WARPS * 32) {
-          const int col = n0 + (e % BN);
-          ss[e] = col < p.cout ? __ldg((e < BN ? p.scale : p.shift) + col) : 0.f;
+        for (int e = tid; e < (has_coord ? 4 : 2) * BN; e += EPI_WARPS * 32) {
+          const int col = n0 + (e % BN), which = e / BN;
+          const float* src = which == 0 ? p.scale : (which == 1 ? p.shift : (which == 2 ? p.coord_w : p.coord_w + p.cout));
+          ss[e] = col < p.cout ? __ldg(src + col) : 0.f;
         }
         cur_n0 = n0;
         asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      float xc = 0.f, yc = 0.f;                             // CoordConv coordinates of this lane's output pixel
+      if (has_coord) {
+        const unsigned pix = (unsigned)(mt * BLOCK_M + row) % hw_out;      // coord_w convs are 1x1: linear M tiles
+        xc = __fdiv_rn((float)(pix % (unsigned)wo), (float)(wo - 1)) * 2.f - 1.f;
+        yc = __fdiv_rn((float)(pix / (unsigned)wo), (float)(ho - 1)) * 2.f - 1.f;
       }
       mbar_wait(tmem_full_bar(acc), (it >> 1) & 1);
       tc_fence_after();
@@ -670,6 +681,12 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             if (has_res) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(rbase + chunk));
             const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8), s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
             const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8), h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
+            if (has_coord) {                                 // rank-2 CoordConv term, added to the accumulator before scale/shift
+              const float* cx = ss + 2 * BN + cc * SUB + q * 8;
+              const float* cy = ss + 3 * BN + cc * SUB + q * 8;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[8 * q + e] = __float_as_uint(__uint_as_float(v[8 * q + e]) + cx[e] * xc + cy[e] * yc);
+            }
             float f[8];
             f[0] = __uint_as_float(v[8 * q + 0]) * s0.x + h0.x + bf_lo(r0); f[1] = __uint_as_float(v[8 * q + 1]) * s0.y + h0.y + bf_hi(r0);
             f[2] = __uint_as_float(v[8 * q + 2]) * s0.z + h0.z + bf_lo(r1); f[3] = __uint_as_float(v[8 * q + 3]) * s0.w + h0.w + bf_hi(r1);
@@ -722,7 +739,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // the fast path needs 16-byte aligned full vectors everywhere; anything else goes through epilogue_slow
     const bool aligned = ((p.y_ld * esz) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
                          (!p.residual || (out_bf16 && ((p.res_ld * 2) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
-                         (!p.bias_map || (p.cout & 7) == 0) && !ACC;            // partial-sum launches: atomics, out of line
+                         (!p.bias_map || (p.cout & 7) == 0) && !ACC && !p.coord_w;   // partial sums (atomics), coord fold: out of line
     const bool has_res = p.residual != nullptr;
     constexpr int NSUB = BN / SUB;               // sub-tiles per tile
     constexpr int MY_SUBS = (NSUB + 1) / 2;      // upper bound of sub-tiles per warp
@@ -1084,6 +1101,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 bool tma_epilogue_ok(const ppy_conv_params* p) {
   if (p->accumulate || getenv("PPY_NO_TMA_EPI")) return false;
   if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
+  if (p->coord_w && p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;
   if (p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;     // 3 operand stages at BLOCK_N 256, 4-6 below
   if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * 2) % 16) return false;
   if (p->residual && ((reinterpret_cast<uintptr_t>(p->residual) & 15) || (p->res_ld * 2) % 16)) return false;

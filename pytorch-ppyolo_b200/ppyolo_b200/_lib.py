@@ -29,6 +29,7 @@ class ConvParams(ctypes.Structure):
         ('y', c_void_p), ('y_ld', c_int), ('out_dtype', c_int), ('upsample2x', c_int),
         ('offset_mask', c_void_p), ('om_ld', c_int),
         ('accumulate', c_int), ('split_k', c_int), ('wgrad_taps', c_int), ('wgrad_pitch', c_int), ('wgrad_tap_stride', c_int),
+        ('coord_w', c_void_p),
     ]
 
 

@@ -180,7 +180,14 @@ class InferenceEngine(object):
         if dst is None:
             oh, ow = (2 * ho, 2 * wo) if upsample else (ho, wo)
             dst = TensorRef(self._new(x.n, oh, ow, ops.round_up(cout, 8), ops.torch_dtype(out_code)), c=cout)
-        bias_map = self._coord_bias_map(weight, c_main, x.h, x.w) if coord else None
+        # CoordConv fold: a 1x1 conv sees the two coordinate channels as the rank-2 term wx*xc + wy*yc (two per-channel vectors
+        # for the TMA epilogue); a 3x3 conv needs the per-pixel map (zero padding breaks the rank-2 structure at the borders)
+        coord_vec = (coord and k == 1 and stride == 1 and self.code == PPY_BF16 and out_code == PPY_BF16 and not upsample and
+                     cout >= 64 and cout % 8 == 0 and k_pad <= (512 if cout % 256 == 0 else 1152) and x.h > 1 and x.w > 1)
+        bias_map = self._coord_bias_map(weight, c_main, x.h, x.w) if (coord and not coord_vec) else None
+        coord_w = None
+        if coord_vec:
+            coord_w = self._keep(weight.detach().float()[:, c_main:c_main + 2, 0, 0].t().contiguous())    # [2][cout]: wx | wy
         p = ConvParams()
         p.x, p.x_ld = x.ptr, x.ld
         p.n, p.h, p.w, p.cin = x.n, x.h, x.w, cin_pad
@@ -189,6 +196,7 @@ class InferenceEngine(object):
         p.k_pad, p.cout_pad = k_pad, cout_pad
         p.scale, p.shift = self._keep(scale).data_ptr(), self._keep(shift).data_ptr()
         p.bias_map = bias_map.data_ptr() if bias_map is not None else None
+        p.coord_w = coord_w.data_ptr() if coord_w is not None else None
         p.residual = residual.ptr if residual is not None else None
         p.res_ld = residual.ld if residual is not None else 0
         p.act = act

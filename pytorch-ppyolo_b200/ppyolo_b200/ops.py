@@ -112,7 +112,7 @@ def pack_weight(weight, code, c_begin=0, c_count=None):
 
 
 def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, residual=None, bias_map=None,
-              out=None, out_code=None, upsample2x=False, offset_mask=None, x_ld=None):
+              out=None, out_code=None, upsample2x=False, offset_mask=None, x_ld=None, coord_w=None):
     """Launch one fused conv on NHWC buffers. ``x`` [N,H,W,ld]; returns ``out`` [N,Ho,Wo,ld_out]."""
     w_packed, cin_pad, k_pad, cout_pad = packed
     n, h, w, ld = x.shape
@@ -130,6 +130,7 @@ def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, res
     p.k_pad, p.cout_pad = k_pad, cout_pad
     p.scale, p.shift = scale.data_ptr(), shift.data_ptr()
     p.bias_map = bias_map.data_ptr() if bias_map is not None else None
+    p.coord_w = coord_w.data_ptr() if coord_w is not None else None
     p.residual = residual.data_ptr() if residual is not None else None
     p.res_ld = residual.shape[-1] if residual is not None else 0
     p.act = act

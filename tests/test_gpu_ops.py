@@ -362,3 +362,24 @@ def test_umma_conv_tma_epilogue(n, cin, cout, k, hw):
     for residual, act, want in ((res, 1, torch.relu(base + res)), (None, 2, torch.nn.functional.leaky_relu(base, 0.1))):
         got = _umma_conv(x, w, scale, shift, 1, act, residual=residual, out_f32=False)
         np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
+
+
+@pytest.mark.parametrize('n,cin,cout,hw', [(2, 64, 128, 19), (1, 256, 256, 38), (3, 128, 64, 11)])
+def test_umma_conv_coord_fold(n, cin, cout, hw):
+    """1x1 conv after CoordConv (model/custom_layers.py:256-272): the two coordinate channels enter as the rank-2 epilogue
+    term wx*xc + wy*yc (ppy_conv_params.coord_w, TMA epilogue) instead of as input channels."""
+    from ppyolo_b200._lib import PPY_BF16
+    o = ops()
+    g = torch.Generator().manual_seed(5 * cin + cout + hw)
+    x = bf16_round(torch.randn((n, cin, hw, hw), generator=g))
+    w = torch.randn((cout, cin + 2, 1, 1), generator=g) * (1.0 / cin ** 0.5)
+    w[:, :cin] = bf16_round(w[:, :cin])
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    want = torch.nn.functional.conv2d(ref.coord_concat(x), w) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    want = torch.nn.functional.leaky_relu(want, 0.1)
+    packed = o.pack_weight(w.to(DEV), PPY_BF16, c_begin=0, c_count=cin)
+    xh = o.to_nhwc(x.to(DEV), PPY_BF16, packed[1])
+    coord_w = w[:, cin:, 0, 0].t().contiguous().to(DEV)
+    y = o.conv_nhwc(xh, packed, cin, cout, 1, 1, 0, scale.to(DEV), shift.to(DEV), 2, PPY_BF16, coord_w=coord_w)
+    got = o.from_nhwc(y, cout).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
