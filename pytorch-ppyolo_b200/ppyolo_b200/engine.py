@@ -288,8 +288,21 @@ class InferenceEngine(object):
         main = (cout // 256) * 256
         self._conv(name, x, w[:main].contiguous(), scale[:main].contiguous(), shift[:main].contiguous(), 1, act,
                    dst=out.slice(0, main), out_code=PPY_F32)
-        self._conv(name + '.tail', x, w[main:].contiguous(), scale[main:].contiguous(), shift[main:].contiguous(), 1, act,
-                   dst=out.slice(main, cout - main), out_code=PPY_F32)
+        # the tail runs 8 channels wide (zero weights past cout, landing in the buffer's padding columns) so its epilogue
+        # takes the aligned 16-byte vector path; the extra columns are never read and not counted as algorithmic FLOPs
+        tail = cout - main
+        wide = min(ops.round_up(tail, 8), out.ld - main)
+        wt = torch.zeros((wide,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+        wt[:tail] = w[main:]
+        sc = torch.ones(wide, dtype=scale.dtype, device=scale.device)
+        sh = torch.zeros(wide, dtype=shift.dtype, device=shift.device)
+        sc[:tail], sh[:tail] = scale[main:], shift[main:]
+        before = self.conv_flops
+        self._conv(name + '.tail', x, wt, sc, sh, 1, act, dst=out.slice(main, wide), out_code=PPY_F32)
+        true_flops = (self.conv_flops - before) * tail // wide
+        self.conv_flops = before + true_flops
+        self.step_info[name + '.tail']['flops'] = true_flops
+        self.step_info[name + '.tail']['n'] = tail
         return out
 
     def _unit_pixel_pairs(self, name, unit, x):
