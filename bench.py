@@ -131,6 +131,28 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def ncu_conv_traffic():
+    """DRAM bytes (read + write) of all conv_umma launches of one step, from the committed ncu launch list of the same
+    workload (profiles/r01_ncu_launches.csv, `tools/gpu_profile.sh`); None when the file is missing."""
+    import csv
+    path = os.path.join(REPO, 'profiles', 'r01_ncu_launches.csv')
+    if not os.path.exists(path):
+        return None
+    total = 0.0
+    with open(path) as f:
+        rows = list(csv.reader(f))
+    try:
+        hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+        ix = {h: i for i, h in enumerate(rows[hi])}
+        for r in rows[hi + 1:]:
+            if len(r) == len(rows[hi]) and 'conv_umma_kernel' in r[ix['Kernel Name']] and \
+                    r[ix['Metric Name']] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                total += float(r[ix['Metric Value']].replace(',', ''))
+    except (IndexError, KeyError, ValueError):
+        return None
+    return total or None
+
+
 def is_glue(name):
     return (name.startswith(('nchw', 'maxpool', 'avgpool', 'spp', 'decode', 'matrix_nms')) or name.endswith('.gather')
             or name == 'stem.conv1_1')
@@ -254,7 +276,10 @@ def run_ours(args, rank, world, local_rank):
     achieved = eng.conv_flops / (conv_ms * 1e-3) / 1e12
     peak = peaks['bf16_tflops_sustained'] if args.precision == 'bf16' else 75.0
     roofline = {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all %d conv launches of one step)' % conv_launches,
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': ncu_conv_traffic(),
+                'traffic_note': 'DRAM read+write bytes of all conv launches of one step (ncu launch list under profiles/); '
+                                'algorithmic minimum in min_bytes_per_step',
+                'min_bytes_per_step': sum(v['bytes'] for k, v in eng.step_info.items() if not is_glue(k)),
                 'peak_source': peak_src + (' bf16_tflops_sustained' if args.precision == 'bf16' else ' (nominal fp32 SIMT)'),
                 'flops_per_step': eng.conv_flops, 'kernel_ms_per_step': conv_ms, 'share_of_step': conv_ms / total_ms}
     os.makedirs(os.path.join(REPO, 'gpurun_out'), exist_ok=True)

@@ -10,10 +10,13 @@ for r in data:
     if len(r) < len(hdr): continue
     per.setdefault(int(r[ix['ID']]), {'name': r[ix['Kernel Name']]})[r[ix['Metric Name']]] = float(r[ix['Metric Value']].replace(',', ''))
 names = open(names_path).read().split('\n')
-# matrix_nms is 3 launches (+1 memset is not a kernel)
+# dense post-processing: every decode step is two launches (anchor math, then the streaming score kernel with the fused
+# score histogram), matrix_nms is collect + matrix (its memset is not a kernel)
 plan = []
 for n in names:
-    plan += [n + ':hist', n + ':collect', n + ':matrix'] if n == 'matrix_nms' else [n]
+    if n == 'matrix_nms': plan += [n + ':collect', n + ':matrix']
+    elif n.startswith('decode'): plan += [n + ':anchors', n + ':scores']
+    else: plan.append(n)
 tot = sum(m['gpu__time_duration.sum'] for m in per.values())
 print('| # | plan step | kernel | time us | share | DRAM rd MB | DRAM wr MB | tensor pipe % | warps active % | grid | regs |')
 print('|---|---|---|---|---|---|---|---|---|---|---|')
