@@ -183,6 +183,15 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uin
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -601,8 +610,24 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       constexpr int G = BN / GROUP_COLS;
       const uint32_t res_smem = smem_base + stg_off;
       int gg = 0;
+      // the residual boxes of the NEXT tile are pulled into L2 while this tile's are consumed: with two 16 KB buffers the loads
+      // below are on the epilogue's critical path, and an L2 hit costs a third of a DRAM round trip
+      auto prefetch_tile = [&](int tile_) {
+        if (tile_ >= num_tiles) return;
+        const int n0_ = (tile_ % num_n_tiles) * BN, mt_ = tile_mt(tile_);
+        for (int g = 0; g < G; ++g) {
+          if (n0_ + g * GROUP_COLS >= p.cout) continue;
+          if (MODE == MODE_TMA_PATCH)
+            tma_prefetch_4d(&tmap_r, n0_ + g * GROUP_COLS, (mt_ % pw_tiles) * PATCH_W, ((mt_ / pw_tiles) % ph_tiles) * PATCH_H,
+                            mt_ / (pw_tiles * ph_tiles));
+          else
+            tma_prefetch_2d(&tmap_r, n0_ + g * GROUP_COLS, mt_ * BLOCK_M);
+        }
+      };
+      prefetch_tile(tile_first);
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int n0 = (tile % num_n_tiles) * BN, mt = tile_mt(tile);
+        prefetch_tile(tile + tile_step);
         for (int g = 0; g < G; ++g) {
           if (n0 + g * GROUP_COLS >= p.cout) continue;             // group beyond cout: skipped by the epilogue too
           const int b = gg & 1;
