@@ -49,26 +49,43 @@ constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = E
 constexpr int EPI_SLAB = 0, EPI_TMA = 1;          // epilogue variants (see the kernel header)
 constexpr int GROUP_COLS = 64;                    // EPI_TMA: residual / output move as [128 rows x 64 ch] bf16 boxes (16 KB)
 constexpr int GROUP_BYTES = BLOCK_M * GROUP_COLS * 2;
-constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3, MODE_TMA_IM2COL = 4;
-__host__ __device__ constexpr bool mode_is_tma(int mode) { return mode == MODE_TMA_A || mode == MODE_TMA_PATCH || mode == MODE_TMA_IM2COL; }
-constexpr int PATCH_W = 16, PATCH_H = 8;          // 3x3 stride-1 convs: the 128 tile rows are a 16x8 pixel patch of one image
+constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3, MODE_TMA_IM2COL = 4, MODE_TMA_SLAB = 5;
+__host__ __device__ constexpr bool mode_is_tma(int mode) {
+  return mode == MODE_TMA_A || mode == MODE_TMA_PATCH || mode == MODE_TMA_IM2COL || mode == MODE_TMA_SLAB;
+}
+// 3x3 stride-1 convs: the 128 tile rows are a pixel patch of one image -- 16 wide x 8 tall (MODE_TMA_PATCH, one box per tap), or
+// 8 wide x 16 tall (MODE_TMA_SLAB).  SLAB: one pipeline stage holds, for one 64-channel block and one kx, the 8 x 18 pixel slab
+// (two halo rows) plus the three weight tiles of taps (ky = 0..2, kx); an 8-pixel slab row is exactly one 1024-byte swizzle
+// atom, so the A operand of tap ky is the SAME slab read at byte offset ky * 1024 -- each input pixel enters shared memory
+// 3.4 times per tile instead of 9, and there is one barrier round trip per THREE taps.
+__host__ __device__ constexpr bool mode_is_patchy(int mode) { return mode == MODE_TMA_PATCH || mode == MODE_TMA_SLAB; }
+__host__ __device__ constexpr int patch_w(int mode) { return mode == MODE_TMA_SLAB ? 8 : 16; }
+__host__ __device__ constexpr int patch_h(int mode) { return mode == MODE_TMA_SLAB ? 16 : 8; }
+constexpr int SLAB_ROWS = 18;                     // patch_h + 2 halo rows
+constexpr int SLAB_BYTES = SLAB_ROWS * 8 * 128;   // 18 rows x 8 pixels x 64 bf16
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
 
-template <int BN, int EPI, bool CTA2 = false> struct TileCfg {
+template <int BN, int MODE, int EPI, bool CTA2 = false> struct TileCfg {
   // CTA2 (cta_group::2 pair, 256 x BN tile): each CTA stages its own 128 rows of A and HALF of the B tile, so stages are smaller
   // and the ring deeper.  EPI_TMA is only dispatched for small K (<= 512 at BLOCK_N 256, <= 1152 below), so fewer stages suffice
-  // there and free shared memory for the tile buffers
-  static constexpr int kBStageBytes = BN * BLOCK_K * 2 / (CTA2 ? 2 : 1);
-  static constexpr int kStages = CTA2 ? (EPI == EPI_TMA ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
-                                      : (EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  // there and free shared memory for the tile buffers.  SLAB stages hold a pixel slab and three weight tiles.
+  static constexpr bool kSlab = MODE == MODE_TMA_SLAB;
+  static constexpr int kBTileBytes = BN * BLOCK_K * 2 / (CTA2 ? 2 : 1);            // one [BN x 64] weight tile (this CTA's half)
+  static constexpr int kAStageBytes = kSlab ? SLAB_BYTES : A_STAGE_BYTES;
+  static constexpr int kBStageBytes = kSlab ? 3 * kBTileBytes : kBTileBytes;
+  static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 4 * BN * 4 : STAGING_BYTES;   // + scale|shift|wx|wy table
+  static constexpr int kFixedBytes = kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kFit = (232448 - kFixedBytes) / (kAStageBytes + kBStageBytes);
+  static constexpr int kWant = CTA2 ? (EPI == EPI_TMA ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
+                                    : (EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  static constexpr int kStages = kSlab ? (kFit < 4 ? kFit : 4) : kWant;
   static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
   static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
-  // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: 2 residual + 2 output boxes and the scale/shift table of the N tile
-  static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 4 * BN * 4 : STAGING_BYTES;   // + scale|shift|wx|wy table
-  static constexpr int kSmemBytes = kStages * (A_STAGE_BYTES + kBStageBytes) + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
-  static_assert(kSmemBytes <= 232448, "shared memory budget");
+  // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: 2 residual + 2 output boxes and the per-channel table of the N tile
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kFixedBytes;
+  static_assert(kStages >= 2 && kSmemBytes <= 232448, "shared memory budget");
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -347,8 +364,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   // M tile 2*unit + cta_rank and stages B rows [rank*BN/2, +BN/2); the leader (rank 0) issues tcgen05.mma.cta_group::2 over both
   // CTAs' shared memory, its commits multicast to both CTAs' barriers.  num_m_tiles then counts PAIRS of M tiles.
   static_assert(!CTA2 || (mode_is_tma(MODE) && !ACC), "the CTA-pair kernel is TMA-fed only");
-  using Cfg = TileCfg<BN, EPI, CTA2>;
+  using Cfg = TileCfg<BN, MODE, EPI, CTA2>;
   constexpr int S = Cfg::kStages;
+  constexpr int A_STAGE = Cfg::kAStageBytes;
+  constexpr int PW = patch_w(MODE), PH = patch_h(MODE);    // pixel patch of a tile (MODE_TMA_PATCH / MODE_TMA_SLAB)
   constexpr int CP_LAG = Cfg::kCpLag;
   const int cta_rank = CTA2 ? (int)(blockIdx.x & 1) : 0;
   const int tile_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -358,8 +377,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + S * A_STAGE_BYTES;
-  const uint32_t stg_off = S * (A_STAGE_BYTES + Cfg::kBStageBytes);
+  const uint32_t smem_b = smem_base + S * A_STAGE;
+  const uint32_t stg_off = S * (A_STAGE + Cfg::kBStageBytes);
   // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2], then the TMEM base slot
   const uint32_t bars = smem_base + stg_off + Cfg::kEpiBytes;
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + Cfg::kEpiBytes + (2 * S + 8) * 8);
@@ -424,7 +443,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
-          const uint32_t dst = smem_a + s * A_STAGE_BYTES + dst0;
+          const uint32_t dst = smem_a + s * A_STAGE + dst0;
           const bool tap_ok = tap < taps;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -487,7 +506,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             }
           }
           mbar_wait(empty_bar(s), ((g / S) & 1) ^ 1);
-          const uint32_t dst_row = smem_a + s * A_STAGE_BYTES + row_off;
+          const uint32_t dst_row = smem_a + s * A_STAGE + row_off;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -515,7 +534,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // TMA producer (weights; + activations in tma_a mode)
     // =====================================================================================
     {
-      constexpr uint32_t tx_bytes = (Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE_BYTES : 0)) * (CTA2 ? 2 : 1);
+      constexpr uint32_t tx_bytes = (Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE : 0)) * (CTA2 ? 2 : 1);
       const int kb_per_tap = p.cin / BLOCK_K;
       int g = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
@@ -527,8 +546,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         // flat pixel offset of this tap -- (ky-1)*pitch + (kx-1)
         const int b_shift = (ACC && num_taps == 9) ? (u.tap / 3 - 1) * p.wgrad_pitch + (u.tap % 3 - 1) : 0;
         int px0 = 0, py0 = 0, img = 0;
-        if (MODE == MODE_TMA_PATCH) {
-          px0 = (mt % pw_tiles) * PATCH_W; py0 = ((mt / pw_tiles) % ph_tiles) * PATCH_H; img = mt / (pw_tiles * ph_tiles);
+        if (mode_is_patchy(MODE)) {
+          px0 = (mt % pw_tiles) * PW; py0 = ((mt / pw_tiles) % ph_tiles) * PH; img = mt / (pw_tiles * ph_tiles);
         }
         if (MODE == MODE_TMA_IM2COL) {           // base pixel of the tile's first output pixel
           const unsigned hw_out = (unsigned)(ho * wo), pix = (unsigned)m0 % hw_out;
@@ -544,23 +563,37 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             const uint32_t lead_full = map_to_cta(full_bar(s), 0);
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
             const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
-            if (MODE == MODE_TMA_A) tma2_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, kb * BLOCK_K, m0);
-            if (MODE == MODE_TMA_PATCH) tma2_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+            if (MODE == MODE_TMA_A) tma2_load_2d(smem_a + s * A_STAGE, &tmap_a, lead_full, kb * BLOCK_K, m0);
+            if (MODE == MODE_TMA_PATCH) tma2_load_4d(smem_a + s * A_STAGE, &tmap_a, lead_full, c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
             if (MODE == MODE_TMA_IM2COL)
-              tma2_load_im2col(smem_a + s * A_STAGE_BYTES, &tmap_a, lead_full, c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+              tma2_load_im2col(smem_a + s * A_STAGE, &tmap_a, lead_full, c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+            if (MODE == MODE_TMA_SLAB) {           // iteration kb = (channel block, kx): the slab and the weight tiles of its three taps
+              const int cb = kb / 3, kx = kb % 3;
+              tma2_load_4d(smem_a + s * A_STAGE, &tmap_a, lead_full, cb * BLOCK_K, px0 + kx - 1, py0 - 1, img);
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky)
+                tma2_load_2d(smem_b + s * Cfg::kBStageBytes + ky * Cfg::kBTileBytes, &tmap_b, lead_full, (ky * 3 + kx) * p.cin + cb * BLOCK_K, n0);
+            } else
             tma2_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, lead_full, kb * BLOCK_K, n0);
           } else {
           mbar_arrive_expect_tx(full_bar(s), tx_bytes);
-          if (MODE == MODE_TMA_A) tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
+          if (MODE == MODE_TMA_A) tma_load_2d(smem_a + s * A_STAGE, &tmap_a, full_bar(s), kb * BLOCK_K, m0);
           if (MODE == MODE_TMA_PATCH) {
             // one tap x 64 channels of the 16x8 patch; the halo (negative / beyond-edge coordinates) is zero-filled by TMA
             const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
-            tma_load_4d(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
+            tma_load_4d(smem_a + s * A_STAGE, &tmap_a, full_bar(s), c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
           }
           if (MODE == MODE_TMA_IM2COL) {
             const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * BLOCK_K;
-            tma_load_im2col(smem_a + s * A_STAGE_BYTES, &tmap_a, full_bar(s), c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+            tma_load_im2col(smem_a + s * A_STAGE, &tmap_a, full_bar(s), c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
           }
+          if (MODE == MODE_TMA_SLAB) {
+            const int cb = kb / 3, kx = kb % 3;
+            tma_load_4d(smem_a + s * A_STAGE, &tmap_a, full_bar(s), cb * BLOCK_K, px0 + kx - 1, py0 - 1, img);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+              tma_load_2d(smem_b + s * Cfg::kBStageBytes + ky * Cfg::kBTileBytes, &tmap_b, full_bar(s), (ky * 3 + kx) * p.cin + cb * BLOCK_K, n0);
+          } else
           tma_load_2d(smem_b + s * Cfg::kBStageBytes, &tmap_b, full_bar(s), kb * BLOCK_K + b_shift, n0);
           }
           }
@@ -585,12 +618,24 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           const int s = g % S;
           mbar_wait(full_bar(s), (g / S) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_a + s * A_STAGE_BYTES, b_addr = smem_b + s * Cfg::kBStageBytes;
+          const uint32_t a_addr = smem_a + s * A_STAGE, b_addr = smem_b + s * Cfg::kBStageBytes;
           if (elect_one()) {                     // warp-uniform loop, one lane issues the MMAs and their commit
+          if (MODE == MODE_TMA_SLAB) {           // three taps per stage: tap ky reads the slab one pixel row (1024 bytes) further down
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                const uint64_t da = make_smem_desc(a_addr + ky * 1024 + k * 32), db = make_smem_desc(b_addr + ky * Cfg::kBTileBytes + k * 32);
+                if (CTA2) umma2_bf16(d_tmem, da, db, idesc, (kb | ky | k) ? 1u : 0u);
+                else umma_bf16(d_tmem, da, db, idesc, (kb | ky | k) ? 1u : 0u);
+              }
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             if (CTA2) umma2_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
             else umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc, ((ACC ? kb - u.kb0 : kb) | k) ? 1u : 0u);
+          }
           }
           if (CTA2) umma_commit2(empty_bar(s)); else umma_commit(empty_bar(s));   // frees the stage (in both CTAs) once read
           }
@@ -617,8 +662,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         const int n0_ = (tile_ % num_n_tiles) * BN, mt_ = tile_mt(tile_);
         for (int g = 0; g < G; ++g) {
           if (n0_ + g * GROUP_COLS >= p.cout) continue;
-          if (MODE == MODE_TMA_PATCH)
-            tma_prefetch_4d(&tmap_r, n0_ + g * GROUP_COLS, (mt_ % pw_tiles) * PATCH_W, ((mt_ / pw_tiles) % ph_tiles) * PATCH_H,
+          if (mode_is_patchy(MODE))
+            tma_prefetch_4d(&tmap_r, n0_ + g * GROUP_COLS, (mt_ % pw_tiles) * PW, ((mt_ / pw_tiles) % ph_tiles) * PH,
                             mt_ / (pw_tiles * ph_tiles));
           else
             tma_prefetch_2d(&tmap_r, n0_ + g * GROUP_COLS, mt_ * BLOCK_M);
@@ -633,9 +678,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           const int b = gg & 1;
           mbar_wait(res_empty_bar(b), ((gg >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(res_full_bar(b), GROUP_BYTES);
-          if (MODE == MODE_TMA_PATCH)
-            tma_load_4d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, (mt % pw_tiles) * PATCH_W,
-                        ((mt / pw_tiles) % ph_tiles) * PATCH_H, mt / (pw_tiles * ph_tiles));
+          if (mode_is_patchy(MODE))
+            tma_load_4d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, (mt % pw_tiles) * PW,
+                        ((mt / pw_tiles) % ph_tiles) * PH, mt / (pw_tiles * ph_tiles));
           else
             tma_load_2d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, mt * BLOCK_M);
           ++gg;
@@ -727,9 +772,9 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           fence_proxy_async();                              // generic-proxy writes of the box -> visible to the TMA store
           asm volatile("bar.sync 2, 256;" ::: "memory");
           if (tid == 0) {
-            if (MODE == MODE_TMA_PATCH)
-              tma_store_4d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, (mt % pw_tiles) * PATCH_W,
-                           ((mt / pw_tiles) % ph_tiles) * PATCH_H, mt / (pw_tiles * ph_tiles));
+            if (mode_is_patchy(MODE))
+              tma_store_4d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, (mt % pw_tiles) * PW,
+                           ((mt / pw_tiles) % ph_tiles) * PH, mt / (pw_tiles * ph_tiles));
             else
               tma_store_2d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, mt * BLOCK_M);
             bulk_commit();
@@ -769,8 +814,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     constexpr int NSUB = BN / SUB;               // sub-tiles per tile
     constexpr int MY_SUBS = (NSUB + 1) / 2;      // upper bound of sub-tiles per warp
     auto row_to_m = [&](int mt, int r) -> int {  // output pixel index of tile row r, -1 if outside
-      if (MODE == MODE_TMA_PATCH) {
-        const int y = ((mt / pw_tiles) % ph_tiles) * PATCH_H + r / PATCH_W, xq = (mt % pw_tiles) * PATCH_W + r % PATCH_W;
+      if (mode_is_patchy(MODE)) {
+        const int y = ((mt / pw_tiles) % ph_tiles) * PH + r / PW, xq = (mt % pw_tiles) * PW + r % PW;
         const int img = mt / (pw_tiles * ph_tiles);
         return (y < ho && xq < wo && img < p.n) ? (img * ho + y) * wo + xq : -1;
       }
@@ -980,11 +1025,11 @@ int encode_2d(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t in
   return PPY_OK;
 }
 
-int encode_patch_4d(EncodeTiledFn enc, CUtensorMap* map, const ppy_conv_params* p) {
-  // NHWC activation as (C, W, H, N); box = 64 channels x 16 x 8 pixels of one image
+int encode_patch_4d(EncodeTiledFn enc, CUtensorMap* map, const ppy_conv_params* p, int box_w, int box_h) {
+  // NHWC activation as (C, W, H, N); box = 64 channels x box_w x box_h pixels of one image
   const cuuint64_t dims[4] = {(cuuint64_t)p->cin, (cuuint64_t)p->w, (cuuint64_t)p->h, (cuuint64_t)p->n};
   const cuuint64_t strides[3] = {(cuuint64_t)p->x_ld * 2, (cuuint64_t)p->w * p->x_ld * 2, (cuuint64_t)p->h * p->w * p->x_ld * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)PATCH_W, (cuuint32_t)PATCH_H, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->x), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1015,12 +1060,12 @@ int encode_im2col_4d(CUtensorMap* map, const ppy_conv_params* p) {
 }
 
 int encode_tile_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int ld, int cols, const ppy_conv_params* p, int ho,
-                    int wo, bool patch) {
+                    int wo, bool patch, int box_w, int box_h) {
   // output / residual tensors: channels innermost; 2-D [M rows][cols] or 4-D (C, W, H, N) for patch tiles
   if (!patch) return encode_2d(enc, map, base, (uint64_t)cols, (uint64_t)p->n * ho * wo, (uint64_t)ld * 2, GROUP_COLS, BLOCK_M);
   const cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)p->n};
   const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)wo * ld * 2, (cuuint64_t)ho * wo * ld * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)GROUP_COLS, (cuuint32_t)PATCH_W, (cuuint32_t)PATCH_H, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)GROUP_COLS, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1053,7 +1098,8 @@ int pick_splits(const ppy_conv_params* p, long long tiles, int num_kb) {
 
 template <int BN, int MODE, int EPI, bool ACC = false, bool CTA2 = false>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
-  using Cfg = TileCfg<BN, EPI, CTA2>;
+  using Cfg = TileCfg<BN, MODE, EPI, CTA2>;
+  constexpr int PW = patch_w(MODE), PH = patch_h(MODE);
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return PPY_ERR_UNSUPPORTED;
   CUtensorMap tmap_b, tmap_a, tmap_y, tmap_r;
@@ -1065,7 +1111,10 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     rc = encode_2d(enc, &tmap_a, p->x, (uint64_t)p->cin, (uint64_t)M, (uint64_t)p->x_ld * 2, BLOCK_K, BLOCK_M);
     if (rc) return rc;
   } else if (MODE == MODE_TMA_PATCH) {
-    rc = encode_patch_4d(enc, &tmap_a, p);
+    rc = encode_patch_4d(enc, &tmap_a, p, PW, PH);
+    if (rc) return rc;
+  } else if (MODE == MODE_TMA_SLAB) {
+    rc = encode_patch_4d(enc, &tmap_a, p, PW, SLAB_ROWS);
     if (rc) return rc;
   } else if (MODE == MODE_TMA_IM2COL) {
     rc = encode_im2col_4d(&tmap_a, p);
@@ -1076,10 +1125,10 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   tmap_y = tmap_b;
   tmap_r = tmap_b;
   if (EPI == EPI_TMA) {
-    rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, MODE == MODE_TMA_PATCH);
+    rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH);
     if (rc) return rc;
     if (p->residual) {
-      rc = encode_tile_map(enc, &tmap_r, p->residual, p->res_ld, p->cout, p, ho, wo, MODE == MODE_TMA_PATCH);
+      rc = encode_tile_map(enc, &tmap_r, p->residual, p->res_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH);
       if (rc) return rc;
     }
   }
@@ -1089,11 +1138,11 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     if (rc) return rc;
     attr_done = true;
   }
-  const int pw_tiles = (int)ceil_div(wo, PATCH_W), ph_tiles = (int)ceil_div(ho, PATCH_H);
-  int num_m_tiles = MODE == MODE_TMA_PATCH ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);
+  const int pw_tiles = (int)ceil_div(wo, PW), ph_tiles = (int)ceil_div(ho, PH);
+  int num_m_tiles = mode_is_patchy(MODE) ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);
   if (CTA2) num_m_tiles = (num_m_tiles + 1) / 2;            // scheduler units are pairs of M tiles
   const int num_n_tiles = (int)ceil_div(p->cout, BN);
-  const int num_kb = p->k_pad / BLOCK_K;
+  const int num_kb = MODE == MODE_TMA_SLAB ? 3 * (p->cin / BLOCK_K) : p->k_pad / BLOCK_K;   // SLAB: one iteration per (channel block, kx)
   const int num_taps = p->wgrad_taps > 0 ? p->wgrad_taps : 1;
   const int num_splits = pick_splits(p, (long long)num_m_tiles * num_n_tiles * num_taps, num_kb);
   const long long tiles = (long long)num_m_tiles * num_n_tiles * num_taps * num_splits;
@@ -1137,7 +1186,7 @@ template <int MODE>
 int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int c = p->cout;
   if (p->accumulate) {       // partial-sum launches (split-K, weight gradients): slab epilogue with fp32 atomics
-    if (MODE == MODE_DCN || MODE == MODE_TMA_PATCH) return PPY_ERR_UNSUPPORTED;
+    if (MODE == MODE_DCN || mode_is_patchy(MODE)) return PPY_ERR_UNSUPPORTED;
     constexpr int M2 = (MODE == MODE_TMA_A) ? MODE_TMA_A : MODE_GATHER;
     if (c <= 32) return launch<32, M2, EPI_SLAB, true>(p, ho, wo, st);
     if (c <= 64) return launch<64, M2, EPI_SLAB, true>(p, ho, wo, st);
@@ -1157,6 +1206,19 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   if (c % 256 == 0) return tma_epi ? launch<256, MODE, EPI_TMA>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB>(p, ho, wo, st);
   return tma_epi ? launch<128, MODE, EPI_TMA>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB>(p, ho, wo, st);
+}
+
+// 3x3 stride-1 convs with 64..128 output channels (the stem and the stage-2/3 bottleneck 3x3s): slab stages, CTA pairs
+int dispatch_slab(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
+  static const bool no_pair = getenv("PPY_NO_CTA2") != nullptr;
+  const bool tma_epi = tma_epilogue_ok(p);
+  const bool pair = !no_pair && p->n * ceil_div(ho, patch_h(MODE_TMA_SLAB)) * ceil_div(wo, patch_w(MODE_TMA_SLAB)) > 1;
+  if (p->cout <= 64) {
+    if (pair) return tma_epi ? launch<64, MODE_TMA_SLAB, EPI_TMA, false, true>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st);
+    return tma_epi ? launch<64, MODE_TMA_SLAB, EPI_TMA>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
+  }
+  if (pair) return tma_epi ? launch<128, MODE_TMA_SLAB, EPI_TMA, false, true>(p, ho, wo, st) : launch<128, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st);
+  return tma_epi ? launch<128, MODE_TMA_SLAB, EPI_TMA>(p, ho, wo, st) : launch<128, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
 }
 
 }  // namespace
@@ -1198,8 +1260,10 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&
                          (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
   if (patchable && !p->accumulate && !getenv("PPY_NO_PATCH")) {
-    const double eff = (double)ho * wo / ((double)ceil_div(ho, PATCH_H) * PATCH_H * ceil_div(wo, PATCH_W) * PATCH_W);
-    if (eff >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
+    auto grid_eff = [&](int pw, int ph) { return (double)ho * wo / ((double)ceil_div(ho, ph) * ph * ceil_div(wo, pw) * pw); };
+    if (p->cout > 32 && p->cout <= 128 && grid_eff(patch_w(MODE_TMA_SLAB), patch_h(MODE_TMA_SLAB)) >= 0.85 && !getenv("PPY_NO_SLAB"))
+      return dispatch_slab(p, ho, wo, as_stream(s));
+    if (grid_eff(patch_w(MODE_TMA_PATCH), patch_h(MODE_TMA_PATCH)) >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
   }
   // any other k x k conv over whole 64-channel blocks: im2col-mode TMA (stride and zero padding done by the copy engine)
   const bool im2col_ok = p->cin % BLOCK_K == 0 && p->k_pad == p->kh * p->kw * p->cin && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&

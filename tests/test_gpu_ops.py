@@ -285,6 +285,7 @@ UMMA_SHAPES = [  # (n, cin, cout, k, stride, hw)
     (2, 64, 64, 3, 1, 30), (1, 128, 128, 3, 1, 46), (3, 64, 32, 3, 1, 16),      # 4-D TMA patch mode (16x8 pixel tiles)
     (2, 128, 128, 3, 2, 19), (3, 64, 64, 3, 2, 38), (2, 256, 256, 3, 1, 38), (5, 64, 64, 3, 1, 5),   # im2col-mode TMA (tile walks rows/images)
     (1, 64, 64, 3, 2, 11), (2, 128, 320, 3, 1, 13),
+    (2, 128, 64, 3, 1, 24), (1, 192, 128, 3, 1, 40), (5, 64, 128, 3, 1, 16), (1, 64, 64, 3, 1, 8),      # slab mode (8x16 tiles, 3 taps per stage)
 ]
 
 
