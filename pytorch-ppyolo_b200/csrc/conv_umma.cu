@@ -47,8 +47,10 @@ constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane qua
 constexpr int NUM_THREADS = 480;                  // 8 epilogue + 4 producer + TMA + MMA + residual-TMA warps
 constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5, RES_WARP = EPI_WARPS + 6;
 constexpr int EPI_SLAB = 0, EPI_TMA = 1;          // epilogue variants (see the kernel header)
-constexpr int GROUP_COLS = 64;                    // EPI_TMA: residual / output move as [128 rows x 64 ch] bf16 boxes (16 KB)
-constexpr int GROUP_BYTES = BLOCK_M * GROUP_COLS * 2;
+constexpr int GROUP_COLS = 64;                    // EPI_TMA: residual / output move as [32 rows x 64 ch] bf16 boxes (4 KB), one warp each
+constexpr int BOX_ROWS = 32;
+constexpr int BOX_BYTES = BOX_ROWS * GROUP_COLS * 2;
+constexpr int EPI_TABLE_FLOATS = 4 * GROUP_COLS;  // per epilogue warp: scale | shift | wx | wy of its current 64 columns
 constexpr int MODE_GATHER = 0, MODE_TMA_A = 1, MODE_DCN = 2, MODE_TMA_PATCH = 3, MODE_TMA_IM2COL = 4, MODE_TMA_SLAB = 5;
 __host__ __device__ constexpr bool mode_is_tma(int mode) {
   return mode == MODE_TMA_A || mode == MODE_TMA_PATCH || mode == MODE_TMA_IM2COL || mode == MODE_TMA_SLAB;
@@ -75,15 +77,19 @@ template <int BN, int MODE, int EPI, bool CTA2 = false> struct TileCfg {
   static constexpr int kBTileBytes = BN * BLOCK_K * 2 / (CTA2 ? 2 : 1);            // one [BN x 64] weight tile (this CTA's half)
   static constexpr int kAStageBytes = kSlab ? SLAB_BYTES : A_STAGE_BYTES;
   static constexpr int kBStageBytes = kSlab ? 3 * kBTileBytes : kBTileBytes;
-  static constexpr int kEpiBytes = EPI == EPI_TMA ? 4 * GROUP_BYTES + 4 * BN * 4 : STAGING_BYTES;   // + scale|shift|wx|wy table
+  // TMA epilogue, per warp: residual boxes (double buffered; single in SLAB mode, whose 3x3 layers rarely carry a residual and
+  // whose stages need the room) + one output box + the per-channel table
+  static constexpr int kResBufs = kSlab ? 1 : 2;
+  static constexpr int kEpiWarpBytes = (kResBufs + 1) * BOX_BYTES;
+  static constexpr int kEpiBytes = EPI == EPI_TMA ? EPI_WARPS * (kEpiWarpBytes + EPI_TABLE_FLOATS * 4) : STAGING_BYTES;
   static constexpr int kFixedBytes = kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int kFit = (232448 - kFixedBytes) / (kAStageBytes + kBStageBytes);
   static constexpr int kWant = CTA2 ? (EPI == EPI_TMA ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
                                     : (EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
-  static constexpr int kStages = kSlab ? (kFit < 4 ? kFit : 4) : kWant;
+  static constexpr int kStages = kSlab ? (kFit < 4 ? kFit : 4) : (kFit < kWant ? kFit : kWant);
   static constexpr int kCpLag = kStages - 2;               // cp.async groups in flight per producer thread
   static constexpr int kTmemCols = 2 * BN;                 // double-buffered accumulator; power of two >= 64
-  // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: 2 residual + 2 output boxes and the per-channel table of the N tile
+  // EPI_SLAB: 8 warp-private fp32 slabs.  EPI_TMA: per warp 2 residual boxes + 1 output box + its per-channel table
   static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kFixedBytes;
   static_assert(kStages >= 2 && kSmemBytes <= 232448, "shared memory budget");
 };
@@ -198,15 +204,6 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -379,15 +376,14 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + S * A_STAGE;
   const uint32_t stg_off = S * (A_STAGE + Cfg::kBStageBytes);
-  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2], then the TMEM base slot
+  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], res_full[8 warps][2], then the TMEM base slot
   const uint32_t bars = smem_base + stg_off + Cfg::kEpiBytes;
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + Cfg::kEpiBytes + (2 * S + 8) * 8);
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + Cfg::kEpiBytes + (2 * S + 4 + 2 * EPI_WARPS) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto res_full_bar = [&](int b) { return bars + 8u * (2 * S + 4 + b); };
-  auto res_empty_bar = [&](int b) { return bars + 8u * (2 * S + 6 + b); };
+  auto res_full_bar = [&](int w, int b) { return bars + 8u * (2 * S + 4 + 2 * w + b); };
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler: role branches are not divergent
@@ -398,9 +394,12 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     const uint32_t full_count = mode_is_tma(MODE) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), CTA2 ? 2 * EPI_WARPS : EPI_WARPS);
-      mbar_init(res_full_bar(a), 1); mbar_init(res_empty_bar(a), 1);
+      // TMA epilogue at BLOCK_N 64 (one column group): the two warps of a TMEM lane quarter take alternate tiles, so each
+      // accumulator buffer is drained by four warps
+      constexpr uint32_t drainers = (EPI == EPI_TMA && BN == GROUP_COLS) ? EPI_WARPS / 2 : EPI_WARPS;
+      mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), CTA2 ? 2 * drainers : drainers);
     }
+    for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(res_full_bar(w, 0), 1); mbar_init(res_full_bar(w, 1), 1); }
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
@@ -648,78 +647,66 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       }
     }
   } else if (warp == RES_WARP) {
-    // =====================================================================================
-    // EPI_TMA: residual tile loader -- one [128 x 64] bf16 box per column group, double buffered
-    // =====================================================================================
-    if (EPI == EPI_TMA && lane == 0 && p.residual != nullptr) {
-      constexpr int G = BN / GROUP_COLS;
-      const uint32_t res_smem = smem_base + stg_off;
-      int gg = 0;
-      // the residual boxes of the NEXT tile are pulled into L2 while this tile's are consumed: with two 16 KB buffers the loads
-      // below are on the epilogue's critical path, and an L2 hit costs a third of a DRAM round trip
-      auto prefetch_tile = [&](int tile_) {
-        if (tile_ >= num_tiles) return;
-        const int n0_ = (tile_ % num_n_tiles) * BN, mt_ = tile_mt(tile_);
-        for (int g = 0; g < G; ++g) {
-          if (n0_ + g * GROUP_COLS >= p.cout) continue;
-          if (mode_is_patchy(MODE))
-            tma_prefetch_4d(&tmap_r, n0_ + g * GROUP_COLS, (mt_ % pw_tiles) * PW, ((mt_ / pw_tiles) % ph_tiles) * PH,
-                            mt_ / (pw_tiles * ph_tiles));
-          else
-            tma_prefetch_2d(&tmap_r, n0_ + g * GROUP_COLS, mt_ * BLOCK_M);
-        }
-      };
-      prefetch_tile(tile_first);
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-        const int n0 = (tile % num_n_tiles) * BN, mt = tile_mt(tile);
-        prefetch_tile(tile + tile_step);
-        for (int g = 0; g < G; ++g) {
-          if (n0 + g * GROUP_COLS >= p.cout) continue;             // group beyond cout: skipped by the epilogue too
-          const int b = gg & 1;
-          mbar_wait(res_empty_bar(b), ((gg >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(res_full_bar(b), GROUP_BYTES);
-          if (mode_is_patchy(MODE))
-            tma_load_4d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, (mt % pw_tiles) * PW,
-                        ((mt / pw_tiles) % ph_tiles) * PH, mt / (pw_tiles * ph_tiles));
-          else
-            tma_load_2d(res_smem + b * GROUP_BYTES, &tmap_r, res_full_bar(b), n0 + g * GROUP_COLS, mt * BLOCK_M);
-          ++gg;
-        }
-      }
-    }
+    // (spare warp: the TMA epilogue's warps fetch their own residual boxes)
   } else if (EPI == EPI_TMA) {
     // =====================================================================================
-    // EPI_TMA epilogue, warps 0-7: no global-memory instruction at all.  Per 64-column group: the residual box arrives
-    // by TMA, every lane (= one tile row) turns 32 accumulator columns from TMEM into bf16 with scale/shift (smem
-    // table), residual and activation, writes them into the swizzled output box, and one thread hands the box to a
-    // TMA store (rows beyond M / columns beyond cout are clipped by the copy engine, so there are no masks here).
+    // EPI_TMA epilogue, warps 0-7: no global-memory instruction and no CTA-wide barrier.  Every warp works alone on
+    // [32 rows x 64 columns] boxes of the tile -- warp w owns TMEM lanes / tile rows 32*(w&3).. and the 64-column groups
+    // g = (w>>2), (w>>2)+2, ..: its lane 0 fetches the residual box by TMA two boxes ahead (double buffered), every lane (= one
+    // tile row) turns 64 accumulator columns into bf16 with the CoordConv term, scale/shift, residual and activation, writes
+    // them into the swizzled output box, and lane 0 hands the box to a TMA store (rows beyond M / columns beyond cout are
+    // clipped by the copy engine, so there are no masks here).  Warps drift apart freely, overlapping each other's latencies.
     // =====================================================================================
     constexpr int G = BN / GROUP_COLS;
+    constexpr int GPW = G >= 2 ? G / 2 : 1;                 // groups per warp and tile
+    constexpr int RB = Cfg::kResBufs;
+    // G >= 2: the two warps of a TMEM lane quarter split the tile's column groups.  G == 1: they take alternate TILES (warp
+    // half h drains accumulator buffer h), so all eight warps stay busy without sharing a box.
+    constexpr int TSTRIDE = G >= 2 ? 1 : 2;
     const int quarter = warp & 3, half = warp >> 2;
-    const uint32_t res_smem = smem_base + stg_off, out_smem = res_smem + 2 * GROUP_BYTES;
-    float* ss = reinterpret_cast<float*>(gen_base + stg_off + 4 * GROUP_BYTES);      // scale[BN] | shift[BN] | wx[BN] | wy[BN] of this N tile
-    const bool has_coord = p.coord_w != nullptr;
-    const unsigned hw_out = (unsigned)(ho * wo);
+    const int my_first = G >= 2 ? tile_first : tile_first + half * tile_step, my_step = TSTRIDE * tile_step;
+    const uint32_t res_s = smem_base + stg_off + (uint32_t)warp * Cfg::kEpiWarpBytes, out_s = res_s + RB * BOX_BYTES;
+    float* tab = reinterpret_cast<float*>(gen_base + stg_off + EPI_WARPS * Cfg::kEpiWarpBytes) + warp * EPI_TABLE_FLOATS;
     const float slope = p.act == PPY_ACT_RELU ? 0.f : (p.act == PPY_ACT_LEAKY ? 0.1f : 1.f);
-    const bool has_res = p.residual != nullptr;
+    const bool has_res = p.residual != nullptr, has_coord = p.coord_w != nullptr;
+    const unsigned hw_out = (unsigned)(ho * wo);
     const int row = quarter * 32 + lane;                    // tile row of this lane
-    const uint32_t row_off = (uint32_t)row * 128u;
-    const uint32_t sw = (uint32_t)(row & 7);
-    int it = 0, gg = 0, cur_n0 = -1;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
     const uint32_t empty_rank0 = CTA2 ? map_to_cta(tmem_empty_bar(0), 0) : 0u;      // the leader's MMA thread waits for both epilogues
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
-      const int acc = it & 1;
-      const int n0 = (tile % num_n_tiles) * BN, mt = tile_mt(tile);
-      if (n0 != cur_n0) {                                   // (re)load the folded-norm table of this N tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // nobody still reads the previous table
-        for (int e = tid; e < (has_coord ? 4 : 2) * BN; e += EPI_WARPS * 32) {
-          const int col = n0 + (e % BN), which = e / BN;
-          const float* src = which == 0 ? p.scale : (which == 1 ? p.shift : (which == 2 ? p.coord_w : p.coord_w + p.cout));
-          ss[e] = col < p.cout ? __ldg(src + col) : 0.f;
-        }
-        cur_n0 = n0;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+    // box j of this warp: tile = my_first + (j / GPW) * my_step, group = half + 2 * (j % GPW) (G >= 2) or 0
+    auto box_col0 = [&](int tile_, int gi) { return (tile_ % num_n_tiles) * BN + (G >= 2 ? half + 2 * gi : 0) * GROUP_COLS; };
+    auto box_move = [&](bool load, uint32_t smem, uint32_t bar, int tile_, int col0) {      // one lane: residual load / output store
+      const int mt_ = tile_mt(tile_);
+      if (mode_is_patchy(MODE)) {
+        const int x0 = (mt_ % pw_tiles) * PW, y0 = ((mt_ / pw_tiles) % ph_tiles) * PH + quarter * (BOX_ROWS / PW), img = mt_ / (pw_tiles * ph_tiles);
+        if (load) tma_load_4d(smem, &tmap_r, bar, col0, x0, y0, img); else tma_store_4d(&tmap_y, smem, col0, x0, y0, img);
+      } else {
+        if (load) tma_load_2d(smem, &tmap_r, bar, col0, mt_ * BLOCK_M + quarter * BOX_ROWS); else tma_store_2d(&tmap_y, smem, col0, mt_ * BLOCK_M + quarter * BOX_ROWS);
       }
+    };
+    int ji = 0, li = 0, lc = 0;                             // next box to request; live boxes requested / consumed
+    auto request_next = [&]() {                             // residual prefetch: skip boxes beyond cout, stop at the end of the walk
+      for (;;) {
+        const int tile_ = my_first + (ji / GPW) * my_step;
+        if (tile_ >= num_tiles) return;
+        const int col0 = box_col0(tile_, ji % GPW);
+        ++ji;
+        if (col0 < p.cout) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(res_full_bar(warp, li % RB), BOX_BYTES);
+            box_move(true, res_s + (li % RB) * BOX_BYTES, res_full_bar(warp, li % RB), tile_, col0);
+          }
+          ++li;
+          return;
+        }
+      }
+    };
+    if (has_res) { request_next(); if (RB == 2) request_next(); }
+    int it = G >= 2 ? 0 : half, tab_col0 = -1;             // `it` counts the CTA's tiles (accumulator buffer / phase bookkeeping)
+    for (int tile = my_first; tile < num_tiles; tile += my_step, it += TSTRIDE) {
+      const int acc = it & 1;
+      const int mt = tile_mt(tile);
       float xc = 0.f, yc = 0.f;                             // CoordConv coordinates of this lane's output pixel
       if (has_coord) {
         const unsigned pix = (unsigned)(mt * BLOCK_M + row) % hw_out;      // coord_w convs are 1x1: linear M tiles
@@ -729,31 +716,50 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       mbar_wait(tmem_full_bar(acc), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+      bool released = false;
+      auto release_acc = [&]() {                            // this warp's TMEM reads of the tile are done
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
+        released = true;
+      };
+      {
 #pragma unroll 1
-      for (int g = 0; g < G; ++g) {
-        const int cc = 2 * g + half;                        // this warp's 32-column sub-tile inside the group
-        const bool live = n0 + g * GROUP_COLS < p.cout;     // whole group beyond cout: only the TMEM bookkeeping
-        uint32_t v[32];
-        tmem_ld32_nowait(t_row + (uint32_t)(cc * SUB), v);
-        if (live) {
-          const int b = gg & 1;
-          if (tid == 0) bulk_wait_read<1>();                // the store that last used out[b] has drained its smem reads
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (has_res) mbar_wait(res_full_bar(b), (gg >> 1) & 1);
+        for (int gi = 0; gi < GPW; ++gi) {
+          const int col0 = box_col0(tile, gi);
+          if (col0 >= p.cout) continue;                     // whole group beyond cout
+          const int gcol = col0 - (tile % num_n_tiles) * BN;     // column of the group inside the accumulator
+          uint32_t v[64];
+          tmem_ld32_nowait(t_row + (uint32_t)gcol, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld32_nowait(t_row + (uint32_t)(gcol + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          if (col0 != tab_col0) {                           // (re)load this warp's per-channel table: lane -> two columns
+            __syncwarp();
+            const int c = col0 + 2 * lane;
+            const bool ok0 = c < p.cout, ok1 = c + 1 < p.cout;
+            tab[2 * lane] = ok0 ? __ldg(p.scale + c) : 0.f;                 tab[2 * lane + 1] = ok1 ? __ldg(p.scale + c + 1) : 0.f;
+            tab[64 + 2 * lane] = ok0 ? __ldg(p.shift + c) : 0.f;            tab[64 + 2 * lane + 1] = ok1 ? __ldg(p.shift + c + 1) : 0.f;
+            if (has_coord) {
+              tab[128 + 2 * lane] = ok0 ? __ldg(p.coord_w + c) : 0.f;          tab[128 + 2 * lane + 1] = ok1 ? __ldg(p.coord_w + c + 1) : 0.f;
+              tab[192 + 2 * lane] = ok0 ? __ldg(p.coord_w + p.cout + c) : 0.f; tab[192 + 2 * lane + 1] = ok1 ? __ldg(p.coord_w + p.cout + c + 1) : 0.f;
+            }
+            tab_col0 = col0;
+          }
+          if (lane == 0) bulk_wait_read<0>();               // the previous store of this warp has drained the output box
+          if (has_res) mbar_wait(res_full_bar(warp, lc % RB), (lc / RB) & 1);
           tmem_wait_ld();
-          const uint32_t rbase = res_smem + b * GROUP_BYTES + row_off, obase = out_smem + b * GROUP_BYTES + row_off;
-          const float* sc = ss + cc * SUB;
-          const float* sh = ss + BN + cc * SUB;
+          __syncwarp();
+          if (gi == GPW - 1) release_acc();
+          const uint32_t rbase = res_s + (lc % RB) * BOX_BYTES + row_off, obase = out_s + row_off;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {                      // 8 channels (one 16-byte chunk) at a time
-            const uint32_t chunk = ((uint32_t)(half * 4 + q) ^ sw) << 4;
+          for (int q = 0; q < 8; ++q) {                      // 8 channels (one 16-byte chunk) at a time
+            const uint32_t chunk = ((uint32_t)q ^ sw) << 4;
             uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
             if (has_res) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(rbase + chunk));
-            const float4 s0 = *reinterpret_cast<const float4*>(sc + q * 8), s1 = *reinterpret_cast<const float4*>(sc + q * 8 + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(sh + q * 8), h1 = *reinterpret_cast<const float4*>(sh + q * 8 + 4);
+            const float4 s0 = *reinterpret_cast<const float4*>(tab + q * 8), s1 = *reinterpret_cast<const float4*>(tab + q * 8 + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(tab + 64 + q * 8), h1 = *reinterpret_cast<const float4*>(tab + 64 + q * 8 + 4);
             if (has_coord) {                                 // rank-2 CoordConv term, added to the accumulator before scale/shift
-              const float* cx = ss + 2 * BN + cc * SUB + q * 8;
-              const float* cy = ss + 3 * BN + cc * SUB + q * 8;
+              const float* cx = tab + 128 + q * 8;
+              const float* cy = tab + 192 + q * 8;
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[8 * q + e] = __float_as_uint(__uint_as_float(v[8 * q + e]) + cx[e] * xc + cy[e] * yc);
             }
@@ -769,29 +775,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + chunk), "r"(pack_bf16(f[0], f[1])),
                          "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
           }
-          fence_proxy_async();                              // generic-proxy writes of the box -> visible to the TMA store
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          if (tid == 0) {
-            if (mode_is_patchy(MODE))
-              tma_store_4d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, (mt % pw_tiles) * PW,
-                           ((mt / pw_tiles) % ph_tiles) * PH, mt / (pw_tiles * ph_tiles));
-            else
-              tma_store_2d(&tmap_y, out_smem + b * GROUP_BYTES, n0 + g * GROUP_COLS, mt * BLOCK_M);
-            bulk_commit();
-            if (has_res) mbar_arrive(res_empty_bar(b));     // everybody is past bar 2: res[b] may be refilled
-          }
-          ++gg;
-        } else {
-          tmem_wait_ld();
-        }
-        if (g == G - 1) {                                   // this warp's TMEM reads of the tile are done
-          tc_fence_before();
+          fence_proxy_async();                              // generic-proxy accesses of both boxes -> ordered before the TMA store / reload
           __syncwarp();
-          if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
+          if (lane == 0) { box_move(false, out_s, 0u, tile, col0); bulk_commit(); }
+          if (has_res) { ++lc; request_next(); }            // the residual buffer just read is free: fetch the box two ahead
         }
       }
+      if (!released) release_acc();
     }
-    if (tid == 0) bulk_wait<0>();                           // all output boxes are in global memory before the CTA exits
+    if (lane == 0) bulk_wait<0>();                          // this warp's output boxes are in global memory before the CTA exits
   } else {
     // =====================================================================================
     // epilogue warps 0-7: warp w reads TMEM lanes 32*(w&3).. and handles sub-tiles cc = (w>>2), (w>>2)+2, ...
@@ -1062,10 +1054,10 @@ int encode_im2col_4d(CUtensorMap* map, const ppy_conv_params* p) {
 int encode_tile_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int ld, int cols, const ppy_conv_params* p, int ho,
                     int wo, bool patch, int box_w, int box_h) {
   // output / residual tensors: channels innermost; 2-D [M rows][cols] or 4-D (C, W, H, N) for patch tiles
-  if (!patch) return encode_2d(enc, map, base, (uint64_t)cols, (uint64_t)p->n * ho * wo, (uint64_t)ld * 2, GROUP_COLS, BLOCK_M);
+  if (!patch) return encode_2d(enc, map, base, (uint64_t)cols, (uint64_t)p->n * ho * wo, (uint64_t)ld * 2, GROUP_COLS, BOX_ROWS);
   const cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)p->n};
   const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)wo * ld * 2, (cuuint64_t)ho * wo * ld * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)GROUP_COLS, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)GROUP_COLS, (cuuint32_t)box_w, (cuuint32_t)(BOX_ROWS / box_w), 1};   // one warp's 32 tile rows
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1146,7 +1138,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int num_taps = p->wgrad_taps > 0 ? p->wgrad_taps : 1;
   const int num_splits = pick_splits(p, (long long)num_m_tiles * num_n_tiles * num_taps, num_kb);
   const long long tiles = (long long)num_m_tiles * num_n_tiles * num_taps * num_splits;
-  if (CTA2) {
+  if constexpr (CTA2) {
     const int pairs = num_sms() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
@@ -1162,12 +1154,13 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
                                        num_splits, num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r));
     if (rc) return rc;
     return check_launch();
+  } else {
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    conv_umma_kernel<BN, MODE, EPI, ACC, false><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
+                                                                                      num_splits, num_taps, pw_tiles, ph_tiles, tmap_b,
+                                                                                      tmap_a, tmap_y, tmap_r);
+    return check_launch();
   }
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_umma_kernel<BN, MODE, EPI, ACC, false><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
-                                                                                    num_splits, num_taps, pw_tiles, ph_tiles, tmap_b,
-                                                                                    tmap_a, tmap_y, tmap_r);
-  return check_launch();
 }
 
 // The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
@@ -1218,7 +1211,7 @@ int dispatch_slab(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     return tma_epi ? launch<64, MODE_TMA_SLAB, EPI_TMA>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
   }
   if (pair) return tma_epi ? launch<128, MODE_TMA_SLAB, EPI_TMA, false, true>(p, ho, wo, st) : launch<128, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st);
-  return tma_epi ? launch<128, MODE_TMA_SLAB, EPI_TMA>(p, ho, wo, st) : launch<128, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
+  return launch<128, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);     // single-tile problems only: no room for the TMA epilogue's boxes
 }
 
 }  // namespace
