@@ -410,6 +410,11 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   if (CTA2) cluster_sync_all(); else __syncthreads();      // pair: the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) may overlap the tail of the previous kernel
+  // of the stream; nothing below touches global memory before that kernel has completed and its writes are visible.  The
+  // dependents of THIS grid may be scheduled as soon as its CTAs free their SMs.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp >= PRODUCER_WARP0 && warp < PRODUCER_WARP0 + 4) {
     // =====================================================================================
@@ -1138,29 +1143,31 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int num_taps = p->wgrad_taps > 0 ? p->wgrad_taps : 1;
   const int num_splits = pick_splits(p, (long long)num_m_tiles * num_n_tiles * num_taps, num_kb);
   const long long tiles = (long long)num_m_tiles * num_n_tiles * num_taps * num_splits;
-  if constexpr (CTA2) {
-    const int pairs = num_sms() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MODE, EPI, ACC, CTA2>, *p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
-                                       num_splits, num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r));
-    if (rc) return rc;
-    return check_launch();
-  } else {
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    conv_umma_kernel<BN, MODE, EPI, ACC, false><<<grid, NUM_THREADS, Cfg::kSmemBytes, st>>>(*p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
-                                                                                      num_splits, num_taps, pw_tiles, ph_tiles, tmap_b,
-                                                                                      tmap_a, tmap_y, tmap_r);
-    return check_launch();
+  static const bool use_pdl = getenv("PPY_NO_PDL") == nullptr;
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = CTA2 ? dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs))) : dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTA2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (use_pdl) {                     // prologue overlaps the previous kernel's tail (griddepcontrol.wait in the kernel)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MODE, EPI, ACC, CTA2>, *p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
+                                     num_splits, num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r));
+  if (rc) return rc;
+  return check_launch();
 }
 
 // The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
