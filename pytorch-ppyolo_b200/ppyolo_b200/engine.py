@@ -394,12 +394,39 @@ class InferenceEngine(object):
         return self._conv(name, x, unit.conv.weight.detach(), scale, shift, unit.stride, act, residual=residual,
                           dst=dst, coord=coord, upsample=upsample, out_code=out_code)
 
+    def _pool_into_conv_ok(self, unit, x):
+        """AvgPool2d(2,2) + 1x1 conv of the vd shortcut (model/resnet_vd.py:29-33) as ONE 2x2 / stride-2 conv with the weight
+        replicated over the window and divided by 4 (exact in bf16): the input is read once instead of pooled, written and
+        read again.  The GEMM does 4x the MACs, so only where the shortcut is clearly HBM-bound (large maps)."""
+        from model.custom_layers import DCNv2
+        return (self.code == PPY_BF16 and not self.train_bn and not isinstance(unit.conv, DCNv2) and unit.conv.weight.shape[-1] == 1 and
+                x.c % 64 == 0 and x.h % 2 == 0 and x.w % 2 == 0 and x.n * (x.h // 2) * (x.w // 2) >= 100000 and
+                getattr(self.model, 'fuse_avgpool', True))
+
+    def _unit_avgpooled(self, name, unit, x):
+        from model.custom_layers import ACT_CODES
+        scale, shift = unit.folded_scale_shift()
+        w = unit.conv.weight.detach().float()
+        w2 = (w * 0.25).expand(-1, -1, 2, 2).contiguous()
+        before = self.conv_flops
+        out = self._conv(name, x, w2, scale, shift, 2, ACT_CODES[unit.act_name])
+        true_flops = (self.conv_flops - before) // 4          # the algorithmic conv is the 1x1 on the pooled map
+        self.conv_flops = before + true_flops
+        info = self.step_info[name]
+        info['flops'], info['k'] = true_flops, info['k'] // 4
+        return out
+
     # ------------------------------------------------------------------ network walk
     def _block(self, name, blk, x, dst=None):
         from model.resnet_vd import ConvBlock, IdentityBlock, BasicBlock
         relu = _lib.ACT_RELU
         if isinstance(blk, ConvBlock):
-            sc = self._unit(name + '.conv4', blk.conv4, x if blk.is_first else self._avgpool(x))
+            if blk.is_first:
+                sc = self._unit(name + '.conv4', blk.conv4, x)
+            elif self._pool_into_conv_ok(blk.conv4, x):
+                sc = self._unit_avgpooled(name + '.conv4', blk.conv4, x)
+            else:
+                sc = self._unit(name + '.conv4', blk.conv4, self._avgpool(x))
             y = self._unit(name + '.conv1', blk.conv1, x)
             y = self._unit(name + '.conv2', blk.conv2, y)
             return self._unit(name + '.conv3', blk.conv3, y, residual=sc, act=relu, dst=dst)
