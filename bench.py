@@ -223,8 +223,10 @@ def run_ours(args, rank, world, local_rank):
     cand_mean = float(eng.candidate_counts().float().mean()) if eng.scores is None else None
 
     # ---- end to end through the public API with host buffers ----------------------------------
+    # two input slots (one captured graph each): batch i+1 is uploaded straight into the engine while batch i computes
     copy_stream = torch.cuda.Stream(device=dev)
-    stage_x = [torch.empty_like(eng.x_in) for _ in range(2)]
+    if len(eng.input_slots) < 2:
+        eng.add_input_slot()
     stage_im = [torch.empty_like(eng.im_size) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -237,14 +239,13 @@ def run_ours(args, rank, world, local_rank):
             b = step % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[b])
-                stage_x[b].copy_(x_host[b], non_blocking=True)
+                eng.input_slots[b].copy_(x_host[b], non_blocking=True)
                 stage_im[b].copy_(im_host[b], non_blocking=True)
                 ready[b].record(copy_stream)
             main.wait_event(ready[b])
-            eng.x_in.copy_(stage_x[b], non_blocking=True)
             eng.im_size.copy_(stage_im[b], non_blocking=True)
+            eng.launch(slot=b)
             consumed[b].record(main)
-            eng.launch()
             out_host[b].copy_(eng.nms_out, non_blocking=True)
             cnt_host[b].copy_(eng.nms_counts, non_blocking=True)
             done[b].record(main)

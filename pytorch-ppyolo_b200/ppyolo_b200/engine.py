@@ -93,7 +93,8 @@ class InferenceEngine(object):
             bn.running_mean.copy_(mean)
             bn.running_var.copy_(var)
         if use_graph:
-            self._capture()
+            self.graph = self._capture()
+            self.graphs = [self.graph]
 
     # ------------------------------------------------------------------ buffers
     def _new(self, n, h, w, c, dtype=None):
@@ -140,11 +141,11 @@ class InferenceEngine(object):
         ho, wo = (self.h - 1) // 2 + 1, (self.w - 1) // 2 + 1
         out = TensorRef(self._new(self.n, ho, wo, 32))
         fp = ctypes.POINTER(ctypes.c_float)
-        args = (ops.ptr(self.x_in), self.n, self.h, self.w, w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp),
+        args = (self.n, self.h, self.w, w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp),
                 sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name], ctypes.c_void_p(out.ptr), out.ld, self.code)
 
-        def run():
-            check(lib.ppy_stem_conv3x3s2(*args, ops.stream_ptr()), 'stem.conv1_1')
+        def run():            # reads the CURRENT input slot (one captured graph per slot, see add_input_slot)
+            check(lib.ppy_stem_conv3x3s2(ops.ptr(self._src), *args, ops.stream_ptr()), 'stem.conv1_1')
         self._add('stem.conv1_1', run)
         self.conv_flops += 2 * self.n * ho * wo * 32 * 27
         return out
@@ -448,6 +449,9 @@ class InferenceEngine(object):
         n_out = len(head.anchor_masks)
         # static input: NCHW fp32 exactly as Decode.predict uploads it (model/decode_np.py:142-147)
         self.x_in = torch.zeros((n, 3, self.h, self.w), dtype=torch.float32, device=self.dev)
+        self._src = self.x_in                 # input slot the first kernel reads
+        self.input_slots = [self.x_in]
+        self.graphs = []
         self.im_size = torch.zeros((n, 2), dtype=torch.float32, device=self.dev)
         stem_units = list(zip(bb._stem_units(), ('conv1_1', 'conv1_2', 'conv1_3')))
         u0 = stem_units[0][0]
@@ -458,8 +462,8 @@ class InferenceEngine(object):
             stem_units = stem_units[1:]
         else:
             x0 = TensorRef(self._new(n, self.h, self.w, 8))
-            args = (ops.ptr(self.x_in), ctypes.c_void_p(x0.ptr), n, 3, self.h, self.w, 8, self.code)
-            self._add('nchw_to_nhwc', lambda: check(lib.ppy_nchw_to_nhwc(*args, ops.stream_ptr()), 'nchw_to_nhwc'))
+            args = (ctypes.c_void_p(x0.ptr), n, 3, self.h, self.w, 8, self.code)
+            self._add('nchw_to_nhwc', lambda: check(lib.ppy_nchw_to_nhwc(ops.ptr(self._src), *args, ops.stream_ptr()), 'nchw_to_nhwc'))
 
         # head level i > 0 consumes cat([upsampled route, backbone feature]); give the backbone stage that
         # produces the feature a destination inside that concat buffer (no copy at run time)
@@ -607,14 +611,28 @@ class InferenceEngine(object):
         torch.cuda.synchronize(self.dev)
         with torch.cuda.graph(g, stream=s):
             self._run_steps()
-        self.graph = g
+        return g
 
-    def launch(self):
-        """Enqueue one forward over the static input buffers on the current stream (no sync)."""
+    def add_input_slot(self):
+        """A second (third, ...) static input buffer with its own captured graph, so a caller can upload batch i+1 straight
+        into the engine while batch i is being computed -- no staging copy.  All other buffers are shared: launches of
+        different slots must be ordered on one stream.  Returns the slot index."""
+        t = torch.zeros_like(self.x_in)
+        self.input_slots.append(t)
         if self.graph is not None:
-            self.graph.replay()
+            self._src = t
+            self.graphs.append(self._capture())
+            self._src = self.x_in
+        return len(self.input_slots) - 1
+
+    def launch(self, slot=0):
+        """Enqueue one forward over the static input buffer `slot` on the current stream (no sync)."""
+        if self.graph is not None:
+            self.graphs[slot].replay()
         else:
+            self._src = self.input_slots[slot]
             self._run_steps()
+            self._src = self.x_in
 
     def run(self, x, im_size):
         """PPYOLO.forward(x, im_size) -> list of [M,6] tensors (reference model/ppyolo.py:19-22)."""
