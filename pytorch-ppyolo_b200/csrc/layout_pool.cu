@@ -99,6 +99,84 @@ __global__ void pool_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y
   }
 }
 
+// bf16 fast path of both pools: one thread = one 16-byte channel vector of TWO horizontally adjacent output pixels; every
+// load of the thread (8 for the average, up to 15 for the max) is issued before the first use, max runs on packed bf16x2
+// (exact), the average in fp32 with the reference's operation order.  MODE 0 = max 3x3 s2 p1, 1 = avg 2x2 s2 p0.
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 max16(uint4 a, uint4 b) {
+  return make_uint4(max_bf16x2(a.x, b.x), max_bf16x2(a.y, b.y), max_bf16x2(a.z, b.z), max_bf16x2(a.w, b.w));
+}
+__device__ __forceinline__ uint32_t avg4_bf16x2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const float lo = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__uint_as_float(a << 16), __uint_as_float(b << 16)), __uint_as_float(c << 16)),
+                                       __uint_as_float(d << 16)), 4.f);
+  const float hi = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__uint_as_float(a & 0xFFFF0000u), __uint_as_float(b & 0xFFFF0000u)),
+                                                 __uint_as_float(c & 0xFFFF0000u)), __uint_as_float(d & 0xFFFF0000u)), 4.f);
+  __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) pool2_bf16_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y, int y_ld,
+                                                         int n, int h, int w, int c, int ho, int wo) {
+  const int cv = c >> 3, wp = (wo + 1) >> 1;                     // channel vectors, output pixel pairs per row
+  const unsigned total = (unsigned)(n * ho * wp * cv);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = (int)(i % (unsigned)cv);
+    unsigned p = i / (unsigned)cv;
+    const int ox = 2 * (int)(p % (unsigned)wp); p /= (unsigned)wp;
+    const int oy = (int)(p % (unsigned)ho);
+    const int img = (int)(p / (unsigned)ho);
+    const bool two = ox + 1 < wo;
+    __nv_bfloat16* dst = y + (((long long)img * ho + oy) * wo + ox) * y_ld + v * 8;
+    if (MODE == 1) {
+      const __nv_bfloat16* base = x + (((long long)img * h + oy * 2) * w + ox * 2) * x_ld + v * 8;
+      const __nv_bfloat16* base2 = base + (long long)w * x_ld;
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = k < 2 || two;
+        a[k] = ok ? ldg16(base + k * x_ld) : make_uint4(0u, 0u, 0u, 0u);
+        b[k] = ok ? ldg16(base2 + k * x_ld) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(avg4_bf16x2(a[0].x, a[1].x, b[0].x, b[1].x), avg4_bf16x2(a[0].y, a[1].y, b[0].y, b[1].y),
+                                                  avg4_bf16x2(a[0].z, a[1].z, b[0].z, b[1].z), avg4_bf16x2(a[0].w, a[1].w, b[0].w, b[1].w));
+      if (two)
+        *reinterpret_cast<uint4*>(dst + y_ld) = make_uint4(avg4_bf16x2(a[2].x, a[3].x, b[2].x, b[3].x), avg4_bf16x2(a[2].y, a[3].y, b[2].y, b[3].y),
+                                                           avg4_bf16x2(a[2].z, a[3].z, b[2].z, b[3].z), avg4_bf16x2(a[2].w, a[3].w, b[2].w, b[3].w));
+    } else {
+      // input columns 2ox-1 .. 2ox+3 (5), rows 2oy-1 .. 2oy+1 (3); out-of-image taps are replaced by an in-window valid tap
+      uint4 t[3][5];
+      const int cx = ox * 2, cy = oy * 2;                        // always-valid centre of the first window
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        int iy = cy - 1 + r;
+        iy = (iy < 0 || iy >= h) ? cy : iy;
+        const __nv_bfloat16* row = x + ((long long)img * h + iy) * w * x_ld + v * 8;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          int ix = cx - 1 + k;
+          // columns 0..2 belong to window 0 (fallback: its centre cx), 2..4 to window 1 (fallback: its centre cx + 2, if it exists)
+          if (ix < 0 || ix >= w) ix = (k < 2 || !two) ? cx : cx + 2;
+          if (!two && k > 2) ix = cx;
+          t[r][k] = ldg16(row + (long long)ix * x_ld);
+        }
+      }
+      uint4 m0 = t[0][0], m1 = t[0][2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { m0 = max16(m0, t[r][k]); m1 = max16(m1, t[r][k + 2]); }
+      }
+      *reinterpret_cast<uint4*>(dst) = m0;
+      if (two) *reinterpret_cast<uint4*>(dst + y_ld) = m1;
+    }
+  }
+}
+
 // SPP: one thread per (pixel, 16-byte channel vector); max over nested 5/9/13 windows in a single sweep
 // of the 13x13 neighbourhood (each tap is classified into the smallest window containing it).
 template <typename T>
@@ -303,6 +381,11 @@ int ppy_maxpool3x3s2(const void* x, int x_ld, void* y, int y_ld, int n, int h, i
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   const long long total = (long long)n * ho * wo * (c / (16 / dtype_size(dtype)));
   PPY_REQUIRE(total < 0x7FFFFFFFll);
+  if (dtype == PPY_BF16) {
+    const long long work = (long long)n * ho * ((wo + 1) / 2) * (c / 8);
+    pool2_bf16_kernel<0><<<grid_for(work, 256), 256, 0, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, n, h, w, c, ho, wo);
+    return check_launch();
+  }
   PPY_DISPATCH(dtype, pool_kernel<T, 0><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c, ho, wo);)
   return check_launch();
 }
@@ -312,6 +395,11 @@ int ppy_avgpool2x2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * (c / (16 / dtype_size(dtype)));
   PPY_REQUIRE(total < 0x7FFFFFFFll);
+  if (dtype == PPY_BF16) {
+    const long long work = (long long)n * ho * ((wo + 1) / 2) * (c / 8);
+    pool2_bf16_kernel<1><<<grid_for(work, 256), 256, 0, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, n, h, w, c, ho, wo);
+    return check_launch();
+  }
   PPY_DISPATCH(dtype, pool_kernel<T, 1><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const T*)x, x_ld, (T*)y, y_ld, n, h, w, c, ho, wo);)
   return check_launch();
 }

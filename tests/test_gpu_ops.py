@@ -408,3 +408,23 @@ def test_stem_conv_bf16_tensor_core(n, hw, act):
                                  ctypes.c_void_p(y.data_ptr()), 32, PPY_BF16, o.stream_ptr()), 'stem')
     got = o.from_nhwc(y, 32).cpu()
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
+
+
+@pytest.mark.parametrize('h,w', [(13, 17), (12, 18), (7, 7), (20, 2)])
+def test_pools_bf16(h, w):
+    """bf16 fast path of MaxPool2d(3,2,1) (model/resnet_vd.py:103) and AvgPool2d(2,2) (:30): two output pixels per thread,
+    odd widths / heights cover the window clamping; max is exact, the average is rounded once to bf16."""
+    from ppyolo_b200._lib import PPY_BF16, lib, check
+    o = ops()
+    g = torch.Generator().manual_seed(h * 31 + w)
+    t = bf16_round(torch.randn((3, 16, h, w), generator=g))
+    xb = o.to_nhwc(t.to(DEV), PPY_BF16)
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    yb = torch.empty((3, ho, wo, 16), dtype=torch.bfloat16, device=DEV)
+    check(lib.ppy_maxpool3x3s2(o.ptr(xb), 16, o.ptr(yb), 16, 3, h, w, 16, PPY_BF16, o.stream_ptr()), 'maxpool')
+    np.testing.assert_array_equal(o.from_nhwc(yb, 16).cpu().numpy(), torch.nn.functional.max_pool2d(t, 3, 2, 1).numpy())
+    if h >= 2 and w >= 2:
+        ya = torch.empty((3, h // 2, w // 2, 16), dtype=torch.bfloat16, device=DEV)
+        check(lib.ppy_avgpool2x2(o.ptr(xb), 16, o.ptr(ya), 16, 3, h, w, 16, PPY_BF16, o.stream_ptr()), 'avgpool')
+        want = torch.nn.functional.avg_pool2d(t, 2, 2).to(torch.bfloat16).float()
+        np.testing.assert_array_equal(o.from_nhwc(ya, 16).cpu().numpy(), want.numpy())
