@@ -97,10 +97,11 @@ typedef struct ppy_conv_params {
   /* --- bf16 path only: partial-sum launches (K splits; the weight-gradient GEMM of the training step) ---------------
    * accumulate=1: results are ADDED (fp32 atomics) into y, which the caller zeroed; act none, no residual/bias_map,
    * shift applied once.  split_k: K splits per output tile (0 = enough to fill the SMs).
-   * Weight gradient of a kxk stride-1 conv as ONE such launch (see ppy_conv_wgrad_bf16): a 1x1 "conv" whose rows are the
-   * conv's output channels (x = dY transposed, [cout][pixels]), whose packed "weight" is the transposed zero-bordered
-   * input ([cin][pixels]) and whose K runs over the pixels; wgrad_taps=9 repeats the GEMM per tap with the B operand
-   * read at flat pixel offset (ky-1)*wgrad_pitch + (kx-1) and the result written to columns [tap*wgrad_tap_stride, ..). */
+   * wgrad_taps / wgrad_pitch / wgrad_tap_stride describe the weight-gradient GEMM of a kxk stride-1 conv as ONE such launch:
+   * a 1x1 "conv" whose rows are the conv's output channels (x = dY transposed, [cout][pixels]), whose packed "weight" is
+   * the transposed zero-bordered input ([cin][pixels]) and whose K runs over the pixels; wgrad_taps=9 repeats the GEMM per
+   * tap with the B operand read at flat pixel offset (ky-1)*wgrad_pitch + (kx-1) and the result written to columns
+   * [tap*wgrad_tap_stride, ..).  (Kernel instantiation only: no host wrapper uses it yet; the head's backward is ATen's.) */
   int accumulate;
   int split_k;
   int wgrad_taps;

@@ -1187,7 +1187,7 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int c = p->cout;
   if (p->accumulate) {       // partial-sum launches (split-K, weight gradients): slab epilogue with fp32 atomics
     if (MODE == MODE_DCN || mode_is_patchy(MODE)) return PPY_ERR_UNSUPPORTED;
-    constexpr int M2 = (MODE == MODE_TMA_A) ? MODE_TMA_A : MODE_GATHER;
+    constexpr int M2 = (MODE == MODE_TMA_A || MODE == MODE_TMA_IM2COL) ? MODE : MODE_GATHER;
     if (c <= 32) return launch<32, M2, EPI_SLAB, true>(p, ho, wo, st);
     if (c <= 64) return launch<64, M2, EPI_SLAB, true>(p, ho, wo, st);
     if (c <= 128) return launch<128, M2, EPI_SLAB, true>(p, ho, wo, st);
@@ -1268,7 +1268,7 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   // any other k x k conv over whole 64-channel blocks: im2col-mode TMA (stride and zero padding done by the copy engine)
   const bool im2col_ok = p->cin % BLOCK_K == 0 && p->k_pad == p->kh * p->kw * p->cin && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
                          (p->x_ld * 2) % 16 == 0 && p->pad <= 8 && p->kh <= 8 && p->kw <= 8 && p->stride <= 8 &&
-                         !p->accumulate && get_encode_im2col_fn() != nullptr && !getenv("PPY_NO_IM2COL");
+                         p->wgrad_taps <= 1 && get_encode_im2col_fn() != nullptr && !getenv("PPY_NO_IM2COL");
   if (im2col_ok) return dispatch<MODE_TMA_IM2COL>(p, ho, wo, as_stream(s));
   return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }

@@ -383,6 +383,7 @@ class InferenceEngine(object):
             one = torch.ones(n_om, dtype=torch.float32, device=self.dev)
             om = self._conv(name + '.offset', x, d.conv_offset.weight.detach(), one,
                             d.conv_offset.bias.detach().float().contiguous(), unit.stride, 0, out_code=PPY_F32)
+            # (no split-K here: atomically added partial sums make the offsets, hence the detections, run-to-run non-deterministic)
             om = TensorRef(om.t)     # the sampler reads the padded row (ld) directly
             if d.dcn_bias is not None:
                 shift = shift + d.dcn_bias.detach().float() * scale

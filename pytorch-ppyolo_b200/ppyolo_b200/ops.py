@@ -112,7 +112,7 @@ def pack_weight(weight, code, c_begin=0, c_count=None):
 
 
 def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, residual=None, bias_map=None,
-              out=None, out_code=None, upsample2x=False, offset_mask=None, x_ld=None, coord_w=None):
+              out=None, out_code=None, upsample2x=False, offset_mask=None, x_ld=None, coord_w=None, accumulate=False, split_k=0):
     """Launch one fused conv on NHWC buffers. ``x`` [N,H,W,ld]; returns ``out`` [N,Ho,Wo,ld_out]."""
     w_packed, cin_pad, k_pad, cout_pad = packed
     n, h, w, ld = x.shape
@@ -131,6 +131,7 @@ def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, res
     p.scale, p.shift = scale.data_ptr(), shift.data_ptr()
     p.bias_map = bias_map.data_ptr() if bias_map is not None else None
     p.coord_w = coord_w.data_ptr() if coord_w is not None else None
+    p.accumulate, p.split_k = (1 if accumulate else 0), split_k      # partial sums are ADDED into a caller-zeroed fp32 `out`
     p.residual = residual.data_ptr() if residual is not None else None
     p.res_ld = residual.shape[-1] if residual is not None else 0
     p.act = act

@@ -428,3 +428,25 @@ def test_pools_bf16(h, w):
         check(lib.ppy_avgpool2x2(o.ptr(xb), 16, o.ptr(ya), 16, 3, h, w, 16, PPY_BF16, o.stream_ptr()), 'avgpool')
         want = torch.nn.functional.avg_pool2d(t, 2, 2).to(torch.bfloat16).float()
         np.testing.assert_array_equal(o.from_nhwc(ya, 16).cpu().numpy(), want.numpy())
+
+
+@pytest.mark.parametrize('n,cin,cout,k,stride,hw,splits', [(1, 512, 27, 3, 1, 19, 0), (2, 256, 64, 1, 1, 12, 4), (1, 128, 40, 3, 2, 21, 3),
+                                                           (2, 64, 128, 3, 1, 9, 2)])
+def test_umma_conv_split_k(n, cin, cout, k, stride, hw, splits):
+    """Partial-sum launches (ppy_conv_params.accumulate / split_k): K splits of one output tile are added atomically into a
+    zeroed fp32 output, the shift enters once -- the DCN offset conv shape (few tiles, K = 4608) is the use case."""
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16
+    o = ops()
+    g = torch.Generator().manual_seed(cin + 7 * cout + splits)
+    x = bf16_round(torch.randn((n, cin, hw, hw), generator=g))
+    w = bf16_round(torch.randn((cout, cin, k, k), generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    want = torch.nn.functional.conv2d(x, w, None, stride, (k - 1) // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    packed = o.pack_weight(w.to(DEV), PPY_BF16)
+    xh = o.to_nhwc(x.to(DEV), PPY_BF16, packed[1])
+    ho = (hw + 2 * ((k - 1) // 2) - k) // stride + 1
+    out = torch.zeros((n, ho, ho, (cout + 7) // 8 * 8), dtype=torch.float32, device=DEV)
+    o.conv_nhwc(xh, packed, cin, cout, k, stride, (k - 1) // 2, scale.to(DEV), shift.to(DEV), 0, PPY_BF16, out=out, out_code=PPY_F32,
+                accumulate=True, split_k=splits)
+    got = o.from_nhwc(out, cout).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-4 * scale_of(want.numpy()))
