@@ -709,6 +709,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     };
     if (has_res) { request_next(); if (RB == 2) request_next(); }
     int it = G >= 2 ? 0 : half, tab_col0 = -1;             // `it` counts the CTA's tiles (accumulator buffer / phase bookkeeping)
+    int nbox = 0;                                           // boxes stored by this warp
     for (int tile = my_first; tile < num_tiles; tile += my_step, it += TSTRIDE) {
       const int acc = it & 1;
       const int mt = tile_mt(tile);
@@ -749,12 +750,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             }
             tab_col0 = col0;
           }
-          if (lane == 0) bulk_wait_read<0>();               // the previous store of this warp has drained the output box
+          // output box rotation: with a residual the warp has ONE output box (wait for its previous store to drain); without,
+          // the residual boxes serve as output boxes too (RB + 1 in rotation: only the store RB boxes back must have drained)
+          const uint32_t out_box = has_res ? out_s : res_s + (uint32_t)(nbox % (RB + 1)) * BOX_BYTES;
+          if (lane == 0) { if (has_res) bulk_wait_read<0>(); else bulk_wait_read<RB>(); }
           if (has_res) mbar_wait(res_full_bar(warp, lc % RB), (lc / RB) & 1);
           tmem_wait_ld();
           __syncwarp();
           if (gi == GPW - 1) release_acc();
-          const uint32_t rbase = res_s + (lc % RB) * BOX_BYTES + row_off, obase = out_s + row_off;
+          const uint32_t rbase = res_s + (lc % RB) * BOX_BYTES + row_off, obase = out_box + row_off;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {                      // 8 channels (one 16-byte chunk) at a time
             const uint32_t chunk = ((uint32_t)q ^ sw) << 4;
@@ -782,7 +786,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           }
           fence_proxy_async();                              // generic-proxy accesses of both boxes -> ordered before the TMA store / reload
           __syncwarp();
-          if (lane == 0) { box_move(false, out_s, 0u, tile, col0); bulk_commit(); }
+          if (lane == 0) { box_move(false, out_box, 0u, tile, col0); bulk_commit(); }
+          ++nbox;
           if (has_res) { ++lc; request_next(); }            // the residual buffer just read is free: fetch the box two ahead
         }
       }
