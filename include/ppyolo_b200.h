@@ -147,6 +147,12 @@ int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long ro
 /* torch.optim.SGD(momentum, weight_decay) update of one fp32 tensor, gradient pre-scaled by grad_scale (1/world). */
 int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, int first_step, ppy_stream_t s);
+/* ExponentialMovingAverage.update, model/EMA.py:31-45, on the device for all trainable tensors in one launch:
+ * shadow[offsets[t] + i] = decay * shadow[..] + one_minus_decay * params[t][i]  (numpy float32 operation order; the reference
+ * round-trips every parameter through host memory each step).  params: device array of num_tensors device pointers;
+ * offsets: device array of num_tensors + 1 element offsets into shadow_flat. */
+int ppy_ema_update(float* shadow_flat, const float* const* params, const long long* offsets, int num_tensors, float decay,
+                   float one_minus_decay, ppy_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * head post-processing

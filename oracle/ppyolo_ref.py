@@ -350,3 +350,10 @@ class Net(object):
         if return_all:
             return dict(feats=feats, outs=outs, boxes=boxes, scores=scores, preds=preds)
         return preds
+
+
+def ema_update(shadow, params, decay, update_step, thres_steps=True):
+    """ExponentialMovingAverage.update, model/EMA.py:31-45, on numpy float32 arrays: returns (new shadows, decay used).
+    ``decay * old + (1 - decay) * new`` with a Python-float decay keeps float32 arrays float32 (numpy weak scalars)."""
+    d = min(decay, (1 + update_step) / (10 + update_step)) if thres_steps else decay
+    return [np.asarray(d * s + (1 - d) * np.asarray(p, dtype=np.float32), dtype=np.float32) for s, p in zip(shadow, params)], d

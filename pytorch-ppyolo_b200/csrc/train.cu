@@ -119,6 +119,17 @@ inline unsigned blocks_for(long long work, int threads, long long cap = 148ll * 
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// blockIdx.y = tensor, blockIdx.x strides its elements; offsets[t] .. offsets[t+1] is tensor t's range in the flat shadow
+__global__ void __launch_bounds__(256) ema_update_kernel(float* __restrict__ shadow, const float* const* __restrict__ params,
+                                                         const long long* __restrict__ offsets, float decay, float one_minus_decay) {
+  const int t = blockIdx.y;
+  const long long begin = offsets[t], count = offsets[t + 1] - begin;
+  const float* __restrict__ p = params[t];
+  float* __restrict__ sh = shadow + begin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    sh[i] = __fadd_rn(__fmul_rn(decay, sh[i]), __fmul_rn(one_minus_decay, p[i]));
+}
+
 }  // namespace
 }  // namespace ppy
 
@@ -172,6 +183,15 @@ int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long 
   PPY_REQUIRE(param && grad && momentum_buf && n > 0);
   sgd_momentum_kernel<<<blocks_for(n, 256), 256, 0, as_stream(s)>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
                                                                     grad_scale, first_step);
+  return check_launch();
+}
+
+// EMA of the trainable parameters (reference model/EMA.py:31-45), all tensors in one launch: shadow and parameters are
+// addressed through a device table; the arithmetic keeps numpy's float32 order: f32(decay)*old + f32(1-decay)*new.
+int ppy_ema_update(float* shadow_flat, const float* const* params, const long long* offsets, int num_tensors, float decay,
+                   float one_minus_decay, ppy_stream_t s) {
+  PPY_REQUIRE(shadow_flat && params && offsets && num_tensors > 0);
+  ema_update_kernel<<<dim3(64, (unsigned)num_tensors), 256, 0, as_stream(s)>>>(shadow_flat, params, offsets, decay, one_minus_decay);
   return check_launch();
 }
 
