@@ -1,5 +1,5 @@
 // bf16 implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, fp32 accumulators in TMEM),
-// with fused scale/shift (+CoordConv bias map, +residual), activation and optional 2x nearest upsample
+// with fused scale/shift (+CoordConv bias map or rank-2 term, +residual), activation and optional 2x nearest upsample
 // in the epilogue.  Also the fused DCNv2 kernel: the same GEMM pipeline with a producer that bilinearly
 // samples the NHWC input at the learned offsets and writes the modulated bf16 A tile straight into the
 // swizzled shared-memory stage -- no im2col / gather temporaries in HBM (reference
@@ -8,25 +8,32 @@
 //   GEMM view: D[M x N] = A[M x K] * B[N x K]^T,  M = n*ho*wo pixels, N = cout, K = kh*kw*cin,
 //   K index = (ky*kw + kx)*cin + c.  CTA tile 128 x BLOCK_N x 64.
 //
-// PERSISTENT, warp-specialised: one CTA per SM walks tiles (n fastest) with stride gridDim.x; the TMEM
-// accumulator is double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
+// PERSISTENT, warp-specialised: one CTA per SM (or one CTA pair per TPC, template flag CTA2: cta_group::2, 256 x BLOCK_N
+// tiles, B split across the pair) walks tiles (n fastest) with stride gridDim.x; the TMEM accumulator is double buffered so the
+// epilogue of tile i overlaps the main loop of tile i+1.  Launched with programmatic stream serialization: the prologue
+// overlaps the previous kernel's tail, griddepcontrol.wait precedes the first global access.
 //
-//   warps 0-7  epilogue: warp w owns TMEM lanes 32(w&3)..+31 and every other 32-column sub-tile; per sub-tile:
-//              tcgen05.ld (next sub-tile prefetched) -> XOR-swizzled warp-private smem slab -> coalesced pass
-//              (lane = 8 channels of a row): CoordConv bias map, scale/shift, residual (16-byte loads issued one
-//              sub-tile ahead), activation, 16-byte stores
-//              (EPI_TMA variant, bf16 layers with K <= 512, i.e. the HBM-bound ones: residual boxes arrive by TMA into
-//              smem, lane = tile row does the math straight from the TMEM registers, output boxes leave by TMA store;
-//              warp 14 is the residual loader)
-//   warps 8-11 A producers (MODE gather): per 64-wide K block each thread issues eight 16-byte cp.async
-//              (zero-fill outside the image) into the 128B-swizzled K-major stage, eight consecutive lanes
-//              covering one pixel's contiguous 128-byte channel run.  (MODE dcn): thread = tile row,
-//              bilinear sample x mask in fp32 -> bf16 st.shared.  (MODE tma_a, 1x1 stride-1): idle, the
-//              A tile is a plain [128 x 64] box of the NHWC matrix and comes in by TMA.
-//   warp 12    TMA producer: weight tile [BLOCK_N x 64] (SWIZZLE_128B) per stage, + the A tile in tma_a mode, or
-//              (MODE tma_patch, 3x3 stride-1) one 4-D box {64 ch, 16, 8, 1} per (tap, channel block) at pixel offset
-//              (kx-1, ky-1): the zero halo comes from TMA's out-of-bounds fill, the 128 tile rows are a 16x8 patch
-//   warp 13    TMEM allocator + MMA issuer: one thread, 4 x tcgen05.mma (K=16) per stage, tcgen05.commit
+//   warps 0-7  epilogue.  EPI_SLAB: warp w owns TMEM lanes 32(w&3)..+31 and every other 32-column sub-tile; tcgen05.ld (next
+//              sub-tile prefetched) -> XOR-swizzled warp-private smem slab -> coalesced pass (lane = 8 channels of a row):
+//              CoordConv bias map, scale/shift, residual (16-byte loads one sub-tile ahead), activation, 16-byte stores.
+//              EPI_TMA (bf16 layers with short K, the HBM-bound ones): every warp works alone on [32 rows x 64 channels] boxes:
+//              its lane 0 fetches the residual box by TMA two boxes ahead, lane = tile row does the math straight from the TMEM
+//              registers (CoordConv rank-2 term, scale/shift from a per-warp smem table, residual, activation) into a swizzled
+//              output box that leaves by TMA store -- no global-memory instruction, no CTA-wide barrier.
+//   warps 8-11 A producers, only for MODE gather (cin % 64 != 0 leftovers: eight 16-byte cp.async per thread and K block,
+//              zero-fill outside the image, straight into the swizzled stage) and MODE dcn (thread = tile row, bilinear
+//              sample x mask in fp32 -> bf16 st.shared); idle in the TMA modes.
+//   warp 12    TMA producer (warp-uniform loop, elect.sync lane issues): weight tile(s) per stage, plus the A operand:
+//              tma_a      1x1 stride-1: plain [128 x 64] box of the NHWC matrix
+//              tma_patch  3x3 stride-1: 4-D box {64 ch, 16, 8, 1} per (tap, channel block) at pixel offset (kx-1, ky-1), zero halo
+//                         from TMA's out-of-bounds fill, the 128 tile rows are a 16x8 pixel patch
+//              tma_slab   3x3 stride-1, cout <= 128: 8x18-pixel slab per (channel block, kx) + the three weight tiles of its
+//                         taps; tap ky reads the same slab at +ky*1024 bytes (see MODE_TMA_SLAB below)
+//              tma_im2col any other k x k / stride: im2col-mode tensor map, 128 consecutive output pixels per box, filter
+//                         offset in the instruction, padding zero-filled by the copy engine
+//   warp 13    TMEM allocator + MMA issuer (warp-uniform loop): 4 x tcgen05.mma (K=16) per 64-wide K block (12 per slab
+//              stage), tcgen05.commit to the stage's empty barrier, one commit per tile to tmem_full
+//   warp 14    spare
 //
 // Shared-memory operand layout is the canonical K-major SWIZZLE_128B one: row r of a stage lives at
 // r*128 bytes, its 16-byte chunk j at ((j ^ (r & 7)) << 4); 8-row groups are 1024 bytes apart (SBO).
@@ -967,6 +974,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// Debug knobs (read once): PPY_NO_PDL / PPY_NO_CTA2 / PPY_NO_TMA_EPI / PPY_NO_PATCH / PPY_NO_SLAB / PPY_NO_IM2COL switch one
+// mechanism off so tools/conv_bench.py can A/B it on the same GPU; every combination is a correct (slower) kernel.
+bool knob_off(const char* name) { return getenv(name) != nullptr; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1148,7 +1159,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int num_taps = p->wgrad_taps > 0 ? p->wgrad_taps : 1;
   const int num_splits = pick_splits(p, (long long)num_m_tiles * num_n_tiles * num_taps, num_kb);
   const long long tiles = (long long)num_m_tiles * num_n_tiles * num_taps * num_splits;
-  static const bool use_pdl = getenv("PPY_NO_PDL") == nullptr;
+  static const bool use_pdl = !knob_off("PPY_NO_PDL");
   const int pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = CTA2 ? dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs))) : dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
@@ -1178,7 +1189,8 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 // The TMA epilogue needs bf16 output, 16-byte aligned rows, no CoordConv bias map / fused upsample, and at least one
 // 64-column group; it is used for K <= 512 (the HBM-bound layers), the slab epilogue with its deeper operand ring elsewhere.
 bool tma_epilogue_ok(const ppy_conv_params* p) {
-  if (p->accumulate || getenv("PPY_NO_TMA_EPI")) return false;
+  static const bool no_tma_epi = knob_off("PPY_NO_TMA_EPI");
+  if (p->accumulate || no_tma_epi) return false;
   if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
   if (p->coord_w && p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;
   if (p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;     // 3 operand stages at BLOCK_N 256, 4-6 below
@@ -1203,7 +1215,7 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   if (c <= 64) return tma_epi ? launch<64, MODE, EPI_TMA>(p, ho, wo, st) : launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
   if constexpr (mode_is_tma(MODE)) {
     // CTA pairs (cta_group::2, 256 x BN tiles, B split across the pair) for every TMA-fed layer with at least two M tiles
-    static const bool no_pair = getenv("PPY_NO_CTA2") != nullptr;
+    static const bool no_pair = knob_off("PPY_NO_CTA2");
     if (!no_pair && (long long)p->n * ho * wo > BLOCK_M) {
       if (c % 256 == 0) return tma_epi ? launch<256, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
       return tma_epi ? launch<128, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
@@ -1215,7 +1227,7 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 
 // 3x3 stride-1 convs with 64..128 output channels (the stem and the stage-2/3 bottleneck 3x3s): slab stages, CTA pairs
 int dispatch_slab(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
-  static const bool no_pair = getenv("PPY_NO_CTA2") != nullptr;
+  static const bool no_pair = knob_off("PPY_NO_CTA2");
   const bool tma_epi = tma_epilogue_ok(p);
   const bool pair = !no_pair && p->n * ceil_div(ho, patch_h(MODE_TMA_SLAB)) * ceil_div(wo, patch_w(MODE_TMA_SLAB)) > 1;
   if (p->cout <= 64) {
@@ -1264,16 +1276,17 @@ int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
   // 3x3 stride-1: A tiles as 16x8 pixel patches fetched by 4-D TMA, when the patch grid wastes < 15% of the tiles
   const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&
                          (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
-  if (patchable && !p->accumulate && !getenv("PPY_NO_PATCH")) {
+  static const bool no_patch = knob_off("PPY_NO_PATCH"), no_slab = knob_off("PPY_NO_SLAB"), no_im2col = knob_off("PPY_NO_IM2COL");
+  if (patchable && !p->accumulate && !no_patch) {
     auto grid_eff = [&](int pw, int ph) { return (double)ho * wo / ((double)ceil_div(ho, ph) * ph * ceil_div(wo, pw) * pw); };
-    if (p->cout > 32 && p->cout <= 128 && grid_eff(patch_w(MODE_TMA_SLAB), patch_h(MODE_TMA_SLAB)) >= 0.85 && !getenv("PPY_NO_SLAB"))
+    if (p->cout > 32 && p->cout <= 128 && grid_eff(patch_w(MODE_TMA_SLAB), patch_h(MODE_TMA_SLAB)) >= 0.85 && !no_slab)
       return dispatch_slab(p, ho, wo, as_stream(s));
     if (grid_eff(patch_w(MODE_TMA_PATCH), patch_h(MODE_TMA_PATCH)) >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
   }
   // any other k x k conv over whole 64-channel blocks: im2col-mode TMA (stride and zero padding done by the copy engine)
   const bool im2col_ok = p->cin % BLOCK_K == 0 && p->k_pad == p->kh * p->kw * p->cin && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
                          (p->x_ld * 2) % 16 == 0 && p->pad <= 8 && p->kh <= 8 && p->kw <= 8 && p->stride <= 8 &&
-                         p->wgrad_taps <= 1 && get_encode_im2col_fn() != nullptr && !getenv("PPY_NO_IM2COL");
+                         p->wgrad_taps <= 1 && get_encode_im2col_fn() != nullptr && !no_im2col;
   if (im2col_ok) return dispatch<MODE_TMA_IM2COL>(p, ho, wo, as_stream(s));
   return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }
