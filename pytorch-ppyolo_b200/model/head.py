@@ -158,7 +158,8 @@ class YOLOv3Head(torch.nn.Module):
         from ppyolo_b200 import autograd_head
         if self.yolo_loss is None:
             raise RuntimeError('YOLOv3Head was built without yolo_loss; pass the YOLOv3Loss object like train.py:246-252')
-        outputs = autograd_head.head_outputs(self, body_feats)
+        impl = getattr(self, 'train_impl', None) or 'aten'         # 'kernels': convs (fwd, dgrad, wgrad) on the tcgen05 kernel
+        outputs = autograd_head.head_outputs(self, body_feats, impl)
         return self.yolo_loss(outputs, gt_box, gt_label, gt_score, targets, self.anchors, self.anchor_masks,
                               self.mask_anchors, self.num_classes)
 

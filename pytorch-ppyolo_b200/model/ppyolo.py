@@ -16,6 +16,7 @@ class PPYOLO(torch.nn.Module):
         self.head = head
         self.precision = 'bf16'
         self.train_precision = 'fp32'     # arithmetic of the frozen-backbone forward inside a training step
+        self.train_head_impl = None       # 'kernels' | 'aten' | None = kernels with a bf16 backbone, ATen (TF32) with fp32
         self.dcn_impl = None          # None = engine default; 'fused' | 'gather_gemm'
         self.postprocess_impl = None  # None = engine default ('sparse'); 'sparse' | 'dense' (see engine.py)
         self.use_engine = True
@@ -67,6 +68,7 @@ class PPYOLO(torch.nn.Module):
         n, _, h, w = x.shape
         with torch.no_grad():
             feats = self.backbone_train_engine(n, h, w).run_backbone(x)
+        self.head.train_impl = self.train_head_impl or ('kernels' if self.train_precision == 'bf16' else 'aten')
         return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
 
     def backbone_train_engine(self, batch, height, width):

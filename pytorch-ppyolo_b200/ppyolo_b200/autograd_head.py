@@ -1,10 +1,18 @@
 """Differentiable evaluation of the YOLOv3 head for the training step.
 
-The head is the only trainable part under the reference's default ``freeze_at=5``; its backward comes from torch
-autograd over plain tensor ops here (conv/BN/pool kernels of ATen on the GPU), NOT from this repo's CUDA kernels --
-hand-written dgrad/wgrad kernels are the next row of the scope table.  ATen's convolutions run at
-torch's default precision (TF32 tensor-core math on this GPU; forcing strict fp32 makes cuDNN JIT-compile a kernel per
-shape, ~10 s each), so losses agree with the fp32 CPU reference to ~1e-3 rather than 1e-5.  Semantics follow the reference:
+The head is the only trainable part under the reference's default ``freeze_at=5``.  Two implementations of its convolutions
+(``impl``):
+
+* ``'kernels'`` (default with a bf16 backbone): every conv runs forward, input-gradient and weight-gradient on this repo's
+  tcgen05 conv kernel through ``conv_autograd.conv2d_kernels`` (bf16 NHWC activations and gradients, fp32 accumulation,
+  fp32 weight gradients); CoordConv's two channels enter as a separate tiny ATen conv over the constant coordinate image
+  (same weight tensor, so autograd sums both gradient parts).  BatchNorm, activations, pooling, upsampling and the losses
+  are ATen tensor code.
+* ``'aten'`` (fp32 parity mode): plain tensor ops, backward from torch autograd over ATen/cuDNN kernels at torch's default
+  precision (TF32 tensor-core math on this GPU; forcing strict fp32 makes cuDNN JIT-compile a kernel per shape, ~10 s each),
+  so losses agree with the fp32 CPU reference to ~1e-3.
+
+Semantics follow the reference:
 DetectionBlock.__call__ model/head.py:223-231, _get_outputs :381-398, CoordConv / SPP / DropBlock
 model/custom_layers.py:256-342, BatchNorm in whatever mode the module is in (train: batch statistics)."""
 import torch
@@ -29,10 +37,34 @@ def drop_block(x, block_size, keep_prob):
     return x * mask * float(mask.numel()) / mask.sum()
 
 
-def conv_unit(u, x):
+# Activations between the head's layers on the 'kernels' path: bf16 NHWC (zero-copy between layers).  Measured on the seeded
+# random net (11 batch-statistic BN layers, bs 2 x 128^2): gradient cosine against the ATen/TF32 head 0.99 next to the outputs,
+# 0.91 at the deepest layer -- the same structure with exact fp32 convs gives 0.993-0.9998, with torch's own bf16 convs
+# 0.85-0.88, and keeping the BN/activation chain in fp32 (True) does not move it: the noise is that of bf16 GEMM operands.
+ACT_FP32 = False
+
+
+def _coord_image(h, w, device):
+    xs = torch.arange(w, dtype=torch.float32, device=device) / (w - 1) * 2.0 - 1
+    ys = torch.arange(h, dtype=torch.float32, device=device) / (h - 1) * 2.0 - 1
+    return torch.stack([xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w)]).unsqueeze(0)       # [1, 2, h, w]
+
+
+def conv_unit(u, x, impl='aten', coord=False):
+    """One Conv2dUnit.  ``coord`` (kernels only): the unit's weight has two extra CoordConv input channels that ``x`` lacks."""
     if not isinstance(u.conv, torch.nn.Conv2d):
         raise NotImplementedError('DCNv2 inside the trainable head is not part of any PP-YOLO config')
-    y = F.conv2d(x, u.conv.weight, u.conv.bias, stride=u.stride, padding=u.padding)
+    if impl == 'kernels':
+        from .conv_autograd import conv2d_kernels
+        if u.stride != 1:
+            raise NotImplementedError('conv2d_kernels: the head only has stride-1 convs')
+        w = u.conv.weight
+        c_main = w.shape[1] - (2 if coord else 0)
+        y = conv2d_kernels(x, w, u.conv.bias, padding=u.padding, c_main=c_main, out_f32=ACT_FP32 or u.bn is None)
+        if coord:
+            y = y + F.conv2d(_coord_image(x.shape[2], x.shape[3], x.device), w[:, c_main:], None, 1, u.padding).to(y.dtype)
+    else:
+        y = F.conv2d(x, u.conv.weight, u.conv.bias, stride=u.stride, padding=u.padding)
     if u.bn is not None:
         bn = u.bn
         y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
@@ -48,12 +80,17 @@ def conv_unit(u, x):
     return y
 
 
-def _run_layers(layers, x):
+def _run_layers(layers, x, impl='aten'):
+    pending_coord = False
     for ly in layers:
         if isinstance(ly, CoordConv):
-            x = coord_concat(x) if ly.coord_conv else x
+            if impl == 'kernels':
+                pending_coord = bool(ly.coord_conv)          # folded into the next conv instead of concatenated
+            else:
+                x = coord_concat(x) if ly.coord_conv else x
         elif isinstance(ly, Conv2dUnit):
-            x = conv_unit(ly, x)
+            x = conv_unit(ly, x, impl, pending_coord)
+            pending_coord = False
         elif isinstance(ly, SPP):
             x = torch.cat([x] + [F.max_pool2d(x, k, 1, k // 2) for k in (5, 9, 13)], dim=1)
         elif isinstance(ly, DropBlock):
@@ -63,17 +100,19 @@ def _run_layers(layers, x):
     return x
 
 
-def head_outputs(head, body_feats):
+def head_outputs(head, body_feats, impl='aten'):
     n_out = len(head.anchor_masks)
     feats = body_feats[-1:-n_out - 1:-1]
+    if impl == 'kernels':                                     # NHWC (channels_last) activations between the layers
+        feats = [f.to(torch.float32 if ACT_FP32 else torch.bfloat16).contiguous(memory_format=torch.channels_last) for f in feats]
     outputs, route = [], None
     for i, feat in enumerate(feats):
         if i > 0:
             feat = torch.cat([route, feat], dim=1)
         blk = head.detection_blocks[i]
-        route = _run_layers(blk.layers, feat)
-        tip = _run_layers(blk.tip_layers, route)
-        outputs.append(conv_unit(head.yolo_output_convs[i], tip))
+        route = _run_layers(blk.layers, feat, impl)
+        tip = _run_layers(blk.tip_layers, route, impl)
+        outputs.append(conv_unit(head.yolo_output_convs[i], tip, impl).float())
         if i < n_out - 1:
-            route = F.interpolate(conv_unit(head.upsample_layers[2 * i], route), scale_factor=2, mode='nearest')
+            route = F.interpolate(conv_unit(head.upsample_layers[2 * i], route, impl), scale_factor=2, mode='nearest')
     return outputs

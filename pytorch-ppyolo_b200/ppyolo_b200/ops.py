@@ -84,17 +84,18 @@ def from_nhwc(y, c):
 _PACK_CACHE = {}
 
 
-def pack_weight(weight, code, c_begin=0, c_count=None):
+def pack_weight(weight, code, c_begin=0, c_count=None, cache=True):
     """OIHW fp32 -> packed K-major [cout_pad, k_pad].
 
     Cached per live tensor object (weak reference + in-place version counter), so module parameters are
-    packed once while temporaries can never alias a stale entry.
+    packed once while temporaries can never alias a stale entry.  ``cache=False`` for weights updated behind torch's
+    back (the fused SGD kernel writes parameters through raw pointers: the version counter does not move).
     """
     _cuda(weight, 'weight')
     cout, cin_total, kh, kw = weight.shape
     c_count = cin_total - c_begin if c_count is None else c_count
     key = (id(weight), code, c_begin, c_count)
-    hit = _PACK_CACHE.get(key)
+    hit = _PACK_CACHE.get(key) if cache else None
     if hit is not None and hit[0]() is weight and hit[1] == weight._version and hit[2] == weight.data_ptr():
         return hit[3]
     cin_pad = round_up(c_count, 8)
@@ -107,6 +108,8 @@ def pack_weight(weight, code, c_begin=0, c_count=None):
     if len(_PACK_CACHE) > 4096:
         _PACK_CACHE.clear()
     result = (packed, cin_pad, k_pad, cout_pad)
+    if not cache:
+        return result
     _PACK_CACHE[key] = (weakref.ref(weight), weight._version, weight.data_ptr(), result)
     return result
 

@@ -60,7 +60,7 @@ if rank == 0:
                       'ms_per_step': ms, 'steps': a.steps, 'warmup': a.warmup, 'scaling': 'weak',
                       'config': {'workload': 'ppyolo_2x %dx%d bs=%d/GPU train step (freeze_at=5)' % (a.size, a.size, a.batch),
                                  'backbone_precision': a.precision, 'trainable_params': int(sum(p.numel() for p in trainer.params)),
-                                 'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'head_backward': 'torch autograd (ATen)'},
+                                 'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'head_convs': model.train_head_impl or ('kernels (tcgen05 fwd/dgrad/wgrad)' if a.precision == 'bf16' else 'aten (TF32)')},
                       'losses': {k: float(v) for k, v in losses.items()}}), flush=True)
 if world > 1:
     dist.destroy_process_group()
