@@ -153,6 +153,38 @@ def ncu_conv_traffic():
     return total or None
 
 
+def matrix_nms_isolation(dev, with_cpu):
+    """BASELINE configs[4] / metric "MatrixNMS us/img": 10k synthetic boxes x 80 classes per image through the C-ABI batched
+    Matrix-NMS (device-resident inputs, CUDA events), at bs 32 and bs 1; next to it the oracle port of model/matrix_nms.py on
+    one image on the host."""
+    from ppyolo_b200 import ops, synth
+    b, s = synth.nms_inputs(10000, 80, seed=0)
+    res = {'config': '10k boxes x 80 classes per image, score_thr=post_thr=0.01, top_k=500, keep=100 (configs[4])'}
+    for bs in (32, 1):
+        boxes = b[None].repeat(bs, 1, 1).to(dev).contiguous()
+        scores = s[None].repeat(bs, 1, 1).to(dev).contiguous()
+        out = torch.empty((bs, 100, 6), dtype=torch.float32, device=dev)
+        counts = torch.empty((bs,), dtype=torch.int32, device=dev)
+        ws = ops.nms_workspace(bs, 10000, 80, dev)
+        run = lambda: ops.matrix_nms_launch(boxes, scores, out, counts, ws, 0.01, 0.01, 500, 100, False, 2.0)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        res['us_per_img_bs%d' % bs] = e0.elapsed_time(e1) / 20 / bs * 1e3
+    if with_cpu:
+        from oracle import ppyolo_ref as ref
+        t0 = time.perf_counter()
+        ref.matrix_nms(b.numpy(), s.numpy(), 0.01, 0.01, 500, 100)
+        res['cpu_port_us_per_img'] = (time.perf_counter() - t0) * 1e6
+    return res
+
+
 def is_glue(name):
     return (name.startswith(('nchw', 'maxpool', 'avgpool', 'spp', 'decode', 'matrix_nms')) or name.endswith('.gather')
             or name == 'stem.conv1_1')
@@ -304,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
             'clocks': clocks, 'gpu_launches': eng.launches_per_run * args.steps * world,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h},
-            'roofline': roofline, 'cpu_baseline': cpu,
+            'roofline': roofline, 'cpu_baseline': cpu, 'matrix_nms': matrix_nms_isolation(dev, world == 1 and not args.no_cpu_baseline),
             'loaded_library': _lib.LIB_PATH}
     print(json.dumps(line), flush=True)
 
