@@ -65,8 +65,9 @@ class IouLoss(object):
                 sx = scale_x_y * sx - 0.5 * (scale_x_y - 1)
                 sy = scale_x_y * sy - 0.5 * (scale_x_y - 1)
             cx, cy = (sx + gx) / size, (sy + gy) / size
-        aw = torch.tensor([float(a) for a in anchors[0::2]], dtype=torch.float32, device=dev).view(1, n_anchor, 1, 1)
-        ah = torch.tensor([float(a) for a in anchors[1::2]], dtype=torch.float32, device=dev).view(1, n_anchor, 1, 1)
+        from model.losses import device_constant
+        aw = device_constant(anchors[0::2], dev).view(1, n_anchor, 1, 1)
+        ah = device_constant(anchors[1::2], dev).view(1, n_anchor, 1, 1)
         pw = (torch.exp(dw) * aw) / (size * downsample_ratio)
         ph = (torch.exp(dh) * ah) / (size * downsample_ratio)
         box = (cx - 0.5 * pw, cy - 0.5 * ph, cx + 0.5 * pw, cy + 0.5 * ph)

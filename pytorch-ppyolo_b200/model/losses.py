@@ -13,6 +13,20 @@ except ImportError:  # pragma: no cover
     from collections import Sequence
 
 
+_DEVICE_CONSTANTS = {}
+
+
+def device_constant(values, device):
+    """Small host constant (anchor sizes) as a cached device tensor: one upload per (values, device) -- also what keeps the
+    loss capturable in a CUDA graph (no host-to-device copy inside the step)."""
+    key = (tuple(float(v) for v in np.asarray(values, dtype=np.float64).reshape(-1)), str(device))
+    t = _DEVICE_CONSTANTS.get(key)
+    if t is None:
+        t = torch.tensor(key[0], dtype=torch.float32, device=device)
+        _DEVICE_CONSTANTS[key] = t
+    return t
+
+
 def _bce(p, t):
     """t * -log(p) + (1 - t) * -log(1 - p) with the reference's 1e-9 guards."""
     return t * (0 - torch.log(p + 1e-9)) + (1 - t) * (0 - torch.log(1 - p + 1e-9))
@@ -21,7 +35,7 @@ def _bce(p, t):
 def decode_boxes_anchor_major(output, anchors, stride, num_classes, scale_x_y):
     """Boxes of ``paddle_yolo_box`` (:22-81) with im_size = 1 and no clipping: [N, A*S*S, 4] xyxy in (a, h, w) order."""
     n, _, size, _ = output.shape
-    anchors = torch.as_tensor(np.asarray(anchors, dtype=np.float32).reshape(-1, 2), device=output.device)
+    anchors = device_constant(anchors, output.device).view(-1, 2)
     a = anchors.shape[0]
     t = output.reshape(n, a, 5 + num_classes, size, size)
     gx = torch.arange(size, dtype=torch.float32, device=output.device).view(1, 1, 1, size)

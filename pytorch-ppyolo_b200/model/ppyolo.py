@@ -17,6 +17,8 @@ class PPYOLO(torch.nn.Module):
         self.precision = 'bf16'
         self.train_precision = 'fp32'     # arithmetic of the frozen-backbone forward inside a training step
         self.train_head_impl = None       # 'kernels' | 'aten' | None = kernels with a bf16 backbone, ATen (TF32) with fp32
+        self.train_graph = False          # capture head forward + losses + backward as CUDA graphs (static shapes; see forward_train)
+        self._graphed_heads = {}
         self.dcn_impl = None          # None = engine default; 'fused' | 'gather_gemm'
         self.postprocess_impl = None  # None = engine default ('sparse'); 'sparse' | 'dense' (see engine.py)
         self.use_engine = True
@@ -69,16 +71,54 @@ class PPYOLO(torch.nn.Module):
         with torch.no_grad():
             feats = self.backbone_train_engine(n, h, w).run_backbone(x)
         self.head.train_impl = self.train_head_impl or ('kernels' if self.train_precision == 'bf16' else 'aten')
+        if self.train_graph:
+            return self._graphed_head_loss(feats, gt_box, gt_label, gt_score, targets)
         return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
+
+    def _graphed_head_loss(self, feats, gt_box, gt_label, gt_score, targets):
+        """Head forward + the six losses (and, through autograd, their backward) replayed as CUDA graphs: the step is
+        launch-bound (hundreds of small loss / BatchNorm / activation kernels), the graphs remove the launches.  One pair of
+        graphs per input shape (``torch.cuda.make_graphed_callables``); BatchNorm buffers are restored after the capture's
+        warm-up passes so capturing does not advance the running statistics."""
+        head = self.head
+        key = (tuple(tuple(f.shape) for f in feats), tuple(gt_box.shape), tuple(tuple(t.shape) for t in targets), head.train_impl)
+        entry = self._graphed_heads.get(key)
+        if entry is None:
+            n_feats, n_targets = len(feats), len(targets)
+
+            class HeadLoss(torch.nn.Module):
+                def __init__(self, head):
+                    super().__init__()
+                    self.head = head
+
+                def forward(self, *args):
+                    fs, rest = list(args[:n_feats]), args[n_feats:]
+                    gb, gl, gs = rest[0], rest[1], rest[2]
+                    tg = list(rest[3:3 + n_targets])
+                    losses = self.head.get_loss_autograd(fs, gb, gl, gs, tg)
+                    return tuple(losses[k] for k in sorted(losses))
+
+            wrapper = HeadLoss(head)
+            sample = tuple(f.detach().clone() for f in feats) + (gt_box.clone(), gt_label.clone(), gt_score.clone()) + \
+                tuple(t.clone() for t in targets)
+            saved = {k: v.clone() for k, v in head.state_dict().items() if 'running_' in k or 'num_batches_tracked' in k}
+            names = sorted(head.get_loss_autograd([f.detach() for f in feats], gt_box, gt_label, gt_score, targets))
+            graphed = torch.cuda.make_graphed_callables(wrapper, sample, allow_unused_input=True)
+            head.load_state_dict(saved, strict=False)
+            entry = (graphed, names)
+            self._graphed_heads[key] = entry
+        graphed, names = entry
+        out = graphed(*[f.detach() for f in feats], gt_box, gt_label, gt_score, *targets)
+        return dict(zip(names, out))
 
     def backbone_train_engine(self, batch, height, width):
         from ppyolo_b200.engine import InferenceEngine
-        key = (batch, height, width, self.train_precision, bool(self.backbone.training), 'train')
+        key = (batch, height, width, self.train_precision, bool(self.backbone.training), bool(self.train_graph), 'train')
         eng = self._engines.get(key)
         if eng is None:
             eng = InferenceEngine(self, batch, height, width, precision=self.train_precision, dcn_impl=self.dcn_impl,
                                   train_bn=self.backbone.stage1_conv1_1.bn is not None and self.backbone.training,
-                                  backbone_only=True, use_graph=False)
+                                  backbone_only=True, use_graph=self.train_graph)
             self._engines[key] = eng
         return eng
 

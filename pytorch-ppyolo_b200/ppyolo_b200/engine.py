@@ -603,6 +603,16 @@ class InferenceEngine(object):
             fn()
 
     def _capture(self):
+        # (train_bn engines: the warm-up pass below must not advance the BatchNorm running statistics)
+        saved = [(bn, bn.running_mean.clone(), bn.running_var.clone()) for bn in self.bn_modules]
+        try:
+            return self._capture_graph()
+        finally:
+            for bn, mean, var in saved:
+                bn.running_mean.copy_(mean)
+                bn.running_var.copy_(var)
+
+    def _capture_graph(self):
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))

@@ -62,8 +62,12 @@ class GradientBucket(object):
 
 
 class Trainer(object):
-    def __init__(self, model, cfg):
+    def __init__(self, model, cfg, graph=None):
+        """``graph``: replay the frozen-backbone forward and the head forward + losses + backward as CUDA graphs (one set per
+        input shape); None = keep the model's ``train_graph`` setting."""
         self.model, self.cfg = model, cfg
+        if graph is not None:
+            model.train_graph = bool(graph)
         self.base_lr = cfg.learningRate['base_lr']
         self.base_wd = cfg.optimizerBuilder['regularizer']['factor']
         self.momentum = cfg.optimizerBuilder['optimizer']['momentum']

@@ -36,6 +36,7 @@ synth.randomize_(model, seed=0)
 model.train(); backbone.freeze()
 model = model.to(dev)
 model.train_precision = a.precision
+model.train_graph = bool(int(os.environ.get('PPY_TRAIN_GRAPH', '1')))
 trainer = Trainer(model, cfg)
 x = synth.images(a.batch, a.size, seed=20 + rank).to(dev)
 gb, gc, gs = tg.synthetic_ground_truth(a.batch, seed=30 + rank)
