@@ -624,6 +624,17 @@ class InferenceEngine(object):
             self._run_steps()
         return g
 
+    def capture_steps(self, keep):
+        """CUDA graph of the plan steps whose name satisfies ``keep`` (same launch parameters and buffers as the full plan;
+        used by bench.py to time one kernel family under the conditions of the real step: graph replay, programmatic
+        dependent launch).  The buffers hold whatever the last full run left in them."""
+        all_steps = self.steps
+        self.steps = [(n, f) for n, f in all_steps if keep(n)]
+        try:
+            return self._capture()
+        finally:
+            self.steps = all_steps
+
     def add_input_slot(self):
         """A second (third, ...) static input buffer with its own captured graph, so a caller can upload batch i+1 straight
         into the engine while batch i is being computed -- no staging copy.  All other buffers are shared: launches of
