@@ -681,6 +681,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     float* tab = reinterpret_cast<float*>(gen_base + stg_off + EPI_WARPS * Cfg::kEpiWarpBytes) + warp * EPI_TABLE_FLOATS;
     const float slope = p.act == PPY_ACT_RELU ? 0.f : (p.act == PPY_ACT_LEAKY ? 0.1f : 1.f);
     const bool has_res = p.residual != nullptr, has_coord = p.coord_w != nullptr;
+    const bool out_f32 = p.out_dtype == PPY_F32;           // fp32 output: the group leaves as two [32 x 32 fp32] boxes (no residual)
     const unsigned hw_out = (unsigned)(ho * wo);
     const int row = quarter * 32 + lane;                    // tile row of this lane
     const uint32_t row_off = (uint32_t)lane * 128u;
@@ -759,8 +760,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           }
           // output box rotation: with a residual the warp has ONE output box (wait for its previous store to drain); without,
           // the residual boxes serve as output boxes too (RB + 1 in rotation: only the store RB boxes back must have drained)
-          const uint32_t out_box = has_res ? out_s : res_s + (uint32_t)(nbox % (RB + 1)) * BOX_BYTES;
-          if (lane == 0) { if (has_res) bulk_wait_read<0>(); else bulk_wait_read<RB>(); }
+          const uint32_t out_box = (has_res || out_f32) ? (out_f32 ? res_s : out_s) : res_s + (uint32_t)(nbox % (RB + 1)) * BOX_BYTES;
+          if (lane == 0) { if (has_res || out_f32) bulk_wait_read<0>(); else bulk_wait_read<RB>(); }
           if (has_res) mbar_wait(res_full_bar(warp, lc % RB), (lc / RB) & 1);
           tmem_wait_ld();
           __syncwarp();
@@ -788,12 +789,24 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], f[e] * slope);
             }
+            if (out_f32) {                                   // channels 8q..8q+7 = 16-byte chunks 2(q&3), 2(q&3)+1 of box q>>2
+              const uint32_t fb = obase + (uint32_t)(q >> 2) * BOX_BYTES;
+              const uint32_t c0 = (((uint32_t)(q & 3) * 2u) ^ sw) << 4, c1 = (((uint32_t)(q & 3) * 2u + 1u) ^ sw) << 4;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fb + c0), "r"(__float_as_uint(f[0])), "r"(__float_as_uint(f[1])),
+                           "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fb + c1), "r"(__float_as_uint(f[4])), "r"(__float_as_uint(f[5])),
+                           "r"(__float_as_uint(f[6])), "r"(__float_as_uint(f[7])) : "memory");
+            } else
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(obase + chunk), "r"(pack_bf16(f[0], f[1])),
                          "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
           }
           fence_proxy_async();                              // generic-proxy accesses of both boxes -> ordered before the TMA store / reload
           __syncwarp();
-          if (lane == 0) { box_move(false, out_box, 0u, tile, col0); bulk_commit(); }
+          if (lane == 0) {
+            box_move(false, out_box, 0u, tile, col0);
+            if (out_f32 && col0 + GROUP_COLS / 2 < p.cout) box_move(false, out_box + BOX_BYTES, 0u, tile, col0 + GROUP_COLS / 2);
+            bulk_commit();
+          }
           ++nbox;
           if (has_res) { ++lc; request_next(); }            // the residual buffer just read is free: fetch the box two ahead
         }
@@ -1026,12 +1039,12 @@ int num_sms() {
 }
 
 int encode_2d(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
-              uint32_t box_inner, uint32_t box_outer) {
+              uint32_t box_inner, uint32_t box_outer, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   const cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult cr = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
@@ -1073,14 +1086,18 @@ int encode_im2col_4d(CUtensorMap* map, const ppy_conv_params* p) {
 }
 
 int encode_tile_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int ld, int cols, const ppy_conv_params* p, int ho,
-                    int wo, bool patch, int box_w, int box_h) {
-  // output / residual tensors: channels innermost; 2-D [M rows][cols] or 4-D (C, W, H, N) for patch tiles
-  if (!patch) return encode_2d(enc, map, base, (uint64_t)cols, (uint64_t)p->n * ho * wo, (uint64_t)ld * 2, GROUP_COLS, BOX_ROWS);
+                    int wo, bool patch, int box_w, int box_h, bool f32 = false) {
+  // output / residual tensors: channels innermost; 2-D [M rows][cols] or 4-D (C, W, H, N) for patch tiles.  A box row is always
+  // 128 bytes: 64 bf16 channels, or 32 fp32 channels (fp32 outputs leave as two boxes per 64-column group)
+  const uint64_t esz = f32 ? 4 : 2;
+  const uint32_t box_cols = f32 ? GROUP_COLS / 2 : GROUP_COLS;
+  const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if (!patch) return encode_2d(enc, map, base, (uint64_t)cols, (uint64_t)p->n * ho * wo, (uint64_t)ld * esz, box_cols, BOX_ROWS, dt);
   const cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)p->n};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)wo * ld * 2, (cuuint64_t)ho * wo * ld * 2};
-  const cuuint32_t box[4] = {(cuuint32_t)GROUP_COLS, (cuuint32_t)box_w, (cuuint32_t)(BOX_ROWS / box_w), 1};   // one warp's 32 tile rows
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * esz, (cuuint64_t)wo * ld * esz, (cuuint64_t)ho * wo * ld * esz};
+  const cuuint32_t box[4] = {box_cols, (cuuint32_t)box_w, (cuuint32_t)(BOX_ROWS / box_w), 1};   // one warp's 32 tile rows
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult cr = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
@@ -1138,7 +1155,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   tmap_y = tmap_b;
   tmap_r = tmap_b;
   if (EPI == EPI_TMA) {
-    rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH);
+    rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH, p->out_dtype == PPY_F32);
     if (rc) return rc;
     if (p->residual) {
       rc = encode_tile_map(enc, &tmap_r, p->residual, p->res_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH);
@@ -1191,10 +1208,10 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 bool tma_epilogue_ok(const ppy_conv_params* p) {
   static const bool no_tma_epi = knob_off("PPY_NO_TMA_EPI");
   if (p->accumulate || no_tma_epi) return false;
-  if (p->out_dtype != PPY_BF16 || p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
-  if (p->coord_w && p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;
+  if (p->bias_map || p->upsample2x || p->cout < GROUP_COLS) return false;
+  if (p->out_dtype == PPY_F32 && p->residual) return false;              // fp32 outputs (head output convs): two boxes per group, no residual
   if (p->k_pad > ((p->cout % 256 == 0) ? 512 : 1152)) return false;     // 3 operand stages at BLOCK_N 256, 4-6 below
-  if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * 2) % 16) return false;
+  if ((reinterpret_cast<uintptr_t>(p->y) & 15) || (p->y_ld * dtype_size(p->out_dtype)) % 16) return false;
   if (p->residual && ((reinterpret_cast<uintptr_t>(p->residual) & 15) || (p->res_ld * 2) % 16)) return false;
   return true;
 }
