@@ -147,6 +147,11 @@ int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long ro
 /* torch.optim.SGD(momentum, weight_decay) update of one fp32 tensor, gradient pre-scaled by grad_scale (1/world). */
 int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, int first_step, ppy_stream_t s);
+/* K-major operand of the weight-gradient GEMM of a k x k stride-1 conv (training step, conv_autograd.py): NHWC bf16 x
+ * [n,h,w,c] -> out [c*k*k rows][m_pad] bf16 with out[(ch*k*k + ky*k + kx)][m] = x[pixel m shifted by (ky-pad, kx-pad)][ch], zero
+ * outside the image and for m in [n*h*w, m_pad); rows follow the OIHW weight order, k = 1 is the plain transpose (also used
+ * for dY).  m_pad % 64 == 0. */
+int ppy_im2col_kmajor(const void* x, int x_ld, int n, int h, int w, int c, int k, int pad, void* out, long long m_pad, ppy_stream_t s);
 /* ExponentialMovingAverage.update, model/EMA.py:31-45, on the device for all trainable tensors in one launch:
  * shadow[offsets[t] + i] = decay * shadow[..] + one_minus_decay * params[t][i]  (numpy float32 operation order; the reference
  * round-trips every parameter through host memory each step).  params: device array of num_tensors device pointers;

@@ -119,6 +119,46 @@ inline unsigned blocks_for(long long work, int threads, long long cap = 148ll * 
   return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// K-major operand builder of the weight-gradient GEMM (conv_autograd.py): out[(c*taps + tap)][m] = x[pixel m shifted by tap][c]
+// (zero outside the image and for m in [M, m_pad)), i.e. the transposed im2col matrix with rows in the weight's OIHW order, or
+// the plain transpose for k = 1.  One 64-pixel x 64-channel tile per CTA and tap, transposed through shared memory: reads are
+// 128-byte channel runs of NHWC pixels, writes 128-byte pixel runs of one output row.
+__global__ void __launch_bounds__(256) kmajor_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int n, int h, int w, int c, int k, int pad,
+                                                     __nv_bfloat16* __restrict__ out, long long m_pad) {
+  __shared__ __nv_bfloat16 tile[64][64 + 2];
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64, tap = blockIdx.z, ky = tap / k, kx = tap % k;
+  const long long M = (long long)n * h * w;
+  // load: thread -> (pixel row r = tid / 4 (+ 0 / 64 stride over two passes), 16 channels = two 16-byte vectors)
+  for (int e = threadIdx.x; e < 64 * 8; e += 256) {
+    const int r = e >> 3, v = e & 7;
+    const long long m = m0 + r;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (m < M && c0 + v * 8 < c) {
+      const int px = (int)(m % w), py = (int)((m / w) % h);
+      const long long img = m / ((long long)w * h);
+      const int iy = py + ky - pad, ix = px + kx - pad;
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+        val = __ldg(reinterpret_cast<const uint4*>(x + ((img * h + iy) * w + ix) * x_ld + c0 + v * 8));
+    }
+    const __nv_bfloat16* ev = reinterpret_cast<const __nv_bfloat16*>(&val);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[r][v * 8 + j] = ev[j];
+  }
+  __syncthreads();
+  // store: thread -> (channel row cc = e / 8, eight consecutive pixels)
+  const int taps = k * k;
+  for (int e = threadIdx.x; e < 64 * 8; e += 256) {
+    const int cc = e >> 3, v = e & 7;
+    if (c0 + cc >= c || m0 + v * 8 >= m_pad) continue;
+    uint4 val;
+    __nv_bfloat16* ev = reinterpret_cast<__nv_bfloat16*>(&val);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ev[j] = tile[v * 8 + j][cc];
+    *reinterpret_cast<uint4*>(out + ((long long)(c0 + cc) * taps + tap) * m_pad + m0 + v * 8) = val;
+  }
+}
+
 // blockIdx.y = tensor, blockIdx.x strides its elements; offsets[t] .. offsets[t+1] is tensor t's range in the flat shadow
 __global__ void __launch_bounds__(256) ema_update_kernel(float* __restrict__ shadow, const float* const* __restrict__ params,
                                                          const long long* __restrict__ offsets, float decay, float one_minus_decay) {
@@ -183,6 +223,16 @@ int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long 
   PPY_REQUIRE(param && grad && momentum_buf && n > 0);
   sgd_momentum_kernel<<<blocks_for(n, 256), 256, 0, as_stream(s)>>>(param, grad, momentum_buf, n, lr, momentum, weight_decay,
                                                                     grad_scale, first_step);
+  return check_launch();
+}
+
+int ppy_im2col_kmajor(const void* x, int x_ld, int n, int h, int w, int c, int k, int pad, void* out, long long m_pad, ppy_stream_t s) {
+  PPY_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && x_ld >= c && (x_ld * 2) % 16 == 0 && k >= 1 && k <= 7 && pad >= 0);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long M = (long long)n * h * w;
+  PPY_REQUIRE(m_pad >= M && m_pad % 64 == 0 && m_pad / 64 < 0x7FFFFFFFll);
+  dim3 grid((unsigned)(m_pad / 64), (unsigned)ceil_div(c, 64), (unsigned)(k * k));
+  kmajor_kernel<<<grid, 256, 0, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, n, h, w, c, k, pad, (__nv_bfloat16*)out, m_pad);
   return check_launch();
 }
 

@@ -62,6 +62,7 @@ SIGNATURES = {
                                     c_int, c_void_p]),
     'ppy_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     'ppy_ema_update': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
+    'ppy_im2col_kmajor': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     'ppy_iou_aware_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_double, c_void_p]),
     'ppy_yolo_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p]),

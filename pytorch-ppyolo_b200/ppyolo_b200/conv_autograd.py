@@ -14,10 +14,9 @@ bf16 (torch ``channels_last`` views, zero-copy between layers) or fp32 (``out_f3
 rounded, the BatchNorm / activation chain in between keeps full precision); weight gradients are always fp32.  Everything else of the head (BatchNorm, activations, pooling, upsampling, the
 losses) stays ATen tensor code.  No CPU / ATen fallback for the convolution itself: non-CUDA tensors raise."""
 import torch
-import torch.nn.functional as F
 
 from . import ops
-from ._lib import PPY_BF16, PPY_F32
+from ._lib import PPY_BF16, PPY_F32, lib, check
 
 _CONST = {}
 
@@ -83,17 +82,14 @@ class _ConvFn(torch.autograd.Function):
             m = n * h * w
             m_pad = ops.round_up(m, 64)
             kk = c_main * k * k
-            # B operand: Xcol^T [C*k*k][M] (K-major in the pixel index), rows in the weight's (c, ky, kx) order
-            x_nchw = xh[..., :c_main].permute(0, 3, 1, 2)
-            if k == 1:
-                cols_t = xh[..., :c_main].reshape(m, c_main).t()
-            else:
-                cols_t = F.unfold(x_nchw, k, padding=pad).permute(1, 0, 2).reshape(kk, m)
-            b_op = torch.zeros((kk, m_pad), dtype=torch.bfloat16, device=dev)
-            b_op[:, :m] = cols_t
-            # A operand: dY^T [cout][M]
-            a_op = torch.zeros((1, 1, cout, m_pad), dtype=torch.bfloat16, device=dev)
-            a_op[0, 0, :, :m] = dyh[..., :cout].reshape(m, cout).t()
+            # B operand: Xcol^T [C*k*k][M] (K-major in the pixel index), rows in the weight's (c, ky, kx) order; A operand: dY^T
+            # [cout][M] -- both written in one pass each by ppy_im2col_kmajor (zero padding of M included)
+            b_op = torch.empty((kk, m_pad), dtype=torch.bfloat16, device=dev)
+            check(lib.ppy_im2col_kmajor(ops.ptr(xh), xh.shape[-1], n, h, w, c_main, k, pad, ops.ptr(b_op), m_pad, ops.stream_ptr()), 'im2col_kmajor')
+            a_rows = ops.round_up(cout, 8)
+            a_full = torch.empty((a_rows, m_pad), dtype=torch.bfloat16, device=dev)
+            check(lib.ppy_im2col_kmajor(ops.ptr(dyh), dyh.shape[-1], n, h, w, a_rows, 1, 0, ops.ptr(a_full), m_pad, ops.stream_ptr()), 'transpose_kmajor')
+            a_op = a_full[:cout].view(1, 1, cout, m_pad)
             kk_pad = ops.round_up(kk, 8)
             out = torch.zeros((1, 1, cout, kk_pad), dtype=torch.float32, device=dev)
             ops.conv_nhwc(a_op, (b_op, m_pad, m_pad, kk), m_pad, kk, 1, 1, 0, _const('one', kk, dev), _const('zero', kk, dev), 0,
