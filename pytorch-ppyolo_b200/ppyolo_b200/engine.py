@@ -402,7 +402,7 @@ class InferenceEngine(object):
         read again.  The GEMM does 4x the MACs, so only where the shortcut is clearly HBM-bound (large maps)."""
         from model.custom_layers import DCNv2
         return (self.code == PPY_BF16 and not self.train_bn and not isinstance(unit.conv, DCNv2) and unit.conv.weight.shape[-1] == 1 and
-                x.c % 64 == 0 and x.h % 2 == 0 and x.w % 2 == 0 and x.n * (x.h // 2) * (x.w // 2) >= 100000 and
+                x.c % 64 == 0 and x.h % 2 == 0 and x.w % 2 == 0 and (x.h // 2) * (x.w // 2) >= 5000 and      # per image: batch-independent results
                 getattr(self.model, 'fuse_avgpool', True))
 
     def _unit_avgpooled(self, name, unit, x):
