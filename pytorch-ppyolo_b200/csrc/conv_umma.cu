@@ -397,6 +397,16 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const long long M = (long long)p.n * ho * wo;
   const int num_tiles = ACC ? num_m_tiles * num_n_tiles * num_splits * num_taps : num_m_tiles * num_n_tiles;
 
+  if (warp == TMA_WARP && lane == 0) {
+    // the copy engine fetches a tensor map (128 B in the kernel parameter space) on first use: start those fetches now, under
+    // the prologue and the tail of the previous kernel, instead of in front of the first operand load
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    if (mode_is_tma(MODE)) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    if (EPI == EPI_TMA) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_y)) : "memory");
+      if (p.residual) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_r)) : "memory");
+    }
+  }
   if (tid == 0) {
     const uint32_t full_count = mode_is_tma(MODE) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
