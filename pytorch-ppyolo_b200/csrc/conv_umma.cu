@@ -20,10 +20,10 @@
 //              its lane 0 fetches the residual box by TMA two boxes ahead, lane = tile row does the math straight from the TMEM
 //              registers (CoordConv rank-2 term, scale/shift from a per-warp smem table, residual, activation) into a swizzled
 //              output box that leaves by TMA store -- no global-memory instruction, no CTA-wide barrier.
-//   warps 8-11 A producers, only for MODE gather (cin % 64 != 0 leftovers: eight 16-byte cp.async per thread and K block,
+//   warps 8-11 A producers, present only in MODE gather (cin % 64 != 0 leftovers: eight 16-byte cp.async per thread and K block,
 //              zero-fill outside the image, straight into the swizzled stage) and MODE dcn (thread = tile row, bilinear
 //              sample x mask in fp32 -> bf16 st.shared); idle in the TMA modes.
-//   warp 12    TMA producer (warp-uniform loop, elect.sync lane issues): weight tile(s) per stage, plus the A operand:
+//   next warp  TMA producer (warp-uniform loop, elect.sync lane issues): weight tile(s) per stage, plus the A operand:
 //              tma_a      1x1 stride-1: plain [128 x 64] box of the NHWC matrix
 //              tma_patch  3x3 stride-1: 4-D box {64 ch, 16, 8, 1} per (tap, channel block) at pixel offset (kx-1, ky-1), zero halo
 //                         from TMA's out-of-bounds fill, the 128 tile rows are a 16x8 pixel patch
@@ -31,9 +31,8 @@
 //                         taps; tap ky reads the same slab at +ky*1024 bytes (see MODE_TMA_SLAB below)
 //              tma_im2col any other k x k / stride: im2col-mode tensor map, 128 consecutive output pixels per box, filter
 //                         offset in the instruction, padding zero-filled by the copy engine
-//   warp 13    TMEM allocator + MMA issuer (warp-uniform loop): 4 x tcgen05.mma (K=16) per 64-wide K block (12 per slab
+//   last warp  TMEM allocator + MMA issuer (warp-uniform loop): 4 x tcgen05.mma (K=16) per 64-wide K block (12 per slab
 //              stage), tcgen05.commit to the stage's empty barrier, one commit per tile to tmem_full
-//   warp 14    spare
 //
 // Shared-memory operand layout is the canonical K-major SWIZZLE_128B one: row r of a stage lives at
 // r*128 bytes, its 16-byte chunk j at ((j ^ (r & 7)) << 4); 8-row groups are 1024 bytes apart (SBO).
@@ -51,8 +50,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating sub-tiles
-constexpr int NUM_THREADS = 480;                  // 8 epilogue + 4 producer + TMA + MMA + residual-TMA warps
-constexpr int PRODUCER_WARP0 = EPI_WARPS, TMA_WARP = EPI_WARPS + 4, MMA_WARP = EPI_WARPS + 5, RES_WARP = EPI_WARPS + 6;
+constexpr int PRODUCER_WARP0 = EPI_WARPS;
 constexpr int EPI_SLAB = 0, EPI_TMA = 1;          // epilogue variants (see the kernel header)
 constexpr int GROUP_COLS = 64;                    // EPI_TMA: residual / output move as [32 rows x 64 ch] bf16 boxes (4 KB), one warp each
 constexpr int BOX_ROWS = 32;
@@ -67,6 +65,13 @@ __host__ __device__ constexpr bool mode_is_tma(int mode) {
 // (two halo rows) plus the three weight tiles of taps (ky = 0..2, kx); an 8-pixel slab row is exactly one 1024-byte swizzle
 // atom, so the A operand of tap ky is the SAME slab read at byte offset ky * 1024 -- each input pixel enters shared memory
 // 3.4 times per tile instead of 9, and there is one barrier round trip per THREE taps.
+// Warp roles.  TMA-fed modes: 8 epilogue warps + TMA producer + MMA issuer = 10 warps (registers are allocated per group of four
+// warps, so 9..12 warps may use 168 registers per thread where 13..16 are capped at 128: the epilogues want them).  gather / dcn
+// modes insert four A-producer warps after the epilogue warps (14 warps).
+__host__ __device__ constexpr int producer_warps(int mode) { return mode_is_tma(mode) ? 0 : 4; }
+__host__ __device__ constexpr int tma_warp(int mode) { return EPI_WARPS + producer_warps(mode); }
+__host__ __device__ constexpr int mma_warp(int mode) { return tma_warp(mode) + 1; }
+__host__ __device__ constexpr int num_threads(int mode) { return 32 * (mma_warp(mode) + 1); }
 __host__ __device__ constexpr bool mode_is_patchy(int mode) { return mode == MODE_TMA_PATCH || mode == MODE_TMA_SLAB; }
 __host__ __device__ constexpr int patch_w(int mode) { return mode == MODE_TMA_SLAB ? 8 : 16; }
 __host__ __device__ constexpr int patch_h(int mode) { return mode == MODE_TMA_SLAB ? 16 : 8; }
@@ -358,7 +363,7 @@ __device__ __noinline__ void epilogue_acc(const ppy_conv_params& p, const float*
 // kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int MODE, int EPI, bool ACC, bool CTA2>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(MODE), 1)
 conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
                  const int num_n_tiles, const int num_splits, const int num_taps, const int pw_tiles, const int ph_tiles,
                  const __grid_constant__ CUtensorMap tmap_b,
@@ -371,6 +376,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   using Cfg = TileCfg<BN, MODE, EPI, CTA2>;
   constexpr int S = Cfg::kStages;
   constexpr int A_STAGE = Cfg::kAStageBytes;
+  constexpr int TMA_WARP = tma_warp(MODE), MMA_WARP = mma_warp(MODE);
   constexpr int PW = patch_w(MODE), PH = patch_h(MODE);    // pixel patch of a tile (MODE_TMA_PATCH / MODE_TMA_SLAB)
   constexpr int CP_LAG = Cfg::kCpLag;
   const int cta_rank = CTA2 ? (int)(blockIdx.x & 1) : 0;
@@ -433,7 +439,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp >= PRODUCER_WARP0 && warp < PRODUCER_WARP0 + 4) {
+  if (!mode_is_tma(MODE) && warp >= PRODUCER_WARP0 && warp < PRODUCER_WARP0 + 4) {
     // =====================================================================================
     // A producers
     // =====================================================================================
@@ -668,8 +674,6 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         __syncwarp();
       }
     }
-  } else if (warp == RES_WARP) {
-    // (spare warp: the TMA epilogue's warps fetch their own residual boxes)
   } else if (EPI == EPI_TMA) {
     // =====================================================================================
     // EPI_TMA epilogue, warps 0-7: no global-memory instruction and no CTA-wide barrier.  Every warp works alone on
@@ -905,6 +909,20 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         if (cc >= NSUB) break;
         uint4 rn[4];
         load_res(cc + 2, rn);
+        // CoordConv bias map rows of this sub-tile: all four passes' loads are issued here, under the TMEM wait and the slab
+        // write, instead of one exposed L2 round trip per pass (the map never fits the L1 left beside the operand stages)
+        float4 bmv[4][2];
+        if (p.bias_map) {
+          const int co_b = n0 + cc * SUB + colv;
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            bmv[ps][0] = bmv[ps][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (aligned && mrow[ps] >= 0 && co_b + 8 <= p.cout) {
+              const float4* bm = reinterpret_cast<const float4*>(p.bias_map + (size_t)((unsigned)mrow[ps] % hw_out) * p.cout + co_b);
+              bmv[ps][0] = __ldg(bm); bmv[ps][1] = __ldg(bm + 1);
+            }
+          }
+        }
         // phase 1: accumulator registers (lane = row) -> swizzled warp-private slab
         tmem_wait_ld();
         {
@@ -938,8 +956,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               float4 a = *reinterpret_cast<const float4*>(sp + ((cpair ^ (row & 7)) << 2));
               float4 b = *reinterpret_cast<const float4*>(sp + (((cpair + 1) ^ (row & 7)) << 2));
               if (p.bias_map) {
-                const float4* bm = reinterpret_cast<const float4*>(p.bias_map + (size_t)((unsigned)m % hw_out) * p.cout + co);
-                const float4 b0 = __ldg(bm), b1 = __ldg(bm + 1);
+                const float4 b0 = bmv[ps][0], b1 = bmv[ps][1];
                 a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w; b.x += b1.x; b.y += b1.y; b.z += b1.z; b.w += b1.w;
               }
               a.x = a.x * s0.x + h0.x; a.y = a.y * s0.y + h0.y; a.z = a.z * s0.z + h0.z; a.w = a.w * s0.w + h0.w;
@@ -1190,7 +1207,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = CTA2 ? dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs))) : dim3((unsigned)(tiles < num_sms() ? tiles : num_sms()));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(num_threads(MODE));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
