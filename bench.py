@@ -12,8 +12,12 @@ on synthetic N(0,1) images and seeded random weights, batch 32 per GPU (weak sca
 
 One step = one forward of one batch.  `value` is device-timed (CUDA events, max over ranks) with the input
 batch already in HBM; `e2e` is the same metric through the public PPYOLO/engine API with the inputs in pinned
-HOST memory: every step uploads its 141.9 MB fp32 batch and downloads the [32,100,6] detections + counts
-(double-buffered copy stream, so upload overlaps the previous step's compute).
+HOST memory: every step uploads its 141.9 MB fp32 batch straight into one of the engine's two input slots (copy
+stream; the upload of batch i+1 overlaps the compute of batch i) and downloads the [32,100,6] detections + counts.
+
+`roofline`: the conv kernel family (84 launches of one step) timed live as its own CUDA graph; `traffic` = DRAM bytes of
+those launches from the committed ncu launch list.  `matrix_nms`: BASELINE configs[4] (10k boxes x 80 classes) in
+isolation, us per image.  `cpu_baseline`: the oracle port of the reference forward on the host cores (bounded sample).
 
 `--impl reference` times the reference's CPU path (oracle port of model/ppyolo.py:19-22 on the host cores;
 the Python reference itself cannot travel to the GPU box) on a bounded sample of the same workload.
