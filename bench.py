@@ -63,33 +63,45 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs (NVML is initialised in
+    the constructor so the first sample falls inside the region; 5 ms period)."""
+    NAMES = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40,
+             'hw_power_brake': 0x80}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._halt = threading.Event()
-
-    def run(self):
+        self._nvml, self._handle = None, None
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
-                     'hw_thermal_slowdown': 0x40, 'hw_power_brake': 0x80}
-            while not self._halt.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                try:
-                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.02)
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
         except Exception as exc:  # NVML missing: report that, do not fail the bench
             self.reasons.add('nvml_unavailable:%s' % type(exc).__name__)
+
+    def _sample(self):
+        nv, h = self._nvml, self._handle
+        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for k, bit in self.NAMES.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def run(self):
+        if self._handle is None:
+            return
+        try:
+            while not self._halt.is_set():
+                self._sample()
+                time.sleep(0.005)
+        except Exception as exc:
+            self.reasons.add('nvml_error:%s' % type(exc).__name__)
 
     def stop(self):
         self._halt.set()
