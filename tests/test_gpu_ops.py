@@ -450,3 +450,37 @@ def test_umma_conv_split_k(n, cin, cout, k, stride, hw, splits):
                 accumulate=True, split_k=splits)
     got = o.from_nhwc(out, cout).cpu()
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-4 * scale_of(want.numpy()))
+
+
+def _random_conv_cases(count, seed):
+    rng = np.random.RandomState(seed)
+    cases = []
+    while len(cases) < count:
+        k = int(rng.choice([1, 3]))
+        stride = int(rng.choice([1, 1, 2])) if k == 3 else 1
+        cin = int(rng.choice([8, 24, 32, 64, 128, 192, 256, 320]))
+        cout = int(rng.choice([16, 27, 32, 64, 72, 96, 128, 136, 256, 258, 320, 512]))
+        hw = int(rng.randint(3, 41))
+        n = int(rng.randint(1, 5))
+        if n * hw * hw * max(cin, cout) > 3_000_000:
+            continue
+        cases.append((n, cin, cout, k, stride, hw, bool(rng.randint(2)), bool(rng.randint(2))))
+    return cases
+
+
+@pytest.mark.parametrize('case', _random_conv_cases(48, seed=20261017), ids=lambda c: 'n%d_c%d_o%d_k%d_s%d_hw%d_r%d_b%d' % c)
+def test_umma_conv_random_sweep(case):
+    """Seeded random sweep over the conv kernel's dispatch space (tma_a / slab / patch / im2col / gather modes, CTA pairs and
+    single CTAs, TMA and slab epilogues, M / N tails, odd map sizes): bf16 conv + scale/shift (+ residual + ReLU | leaky) against
+    torch on the same bf16-rounded operands."""
+    n, cin, cout, k, stride, hw, with_res, out_bf16 = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = bf16_round(torch.randn((n, cin, hw, hw), generator=g))
+    w = bf16_round(torch.randn((cout, cin, k, k), generator=g) * (1.0 / (cin * k * k) ** 0.5))
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    base = torch.nn.functional.conv2d(x, w, None, stride, (k - 1) // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = bf16_round(torch.randn(base.shape, generator=g)) if (with_res and out_bf16) else None
+    want = torch.relu(base + res) if res is not None else torch.nn.functional.leaky_relu(base, 0.1)
+    got = _umma_conv(x, w, scale, shift, stride, 1 if res is not None else 2, residual=res, out_f32=not out_bf16)
+    tol = 8e-3 if out_bf16 else 2e-4
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=tol if out_bf16 else 0, atol=tol * scale_of(want.numpy()))
