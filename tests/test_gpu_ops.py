@@ -135,6 +135,26 @@ def test_decode_golden(golden, tag, stride, mask, iou_aware):
         np.testing.assert_allclose(scores.cpu().numpy(), z[tag + '_scores'], rtol=1e-5, atol=1e-9)
 
 
+@pytest.mark.parametrize('n,size,an,nc,stride,sxy,iou_aware', [
+    (1, 1, 3, 80, 32, 1.05, True), (3, 7, 3, 80, 32, 1.05, True), (2, 19, 3, 80, 32, 1.05, False), (5, 13, 3, 20, 16, 1.0, True),
+    (2, 40, 2, 20, 8, 1.05, True), (1, 76, 3, 80, 8, 1.05, True), (4, 10, 4, 1, 32, 1.2, False), (2, 26, 1, 90, 16, 1.05, True)])
+def test_decode_sweep_vs_oracle(n, size, an, nc, stride, sxy, iou_aware):
+    """Fused (iou-aware +) yolo_box against the oracle over grid sizes, batch sizes, anchor counts and class counts the
+    goldens do not hold (the generic kernel instantiation included), with per-image im_size and both clip settings."""
+    g = torch.Generator().manual_seed(size * 1000 + nc * 10 + an)
+    ch = an * (nc + (6 if iou_aware else 5))
+    x = torch.randn((n, ch, size, size), generator=g) * 2.0
+    anchors = (torch.rand((an, 2), generator=g) * 300 + 8).numpy().astype(np.float32)
+    im_size = torch.stack([torch.randint(200, 900, (n,), generator=g), torch.randint(200, 900, (n,), generator=g)], 1).float()
+    y = ref.iou_aware_score(x, an, nc, 0.4) if iou_aware else x
+    for clip in (True, False):
+        wb, ws = ref.yolo_box(y, anchors, stride, nc, sxy, im_size, clip)
+        gb, gs = ops().yolo_box(x.to(DEV), anchors, stride, nc, sxy, im_size.to(DEV), clip, iou_aware=iou_aware,
+                                iou_aware_factor=0.4)
+        np.testing.assert_allclose(gb.cpu().numpy(), wb.numpy(), rtol=1e-5, atol=2e-4)
+        np.testing.assert_allclose(gs.cpu().numpy(), ws.numpy(), rtol=2e-5, atol=1e-9)
+
+
 @pytest.mark.parametrize('obj_bias,gauss', [(-4.0, False), (0.5, False), (-2.0, True)])
 def test_sparse_decode_nms_equals_dense(obj_bias, gauss):
     """ppy_yolo_decode_candidates + ppy_matrix_nms_candidates == ppy_yolo_decode + ppy_matrix_nms_batched, bit for bit,
@@ -346,6 +366,32 @@ def test_umma_dcn(stride, hw):
                     torch.zeros(cout, device=DEV), 0, PPY_BF16, out_code=PPY_F32, offset_mask=om)
     got = o.from_nhwc(y, cout).cpu()
     # A operand (modulated bilinear sample) is rounded to bf16 before the MMA: ~2^-9 relative per element
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=4e-3 * scale_of(want.numpy()))
+
+
+@pytest.mark.parametrize('n,c,cout,stride,h,w,off_scale', [
+    (1, 64, 64, 1, 13, 21, 0.03), (2, 192, 96, 1, 10, 17, 0.1), (1, 256, 256, 2, 20, 20, 0.3), (3, 64, 40, 2, 10, 14, 0.3),
+    (1, 512, 512, 1, 19, 19, 0.05), (2, 128, 128, 1, 38, 38, 1.0)])
+def test_umma_dcn_sweep(n, c, cout, stride, h, w, off_scale):
+    """Fused DCNv2 over non-square maps, channel counts off the tile size and offset magnitudes from sub-pixel to far outside
+    the image (offset sigma = 10 * off_scale px: at 1.0 most corners fall outside a 38x38 map and must contribute zero).
+    Stride 2 only on even maps: the reference's output-size rule (custom_layers.py:567-568) equals the offset conv's own
+    output size only there, and every input that is a multiple of 32 gives the stride-2 DCN block an even map."""
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16
+    o = ops()
+    g = torch.Generator().manual_seed(c * 7 + h * 3 + w + stride)
+    x = bf16_round(torch.randn((n, c, h, w), generator=g))
+    ow = bf16_round(torch.randn((27, c, 3, 3), generator=g) * off_scale / (c * 9) ** 0.5 * 10)
+    ob = torch.randn(27, generator=g)
+    wt = bf16_round(torch.randn((cout, c, 3, 3), generator=g) / (c * 9) ** 0.5)
+    want = ref.dcnv2(x, ow, ob, wt, stride, 1)
+    xh = o.to_nhwc(x.to(DEV), PPY_BF16)
+    om = o.conv_nhwc(xh, o.pack_weight(ow.to(DEV), PPY_BF16), c, 27, 3, stride, 1, torch.ones(27, device=DEV),
+                     ob.to(DEV), 0, PPY_BF16, out_code=PPY_F32)
+    y = o.conv_nhwc(xh, o.pack_weight(wt.to(DEV), PPY_BF16), c, cout, 3, stride, 1, torch.ones(cout, device=DEV),
+                    torch.zeros(cout, device=DEV), 0, PPY_BF16, out_code=PPY_F32, offset_mask=om)
+    got = o.from_nhwc(y, cout).cpu()
+    assert scale_of(want.numpy()) > 0.05
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=4e-3 * scale_of(want.numpy()))
 
 
