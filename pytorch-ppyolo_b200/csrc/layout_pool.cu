@@ -505,6 +505,90 @@ __global__ void __launch_bounds__(256) dcn_gather_kernel(const T* __restrict__ x
     }
   }
 }
+
+// k == 3 specialisation with the channel count fixed at compile time (C = ITERS * 32 lanes * 16-byte vectors): one warp per
+// (output pixel, TPW taps).  The generic kernel above is bound by two chained L2 round trips per 1 KB of output (offset
+// fetch, then one 4-corner load group per loop trip); here the warp's 3*TPW offset/mask values arrive in ONE coalesced
+// load and are broadcast by shuffle, and all 4*ITERS corner loads of a tap are issued before the first blend, so the
+// taps of a warp overlap each other's latency.  Out-of-image corners are loaded from a clamped in-image address with
+// weight 0 (fma(0, t, acc) == acc), so results are bit-identical to the generic kernel.
+template <typename T, int ITERS, int TPW>
+__global__ void __launch_bounds__(256) dcn_gather3_kernel(const T* __restrict__ x, int x_ld, int n, int h, int w,
+                                                          const float* __restrict__ om, int om_ld, int stride, int pad,
+                                                          int ho, int wo, T* __restrict__ out) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int C = ITERS * 32 * V;
+  constexpr int GROUPS = 9 / TPW;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)n * ho * wo * GROUPS;
+  for (long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < total; wi += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int grp = (int)(wi % GROUPS);
+    const long long m = wi / GROUPS;
+    const int ox = (int)(m % wo), oy = (int)((m / wo) % ho), img = (int)(m / ((long long)wo * ho));
+    const float* o = om + m * om_ld;
+    float val = 0.f;
+    if (lane < 3 * TPW) {                        // lane = kind * TPW + j; kind 0: dy, 1: dx, 2: mask logit
+      const int kind = lane / TPW, tap = grp * TPW + lane % TPW;
+      val = __ldg(o + (kind == 2 ? 18 + tap : 2 * tap + kind));
+    }
+    const T* xi = x + (long long)img * h * w * x_ld;
+    T* dst = out + (m * 9 + grp * TPW) * C;
+#pragma unroll
+    for (int j = 0; j < TPW; ++j) {
+      const int tap = grp * TPW + j;
+      const float dy = __shfl_sync(0xffffffffu, val, j), dx = __shfl_sync(0xffffffffu, val, TPW + j);
+      const float ml = __shfl_sync(0xffffffffu, val, 2 * TPW + j);
+      const float mask = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-ml)));
+      const float py = (float)(oy * stride - pad + tap / 3) + dy, px = (float)(ox * stride - pad + tap % 3) + dx;
+      const float fy = floorf(py), fx = floorf(px);
+      const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+      const int y0 = (int)fminf(fmaxf(fy, -2.f), (float)h), x0 = (int)fminf(fmaxf(fx, -2.f), (float)w);
+      float wq[4] = {hy * hx * mask, hy * lx * mask, ly * hx * mask, ly * lx * mask};
+      const T* src[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int yy = y0 + (q >> 1), xx = x0 + (q & 1);
+        const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < w;
+        if (!ok) wq[q] = 0.f;
+        src[q] = xi + ((long long)min(max(yy, 0), h - 1) * w + min(max(xx, 0), w - 1)) * x_ld + lane * V;
+      }
+      uint4 raw[ITERS][4];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) raw[it][q] = __ldg(reinterpret_cast<const uint4*>(src[q] + it * 32 * V));
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        float acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const T* t = reinterpret_cast<const T*>(&raw[it][q]);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] += wq[q] * to_f<T>(t[e]);
+        }
+        store_vec<T>(dst + j * C + (it * 32 + lane) * V, acc);
+      }
+    }
+  }
+}
+
+template <typename T, int TPW>
+bool launch_gather3(const T* x, int x_ld, int n, int h, int w, int c, const float* om, int om_ld, int stride, int pad, int ho,
+                    int wo, T* out, cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
+  const long long warps = (long long)n * ho * wo * (9 / TPW);
+  long long blocks = ceil_div(warps, 8);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+#define PPY_G3(IT) dcn_gather3_kernel<T, IT, TPW><<<(unsigned)blocks, 256, 0, st>>>(x, x_ld, n, h, w, om, om_ld, stride, pad, ho, wo, out)
+  if (c == 32 * V) PPY_G3(1);
+  else if (c == 64 * V) PPY_G3(2);
+  else if (c == 128 * V) PPY_G3(4);
+  else return false;
+#undef PPY_G3
+  return true;
+}
 }  // namespace
 }  // namespace ppy
 
@@ -515,6 +599,12 @@ extern "C" int ppy_dcn_gather(const void* x, int x_ld, int n, int h, int w, int 
   PPY_REQUIRE(vec_ok(x, x_ld, c, dtype) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && om_ld >= 3 * k * k);
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   PPY_REQUIRE(ho > 0 && wo > 0);
+  if (k == 3) {   // compile-time-C specialisation, 3 taps per warp (75.8 -> 49.2 us at bs 32 x 19x19 x 512, bit-identical)
+    bool done = false;
+    PPY_DISPATCH(dtype, done = launch_gather3<T, 3>((const T*)x, x_ld, n, h, w, c, offset_mask, om_ld, stride, pad, ho, wo, (T*)out,
+                                                   as_stream(s));)
+    if (done) return check_launch();
+  }
   const long long warps = (long long)n * ho * wo * k * k;
   long long blocks = ceil_div(warps, 8);
   if (blocks > 148 * 64) blocks = 148 * 64;

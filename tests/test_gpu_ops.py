@@ -395,6 +395,34 @@ def test_umma_dcn_sweep(n, c, cout, stride, h, w, off_scale):
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=4e-3 * scale_of(want.numpy()))
 
 
+@pytest.mark.parametrize('n,c,stride,h,w,code', [(2, 256, 1, 11, 14, 'bf16'), (1, 512, 1, 19, 19, 'bf16'), (2, 1024, 2, 10, 8, 'bf16'),
+                                                 (1, 192, 1, 9, 9, 'bf16'), (1, 128, 1, 7, 9, 'fp32'), (2, 64, 2, 8, 6, 'fp32')])
+def test_dcn_gather_stage(n, c, stride, h, w, code):
+    """ppy_dcn_gather (the sampling stage of the two-kernel DCNv2 the engine runs): its [M x 9C] matrix times the dcn weight
+    in (tap, c) order must equal the oracle's DCNv2 given the same offset/mask conv output.  Covers the compile-time-C
+    specialisation (C = 256/512/1024 bf16, 128 fp32) and the generic kernel (C = 192, 64)."""
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16, lib, check
+    o = ops()
+    dt = PPY_BF16 if code == 'bf16' else PPY_F32
+    g = torch.Generator().manual_seed(c + h * 31 + w)
+    x = bf16_round(torch.randn((n, c, h, w), generator=g))
+    ow = bf16_round(torch.randn((27, c, 3, 3), generator=g) * 2.0 / (c * 9) ** 0.5)
+    ob = torch.randn(27, generator=g)
+    wt = torch.randn((8, c, 3, 3), generator=g) / (c * 9) ** 0.5
+    want = ref.dcnv2(x, ow, ob, wt, stride, 1)
+    ho, wo = want.shape[2:]
+    om = torch.nn.functional.conv2d(x, ow, ob, stride=stride, padding=1).permute(0, 2, 3, 1).contiguous()      # NHWC [.., 27]
+    om_pad = torch.zeros((n, ho, wo, 32)); om_pad[..., :27] = om
+    xh = o.to_nhwc(x.to(DEV), dt)
+    out = torch.empty((n * ho * wo, 9 * c), dtype=torch.bfloat16 if code == 'bf16' else torch.float32, device=DEV)
+    omd = om_pad.to(DEV)
+    check(lib.ppy_dcn_gather(o.ptr(xh), xh.shape[-1], n, h, w, c, o.ptr(omd), 32, 3, stride, 1, o.ptr(out), dt, o.stream_ptr()), 'gather')
+    torch.cuda.synchronize()
+    wk = wt.permute(0, 2, 3, 1).reshape(8, 9 * c)                       # (tap, c) K order of the gathered matrix
+    got = (out.float().cpu() @ wk.t()).reshape(n, ho, wo, 8).permute(0, 3, 1, 2)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=(4e-3 if code == 'bf16' else 1e-5) * scale_of(want.numpy()))
+
+
 @pytest.mark.parametrize('n,cin,cout,k,hw', [(2, 64, 256, 1, 19), (1, 128, 512, 1, 30), (3, 64, 96, 1, 11), (2, 64, 64, 3, 32),
                                              (1, 256, 128, 1, 24), (2, 64, 128, 3, 46), (3, 64, 128, 3, 19), (2, 128, 64, 3, 13)])
 def test_umma_conv_tma_epilogue(n, cin, cout, k, hw):
