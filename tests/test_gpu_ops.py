@@ -460,25 +460,27 @@ def test_umma_conv_coord_fold(n, cin, cout, hw):
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
 
 
-@pytest.mark.parametrize('n,hw,act', [(2, 64, 1), (1, 37, 2), (3, 52, 1), (2, 36, 2)])
-def test_stem_conv_bf16_tensor_core(n, hw, act):
+@pytest.mark.parametrize('n,h,w,act', [(2, 64, 64, 1), (1, 37, 37, 2), (3, 52, 52, 1), (2, 36, 36, 2), (2, 38, 136, 1), (1, 70, 260, 2),
+                                       (33, 32, 32, 1)])
+def test_stem_conv_bf16_tensor_core(n, h, w, act):
     """ppy_stem_conv3x3s2, bf16 output: NCHW fp32 image -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100) + folded BN + act
-    on mma.sync tensor cores, against conv2d on the same bf16-rounded image and weights (odd sizes cover the borders)."""
+    on tcgen05 tensor cores (w % 4 == 0; other widths take the fp32 SIMT kernel), against conv2d on the same bf16-rounded image and
+    weights (odd sizes cover the borders, odd output heights the half-dead tiles, wide maps several tiles per row)."""
     import ctypes
     from ppyolo_b200._lib import lib, check, PPY_BF16
     o = ops()
-    g = torch.Generator().manual_seed(100 + hw)
-    x = torch.randn((n, 3, hw, hw), generator=g)
-    w = torch.randn((32, 3, 3, 3), generator=g) * 0.2
+    g = torch.Generator().manual_seed(100 + h + w)
+    x = torch.randn((n, 3, h, w), generator=g)
+    wt = torch.randn((32, 3, 3, 3), generator=g) * 0.2
     scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
-    want = torch.nn.functional.conv2d(bf16_round(x), bf16_round(w), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    want = torch.nn.functional.conv2d(bf16_round(x), bf16_round(wt), None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     want = torch.relu(want) if act == 1 else torch.nn.functional.leaky_relu(want, 0.1)
-    ho = (hw - 1) // 2 + 1
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     xd = x.to(DEV).contiguous()
-    y = torch.zeros((n, ho, ho, 32), dtype=torch.bfloat16, device=DEV)
+    y = torch.zeros((n, ho, wo, 32), dtype=torch.bfloat16, device=DEV)
     fp = ctypes.POINTER(ctypes.c_float)
-    wn, sn, hn = (np.ascontiguousarray(t.numpy()) for t in (w, scale, shift))
-    check(lib.ppy_stem_conv3x3s2(o.ptr(xd), n, hw, hw, wn.ctypes.data_as(fp), sn.ctypes.data_as(fp), hn.ctypes.data_as(fp), 32, act,
+    wn, sn, hn = (np.ascontiguousarray(t.numpy()) for t in (wt, scale, shift))
+    check(lib.ppy_stem_conv3x3s2(o.ptr(xd), n, h, w, wn.ctypes.data_as(fp), sn.ctypes.data_as(fp), hn.ctypes.data_as(fp), 32, act,
                                  ctypes.c_void_p(y.data_ptr()), 32, PPY_BF16, o.stream_ptr()), 'stem')
     got = o.from_nhwc(y, 32).cpu()
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=8e-3, atol=8e-3 * scale_of(want.numpy()))
