@@ -116,7 +116,9 @@ typedef struct ppy_conv_params {
 
 /* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)
  * + folded BN + act -> NHWC.  weight (OIHW [32,3,3,3]), scale, shift are HOST pointers (they travel in the kernel
- * parameter / constant bank). */
+ * parameter / constant bank).  y_dtype PPY_BF16 with y_ld == 32, w % 4 == 0 and a 16-byte aligned x runs on tcgen05
+ * (image and weights rounded to bf16, fp32 accumulate -- the precision of every other bf16 conv); PPY_F32 output and the
+ * remaining shapes run the fp32 SIMT kernel. */
 int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, const float* weight_oihw_host, const float* scale_host,
                        const float* shift_host, int cout, int act, void* y, int y_ld, int y_dtype, ppy_stream_t s);
 
