@@ -33,7 +33,10 @@ enum ppy_status {
   PPY_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed; see ppy_last_cuda_error() */
   PPY_ERR_UNSUPPORTED = -4  /* configuration not built (e.g. tcgen05 path on a non-sm_100 device) */
 };
-enum ppy_dtype { PPY_F32 = 0, PPY_BF16 = 1 };
+/* PPY_F16X2: an fp32-grade value carried as TWO fp16 numbers (hi = fp16(v), lo = fp16(v - hi), v ~ hi + lo to 2^-22) in
+ * two planes of the same geometry: element i of the hi plane at base + i, of the lo plane at base + plane + i (plane = an
+ * element offset passed next to the pointer).  The operand format of the fp32-grade tensor-core path (ppy_conv_f16x2). */
+enum ppy_dtype { PPY_F32 = 0, PPY_BF16 = 1, PPY_F16X2 = 2 };
 enum ppy_act { PPY_ACT_NONE = 0, PPY_ACT_RELU = 1, PPY_ACT_LEAKY = 2, PPY_ACT_MISH = 3 };
 
 int ppy_abi_version(void);
@@ -112,6 +115,13 @@ typedef struct ppy_conv_params {
    * epilogue adds to the accumulator (before scale/shift) from coord_w = [wx[cout] | wy[cout]] fp32, instead of reading a
    * per-pixel bias_map.  NULL = off; mutually exclusive with bias_map; requires kh == kw == 1. */
   const float* coord_w;
+  /* --- PPY_F16X2 path only (ppy_conv_f16x2): element offsets from the hi plane to the lo plane of x / y / residual (the packed
+   * weight's lo plane follows its hi plane at cout_pad*k_pad); overflow: optional device int, set to 1 when an output value
+   * leaves the range an fp16 pair can carry (|v| > 65504) -- the caller must then discard the results. */
+  long long x_plane;
+  long long y_plane;
+  long long res_plane;
+  int* overflow;
 } ppy_conv_params;
 
 /* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)
@@ -121,6 +131,24 @@ typedef struct ppy_conv_params {
  * remaining shapes run the fp32 SIMT kernel. */
 int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, const float* weight_oihw_host, const float* scale_host,
                        const float* shift_host, int cout, int act, void* y, int y_ld, int y_dtype, ppy_stream_t s);
+
+/* The same layer with a PPY_F16X2 output (fp32 SIMT math; results split into the hi plane at y and the lo plane at
+ * y + y_plane): first kernel of the fp32-grade tensor-core engine. */
+int ppy_stem_conv3x3s2_f16x2(const float* x_nchw, int n, int h, int w, const float* weight_oihw_host, const float* scale_host,
+                             const float* shift_host, int cout, int act, void* y, int y_ld, long long y_plane, ppy_stream_t s);
+
+/* Glue of the fp32-grade tensor-core path on PPY_F16X2 tensors (hi plane at the pointer, lo plane `plane` elements further):
+ * MaxPool2d(3,2,1) model/resnet_vd.py:103, AvgPool2d(2,2) :30, SPP model/custom_layers.py:275-290 (y[..., 0:c]=x,
+ * [c:2c]=maxpool5, [2c:3c]=maxpool9, [3c:4c]=maxpool13).  Max-type results equal the fp32 kernels' on the joined tensors. */
+int ppy_maxpool3x3s2_f16x2(const void* x, int x_ld, long long x_plane, void* y, int y_ld, long long y_plane, int n, int h, int w,
+                           int c, ppy_stream_t s);
+int ppy_avgpool2x2_f16x2(const void* x, int x_ld, long long x_plane, void* y, int y_ld, long long y_plane, int n, int h, int w, int c,
+                         ppy_stream_t s);
+int ppy_spp_f16x2(const void* x, int x_ld, long long x_plane, void* y, int y_ld, long long y_plane, int n, int h, int w, int c,
+                  ppy_stream_t s);
+/* fp32 rows [rows][x_ld] -> pair planes, and back (module-level interop, tests). */
+int ppy_split_f16x2(const float* x, int x_ld, void* y, int y_ld, long long y_plane, long long rows, int c, ppy_stream_t s);
+int ppy_join_f16x2(const void* x, int x_ld, long long x_plane, float* y, int y_ld, long long rows, int c, ppy_stream_t s);
 
 /* Stage 1 of the two-kernel DCNv2 (model/custom_layers.py:551-674): bilinear sample x sigmoid(mask) for every
  * (output pixel, tap) -> out[m][tap*c + ch], the K-major A matrix a 1x1 ppy_conv_* over [n,ho,wo,k*k*c] consumes with
@@ -134,6 +162,12 @@ int ppy_conv_f32(const ppy_conv_params* p, ppy_stream_t s);
 int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s);
 /* 1 when the tcgen05 path can run on the current device (compute capability 10.x). */
 int ppy_conv_bf16_supported(void);
+/* fp32-grade tcgen05 implicit GEMM: x, weight (ppy_pack_conv_weight with PPY_F16X2), residual and y (out_dtype PPY_F16X2;
+ * PPY_F32 also allowed for y) are fp16 hi/lo pairs; every K block issues hi*hi + hi*lo + lo*hi into the fp32 TMEM
+ * accumulator (kind::f16, fp16 operands): products carry 22 bits, the dropped lo*lo term is 2^-22 relative -- the accuracy of an
+ * fp32 FMA chain at a third of the bf16 tensor rate.  Same operator contract as ppy_conv_bf16 (Conv2dUnit.forward,
+ * model/custom_layers.py:243-253; DCNv2.forward :551-677); no partial-sum (accumulate) launches. */
+int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s);
 
 /* ------------------------------------------------------------------------------------------------
  * training side (train.py:427-442; frozen-backbone BNs run on BATCH statistics, custom_layers.py:122)

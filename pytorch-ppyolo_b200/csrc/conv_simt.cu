@@ -6,6 +6,7 @@
 //
 //   GEMM view: M = n*ho*wo output pixels, N = cout, K = kh*kw*cin with K index (ky*kw + kx)*cin + c.
 //   Tile 64x64x16, 256 threads, 4x4 register block per thread, shared-memory staged.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace ppy {
@@ -24,6 +25,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     if (co < cout && tap < kh * kw && c < c_count)
       v = __ldg(w + (((long long)co * cin_total + c_begin + c) * kh + tap / kw) * kw + tap % kw);
     out[i] = from_f<T>(v);
+  }
+}
+
+// PPY_F16X2 packing: [2][cout_pad][k_pad] fp16 -- hi plane, then lo plane (w ~ hi + lo to 2^-22).  The caller pre-scales every
+// output channel by a power of two so that the lo parts stay clear of the fp16 subnormal range.
+__global__ void pack_weight_pair_kernel(const float* __restrict__ w, int cout, int cin_total, int kh, int kw, int c_begin,
+                                        int c_count, __half* __restrict__ out, int cout_pad, int cin_pad, int k_pad) {
+  const long long total = (long long)cout_pad * k_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / k_pad), k = (int)(i % k_pad);
+    const int tap = k / cin_pad, c = k % cin_pad;
+    float v = 0.f;
+    if (co < cout && tap < kh * kw && c < c_count)
+      v = __ldg(w + (((long long)co * cin_total + c_begin + c) * kh + tap / kw) * kw + tap % kw);
+    const __half hi = __float2half_rn(v);
+    out[i] = hi;
+    out[total + i] = __float2half_rn(v - __half2float(hi));
   }
 }
 
@@ -153,7 +171,7 @@ int validate_conv(const ppy_conv_params* p, int elem_bytes, int* ho, int* wo) {
   PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (p->x_ld * elem_bytes) % 16 == 0);
   PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->weight) & 15) == 0);
   PPY_REQUIRE(p->act >= PPY_ACT_NONE && p->act <= PPY_ACT_MISH);
-  PPY_REQUIRE(p->out_dtype == PPY_F32 || p->out_dtype == PPY_BF16);
+  PPY_REQUIRE(p->out_dtype == PPY_F32 || p->out_dtype == PPY_BF16 || p->out_dtype == PPY_F16X2);
   if (p->residual) PPY_REQUIRE(p->res_ld >= p->cout && !p->upsample2x);
   // the reference's DCN output size (H + 2p - (k-1)) // stride equals this for every shape it supports
   *ho = (p->h + 2 * p->pad - (p->kh - 1) - 1) / p->stride + 1;
@@ -183,6 +201,9 @@ int ppy_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int kh, i
   else if (dtype == PPY_F32)
     pack_weight_kernel<float><<<(unsigned)blocks, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, kh, kw, c_begin,
                                                                            c_count, (float*)packed, cout_pad, cin_pad, k_pad);
+  else if (dtype == PPY_F16X2)
+    pack_weight_pair_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, kh, kw, c_begin, c_count,
+                                                                         (__half*)packed, cout_pad, cin_pad, k_pad);
   else return PPY_ERR_INVALID;
   return check_launch();
 }
@@ -192,6 +213,7 @@ int ppy_conv_f32(const ppy_conv_params* p, ppy_stream_t s) {
   int rc = validate_conv(p, 4, &ho, &wo);
   if (rc) return rc;
   if (p->accumulate || p->split_k > 1 || p->wgrad_taps > 1) return PPY_ERR_UNSUPPORTED;   // tcgen05 path only
+  PPY_REQUIRE(p->out_dtype == PPY_F32);
   const long long M = (long long)p->n * ho * wo;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p->cout, BN));
   const int k_true = p->kh * p->kw * p->cin;

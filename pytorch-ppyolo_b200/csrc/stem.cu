@@ -11,8 +11,10 @@
 // tcgen05.mma (128x32x16) against the [32 x 32] weight tile into a 32-column TMEM accumulator, and the same thread
 // reads its pixel's 32 channels back (tcgen05.ld 32x32b.x32) for scale/shift/activation and four 16-byte stores.
 // Several CTAs per SM (20 KB of shared memory, 32 TMEM columns each) overlap each other's load / MMA / store phases.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace ppy {
@@ -29,7 +31,7 @@ struct StemParams {
 template <typename T>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, int n, int h, int w, int ho, int wo,
                                                         const __grid_constant__ StemParams prm, float slope, T* __restrict__ y,
-                                                        int y_ld) {
+                                                        int y_ld, long long y_plane = 0 /* > 0: T = __half, fp16 hi/lo pair output */) {
   const long long total = (long long)n * ho * wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(i % wo), oy = (int)((i / wo) % ho), img = (int)(i / ((long long)wo * ho));
@@ -53,6 +55,26 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
       }
     }
     T* dst = y + i * y_ld;
+    if (y_plane > 0) {                             // PPY_F16X2: split every fp32 result into the hi and the lo plane
+#pragma unroll
+      for (int co = 0; co < STEM_COUT; co += 8) {
+        uint4 hi, lo;
+        __half2* hp = reinterpret_cast<__half2*>(&hi);
+        __half2* lp = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+          float f0 = acc[co + k] * prm.scale[co + k] + prm.shift[co + k], f1 = acc[co + k + 1] * prm.scale[co + k + 1] + prm.shift[co + k + 1];
+          f0 = f0 > 0.f ? f0 : f0 * slope;
+          f1 = f1 > 0.f ? f1 : f1 * slope;
+          hp[k >> 1] = __floats2half2_rn(f0, f1);
+          const float2 hf = __half22float2(hp[k >> 1]);
+          lp[k >> 1] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+        }
+        *reinterpret_cast<uint4*>(dst + co) = hi;
+        *reinterpret_cast<uint4*>(dst + y_plane + co) = lo;
+      }
+      continue;
+    }
 #pragma unroll
     for (int co = 0; co < STEM_COUT; co += 16 / sizeof(T)) {
       uint4 raw;
@@ -61,7 +83,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
       for (int k = 0; k < (int)(16 / sizeof(T)); ++k) {
         float f = acc[co + k] * prm.scale[co + k] + prm.shift[co + k];
         f = f > 0.f ? f : f * slope;
-        e[k] = from_f<T>(f);
+        if constexpr (!std::is_same<T, __half>::value) e[k] = from_f<T>(f);
       }
       *reinterpret_cast<uint4*>(dst + co) = raw;
     }
@@ -329,5 +351,29 @@ extern "C" int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, cons
   else if (y_dtype == PPY_F32)
     stem_conv_kernel<float><<<(unsigned)blocks, 128, 0, as_stream(s)>>>(x_nchw, n, h, w, ho, wo, prm, slope, (float*)y, y_ld);
   else return PPY_ERR_INVALID;
+  return check_launch();
+}
+
+// Same layer with a PPY_F16X2 output (fp32 SIMT math, results split into fp16 hi/lo planes): first kernel of the fp32-grade
+// tensor-core engine.
+extern "C" int ppy_stem_conv3x3s2_f16x2(const float* x_nchw, int n, int h, int w, const float* weight_oihw_host,
+                                        const float* scale_host, const float* shift_host, int cout, int act, void* y, int y_ld,
+                                        long long y_plane, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(x_nchw && weight_oihw_host && scale_host && shift_host && y);
+  PPY_REQUIRE(n > 0 && h > 1 && w > 1 && cout == STEM_COUT && y_ld >= cout && y_plane > 0 && y_plane % 8 == 0);
+  PPY_REQUIRE(act == PPY_ACT_NONE || act == PPY_ACT_RELU || act == PPY_ACT_LEAKY);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (y_ld * 2) % 16 == 0);
+  const float slope = act == PPY_ACT_RELU ? 0.f : (act == PPY_ACT_LEAKY ? 0.1f : 1.f);
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  StemParams prm;
+  for (int co = 0; co < STEM_COUT; ++co) {
+    for (int t = 0; t < STEM_TAPS; ++t) prm.w[t][co] = weight_oihw_host[co * STEM_TAPS + t];
+    prm.scale[co] = scale_host[co];
+    prm.shift[co] = shift_host[co];
+  }
+  long long blocks = ceil_div((long long)n * ho * wo, 128);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  stem_conv_kernel<__half><<<(unsigned)blocks, 128, 0, as_stream(s)>>>(x_nchw, n, h, w, ho, wo, prm, slope, (__half*)y, y_ld, y_plane);
   return check_launch();
 }

@@ -3,8 +3,14 @@
 In eval mode on a CUDA device the whole network runs through ``ppyolo_b200.engine.InferenceEngine``:
 a static plan of fused sm_100a kernels over pre-allocated NHWC buffers (built lazily per input shape,
 replayed as a CUDA graph).  ``precision`` selects the arithmetic of the conv kernels:
-``'bf16'`` (tcgen05 tensor cores, fp32 accumulate; the throughput path) or ``'fp32'`` (SIMT fp32,
-the 1e-4 parity path).
+``'f16x2'`` (default: tcgen05 tensor cores on fp16 hi/lo pairs, three MMAs per K block, fp32 accumulate -- the accuracy of
+the reference's fp32 arithmetic), ``'bf16'`` (tcgen05, bf16 operands; fastest, ~1e-2 of scale drift) or ``'fp32'`` (SIMT
+fp32; the slow exact path).
+
+Compiled plans snapshot packed conv weights and folded BN parameters.  They are dropped by ``load_state_dict``, by the
+EMA's ``apply``/``restore``, by ``Trainer.step`` and -- when any parameter or buffer changed (version counters / storage
+pointers) -- by ``model.eval()`` / ``model.train()``; after any OTHER in-place weight update call
+``model.invalidate_engines()`` before the next ``model(x, im_size)``.
 """
 import torch
 
@@ -14,13 +20,15 @@ class PPYOLO(torch.nn.Module):
         super().__init__()
         self.backbone = backbone
         self.head = head
-        self.precision = 'bf16'
+        self.precision = 'f16x2'
         self.train_precision = 'fp32'     # arithmetic of the frozen-backbone forward inside a training step
         self.train_head_impl = None       # 'kernels' | 'aten' | None = kernels with a bf16 backbone, ATen (TF32) with fp32
         self.train_graph = False          # capture head forward + losses + backward as CUDA graphs (static shapes; see forward_train)
         self._graphed_heads = {}
         self.dcn_impl = None          # None = engine default; 'fused' | 'gather_gemm'
-        self.postprocess_impl = None  # None = engine default ('sparse'); 'sparse' | 'dense' (see engine.py)
+        self.postprocess_impl = None  # None = engine default ('dense'); 'sparse' | 'dense' (see engine.py)
+        self.f16x2_act_scale = 8.0    # power of two the 'f16x2' engine stores its activations multiplied by (see engine.py)
+        self._weights_seen = None
         self.use_engine = True
         self._engines = {}
 
@@ -31,16 +39,36 @@ class PPYOLO(torch.nn.Module):
         if eng is None:
             eng = InferenceEngine(self, batch, height, width, precision=self.precision, dcn_impl=self.dcn_impl)
             self._engines[key] = eng
+            self._weights_seen = self._weights_fingerprint()
         return eng
 
     def invalidate_engines(self):
-        """Drop compiled plans (call after mutating weights, e.g. load_state_dict)."""
+        """Drop compiled plans and packed-weight caches (call after mutating weights in place)."""
+        from ppyolo_b200 import ops
         self._engines = {}
+        ops._PACK_CACHE.clear()
+
+    def _weights_fingerprint(self):
+        acc = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            acc = (acc * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        return acc
+
+    def train(self, mode=True):
+        """Mode switches are where the reference's loops go from optimising to evaluating (train.py:484-489): drop the
+        compiled plans if any parameter or buffer changed since they were built."""
+        fp = self._weights_fingerprint()
+        if self._weights_seen is not None and fp != self._weights_seen and self._engines:
+            self.invalidate_engines()
+        self._weights_seen = fp
+        return super().train(mode)
 
     def invalidate_engines_for_weights(self):
         """After an optimizer step only the (eval) inference plans hold stale folded head weights; the frozen-backbone
         training engine reads BN statistics and conv weights that did not change."""
+        from ppyolo_b200 import ops
         self._engines = {k: v for k, v in self._engines.items() if k[-1] == 'train'}
+        ops._PACK_CACHE.clear()
 
     def load_state_dict(self, *args, **kwargs):
         self.invalidate_engines()

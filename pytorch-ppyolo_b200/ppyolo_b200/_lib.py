@@ -11,7 +11,8 @@ from . import build as _build
 c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
 
-PPY_F32, PPY_BF16 = 0, 1
+PPY_F32, PPY_BF16, PPY_F16X2 = 0, 1, 2
+ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
 
 
@@ -30,6 +31,7 @@ class ConvParams(ctypes.Structure):
         ('offset_mask', c_void_p), ('om_ld', c_int),
         ('accumulate', c_int), ('split_k', c_int), ('wgrad_taps', c_int), ('wgrad_pitch', c_int), ('wgrad_tap_stride', c_int),
         ('coord_w', c_void_p),
+        ('x_plane', c_ll), ('y_plane', c_ll), ('res_plane', c_ll), ('overflow', c_void_p),
     ]
 
 
@@ -56,6 +58,14 @@ SIGNATURES = {
     'ppy_conv_f32': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_conv_bf16': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_conv_bf16_supported': (c_int, []),
+    'ppy_conv_f16x2': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
+    'ppy_stem_conv3x3s2_f16x2': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float),
+                                         ctypes.POINTER(c_float), c_int, c_int, c_void_p, c_int, c_ll, c_void_p]),
+    'ppy_maxpool3x3s2_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_avgpool2x2_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_spp_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_split_f16x2': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_ll, c_int, c_void_p]),
+    'ppy_join_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_void_p]),
     'ppy_bn_batch_stats': (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ppy_scale_shift_act': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
@@ -87,13 +97,19 @@ SIGNATURES = {
 
 def _load():
     path = _build.LIB_PATH
-    if not os.path.exists(path):
+    # rebuild when a source is newer than the library (a stale .so would read past an older struct layout); a box without nvcc
+    # (sources untouched since the build) never gets here
+    if _build.needs_build() and (not os.path.exists(path) or _build.have_nvcc()):
         try:
             _build.build()
         except Exception as exc:  # no nvcc / compile error: fail loudly, never fall back
             raise ImportError('libppyolo_b200.so is missing and could not be built (%s). Run '
                               '`python -c "import __graft_entry__ as g; g.build()"` at the repo root.' % exc)
     lib = ctypes.CDLL(path)
+    lib.ppy_abi_version.restype = c_int
+    if lib.ppy_abi_version() != ABI_VERSION:
+        raise ImportError('%s has ABI version %d, this package needs %d: rebuild it (python -c "import __graft_entry__ as g; '
+                          'g.build()")' % (path, lib.ppy_abi_version(), ABI_VERSION))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.restype = res

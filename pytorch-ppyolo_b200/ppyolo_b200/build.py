@@ -17,12 +17,34 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
 
 
+def have_nvcc():
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    return os.path.exists(nvcc)
+
+
+def source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + sorted(glob.glob(os.path.join(ROOT, 'include', '*.h')))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, 'rb') as f:
+            h.update(f.read())
+    h.update(' '.join(NVCC_FLAGS[:8]).encode())
+    return h.hexdigest()
+
+
+HASH_PATH = LIB_PATH + '.srchash'
+
+
 def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(ROOT, 'include', '*.h'))
-    return any(os.path.getmtime(d) > t for d in deps)
+    if not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -47,6 +69,8 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
     link = [nvcc, '--shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH] + objs
     subprocess.check_call(link)
+    with open(HASH_PATH, 'w') as f:
+        f.write(source_hash())
     return LIB_PATH
 
 

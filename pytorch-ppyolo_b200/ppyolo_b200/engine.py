@@ -22,21 +22,34 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16
+from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16, PPY_F16X2
 
 
 class TensorRef(object):
-    """A channel slice [c_off, c_off+c) of an NHWC buffer [N,H,W,ld]."""
+    """A channel slice [c_off, c_off+c) of an NHWC buffer [N,H,W,ld] -- or of a PPY_F16X2 buffer [2,N,H,W,ld] (fp16 hi plane,
+    lo plane; ``plane`` = element offset between them)."""
 
     def __init__(self, t, c=None, c_off=0):
         self.t, self.c_off = t, c_off
         self.c = t.shape[-1] - c_off if c is None else c
 
-    n = property(lambda self: self.t.shape[0])
-    h = property(lambda self: self.t.shape[1])
-    w = property(lambda self: self.t.shape[2])
-    ld = property(lambda self: self.t.shape[3])
-    code = property(lambda self: PPY_BF16 if self.t.dtype == torch.bfloat16 else PPY_F32)
+    pair = property(lambda self: self.t.dim() == 5)
+    n = property(lambda self: self.t.shape[-4])
+    h = property(lambda self: self.t.shape[-3])
+    w = property(lambda self: self.t.shape[-2])
+    ld = property(lambda self: self.t.shape[-1])
+    plane = property(lambda self: self.t.stride(0) if self.t.dim() == 5 else 0)
+    esz = property(lambda self: self.t.element_size() * (2 if self.t.dim() == 5 else 1))      # bytes per value
+    code = property(lambda self: PPY_F16X2 if self.t.dim() == 5 else (PPY_BF16 if self.t.dtype == torch.bfloat16 else PPY_F32))
+
+    def pixel_pairs(self):
+        """[.., H, W, C] seen as [.., H, W/2, 2C] (free reinterpretation)."""
+        shp = tuple(self.t.shape[:-2]) + (self.t.shape[-2] // 2, 2 * self.t.shape[-1])
+        return TensorRef(self.t.view(shp))
+
+    def pixel_unpairs(self, c):
+        shp = tuple(self.t.shape[:-2]) + (self.t.shape[-2] * (self.t.shape[-1] // c), c)
+        return TensorRef(self.t.view(shp))
 
     @property
     def ptr(self):
@@ -51,9 +64,9 @@ class InferenceEngine(object):
                  backbone_only=False):
         if not torch.cuda.is_available():
             raise RuntimeError('InferenceEngine needs a CUDA device (no CPU fallback)')
-        if precision not in ('bf16', 'fp32'):
+        if precision not in ops.PRECISIONS:
             raise ValueError(precision)
-        if precision == 'bf16' and not lib.ppy_conv_bf16_supported():
+        if precision in ('bf16', 'f16x2') and not lib.ppy_conv_bf16_supported():
             raise RuntimeError('the tcgen05 conv path needs an sm_100 device')
         if height % 32 or width % 32 or height != width:
             raise ValueError('input must be square with a side that is a multiple of 32 (reference yolo_box '
@@ -67,6 +80,13 @@ class InferenceEngine(object):
         # DCNv2 on the bf16 path: 'gather_gemm' = sampling kernel -> L2-resident A matrix -> TMA-fed 1x1 tcgen05 GEMM
         # (fastest today); 'fused' = the single im2col-free kernel with the bilinear producer
         self.dcn_impl = dcn_impl or getattr(model, 'dcn_impl', None) or ('gather_gemm' if precision == 'bf16' else 'fused')
+        if precision == 'f16x2':
+            self.dcn_impl = 'fused'            # (the sampling kernel has no pair variant)
+            if train_bn:
+                raise NotImplementedError('batch-statistic BatchNorm engines run in bf16 or fp32')
+        # 'f16x2': every activation is stored as act_scale * value (a power of two, exact): lifts typical O(1) activations away
+        # from the fp16 subnormal range of their lo parts; values beyond 65504 / act_scale raise the overflow flag
+        self.act_scale = float(getattr(model, 'f16x2_act_scale', 8.0)) if precision == 'f16x2' else 1.0
         # train_bn: BatchNorm layers normalise with BATCH statistics and update their running stats, as the reference's
         # frozen backbone does during training; backbone_only: stop at the C3/C4/C5 feature maps
         self.train_bn, self.backbone_only = train_bn, backbone_only
@@ -98,7 +118,10 @@ class InferenceEngine(object):
 
     # ------------------------------------------------------------------ buffers
     def _new(self, n, h, w, c, dtype=None):
-        t = torch.zeros((n, h, w, c), dtype=dtype or self.act_dtype, device=self.dev)
+        if dtype is None and self.code == PPY_F16X2:       # activation of the pair path: hi plane | lo plane
+            t = torch.zeros((2, n, h, w, c), dtype=torch.float16, device=self.dev)
+        else:
+            t = torch.zeros((n, h, w, c), dtype=dtype or self.act_dtype, device=self.dev)
         self.keep.append(t)
         return t
 
@@ -112,7 +135,11 @@ class InferenceEngine(object):
 
     def _simple(self, name, cfn, x, out, *extra):
         """pool-like op: cfn(x_ptr, x_ld, y_ptr, y_ld, n, h, w, c, dtype, stream)"""
-        args = (ctypes.c_void_p(x.ptr), x.ld, ctypes.c_void_p(out.ptr), out.ld, x.n, x.h, x.w, x.c, x.code)
+        if x.pair:
+            cfn = getattr(lib, cfn.__name__ + '_f16x2')
+            args = (ctypes.c_void_p(x.ptr), x.ld, x.plane, ctypes.c_void_p(out.ptr), out.ld, out.plane, x.n, x.h, x.w, x.c)
+        else:
+            args = (ctypes.c_void_p(x.ptr), x.ld, ctypes.c_void_p(out.ptr), out.ld, x.n, x.h, x.w, x.c, x.code)
 
         def run():
             check(cfn(*args, ops.stream_ptr()), name)
@@ -127,7 +154,9 @@ class InferenceEngine(object):
         out = TensorRef(self._new(x.n, x.h // 2, x.w // 2, x.c))
         return self._simple('avgpool2x2', lib.ppy_avgpool2x2, x, out)
 
-    def _spp(self, x):
+    def _spp(self, x, seq='asc'):
+        if seq != 'asc':
+            raise NotImplementedError("SPP(seq='desc') is not on any config's path (model/custom_layers.py:286-289)")
         out = TensorRef(self._new(x.n, x.h, x.w, 4 * x.c))
         return self._simple('spp', lib.ppy_spp, x, out)
 
@@ -137,15 +166,19 @@ class InferenceEngine(object):
         w_host = np.ascontiguousarray(unit.conv.weight.detach().float().cpu().numpy())
         sc_host = np.ascontiguousarray(scale.cpu().numpy())
         sh_host = np.ascontiguousarray(shift.cpu().numpy())
+        if self.act_scale != 1.0:            # pair path: activations are stored scaled (the activation commutes with it)
+            sc_host, sh_host = sc_host * np.float32(self.act_scale), sh_host * np.float32(self.act_scale)
         self.keep += [w_host, sc_host, sh_host]
         ho, wo = (self.h - 1) // 2 + 1, (self.w - 1) // 2 + 1
         out = TensorRef(self._new(self.n, ho, wo, 32))
         fp = ctypes.POINTER(ctypes.c_float)
         args = (self.n, self.h, self.w, w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp),
-                sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name], ctypes.c_void_p(out.ptr), out.ld, self.code)
+                sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name], ctypes.c_void_p(out.ptr), out.ld)
+        stem_fn = lib.ppy_stem_conv3x3s2_f16x2 if out.pair else lib.ppy_stem_conv3x3s2
+        args += (out.plane,) if out.pair else (self.code,)
 
         def run():            # reads the CURRENT input slot (one captured graph per slot, see add_input_slot)
-            check(lib.ppy_stem_conv3x3s2(ops.ptr(self._src), *args, ops.stream_ptr()), 'stem.conv1_1')
+            check(stem_fn(ops.ptr(self._src), *args, ops.stream_ptr()), 'stem.conv1_1')
         self._add('stem.conv1_1', run)
         self.conv_flops += 2 * self.n * ho * wo * 32 * 27
         return out
@@ -173,19 +206,38 @@ class InferenceEngine(object):
         if c_main != x.c and not (c_main < x.c and x.c == ops.round_up(c_main, 8)):
             raise ValueError('%s: weight expects %d input channels, buffer has %d' % (name, c_main, x.c))
         pad = (k - 1) // 2
-        packed, cin_pad, k_pad, cout_pad = ops.pack_weight(weight, self.code, c_begin=0, c_count=c_main)
+        pair = self.code == PPY_F16X2
+        chan_scale = None
+        if pair:
+            packed, cin_pad, k_pad, cout_pad, chan_scale = ops.pack_weight_pair(weight, 0, c_main)
+        else:
+            packed, cin_pad, k_pad, cout_pad = ops.pack_weight(weight, self.code, c_begin=0, c_count=c_main)
         self._keep(packed)
         ho = (x.h + 2 * pad - k) // stride + 1
         wo = (x.w + 2 * pad - k) // stride + 1
         out_code = self.code if out_code is None else out_code
         if dst is None:
             oh, ow = (2 * ho, 2 * wo) if upsample else (ho, wo)
-            dst = TensorRef(self._new(x.n, oh, ow, ops.round_up(cout, 8), ops.torch_dtype(out_code)), c=cout)
+            dst = TensorRef(self._new(x.n, oh, ow, ops.round_up(cout, 8), None if out_code == self.code else ops.torch_dtype(out_code)),
+                            c=cout)
         # CoordConv fold: a 1x1 conv sees the two coordinate channels as the rank-2 term wx*xc + wy*yc (two per-channel vectors
         # for the TMA epilogue); a 3x3 conv needs the per-pixel map (zero padding breaks the rank-2 structure at the borders)
         coord_vec = (coord and k == 1 and stride == 1 and self.code == PPY_BF16 and out_code == PPY_BF16 and not upsample and
                      cout >= 64 and cout % 8 == 0 and k_pad <= (512 if cout % 256 == 0 else 1152) and x.h > 1 and x.w > 1)
         bias_map = self._coord_bias_map(weight, c_main, x.h, x.w) if (coord and not coord_vec) else None
+        if pair:
+            # the accumulator holds act_scale * chan_scale * (true pre-norm value): x is stored scaled by act_scale, every weight
+            # row by chan_scale (both powers of two, so all of this is exact).  Pair outputs are stored scaled by act_scale again
+            # (relu / leaky commute with a positive factor); fp32 outputs (head outputs, DCN offsets) are true values.
+            a = self.act_scale
+            to_acc = chan_scale * a
+            if bias_map is not None:
+                bias_map = self._keep((bias_map * to_acc).contiguous())
+            if out_code == PPY_F16X2:
+                scale, shift = scale / chan_scale, shift * a
+            else:
+                scale = scale / to_acc
+            scale, shift = scale.contiguous(), shift.contiguous()
         coord_w = None
         if coord_vec:
             coord_w = self._keep(weight.detach().float()[:, c_main:c_main + 2, 0, 0].t().contiguous())    # [2][cout]: wx | wy
@@ -205,11 +257,15 @@ class InferenceEngine(object):
         p.upsample2x = 1 if upsample else 0
         p.offset_mask = offset_mask.ptr if offset_mask is not None else None
         p.om_ld = offset_mask.ld if offset_mask is not None else 0
+        if pair:
+            p.x_plane, p.y_plane = x.plane, dst.plane
+            p.res_plane = residual.plane if residual is not None else 0
+            p.overflow = self.overflow.data_ptr()
         # split_k: few output tiles and a long K (the DCN offset conv): K splits added atomically into the zeroed fp32 output
         split_k = split_k and self.code == PPY_BF16 and out_code == PPY_F32 and act == 0 and residual is None and not coord
         p.accumulate = 1 if split_k else 0
         self._keep(p)
-        fn = lib.ppy_conv_bf16 if self.code == PPY_BF16 else lib.ppy_conv_f32
+        fn = {PPY_BF16: lib.ppy_conv_bf16, PPY_F16X2: lib.ppy_conv_f16x2}.get(self.code, lib.ppy_conv_f32)
         ref = ctypes.byref(p)
         zero_t = dst.t
 
@@ -220,7 +276,7 @@ class InferenceEngine(object):
         self._add(name, run)
         flops = 2 * x.n * ho * wo * cout * cin_total * k * k
         self.conv_flops += flops
-        esz_in, esz_out = x.t.element_size(), dst.t.element_size()
+        esz_in, esz_out = x.esz, dst.esz
         nbytes = (x.n * x.h * x.w * c_main * esz_in + packed.numel() * packed.element_size() +
                   x.n * ho * wo * cout * esz_out * (4 if upsample else 1) + (x.n * ho * wo * cout * esz_out if residual is not None else 0))
         self.step_info[name] = {'flops': flops, 'bytes': nbytes, 'm': x.n * ho * wo, 'n': cout, 'k': cin_total * k * k}
@@ -279,7 +335,7 @@ class InferenceEngine(object):
         tile (re-reading the whole input for 2 columns); instead the first 256 channels run as full 256-wide tiles and
         the 2 leftover channels as a 32-wide launch into the same buffer."""
         cout = unit.filters
-        if self.code != PPY_BF16 or cout <= 256 or cout % 256 > 32 or unit.bn is not None:
+        if self.code == PPY_F32 or cout <= 256 or cout % 256 > 32 or unit.bn is not None:
             return self._unit(name, unit, x, out_code=PPY_F32)
         from model.custom_layers import ACT_CODES
         scale, shift = unit.folded_scale_shift()
@@ -325,11 +381,11 @@ class InferenceEngine(object):
                         w2[px * cout:(px + 1) * cout, qx * cin:(qx + 1) * cin, :, d + 1] = w[:, :, :, kx]
         scale, shift = unit.folded_scale_shift()
         scale2, shift2 = torch.cat([scale, scale]).contiguous(), torch.cat([shift, shift]).contiguous()
-        xp = TensorRef(x.t.view(x.n, x.h, x.w // 2, 2 * x.c))
+        xp = x.pixel_pairs()
         flops_before = self.conv_flops
         out = self._conv(name, xp, self._keep(w2), scale2, shift2, 1, ACT_CODES[unit.act_name])
         self.conv_flops = flops_before + 2 * x.n * x.h * x.w * cout * cin * 9
-        return TensorRef(out.t.view(x.n, x.h, x.w, cout))
+        return out.pixel_unpairs(cout)
 
     def _unit_batch_stats(self, name, unit, x, residual, act, dst, coord):
         """conv (raw) -> per-channel batch statistics (+ running-stat update) -> normalise + residual + act."""
@@ -385,8 +441,7 @@ class InferenceEngine(object):
                             d.conv_offset.bias.detach().float().contiguous(), unit.stride, 0, out_code=PPY_F32)
             # (no split-K here: atomically added partial sums make the offsets, hence the detections, run-to-run non-deterministic)
             om = TensorRef(om.t)     # the sampler reads the padded row (ld) directly
-            if d.dcn_bias is not None:
-                shift = shift + d.dcn_bias.detach().float() * scale
+            # (folded_scale_shift() already carries a DCN bias through the norm: nothing to add here)
             if self.dcn_impl == 'gather_gemm' and x.c % 64 == 0:
                 xcol = self._dcn_gather(name + '.gather', x, om, d.dcn_weight.shape[-1], unit.stride)
                 return self._conv(name, xcol, d.dcn_weight.detach(), scale, shift, 1, act, residual=residual, dst=dst,
@@ -450,6 +505,11 @@ class InferenceEngine(object):
         n_out = len(head.anchor_masks)
         # static input: NCHW fp32 exactly as Decode.predict uploads it (model/decode_np.py:142-147)
         self.x_in = torch.zeros((n, 3, self.h, self.w), dtype=torch.float32, device=self.dev)
+        # per-image detection counts + one overflow flag of the pair path, read back together (the one host sync of a run)
+        self._flags = torch.zeros((n + 1,), dtype=torch.int32, device=self.dev)
+        self.overflow = self._flags[n:]
+        if self.code == PPY_F16X2:
+            self._add('reset_flags', lambda: self.overflow.zero_())
         self._src = self.x_in                 # input slot the first kernel reads
         self.input_slots = [self.x_in]
         self.graphs = []
@@ -484,7 +544,7 @@ class InferenceEngine(object):
 
         x = x0
         for u, nm in stem_units:
-            pairable = (self.code == PPY_BF16 and not self.train_bn and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
+            pairable = (self.code in (PPY_BF16, PPY_F16X2) and not self.train_bn and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
                         tuple(u.conv.weight.shape[1:]) == (32, 3, 3) and x.c == 32 and x.ld == 32 and x.c_off == 0 and
                         x.w % 2 == 0 and u.conv.weight.shape[0] % 8 == 0 and u.conv.bias is None)
             x = self._unit_pixel_pairs('stem.' + nm, u, x) if pairable else self._unit('stem.' + nm, u, x)
@@ -518,7 +578,7 @@ class InferenceEngine(object):
                         x = self._unit('%s.%d' % (prefix, j), ly, x, coord=coord)
                         coord = False
                     elif isinstance(ly, SPP):
-                        x = self._spp(x)
+                        x = self._spp(x, ly.seq)
                     elif isinstance(ly, DropBlock):
                         if not ly.is_test:
                             raise RuntimeError('DropBlock must be in test mode for inference (head.set_dropblock(True))')
@@ -545,7 +605,7 @@ class InferenceEngine(object):
             raise NotImplementedError('only matrix_nms is on the PP-YOLO path')
         self.keep_top_k = cfg['keep_top_k']
         self.nms_out = torch.zeros((n, self.keep_top_k, 6), dtype=torch.float32, device=self.dev)
-        self.nms_counts = torch.zeros((n,), dtype=torch.int32, device=self.dev)
+        self.nms_counts = self._flags[:n]
         nms_args = (cfg['score_threshold'], cfg['post_threshold'], cfg['nms_top_k'], cfg['keep_top_k'],
                     cfg.get('use_gaussian', False), cfg.get('gaussian_sigma', 2.0))
         # 'dense' (default): yolo_box's dense scores; the decode kernels also fill the per-image score histogram, so the
@@ -663,9 +723,17 @@ class InferenceEngine(object):
         self.x_in.copy_(x, non_blocking=True)
         self.im_size.copy_(im_size.reshape(self.n, 2), non_blocking=True)
         self.launch()
-        counts = self.nms_counts.cpu().tolist()          # the one host sync
+        flags = self._flags.cpu().tolist()               # the one host sync
+        self.check_overflow(flags[self.n])
         out = self.nms_out.clone()
-        return ops.split_predictions(out, counts)
+        return ops.split_predictions(out, flags[:self.n])
+
+    def check_overflow(self, flag=None):
+        flag = int(self.overflow.item()) if flag is None else flag
+        if flag:
+            raise _lib.KernelError("precision 'f16x2': an activation left the range of an fp16 pair (|v| * act_scale > 65504, "
+                                   "or NaN); the results of this batch are invalid -- lower model.f16x2_act_scale or use "
+                                   "model.precision = 'fp32'")
 
     def candidate_counts(self):
         """Scores above score_threshold per image in the last run (sparse post-processing only): int32 [n] tensor."""
@@ -685,4 +753,15 @@ class InferenceEngine(object):
         if self.train_bn:
             for bn in self.bn_modules:
                 bn.num_batches_tracked += 1
-        return [ops.from_nhwc(f.t[..., f.c_off:f.c_off + f.c].contiguous() if f.c_off else f.t, f.c) for f in self.feats]
+        return self.feature_maps_nchw()
+
+    def feature_maps_nchw(self):
+        """Backbone feature maps of the last run as NCHW fp32 tensors (true values)."""
+        outs = []
+        for f in self.feats:
+            if f.pair:
+                t = ops.join_pair(f.t)[..., f.c_off:f.c_off + f.c] / self.act_scale
+                outs.append(t.permute(0, 3, 1, 2).contiguous())
+            else:
+                outs.append(ops.from_nhwc(f.t[..., f.c_off:f.c_off + f.c].contiguous() if f.c_off else f.t, f.c))
+        return outs

@@ -13,9 +13,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16
+from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16, PPY_F16X2
 
 _PRECISION = 'fp32'      # arithmetic of module-level convs: 'fp32' (SIMT) or 'bf16' (tcgen05)
+PRECISIONS = ('bf16', 'fp32', 'f16x2')      # engine precisions; 'f16x2' = fp32-grade tensor-core path (fp16 hi/lo pairs)
 
 
 def set_precision(p):
@@ -48,11 +49,11 @@ def ptr(t):
 
 
 def torch_dtype(code):
-    return torch.bfloat16 if code == PPY_BF16 else torch.float32
+    return {PPY_BF16: torch.bfloat16, PPY_F16X2: torch.float16}.get(code, torch.float32)
 
 
 def dtype_code(precision):
-    return PPY_BF16 if precision == 'bf16' else PPY_F32
+    return {'bf16': PPY_BF16, 'f16x2': PPY_F16X2}.get(precision, PPY_F32)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -114,6 +115,49 @@ def pack_weight(weight, code, c_begin=0, c_count=None, cache=True):
     return result
 
 
+def pack_weight_pair(weight, c_begin=0, c_count=None):
+    """OIHW fp32 -> PPY_F16X2 packing [2, cout_pad, k_pad] fp16 (hi plane, lo plane) for ppy_conv_f16x2.
+
+    Every output channel is first multiplied by a power of two ``chan_scale[co]`` that brings its largest weight into
+    [2^13, 2^14), so hi AND lo parts of all but vanishing weights are normal fp16 numbers (22 significant bits); the
+    caller divides the channel's epilogue scale by ``chan_scale`` (exact).  Returns (packed, cin_pad, k_pad, cout_pad,
+    chan_scale[cout] fp32)."""
+    _cuda(weight, 'weight')
+    cout, cin_total, kh, kw = weight.shape
+    c_count = cin_total - c_begin if c_count is None else c_count
+    cin_pad = round_up(c_count, 8)
+    k_pad = round_up(kh * kw * cin_pad, 64)
+    cout_pad = round_up(cout, 32)
+    w32 = weight.detach().float()
+    amax = w32[:, c_begin:c_begin + c_count].abs().amax(dim=(1, 2, 3))
+    _, ex = torch.frexp(amax)                       # amax = m * 2^ex, m in [0.5, 1)
+    chan_scale = torch.where(amax > 0, torch.ldexp(torch.ones_like(amax), (14 - ex).clamp(-30, 40)), torch.ones_like(amax))
+    w32 = (w32 * chan_scale.view(-1, 1, 1, 1)).contiguous()
+    packed = torch.empty((2, cout_pad, k_pad), dtype=torch.float16, device=weight.device)
+    check(lib.ppy_pack_conv_weight(ptr(w32), cout, cin_total, kh, kw, c_begin, c_count, ptr(packed), cout_pad, cin_pad,
+                                   k_pad, PPY_F16X2, stream_ptr()), 'pack_conv_weight')
+    return packed, cin_pad, k_pad, cout_pad, chan_scale.contiguous()
+
+
+def split_pair(x_nhwc):
+    """NHWC fp32 tensor -> PPY_F16X2 tensor [2, N, H, W, C] (hi plane, lo plane)."""
+    _cuda(x_nhwc)
+    x = x_nhwc.detach().float().contiguous()
+    n, h, w, c = x.shape
+    y = torch.empty((2, n, h, w, c), dtype=torch.float16, device=x.device)
+    check(lib.ppy_split_f16x2(ptr(x), c, ptr(y), c, y.stride(0), n * h * w, c, stream_ptr()), 'split_f16x2')
+    return y
+
+
+def join_pair(y, c=None):
+    """PPY_F16X2 tensor [2, N, H, W, ld] -> NHWC fp32 tensor with the first ``c`` channels."""
+    _, n, h, w, ld = y.shape
+    c = ld if c is None else c
+    out = torch.empty((n, h, w, c), dtype=torch.float32, device=y.device)
+    check(lib.ppy_join_f16x2(ptr(y), ld, y.stride(0), ptr(out), c, n * h * w, c, stream_ptr()), 'join_f16x2')
+    return out
+
+
 def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, residual=None, bias_map=None,
               out=None, out_code=None, upsample2x=False, offset_mask=None, x_ld=None, coord_w=None, accumulate=False, split_k=0):
     """Launch one fused conv on NHWC buffers. ``x`` [N,H,W,ld]; returns ``out`` [N,Ho,Wo,ld_out]."""
@@ -144,6 +188,50 @@ def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, res
     p.om_ld = offset_mask.shape[-1] if offset_mask is not None else 0
     fn = lib.ppy_conv_bf16 if code == PPY_BF16 else lib.ppy_conv_f32
     check(fn(ctypes.byref(p), stream_ptr()), 'conv_bf16' if code == PPY_BF16 else 'conv_f32')
+    return out
+
+
+def conv_pair(x, weight, scale, shift, stride=1, pad=0, act=0, residual=None, bias_map=None, out_f32=False,
+              upsample2x=False, offset_mask=None, c_count=None, overflow=None):
+    """One fused conv of the fp32-grade tensor-core path (ppy_conv_f16x2): ``x`` / ``residual`` are PPY_F16X2 tensors
+    [2, N, H, W, ld] (fp16 hi | lo planes), ``weight`` the OIHW fp32 tensor (its first ``c_count`` input channels are
+    used).  Returns a pair tensor [2, N, Ho, Wo, ld_out], or an NHWC fp32 tensor with ``out_f32``."""
+    _cuda(x, 'input')
+    assert x.dtype == torch.float16 and x.dim() == 5 and x.shape[0] == 2
+    cout, cin_total, k, _ = weight.shape
+    packed, cin_pad, k_pad, cout_pad, cs = pack_weight_pair(weight, 0, c_count)
+    _, n, h, w, ld = x.shape
+    ho = (h + 2 * pad - k) // stride + 1
+    wo = (w + 2 * pad - k) // stride + 1
+    oh, ow = (2 * ho, 2 * wo) if upsample2x else (ho, wo)
+    ldo = round_up(cout, 8)
+    if out_f32:
+        out = torch.zeros((n, oh, ow, ldo), dtype=torch.float32, device=x.device)
+    else:
+        out = torch.zeros((2, n, oh, ow, ldo), dtype=torch.float16, device=x.device)
+    sc = (_f32(scale).to(x.device) / cs).contiguous()
+    sh = _f32(shift).to(x.device)
+    bm = (bias_map.float().to(x.device) * cs).contiguous() if bias_map is not None else None
+    p = ConvParams()
+    p.x, p.x_ld, p.x_plane = x.data_ptr(), ld, x.stride(0)
+    p.n, p.h, p.w, p.cin = n, h, w, cin_pad
+    p.weight = packed.data_ptr()
+    p.cout, p.kh, p.kw, p.stride, p.pad = cout, k, k, stride, pad
+    p.k_pad, p.cout_pad = k_pad, cout_pad
+    p.scale, p.shift = sc.data_ptr(), sh.data_ptr()
+    p.bias_map = bm.data_ptr() if bm is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.res_ld = residual.shape[-1] if residual is not None else 0
+    p.res_plane = residual.stride(0) if residual is not None else 0
+    p.act = act
+    p.y, p.y_ld = out.data_ptr(), ldo
+    p.out_dtype = PPY_F32 if out_f32 else PPY_F16X2
+    p.y_plane = 0 if out_f32 else out.stride(0)
+    p.upsample2x = 1 if upsample2x else 0
+    p.offset_mask = offset_mask.data_ptr() if offset_mask is not None else None
+    p.om_ld = offset_mask.shape[-1] if offset_mask is not None else 0
+    p.overflow = overflow.data_ptr() if overflow is not None else None
+    check(lib.ppy_conv_f16x2(ctypes.byref(p), stream_ptr()), 'conv_f16x2')
     return out
 
 

@@ -99,6 +99,8 @@ class Trainer(object):
             check(lib.ppy_sgd_momentum(ops.ptr(p.data), ctypes.c_void_p(gv.data_ptr()), ops.ptr(self.momentum_bufs[i]), p.numel(),
                                        float(group_lr), float(self.momentum), float(g['weight_decay']), float(grad_scale), first,
                                        ops.stream_ptr()), 'sgd_momentum')
+        for p in self.params:                 # the kernel wrote through raw pointers: move torch's version counters too
+            torch._C._increment_version(p)
         self.iter_id += 1
         self.model.invalidate_engines_for_weights()
         return {k: v.detach() for k, v in losses.items()}

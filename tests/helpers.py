@@ -46,3 +46,41 @@ def assert_preds_match(got, want, rtol=2e-3, atol=5e-2, max_row_mismatch=0.03):
     ok = (got[:, 0] == want[:, 0]) & np.all(np.abs(got[:, 1:] - want[:, 1:]) <= atol + rtol * np.abs(want[:, 1:]), axis=1)
     bad = int((~ok).sum())
     assert bad <= max(1, int(max_row_mismatch * len(got))), '%d of %d rows differ' % (bad, len(got))
+
+
+def detection_drift(got, want, iou_thr=0.9):
+    """How far a list of per-image [M,6] detections (label, score, x0, y0, x1, y1) is from the reference's.
+
+    Every reference row is paired with the unused row of ``got`` that has the same label and the highest IoU; a pair
+    with IoU >= ``iou_thr`` is a match.  Returns the fraction of reference rows matched, the fraction of rows whose
+    label agrees at the same rank, and the largest score / box-coordinate difference over the matched pairs."""
+    total = matched = same_rank = 0
+    max_box = max_score = 0.0
+    for g, w in zip(got, want):
+        g, w = np.asarray(g, dtype=np.float64), np.asarray(w, dtype=np.float64)
+        if w.shape[0] == 1 and w[0, 0] < 0:
+            w = w[:0]
+        if g.shape[0] == 1 and g[0, 0] < 0:
+            g = g[:0]
+        total += len(w)
+        k = min(len(g), len(w))
+        same_rank += int((g[:k, 0] == w[:k, 0]).sum())
+        used = np.zeros(len(g), dtype=bool)
+        for row in w:
+            cand = np.where((g[:, 0] == row[0]) & ~used)[0]
+            if not len(cand):
+                continue
+            b = g[cand, 2:]
+            ix = np.clip(np.minimum(b[:, 2], row[4]) - np.maximum(b[:, 0], row[2]), 0, None)
+            iy = np.clip(np.minimum(b[:, 3], row[5]) - np.maximum(b[:, 1], row[3]), 0, None)
+            inter = ix * iy
+            union = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]) + (row[4] - row[2]) * (row[5] - row[3]) - inter
+            iou = inter / np.maximum(union, 1e-12)
+            j = int(np.argmax(iou))
+            if iou[j] >= iou_thr:
+                used[cand[j]] = True
+                matched += 1
+                max_box = max(max_box, float(np.abs(b[j] - row[2:]).max()))
+                max_score = max(max_score, abs(float(g[cand[j], 1] - row[1])))
+    return {'reference_rows': total, 'matched_frac': matched / max(total, 1), 'same_label_at_rank_frac': same_rank / max(total, 1),
+            'max_box_err_px': max_box, 'max_score_err': max_score}

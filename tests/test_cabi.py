@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 
 def test_status_strings_and_version():
     from ppyolo_b200 import _lib
-    assert _lib.lib.ppy_abi_version() == 1
+    assert _lib.lib.ppy_abi_version() == _lib.ABI_VERSION
     assert _lib.lib.ppy_status_string(0) == b'ok'
     assert b'workspace' in _lib.lib.ppy_status_string(-2)
     assert _lib.launch_count() >= 0
