@@ -49,11 +49,11 @@ def conv_norm_act(x, weight, bias=None, bn=None, stride=1, act=None):
 def coord_concat(x):
     """CoordConv, model/custom_layers.py:256-272: cat([x, xs, ys]) with xs=i/(w-1)*2-1 along W, ys along H."""
     b, _, h, w = x.shape
-    xs = torch.arange(w, dtype=torch.float32) / (w - 1) * 2.0 - 1
-    ys = torch.arange(h, dtype=torch.float32) / (h - 1) * 2.0 - 1
+    xs = torch.arange(w, dtype=torch.float32, device=x.device) / (w - 1) * 2.0 - 1
+    ys = torch.arange(h, dtype=torch.float32, device=x.device) / (h - 1) * 2.0 - 1
     xs = xs.view(1, 1, 1, w).expand(b, 1, h, w)
     ys = ys.view(1, 1, h, 1).expand(b, 1, h, w)
-    return torch.cat([x, xs, ys], dim=1)
+    return torch.cat([x, xs.to(x.dtype), ys.to(x.dtype)], dim=1)
 
 
 def spp(x):
@@ -81,23 +81,27 @@ def dcnv2(x, offset_w, offset_b, dcn_w, stride=1, padding=1):
     taps = kh * kw
     off = om[:, :2 * taps].reshape(n, taps, 2, ho, wo)
     mask = torch.sigmoid(om[:, 2 * taps:])                                   # [n, taps, ho, wo]
-    base_y = (torch.arange(ho, dtype=torch.float32) * stride - padding).view(1, 1, ho, 1)
-    base_x = (torch.arange(wo, dtype=torch.float32) * stride - padding).view(1, 1, 1, wo)
-    tap_y = torch.arange(kh, dtype=torch.float32).repeat_interleave(kw).view(1, taps, 1, 1)
-    tap_x = torch.arange(kw, dtype=torch.float32).repeat(kh).view(1, taps, 1, 1)
+    dev = x.device
+    om = om.float()
+    off = om[:, :2 * taps].reshape(n, taps, 2, ho, wo)
+    mask = torch.sigmoid(om[:, 2 * taps:])
+    base_y = (torch.arange(ho, dtype=torch.float32, device=dev) * stride - padding).view(1, 1, ho, 1)
+    base_x = (torch.arange(wo, dtype=torch.float32, device=dev) * stride - padding).view(1, 1, 1, wo)
+    tap_y = torch.arange(kh, dtype=torch.float32, device=dev).repeat_interleave(kw).view(1, taps, 1, 1)
+    tap_x = torch.arange(kw, dtype=torch.float32, device=dev).repeat(kh).view(1, taps, 1, 1)
     py = base_y + tap_y + off[:, :, 0]                                       # [n, taps, ho, wo]
     px = base_x + tap_x + off[:, :, 1]
     y0, x0 = torch.floor(py), torch.floor(px)
     ly, lx = py - y0, px - x0
     flat = x.reshape(n, c, h * w)
-    cols = torch.zeros(n, c, taps, ho, wo, dtype=torch.float32)
+    cols = torch.zeros(n, c, taps, ho, wo, dtype=x.dtype, device=dev)
     for dy, dx, wgt in ((0, 0, (1 - ly) * (1 - lx)), (0, 1, (1 - ly) * lx), (1, 0, ly * (1 - lx)), (1, 1, ly * lx)):
         yy, xx = y0 + dy, x0 + dx
         ok = (yy >= 0) & (yy <= h - 1) & (xx >= 0) & (xx <= w - 1)
         idx = (yy.clamp(0, h - 1) * w + xx.clamp(0, w - 1)).long()           # [n, taps, ho, wo]
         g = torch.gather(flat, 2, idx.reshape(n, 1, -1).expand(n, c, -1)).reshape(n, c, taps, ho, wo)
-        cols = cols + g * (wgt * ok.float()).unsqueeze(1)
-    cols = cols * mask.unsqueeze(1)
+        cols = cols + g * (wgt * ok.float()).unsqueeze(1).to(x.dtype)
+    cols = cols * mask.unsqueeze(1).to(x.dtype)
     cols = cols.reshape(n, c * taps, ho * wo)                                # K order (c, kh, kw)
     out = torch.matmul(dcn_w.reshape(cout, c * taps), cols)
     return out.reshape(n, cout, ho, wo)
@@ -131,11 +135,11 @@ def yolo_box(conv_output, anchors, stride, num_classes, scale_x_y, im_size, clip
     """yolo_box, model/head.py:21-80.  Returns boxes [N, H*W*A, 4] (xyxy, image pixels) and scores
     [N, H*W*A, C]; box order (h, w, anchor) (:58); assumes square maps like the reference (:25-27)."""
     n, _, size, _ = conv_output.shape
-    anchors = torch.as_tensor(np.asarray(anchors, dtype=np.float32)).reshape(-1, 2)
+    anchors = torch.as_tensor(np.asarray(anchors, dtype=np.float32)).reshape(-1, 2).to(conv_output.device)
     a = anchors.shape[0]
     t = conv_output.permute(0, 2, 3, 1).reshape(n, size, size, a, 5 + num_classes)
-    gx = torch.arange(size, dtype=torch.float32).view(1, 1, size, 1)
-    gy = torch.arange(size, dtype=torch.float32).view(1, size, 1, 1)
+    gx = torch.arange(size, dtype=torch.float32, device=conv_output.device).view(1, 1, size, 1)
+    gy = torch.arange(size, dtype=torch.float32, device=conv_output.device).view(1, size, 1, 1)
     grid = torch.stack([gx.expand(1, size, size, 1), gy.expand(1, size, size, 1)], dim=-1)   # (x_idx, y_idx) :33-37
     xy = (scale_x_y * torch.sigmoid(t[..., 0:2]) + grid - (scale_x_y - 1.0) * 0.5) * stride
     wh = torch.exp(t[..., 2:4]) * anchors
@@ -213,8 +217,18 @@ class Net(object):
     (the reference's ``config/ppyolo_*.py`` classes or this repo's mirrors).
     """
 
-    def __init__(self, state_dict, cfg):
-        self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    def __init__(self, state_dict, cfg, device='cpu', dtype=torch.float32, channels_last=False):
+        """``device`` / ``dtype`` / ``channels_last``: bench.py also runs this stock-PyTorch restatement on the GPU (cuDNN /
+        cuBLAS kernels only) as the "reference on the same B200" baseline; tests and the CPU arm use the defaults."""
+        self.device, self.dtype, self.channels_last = torch.device(device), dtype, channels_last
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
+        if dtype != torch.float32 or channels_last:
+            for k, v in self.sd.items():
+                if v.dim() == 4:
+                    v = v.to(dtype)
+                    self.sd[k] = v.contiguous(memory_format=torch.channels_last) if channels_last else v
+                elif k.endswith(('.bias', '.weight', 'running_mean', 'running_var')) and not k.endswith('conv_offset.bias'):
+                    self.sd[k] = v.to(dtype) if '.bn.' not in k else v
         self.cfg = cfg
 
     # -- one Conv2dUnit -----------------------------------------------------------------------
@@ -224,7 +238,7 @@ class Net(object):
         if prefix + '.bn.weight' in sd:
             bn = tuple(sd[prefix + '.bn.' + k] for k in ('weight', 'bias', 'running_mean', 'running_var'))
         if prefix + '.conv.dcn_weight' in sd:
-            y = dcnv2(x, sd[prefix + '.conv.conv_offset.weight'], sd[prefix + '.conv.conv_offset.bias'],
+            y = dcnv2(x, sd[prefix + '.conv.conv_offset.weight'], sd[prefix + '.conv.conv_offset.bias'].to(x.dtype),
                       sd[prefix + '.conv.dcn_weight'], stride=stride, padding=1)
             if bn is not None:
                 y = F.batch_norm(y, bn[2], bn[3], bn[0], bn[1], training=False, eps=BN_EPS)
@@ -341,15 +355,27 @@ class Net(object):
 
     def forward(self, x, im_size, return_all=False):
         """PPYOLO.forward(eval=True), model/ppyolo.py:19-22 -> list of [M,6] numpy arrays."""
-        with torch.no_grad():
-            feats = self.backbone(x.float())
-            outs = self.head_outputs(feats)
-            boxes, scores = self.decode(outs, im_size.float())
+        boxes, scores, feats, outs = self.forward_dense(x, im_size)
         nms = {k: v for k, v in self.cfg.nms_cfg.items() if k != 'nms_type'}
-        preds = [matrix_nms(boxes[i].numpy(), scores[i].numpy(), **nms) for i in range(boxes.shape[0])]
+        preds = [matrix_nms(boxes[i].cpu().numpy(), scores[i].cpu().numpy(), **nms) for i in range(boxes.shape[0])]
         if return_all:
             return dict(feats=feats, outs=outs, boxes=boxes, scores=scores, preds=preds)
         return preds
+
+
+def _forward_dense(self, x, im_size):
+    """Backbone + head + box decode (everything before the per-image NMS loop), on ``self.device``."""
+    with torch.no_grad():
+        x = x.to(self.device, self.dtype)
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        feats = self.backbone(x)
+        outs = [o.float() for o in self.head_outputs(feats)]
+        boxes, scores = self.decode(outs, im_size.float().to(self.device))
+    return boxes, scores, feats, outs
+
+
+Net.forward_dense = _forward_dense
 
 
 def ema_update(shadow, params, decay, update_step, thres_steps=True):

@@ -93,6 +93,14 @@ constexpr int SLAB_BYTES = SLAB_ROWS * 8 * 128;   // 18 rows x 8 pixels x 64 bf1
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
+// Split mode, K chunks.  The tensor core adds every MMA (K = 16) into the fp32 accumulator with truncation, a bias that grows
+// linearly with the number of MMAs per accumulator (measured 1.5e-5 of the output scale at K = 4608 with one accumulator).  So a
+// TMEM accumulator only ever holds the partial sum of one K CHUNK (chunk_kb pipeline iterations, <= 72 MMAs); the epilogue warps
+// drain every chunk into REGISTER accumulators with round-to-nearest adds while the MMA issuer fills the other TMEM buffer.
+// BLOCK_N <= 128 in split mode (64 accumulator registers per epilogue thread).
+// Tiles whose whole K fits one chunk (K <= 256 of a 1x1 conv: the HBM-bound layers) skip the register stage (template flag
+// CHUNKED off) and keep BLOCK_N up to 256.
+__host__ __device__ constexpr int chunk_kb(int mode) { return mode == MODE_TMA_SLAB ? 2 : 4; }
 
 template <int BN, int MODE, int EPI, bool CTA2 = false> struct TileCfg {
   // CTA2 (cta_group::2 pair, 256 x BN tile): each CTA stages its own 128 rows of A and HALF of the B tile, so stages are smaller
@@ -421,7 +429,7 @@ __device__ __noinline__ void epilogue_acc(const ppy_conv_params& p, const float*
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int MODE, int EPI, bool ACC, bool CTA2>
+template <int BN, int MODE, int EPI, bool ACC, bool CTA2, bool CHUNKED>
 __global__ void __launch_bounds__(num_threads(MODE), 1)
 conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int num_kb, const int num_m_tiles,
                  const int num_n_tiles, const int num_splits, const int num_taps, const int pw_tiles, const int ph_tiles,
@@ -433,6 +441,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   // CTAs' shared memory, its commits multicast to both CTAs' barriers.  num_m_tiles then counts PAIRS of M tiles.
   static_assert(!CTA2 || (mode_is_tma(MODE) && !ACC), "the CTA-pair kernel is TMA-fed only");
   static_assert(!SPLIT || (EPI == EPI_SLAB && !ACC), "split mode: slab epilogue, no partial sums");
+  static_assert(!CHUNKED || (SPLIT && BN <= 128), "K chunks: split mode, at most two sub-tiles per epilogue warp");
   using Cfg = TileCfg<BN, MODE, EPI, CTA2>;
   constexpr int S = Cfg::kStages;
   constexpr int A_STAGE = Cfg::kAStageBytes;
@@ -708,14 +717,17 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     // =====================================================================================
     if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BN);
-      int g = 0, it = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+      constexpr int CH = CHUNKED ? chunk_kb(MODE) : (1 << 28);
+      int g = 0, it = 0;                         // it: uses of the accumulator buffers = tiles (CHUNKED: K chunks)
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
+        for (int kc0 = u.kb0; kc0 < u.kb1; kc0 += CH, ++it) {
         const int acc = it & 1;
         mbar_wait(tmem_empty_bar(acc), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
-        for (int kb = u.kb0; kb < u.kb1; ++kb, ++g) {
+        const int kc1 = (u.kb1 - kc0 > CH) ? kc0 + CH : u.kb1;
+        for (int kb = kc0; kb < kc1; ++kb, ++g) {
           const int s = g % S;
           mbar_wait(full_bar(s), (g / S) & 1);
           tc_fence_after();
@@ -732,15 +744,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 16; ++k) {
                 const uint64_t da = make_smem_desc(a_pl + ky * 1024 + k * 32), db = make_smem_desc(b_pl + ky * Cfg::kBTileBytes + k * 32);
-                if (CTA2) umma2_bf16(d_tmem, da, db, idesc, (kb | cb | ky | k) ? 1u : 0u);
-                else umma_bf16(d_tmem, da, db, idesc, (kb | cb | ky | k) ? 1u : 0u);
+                if (CTA2) umma2_bf16(d_tmem, da, db, idesc, ((kb - kc0) | cb | ky | k) ? 1u : 0u);
+                else umma_bf16(d_tmem, da, db, idesc, ((kb - kc0) | cb | ky | k) ? 1u : 0u);
               }
             }
           } else {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            if (CTA2) umma2_bf16(d_tmem, make_smem_desc(a_pl + k * 32), make_smem_desc(b_pl + k * 32), idesc, (kb | cb | k) ? 1u : 0u);
-            else umma_bf16(d_tmem, make_smem_desc(a_pl + k * 32), make_smem_desc(b_pl + k * 32), idesc, ((ACC ? kb - u.kb0 : kb) | cb | k) ? 1u : 0u);
+            if (CTA2) umma2_bf16(d_tmem, make_smem_desc(a_pl + k * 32), make_smem_desc(b_pl + k * 32), idesc, ((kb - kc0) | cb | k) ? 1u : 0u);
+            else umma_bf16(d_tmem, make_smem_desc(a_pl + k * 32), make_smem_desc(b_pl + k * 32), idesc, ((kb - kc0) | cb | k) ? 1u : 0u);
           }
           }
           }
@@ -749,9 +761,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           __syncwarp();
         }
         if (elect_one()) {
-          if (CTA2) umma_commit2(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));   // accumulator complete -> epilogue(s)
+          if (CTA2) umma_commit2(tmem_full_bar(acc)); else umma_commit(tmem_full_bar(acc));   // accumulator (chunk) complete -> epilogue(s)
         }
         __syncwarp();
+        }
       }
     }
   } else if (EPI == EPI_TMA) {
@@ -958,7 +971,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     prefetch_residual(tile_first);
     const uint32_t empty_rank0 = CTA2 ? map_to_cta(tmem_empty_bar(0), 0) : 0u;      // the leader's MMA thread waits for both epilogues
     int it = 0;
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, it += CHUNKED ? 0 : 1) {    // (CHUNKED: `it` counts K chunks)
       const int acc = it & 1;
       const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
       const int n0 = u.nt * BN;
@@ -983,12 +996,40 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       };
       // residual of the first sub-tile is requested before the accumulator is even ready
       uint4 rv[4], rv2[SPLIT ? 4 : 1];
-      load_res(half, rv, rv2);
+      if (!CHUNKED) load_res(half, rv, rv2);       // (CHUNKED: after the K-chunk drain, whose loop wants the registers)
+      uint32_t v[32];
+      // split mode: this warp's (up to two) 32-column sub-tiles accumulate in registers over the K chunks of the tile
+      uint32_t racc0[CHUNKED ? 32 : 1], racc1[CHUNKED ? 32 : 1];
+      if constexpr (CHUNKED) {
+        constexpr int CH = chunk_kb(MODE);
+        const int nchunks = (num_kb + CH - 1) / CH;
+        for (int c = 0; c < nchunks; ++c, ++it) {
+          const int accb = it & 1;
+          mbar_wait(tmem_full_bar(accb), (it >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t_rowc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(accb * BN);
+          // one sub-tile at a time through the same 32 staging registers (both at once would not fit next to the 64 sums)
+          if (half < NSUB) tmem_ld32_nowait(t_rowc + (uint32_t)(half * SUB), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) racc0[e] = c == 0 ? v[e] : __float_as_uint(__fadd_rn(__uint_as_float(racc0[e]), __uint_as_float(v[e])));
+          if (BN > 64) {
+            if (half + 2 < NSUB) tmem_ld32_nowait(t_rowc + (uint32_t)((half + 2) * SUB), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) racc1[e] = c == 0 ? v[e] : __float_as_uint(__fadd_rn(__uint_as_float(racc1[e]), __uint_as_float(v[e])));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * accb); else mbar_arrive(tmem_empty_bar(accb)); }
+        }
+        load_res(half, rv, rv2);
+      } else {
       mbar_wait(tmem_full_bar(acc), (it >> 1) & 1);
       tc_fence_after();
+      }
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      uint32_t v[32];
-      if (half < NSUB) tmem_ld32_nowait(t_row + (uint32_t)(half * SUB), v);
+      if (!CHUNKED && half < NSUB) tmem_ld32_nowait(t_row + (uint32_t)(half * SUB), v);
 #pragma unroll 1
       for (int k = 0; k < MY_SUBS; ++k) {
         const int cc = half + 2 * k;
@@ -1012,16 +1053,30 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           }
         }
         // phase 1: accumulator registers (lane = row) -> swizzled warp-private slab
-        tmem_wait_ld();
+        if (!CHUNKED) tmem_wait_ld();
         {
           const uint32_t st_row = slab_u32 + (uint32_t)lane * (ST_LD * 4);
           const uint32_t sw = (uint32_t)(lane & 7);
+          if (CHUNKED && k == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((((uint32_t)q) ^ sw) << 4)),
+                           "r"(racc1[CHUNKED ? 4 * q : 0]), "r"(racc1[CHUNKED ? 4 * q + 1 : 0]), "r"(racc1[CHUNKED ? 4 * q + 2 : 0]), "r"(racc1[CHUNKED ? 4 * q + 3 : 0]) : "memory");
+          } else if (CHUNKED) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((((uint32_t)q) ^ sw) << 4)),
+                           "r"(racc0[CHUNKED ? 4 * q : 0]), "r"(racc0[CHUNKED ? 4 * q + 1 : 0]), "r"(racc0[CHUNKED ? 4 * q + 2 : 0]), "r"(racc0[CHUNKED ? 4 * q + 3 : 0]) : "memory");
+          } else {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ((((uint32_t)q) ^ sw) << 4)),
                          "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3]) : "memory");
+          }
         }
-        if (cc + 2 < NSUB) {
+        if (CHUNKED) {
+          __syncwarp();                              // (the accumulator buffers were released chunk by chunk)
+        } else if (cc + 2 < NSUB) {
           tmem_ld32_nowait(t_row + (uint32_t)((cc + 2) * SUB), v);     // next sub-tile streams in during phase 2
           __syncwarp();
         } else {                                   // this warp's TMEM reads of the tile are done: release the accumulator
@@ -1097,7 +1152,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         }
         __syncwarp();                            // slab is rewritten by the next sub-tile
       }
-      if (half >= NSUB) {                        // BN == 32: the second warp of a quarter has no sub-tile, still releases
+      if (!CHUNKED && half >= NSUB) {            // BN == 32: the second warp of a quarter has no sub-tile, still releases
         tc_fence_before();
         if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
       }
@@ -1256,7 +1311,7 @@ int pick_splits(const ppy_conv_params* p, long long tiles, int num_kb) {
   return best;
 }
 
-template <int BN, int MODE, int EPI, bool ACC = false, bool CTA2 = false>
+template <int BN, int MODE, int EPI, bool ACC = false, bool CTA2 = false, bool CHUNKED = false>
 int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   using Cfg = TileCfg<BN, MODE, EPI, CTA2>;
   constexpr int PW = patch_w(MODE), PH = patch_h(MODE);
@@ -1296,7 +1351,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI, ACC, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI, ACC, CTA2, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (rc) return rc;
     attr_done = true;
   }
@@ -1329,7 +1384,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MODE, EPI, ACC, CTA2>, *p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
+  rc = check_cuda(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, MODE, EPI, ACC, CTA2, CHUNKED>, *p, ho, wo, num_kb, num_m_tiles, num_n_tiles,
                                      num_splits, num_taps, pw_tiles, ph_tiles, tmap_b, tmap_a, tmap_y, tmap_r, tmap_a2));
   if (rc) return rc;
   return check_launch();
@@ -1353,17 +1408,23 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   const int c = p->cout;
   if constexpr (SPLIT) {     // fp16-pair operands: slab epilogue only, no partial sums
     if (p->accumulate) return PPY_ERR_UNSUPPORTED;
-    if (c <= 32) return launch<32, MODE, EPI_SLAB>(p, ho, wo, st);
-    if (c <= 64) return launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
-    if constexpr (mode_is_tma(MODE)) {
-      static const bool no_pair = knob_off("PPY_NO_CTA2");
-      if (!no_pair && (long long)p->n * ho * wo > BLOCK_M) {
-        if (c % 256 == 0) return launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
-        return launch<128, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
+    static const bool no_pair = knob_off("PPY_NO_CTA2");
+    const bool pair = mode_is_tma(MODE) && !no_pair && (long long)p->n * ho * wo > BLOCK_M;
+    if (p->k_pad / BLOCK_K <= chunk_kb(MODE)) {    // the whole K is one chunk (K <= 256): no register stage, BLOCK_N up to 256
+      if (c <= 32) return launch<32, MODE, EPI_SLAB>(p, ho, wo, st);
+      if (c <= 64) return launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
+      if constexpr (mode_is_tma(MODE)) {
+        if (pair) return c % 256 == 0 ? launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
       }
+      return c % 256 == 0 ? launch<256, MODE, EPI_SLAB>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB>(p, ho, wo, st);
     }
-    if (c % 256 == 0) return launch<256, MODE, EPI_SLAB>(p, ho, wo, st);
-    return launch<128, MODE, EPI_SLAB>(p, ho, wo, st);
+    // K chunks summed in the epilogue warps' registers: BLOCK_N <= 128
+    if (c <= 32) return launch<32, MODE, EPI_SLAB, false, false, true>(p, ho, wo, st);
+    if (c <= 64) return launch<64, MODE, EPI_SLAB, false, false, true>(p, ho, wo, st);
+    if constexpr (mode_is_tma(MODE)) {
+      if (pair) return launch<128, MODE, EPI_SLAB, false, true, true>(p, ho, wo, st);
+    }
+    return launch<128, MODE, EPI_SLAB, false, false, true>(p, ho, wo, st);
   } else {
   if (p->accumulate) {       // partial-sum launches (split-K, weight gradients): slab epilogue with fp32 atomics
     if (MODE == MODE_DCN || mode_is_patchy(MODE)) return PPY_ERR_UNSUPPORTED;
@@ -1394,9 +1455,9 @@ int dispatch_slab(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   static const bool no_pair = knob_off("PPY_NO_CTA2");
   const bool tma_epi = tma_epilogue_ok(p);
   const bool pair = !no_pair && p->n * ceil_div(ho, patch_h(MODE_TMA_SLAB)) * ceil_div(wo, patch_w(MODE_TMA_SLAB)) > 1;
-  if constexpr (SPLIT) {
-    if (p->cout <= 64) return pair ? launch<64, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
-    if (pair) return launch<128, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st);
+  if constexpr (SPLIT) {     // (3x3: always more than one K chunk)
+    if (p->cout <= 64) return pair ? launch<64, MODE_TMA_SLAB, EPI_SLAB, false, true, true>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB, false, false, true>(p, ho, wo, st);
+    if (pair) return launch<128, MODE_TMA_SLAB, EPI_SLAB, false, true, true>(p, ho, wo, st);
     return dispatch<MODE_TMA_IM2COL>(p, ho, wo, st);            // single-tile problem: a 128-wide slab stage pair does not fit twice
   } else {
   if (p->cout <= 64) {

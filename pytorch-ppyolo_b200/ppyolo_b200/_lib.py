@@ -117,8 +117,30 @@ def _load():
     return lib
 
 
-lib = _load()
+class _LazyLibrary(object):
+    """Loads libppyolo_b200.so on the first use of an entry point (so building a model's parameter containers -- e.g. for the
+    CPU reference arm of bench.py -- maps no native code); every later attribute access goes straight to the CDLL."""
+    _real = None
+
+    def _get(self):
+        real = object.__getattribute__(self, '_real')
+        if real is None:
+            real = _load()
+            _LazyLibrary._real = real
+        return real
+
+    def __getattr__(self, name):
+        fn = getattr(self._get(), name)
+        object.__setattr__(self, name, fn)          # next access bypasses __getattr__
+        return fn
+
+
+lib = _LazyLibrary()
 LIB_PATH = _build.LIB_PATH
+
+
+def is_loaded():
+    return _LazyLibrary._real is not None
 
 
 class KernelError(RuntimeError):
