@@ -77,9 +77,10 @@ class InferenceEngine(object):
         if self.dev.type != 'cuda':
             raise RuntimeError('model must be on a CUDA device')
         self.act_dtype = ops.torch_dtype(self.code)
-        # DCNv2 on the bf16 path: 'gather_gemm' = sampling kernel -> L2-resident A matrix -> TMA-fed 1x1 tcgen05 GEMM
-        # (fastest today); 'fused' = the single im2col-free kernel with the bilinear producer
-        self.dcn_impl = dcn_impl or getattr(model, 'dcn_impl', None) or ('gather_gemm' if precision == 'bf16' else 'fused')
+        # DCNv2: 'fused' (default) = the im2col-free whole-layer kernel (csrc/dcn_umma.cu: CTA pairs, full-N accumulators,
+        # coalesced corner gather; the generic producer mode of the conv kernel for layers it does not fit);
+        # 'gather_gemm' (bf16 / fp32 only) = sampling kernel -> [M x 9C] matrix -> TMA-fed 1x1 GEMM (round 1's default)
+        self.dcn_impl = dcn_impl or getattr(model, 'dcn_impl', None) or 'fused'
         if precision == 'f16x2':
             self.dcn_impl = 'fused'            # (the sampling kernel has no pair variant)
             if train_bn:

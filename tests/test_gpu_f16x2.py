@@ -205,3 +205,43 @@ def test_pair_stem():
     chk(lib.ppy_stem_conv3x3s2_f16x2(o.ptr(x.to(DEV)), 2, 64, 96, wn.ctypes.data_as(fp), scn.ctypes.data_as(fp), shn.ctypes.data_as(fp),
                                      32, 1, o.ptr(y), 32, y.stride(0), o.stream_ptr()), 'stem')
     check(from_pair(y, 32), want, 'stem pair')
+
+
+@pytest.mark.parametrize('mode', ['bf16', 'f16x2'])
+@pytest.mark.parametrize('n,c,cout,stride,hw,res', [(4, 512, 512, 1, 19, True), (3, 512, 512, 2, 38, False), (2, 128, 256, 1, 13, True),
+                                                    (1, 64, 512, 1, 40, False)])
+def test_whole_layer_dcn_kernel(mode, n, c, cout, stride, hw, res):
+    """dcn_umma.cu (CTA pairs, full-N accumulators, coalesced corner gather, sampling table) at the shapes of the ppyolo_2x
+    stage-5 DCNs (512 -> 512 at 19x19 stride 1 and 38 -> 19 stride 2) and smaller ones, with residual + ReLU, against the
+    fp32 CPU oracle fed the kernel's own offsets.  bf16: operands rounded to bf16 first, 4e-3 of scale (the A operand is rounded
+    to bf16 after the blend); f16x2: 5e-5 of scale."""
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16
+    o = ops()
+    g = torch.Generator().manual_seed(c + cout + hw + stride)
+    rnd = (lambda t: t.to(torch.bfloat16).float()) if mode == 'bf16' else (lambda t: t)
+    x = rnd(torch.randn((n, c, hw, hw), generator=g))
+    ow = rnd(torch.randn((27, c, 3, 3), generator=g) * 1.5 / (c * 9) ** 0.5)
+    ob = torch.randn(27, generator=g)
+    wt = rnd(torch.randn((cout, c, 3, 3), generator=g) / (c * 9) ** 0.5)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ho = (hw + 2 - 3) // stride + 1
+    r = rnd(torch.randn((n, cout, ho, ho), generator=g)) if res else None
+    want = ref.dcnv2(x, ow, ob, wt, stride, 1).double() * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    if res:
+        want = want + r.double()
+    want = torch.relu(want)
+    if mode == 'f16x2':
+        xp = to_pair(x)
+        om = o.conv_pair(xp, ow.to(DEV), torch.ones(27), ob, stride, 1, 0, out_f32=True)
+        y = o.conv_pair(xp, wt.to(DEV), scale, shift, stride, 1, 1, residual=to_pair(r) if res else None, offset_mask=om)
+        got = from_pair(y, cout)
+        tol = 5e-5
+    else:
+        xh = o.to_nhwc(x.to(DEV), PPY_BF16)
+        om = o.conv_nhwc(xh, o.pack_weight(ow.to(DEV), PPY_BF16), c, 27, 3, stride, 1, torch.ones(27, device=DEV), ob.to(DEV), 0, PPY_BF16,
+                         out_code=PPY_F32)
+        y = o.conv_nhwc(xh, o.pack_weight(wt.to(DEV), PPY_BF16), c, cout, 3, stride, 1, scale.to(DEV), shift.to(DEV), 1, PPY_BF16,
+                        residual=o.to_nhwc(r.to(DEV), PPY_BF16) if res else None, offset_mask=om)
+        got = o.from_nhwc(y, cout).cpu()
+        tol = 8e-3                       # output rounded to bf16 as well
+    check(got, want, 'whole-layer dcn %s %s' % (mode, (n, c, cout, stride, hw, res)), tol=tol)

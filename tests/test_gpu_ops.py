@@ -277,6 +277,46 @@ def test_dcn_golden(golden, precision, tag, stride):
         pytest.skip('bf16 DCN needs cin % 64 == 0; covered by test_umma_dcn')
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'f16x2'])
+@pytest.mark.parametrize('tag,stride', [('s1', 1), ('s2', 2)])
+def test_dcn_far_offsets_golden(golden, precision, tag, stride):
+    """DCNv2 with offsets up to ~24 px on a 20x20 map (most samples far outside the image) against the REFERENCE's output
+    (tests/golden/dcn_far.npz): fp32 SIMT kernel and f16x2 tensor-core kernel at 1e-4 of scale (measured 1e-5 / 1.6e-5); bf16
+    recorded with a loose 1e-1 bound (measured 4-5e-2: a 20 px offset computed from bf16 operands is off by ~0.05 px, and a
+    sample that moves by that much near the border changes visibly -- bf16 is the throughput mode, not the parity mode)."""
+    from model.custom_layers import Conv2dUnit
+    from ppyolo_b200._lib import PPY_F32, PPY_BF16
+    o = ops()
+    z = golden('dcn_far')
+    u = Conv2dUnit(64, 24, 3, stride=stride, bn=1, act='relu', use_dcn=True)
+    synth.randomize_(u, seed=33, offset_scale=0.25)
+    u = u.to(DEV).eval()
+    x = torch.from_numpy(z[tag + '_in']).to(DEV)
+    want = z[tag + '_raw']
+    d = u.conv
+    if precision == 'fp32':
+        got = d(x).cpu().numpy()
+        tol = 1e-4
+    elif precision == 'f16x2':
+        xp = o.split_pair(o.to_nhwc(x, PPY_F32))
+        om = o.conv_pair(xp, d.conv_offset.weight, torch.ones(27), d.conv_offset.bias, stride, 1, 0, out_f32=True)
+        y = o.conv_pair(xp, d.dcn_weight, torch.ones(24), torch.zeros(24), stride, 1, 0, out_f32=True, offset_mask=om)
+        got = o.from_nhwc(y, 24).cpu().numpy()
+        tol = 1e-4
+    else:
+        xh = o.to_nhwc(x, PPY_BF16)
+        one = torch.ones(27, device=DEV)
+        om = o.conv_nhwc(xh, o.pack_weight(d.conv_offset.weight, PPY_BF16), 64, 27, 3, stride, 1, one, d.conv_offset.bias.detach().float(), 0,
+                         PPY_BF16, out_code=PPY_F32)
+        y = o.conv_nhwc(xh, o.pack_weight(d.dcn_weight, PPY_BF16), 64, 24, 3, stride, 1, torch.ones(24, device=DEV), torch.zeros(24, device=DEV),
+                        0, PPY_BF16, out_code=PPY_F32, offset_mask=om)
+        got = o.from_nhwc(y, 24).cpu().numpy()
+        tol = 1e-1
+    err = np.abs(got - want).max() / scale_of(want)
+    print('dcn far offsets %s %s: max err / scale = %.2e' % (precision, tag, err))
+    assert err < tol
+
+
 # ------------------------------------------------------------------ tcgen05 conv kernel, tight check
 def _umma_conv(x, w, scale, shift, stride, act, residual=None, bias_map=None, upsample=False, out_f32=True,
                offset_mask=None):

@@ -104,6 +104,22 @@ def test_dcn(golden, tag, stride):
     np.testing.assert_allclose(raw.numpy(), z[tag + '_raw'], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize('tag,stride', [('s1', 1), ('s2', 2)])
+def test_dcn_far_offsets(golden, tag, stride):
+    """Offsets of sigma ~6 px (max ~24 px) on a 20x20 map: most samples fall far outside the image, beyond the reference's
+    one-pixel zero border -- the oracle's "outside -> 0" rule must equal the reference's clamp-into-the-border trick there too
+    (golden from the unmodified reference, tests/golden/make_golden_dcn_far.py)."""
+    z = golden('dcn_far')
+    from model.custom_layers import Conv2dUnit
+    u = Conv2dUnit(64, 24, 3, stride=stride, bn=1, act='relu', use_dcn=True)
+    synth.randomize_(u, seed=33, offset_scale=0.25)
+    x = torch.from_numpy(z[tag + '_in'])
+    assert np.abs(z[tag + '_offsetmask'][:, :18]).max() > 18.0
+    with torch.no_grad():
+        raw = ref.dcnv2(x, u.conv.conv_offset.weight, u.conv.conv_offset.bias, u.conv.dcn_weight, stride, 1)
+    np.testing.assert_allclose(raw.numpy(), z[tag + '_raw'], rtol=1e-4, atol=2e-5 * np.abs(z[tag + '_raw']).max())
+
+
 def test_dcn_zero_offset_identity():
     """external/DCNv2/test.py:32-67 recipe: zero offset conv => mask 0.5 => 2*DCN(x) == conv(x)."""
     g = torch.Generator().manual_seed(3)
