@@ -137,6 +137,15 @@ int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, const float* we
 int ppy_stem_conv3x3s2_f16x2(const float* x_nchw, int n, int h, int w, const float* weight_oihw_host, const float* scale_host,
                              const float* shift_host, int cout, int act, void* y, int y_ld, long long y_plane, ppy_stream_t s);
 
+/* The same layer fed the RESIZED uint8 RGB batch [n, h, w, 3] (HWC: what cv2.resize hands Decode.process_image,
+ * model/decode_np.py:125-134) instead of the normalised float CHW tensor: NormalizeImage (tools/transform.py:891-921) and Permute
+ * (:1020-1055) happen inside the kernel through `lut` (DEVICE pointer, [3][256] floats: lut[c][u] = the reference's numpy
+ * expression ((u / 255) - mean[c]) / std[c] evaluated on the host, so the result is bit-identical) -- a quarter of the upload
+ * bytes.  y_dtype PPY_F32 / PPY_BF16 / PPY_F16X2 (then y_plane > 0). */
+int ppy_stem_conv3x3s2_u8(const uint8_t* x_nhwc_u8, int n, int h, int w, const float* lut, const float* weight_oihw_host,
+                          const float* scale_host, const float* shift_host, int cout, int act, void* y, int y_ld, int y_dtype,
+                          long long y_plane, ppy_stream_t s);
+
 /* Glue of the fp32-grade tensor-core path on PPY_F16X2 tensors (hi plane at the pointer, lo plane `plane` elements further):
  * MaxPool2d(3,2,1) model/resnet_vd.py:103, AvgPool2d(2,2) :30, SPP model/custom_layers.py:275-290 (y[..., 0:c]=x,
  * [c:2c]=maxpool5, [2c:3c]=maxpool9, [3c:4c]=maxpool13).  Max-type results equal the fp32 kernels' on the joined tensors. */
@@ -180,9 +189,31 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
 /* y = act(x*scale[c] + shift[c] (+ residual)) on NHWC rows. */
 int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* scale,
                         const float* shift, const void* residual, int res_ld, int act, ppy_stream_t s);
+/* DropBlock, model/custom_layers.py:293-342 (train only; one per detection block, block_size 3, keep_prob 0.9), without a host
+ * round trip: ppy_dropblock_mask draws Bernoulli(gamma) seeds with Philox4x32-10 -- one call per four consecutive LOGICAL
+ * (n,c,h,w) elements, key/counter = the (seed, offset) pair in DEVICE memory at rng_state[0..1] (the kernel advances the offset,
+ * so a captured CUDA graph draws fresh numbers at every replay) --, grows them with the 3x3 / stride 1 / padding 1 max-pool
+ * (:333-334) into mask = 1 - pooled and accumulates sum(mask) in *count (device).  seeds and mask are uint8 tensors sharing the
+ * element strides (sn, sc, sh, sw) of the activation (NCHW-contiguous or channels_last).  ppy_dropblock_apply then computes
+ * y = x * mask * numel / sum(mask) in the reference's operation order (:341) over the flat storage -- forward (x -> y) and
+ * backward (dy -> dx) alike.  block_size != 3 is PPY_ERR_UNSUPPORTED (the reference's own pooling only keeps the shape for 3).
+ * ppy_dropblock_mask_from_seeds runs the second stage on caller-provided seeds (tests). */
+int ppy_dropblock_mask(uint8_t* seeds, uint8_t* mask, int n, int c, int h, int w, long long sn, long long sc, long long sh, long long sw,
+                       int block_size, float gamma, unsigned long long* rng_state, unsigned int* count, ppy_stream_t s);
+int ppy_dropblock_mask_from_seeds(const uint8_t* seeds, uint8_t* mask, int n, int c, int h, int w, long long sn, long long sc, long long sh,
+                                  long long sw, unsigned long long* rng_state, unsigned int* count, ppy_stream_t s);
+int ppy_dropblock_apply(const void* x, void* y, const uint8_t* mask, const unsigned int* count, long long numel, int dtype, ppy_stream_t s);
 /* torch.optim.SGD(momentum, weight_decay) update of one fp32 tensor, gradient pre-scaled by grad_scale (1/world). */
 int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, int first_step, ppy_stream_t s);
+/* The whole optimizer step in ONE launch: for every trainable tensor t the ppy_sgd_momentum update read from the (all-reduced)
+ * flat gradient bucket -- params[t] (device pointer table), grad_flat / momentum_flat ranges [offsets[t], offsets[t+1]), learning
+ * rate lr * lr_mult[t], weight decay weight_decay[t] (the reference's per-layer groups, model/custom_layers.py:167-241) -- followed,
+ * when shadow_flat != NULL, by ppy_ema_update of the new value into shadow_flat + shadow_offsets[t] (model/EMA.py:31-45; the
+ * reference copies every parameter to the host for this each step).  Bit-identical to the two separate kernels. */
+int ppy_sgd_ema_multi(float* const* params, const float* grad_flat, float* momentum_flat, float* shadow_flat, const long long* offsets,
+                      const long long* shadow_offsets, const float* lr_mult, const float* weight_decay, int num_tensors, float lr,
+                      float momentum, float grad_scale, int first_step, float ema_decay, float ema_one_minus_decay, ppy_stream_t s);
 /* K-major operand of the weight-gradient GEMM of a k x k stride-1 conv (training step, conv_autograd.py): NHWC bf16 x
  * [n,h,w,c] -> out [c*k*k rows][m_pad] bf16 with out[(ch*k*k + ky*k + kx)][m] = x[pixel m shifted by (ky-pad, kx-pad)][ch], zero
  * outside the image and for m in [n*h*w, m_pad); rows follow the OIHW weight order, k = 1 is the plain transpose (also used

@@ -28,10 +28,21 @@ struct StemParams {
   float shift[STEM_COUT];
 };
 
-template <typename T>
+// U8: x is the resized uint8 RGB image batch [n, h, w, 3] (HWC, what cv2 hands Decode.process_image after ResizeImage) and
+// `lut` [3][256] maps a byte of channel c to the reference's normalised float ((u / 255 - mean[c]) / std[c], computed on the
+// host with the reference's numpy expression, so NormalizeImage + Permute are bit-exact by construction): a quarter of the
+// upload bytes, no separate normalisation pass.
+template <typename T, bool U8 = false>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, int n, int h, int w, int ho, int wo,
                                                         const __grid_constant__ StemParams prm, float slope, T* __restrict__ y,
-                                                        int y_ld, long long y_plane = 0 /* > 0: T = __half, fp16 hi/lo pair output */) {
+                                                        int y_ld, long long y_plane = 0 /* > 0: T = __half, fp16 hi/lo pair output */,
+                                                        const float* __restrict__ lut = nullptr) {
+  __shared__ float s_lut[U8 ? 3 * 256 : 1];
+  if (U8) {
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) s_lut[U8 ? i : 0] = __ldg(lut + i);
+    __syncthreads();
+  }
+  const uint8_t* x8 = reinterpret_cast<const uint8_t*>(x);
   const long long total = (long long)n * ho * wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(i % wo), oy = (int)((i / wo) % ho), img = (int)(i / ((long long)wo * ho));
@@ -48,7 +59,10 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
         for (int kx = 0; kx < 3; ++kx) {
           const int ix = ox * 2 - 1 + kx;
           float v = 0.f;
-          if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(xi + ((long long)c * h + iy) * w + ix);
+          if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+            if (U8) v = s_lut[U8 ? c * 256 + (int)__ldg(x8 + (((long long)img * h + iy) * w + ix) * 3 + c) : 0];
+            else v = __ldg(xi + ((long long)c * h + iy) * w + ix);
+          }
 #pragma unroll
           for (int co = 0; co < STEM_COUT; ++co) acc[co] = fmaf(v, prm.w[c * 9 + ky * 3 + kx][co], acc[co]);
         }
@@ -350,6 +364,36 @@ extern "C" int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, cons
                                                                                 (__nv_bfloat16*)y, y_ld);
   else if (y_dtype == PPY_F32)
     stem_conv_kernel<float><<<(unsigned)blocks, 128, 0, as_stream(s)>>>(x_nchw, n, h, w, ho, wo, prm, slope, (float*)y, y_ld);
+  else return PPY_ERR_INVALID;
+  return check_launch();
+}
+
+// Same layer reading the resized uint8 HWC batch through the normalisation table (see stem_conv_kernel<T, U8>): y_dtype PPY_F32,
+// PPY_BF16 (fp32 SIMT math) or PPY_F16X2 (y_plane > 0).  lut: DEVICE pointer, [3][256] floats.
+extern "C" int ppy_stem_conv3x3s2_u8(const uint8_t* x_nhwc_u8, int n, int h, int w, const float* lut, const float* weight_oihw_host,
+                                     const float* scale_host, const float* shift_host, int cout, int act, void* y, int y_ld,
+                                     int y_dtype, long long y_plane, ppy_stream_t s) {
+  using namespace ppy;
+  PPY_REQUIRE(x_nhwc_u8 && lut && weight_oihw_host && scale_host && shift_host && y);
+  PPY_REQUIRE(n > 0 && h > 1 && w > 1 && cout == STEM_COUT && y_ld >= cout);
+  PPY_REQUIRE(act == PPY_ACT_NONE || act == PPY_ACT_RELU || act == PPY_ACT_LEAKY);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (y_ld * dtype_size(y_dtype)) % 16 == 0);
+  PPY_REQUIRE(y_dtype != PPY_F16X2 || (y_plane > 0 && y_plane % 8 == 0));
+  const float slope = act == PPY_ACT_RELU ? 0.f : (act == PPY_ACT_LEAKY ? 0.1f : 1.f);
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  StemParams prm;
+  for (int co = 0; co < STEM_COUT; ++co) {
+    for (int t = 0; t < STEM_TAPS; ++t) prm.w[t][co] = weight_oihw_host[co * STEM_TAPS + t];
+    prm.scale[co] = scale_host[co];
+    prm.shift[co] = shift_host[co];
+  }
+  long long blocks = ceil_div((long long)n * ho * wo, 128);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  const float* xf = reinterpret_cast<const float*>(x_nhwc_u8);
+  cudaStream_t st = as_stream(s);
+  if (y_dtype == PPY_F16X2) stem_conv_kernel<__half, true><<<(unsigned)blocks, 128, 0, st>>>(xf, n, h, w, ho, wo, prm, slope, (__half*)y, y_ld, y_plane, lut);
+  else if (y_dtype == PPY_BF16) stem_conv_kernel<__nv_bfloat16, true><<<(unsigned)blocks, 128, 0, st>>>(xf, n, h, w, ho, wo, prm, slope, (__nv_bfloat16*)y, y_ld, 0, lut);
+  else if (y_dtype == PPY_F32) stem_conv_kernel<float, true><<<(unsigned)blocks, 128, 0, st>>>(xf, n, h, w, ho, wo, prm, slope, (float*)y, y_ld, 0, lut);
   else return PPY_ERR_INVALID;
   return check_launch();
 }

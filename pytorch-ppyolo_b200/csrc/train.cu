@@ -170,11 +170,51 @@ __global__ void __launch_bounds__(256) ema_update_kernel(float* __restrict__ sha
     sh[i] = __fadd_rn(__fmul_rn(decay, sh[i]), __fmul_rn(one_minus_decay, p[i]));
 }
 
+// Whole optimizer step in ONE launch (train.py:437-442 + model/EMA.py:31-45): for every trainable tensor t (blockIdx.y) the
+// torch.optim.SGD momentum update from the all-reduced flat gradient bucket, then -- when shadow != nullptr -- the EMA of the
+// updated value, in the operation order of the two separate kernels above (results are bit-identical to running them one after
+// the other).  offsets: tensor ranges in the flat gradient / momentum buffers; shadow_offsets: start of tensor t in the EMA's
+// flat shadow (its own tensor order); lr_mult / wd: per tensor (the reference's per-layer parameter groups).
+__global__ void __launch_bounds__(256) sgd_ema_multi_kernel(float* const* __restrict__ params, const float* __restrict__ grad,
+                                                            float* __restrict__ mom, float* __restrict__ shadow,
+                                                            const long long* __restrict__ offsets, const long long* __restrict__ shadow_offsets,
+                                                            const float* __restrict__ lr_mult, const float* __restrict__ wd, float lr,
+                                                            float momentum, float grad_scale, int first_step, float decay,
+                                                            float one_minus_decay) {
+  const int t = blockIdx.y;
+  const long long begin = offsets[t], count = offsets[t + 1] - begin;
+  float* __restrict__ p = params[t];
+  const float* __restrict__ g = grad + begin;
+  float* __restrict__ buf = mom + begin;
+  float* __restrict__ sh = shadow ? shadow + shadow_offsets[t] : nullptr;
+  const float lr_t = lr * lr_mult[t], wd_t = wd[t];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    const float d = g[i] * grad_scale + wd_t * w;
+    const float b = first_step ? d : momentum * buf[i] + d;
+    buf[i] = b;
+    const float w2 = w - lr_t * b;
+    p[i] = w2;
+    if (sh) sh[i] = __fadd_rn(__fmul_rn(decay, sh[i]), __fmul_rn(one_minus_decay, w2));
+  }
+}
+
 }  // namespace
 }  // namespace ppy
 
 extern "C" {
 using namespace ppy;
+
+int ppy_sgd_ema_multi(float* const* params, const float* grad_flat, float* momentum_flat, float* shadow_flat, const long long* offsets,
+                      const long long* shadow_offsets, const float* lr_mult, const float* weight_decay, int num_tensors, float lr,
+                      float momentum, float grad_scale, int first_step, float ema_decay, float ema_one_minus_decay, ppy_stream_t s) {
+  PPY_REQUIRE(params && grad_flat && momentum_flat && offsets && lr_mult && weight_decay && num_tensors > 0);
+  PPY_REQUIRE(!shadow_flat || shadow_offsets);
+  sgd_ema_multi_kernel<<<dim3(64, (unsigned)num_tensors), 256, 0, as_stream(s)>>>(params, grad_flat, momentum_flat, shadow_flat, offsets,
+                                                                                  shadow_offsets, lr_mult, weight_decay, lr, momentum,
+                                                                                  grad_scale, first_step, ema_decay, ema_one_minus_decay);
+  return check_launch();
+}
 
 int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,

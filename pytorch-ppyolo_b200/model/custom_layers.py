@@ -215,7 +215,7 @@ class DropBlock(torch.nn.Module):
     def forward(self, x):
         if self.is_test:
             return x
-        raise NotImplementedError('DropBlock training path is not built yet (inference uses is_test=True)')
+        return ops.drop_block(x, self.block_size, self.keep_prob)
 
 
 class Mish(torch.nn.Module):

@@ -29,15 +29,16 @@ class PPYOLO(torch.nn.Module):
         self.postprocess_impl = None  # None = engine default ('dense'); 'sparse' | 'dense' (see engine.py)
         self.f16x2_act_scale = 8.0    # power of two the 'f16x2' engine stores its activations multiplied by (see engine.py)
         self._weights_seen = None
+        self.normalize = None         # dict(mean, std, is_scale) of the uint8 input path; None = the configs' ImageNet values
         self.use_engine = True
         self._engines = {}
 
-    def engine(self, batch, height, width):
+    def engine(self, batch, height, width, input_u8=False):
         from ppyolo_b200.engine import InferenceEngine
-        key = (batch, height, width, self.precision, self.dcn_impl, self.postprocess_impl)
+        key = (batch, height, width, self.precision, self.dcn_impl, self.postprocess_impl, bool(input_u8))
         eng = self._engines.get(key)
         if eng is None:
-            eng = InferenceEngine(self, batch, height, width, precision=self.precision, dcn_impl=self.dcn_impl)
+            eng = InferenceEngine(self, batch, height, width, precision=self.precision, dcn_impl=self.dcn_impl, input_u8=input_u8)
             self._engines[key] = eng
             self._weights_seen = self._weights_fingerprint()
         return eng
@@ -76,6 +77,9 @@ class PPYOLO(torch.nn.Module):
 
     def forward(self, x, im_size, eval=True, gt_box=None, gt_label=None, gt_score=None, targets=None):
         if eval and self.use_engine and not self.training and x.is_cuda:
+            if x.dtype == torch.uint8:       # resized uint8 RGB batch [N, H, W, 3]: normalisation + permute inside the stem kernel
+                n, h, w, _ = x.shape
+                return self.engine(n, h, w, input_u8=True).run(x, im_size)
             n, _, h, w = x.shape
             return self.engine(n, h, w).run(x, im_size)
         if not eval:

@@ -61,6 +61,8 @@ SIGNATURES = {
     'ppy_conv_f16x2': (c_int, [ctypes.POINTER(ConvParams), c_void_p]),
     'ppy_stem_conv3x3s2_f16x2': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float),
                                          ctypes.POINTER(c_float), c_int, c_int, c_void_p, c_int, c_ll, c_void_p]),
+    'ppy_stem_conv3x3s2_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float),
+                                      ctypes.POINTER(c_float), c_int, c_int, c_void_p, c_int, c_int, c_ll, c_void_p]),
     'ppy_maxpool3x3s2_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_avgpool2x2_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_spp_f16x2': (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
@@ -70,7 +72,14 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ppy_scale_shift_act': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p]),
+    'ppy_dropblock_mask': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, c_void_p,
+                                   c_void_p, c_void_p]),
+    'ppy_dropblock_mask_from_seeds': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_void_p, c_void_p,
+                                              c_void_p]),
+    'ppy_dropblock_apply': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     'ppy_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int, c_void_p]),
+    'ppy_sgd_ema_multi': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                                  c_float, c_int, c_float, c_float, c_void_p]),
     'ppy_ema_update': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     'ppy_im2col_kmajor': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     'ppy_iou_aware_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_double, c_void_p]),

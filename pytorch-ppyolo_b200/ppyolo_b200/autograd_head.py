@@ -29,12 +29,10 @@ def coord_concat(x):
 
 
 def drop_block(x, block_size, keep_prob):
-    """Reference custom_layers.py:303-342: Bernoulli(gamma) seeds grown by a max-pool, output renormalised."""
-    h = x.shape[2]
-    gamma = (1.0 - keep_prob) * h * h / float(block_size * block_size * (h - block_size + 1) ** 2)
-    seeds = (torch.rand(x.shape, device=x.device) < gamma).float()
-    mask = 1.0 - F.max_pool2d(seeds, (block_size, block_size), stride=1, padding=1)
-    return x * mask * float(mask.numel()) / mask.sum()
+    """Reference custom_layers.py:303-342: Bernoulli(gamma) seeds grown by a max-pool, output renormalised -- the library's
+    DropBlock kernels (device-side Philox stream, no host round trip, graph-capturable); differentiable."""
+    from . import ops
+    return ops.drop_block(x, block_size, keep_prob)
 
 
 # Activations between the head's layers on the 'kernels' path: bf16 NHWC (zero-copy between layers).  Measured on the seeded

@@ -25,6 +25,22 @@ from . import _lib, ops
 from ._lib import lib, check, ConvParams, PPY_F32, PPY_BF16, PPY_F16X2
 
 
+DEFAULT_NORMALIZE = dict(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225], is_scale=True)      # config/ppyolo_2x.py:205-210
+
+
+def normalize_lut(mean, std, is_scale=True):
+    """[3][256] float32 table of the reference's NormalizeImage (tools/transform.py:906-917, is_channel_first=False) applied to
+    every byte value: the same numpy expression on a 256 x 1 x 3 uint8 image (float32 array, float64 mean/std operands of the
+    in-place ops), so a table lookup reproduces the reference's floats bit for bit."""
+    im = np.tile(np.arange(256, dtype=np.uint8)[:, None, None], (1, 1, 3))
+    im = im.astype(np.float32, copy=False)
+    if is_scale:
+        im = im / 255.0
+    im -= np.array(mean)[np.newaxis, np.newaxis, :]
+    im /= np.array(std)[np.newaxis, np.newaxis, :]
+    return np.ascontiguousarray(im[:, 0, :].T.astype(np.float32))
+
+
 class TensorRef(object):
     """A channel slice [c_off, c_off+c) of an NHWC buffer [N,H,W,ld] -- or of a PPY_F16X2 buffer [2,N,H,W,ld] (fp16 hi plane,
     lo plane; ``plane`` = element offset between them)."""
@@ -61,7 +77,7 @@ class TensorRef(object):
 
 class InferenceEngine(object):
     def __init__(self, model, batch, height, width, precision='bf16', use_graph=True, dcn_impl=None, train_bn=False,
-                 backbone_only=False):
+                 backbone_only=False, input_u8=False):
         if not torch.cuda.is_available():
             raise RuntimeError('InferenceEngine needs a CUDA device (no CPU fallback)')
         if precision not in ops.PRECISIONS:
@@ -91,6 +107,9 @@ class InferenceEngine(object):
         # train_bn: BatchNorm layers normalise with BATCH statistics and update their running stats, as the reference's
         # frozen backbone does during training; backbone_only: stop at the C3/C4/C5 feature maps
         self.train_bn, self.backbone_only = train_bn, backbone_only
+        # input_u8: the static input is the RESIZED uint8 RGB batch [n, h, w, 3] (a quarter of the upload bytes); the reference's
+        # NormalizeImage + Permute run inside the stem kernel through a 3 x 256 table built with the reference's numpy expression
+        self.input_u8 = bool(input_u8)
         self.postprocess_impl = getattr(model, 'postprocess_impl', None) or 'dense'
         if self.postprocess_impl not in ('sparse', 'dense'):
             raise ValueError(self.postprocess_impl)
@@ -173,10 +192,15 @@ class InferenceEngine(object):
         ho, wo = (self.h - 1) // 2 + 1, (self.w - 1) // 2 + 1
         out = TensorRef(self._new(self.n, ho, wo, 32))
         fp = ctypes.POINTER(ctypes.c_float)
-        args = (self.n, self.h, self.w, w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp),
-                sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name], ctypes.c_void_p(out.ptr), out.ld)
-        stem_fn = lib.ppy_stem_conv3x3s2_f16x2 if out.pair else lib.ppy_stem_conv3x3s2
-        args += (out.plane,) if out.pair else (self.code,)
+        wargs = (w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp), sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name],
+                 ctypes.c_void_p(out.ptr), out.ld)
+        if self.input_u8:
+            lut = self._keep(torch.from_numpy(normalize_lut(**self.normalize)).to(self.dev))
+            args = (self.n, self.h, self.w, ops.ptr(lut)) + wargs + (self.code, out.plane)
+            stem_fn = lib.ppy_stem_conv3x3s2_u8
+        else:
+            args = (self.n, self.h, self.w) + wargs + ((out.plane,) if out.pair else (self.code,))
+            stem_fn = lib.ppy_stem_conv3x3s2_f16x2 if out.pair else lib.ppy_stem_conv3x3s2
 
         def run():            # reads the CURRENT input slot (one captured graph per slot, see add_input_slot)
             check(stem_fn(ops.ptr(self._src), *args, ops.stream_ptr()), 'stem.conv1_1')
@@ -505,7 +529,11 @@ class InferenceEngine(object):
         bb, head = m.backbone, m.head
         n_out = len(head.anchor_masks)
         # static input: NCHW fp32 exactly as Decode.predict uploads it (model/decode_np.py:142-147)
-        self.x_in = torch.zeros((n, 3, self.h, self.w), dtype=torch.float32, device=self.dev)
+        if self.input_u8:
+            self.x_in = torch.zeros((n, self.h, self.w, 3), dtype=torch.uint8, device=self.dev)
+            self.normalize = dict(getattr(m, 'normalize', None) or DEFAULT_NORMALIZE)
+        else:
+            self.x_in = torch.zeros((n, 3, self.h, self.w), dtype=torch.float32, device=self.dev)
         # per-image detection counts + one overflow flag of the pair path, read back together (the one host sync of a run)
         self._flags = torch.zeros((n + 1,), dtype=torch.int32, device=self.dev)
         self.overflow = self._flags[n:]
@@ -522,6 +550,8 @@ class InferenceEngine(object):
             # conv1_1 fused with the NCHW->NHWC change (K = 27: HBM-bound, fp32 SIMT, weights in the constant bank)
             x0 = self._stem(u0)
             stem_units = stem_units[1:]
+        elif self.input_u8:
+            raise NotImplementedError('uint8 input needs the fused 3 -> 32 stride-2 stem conv (both PP-YOLO backbones have it)')
         else:
             x0 = TensorRef(self._new(n, self.h, self.w, 8))
             args = (ctypes.c_void_p(x0.ptr), n, 3, self.h, self.w, 8, self.code)

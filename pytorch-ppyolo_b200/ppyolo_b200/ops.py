@@ -355,6 +355,83 @@ def activation(x, act):
 
 
 # ------------------------------------------------------------------------------------------------
+# DropBlock (training)
+# ------------------------------------------------------------------------------------------------
+_DROPBLOCK_RNG = {}
+
+
+def dropblock_rng(device):
+    """Device-resident (seed, offset) pair of the DropBlock Philox streams (int64[2]); advanced by the kernels."""
+    st = _DROPBLOCK_RNG.get(device)
+    if st is None:
+        st = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        _DROPBLOCK_RNG[device] = st
+    return st
+
+
+def dropblock_seed(seed, device='cuda'):
+    device = torch.device(device) if not isinstance(device, torch.device) else device
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    dropblock_rng(device).copy_(torch.tensor([int(seed), 0], dtype=torch.int64))
+
+
+def dropblock_gamma(h, block_size, keep_prob):
+    """CalculateGamma, model/custom_layers.py:307-323 (fp32 tensor arithmetic in the reference)."""
+    f = np.float32
+    return float(f(f(h) * f(h)) * f(1 - keep_prob) / (f(block_size * block_size) * f((h - block_size + 1) ** 2)))
+
+
+def _dense_like(x):
+    return x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)
+
+
+class _DropBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, block_size, keep_prob, seeds):
+        _cuda(x, 'input')
+        if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
+            raise TypeError('drop_block: fp32 / bf16 NCHW-shaped tensors only')
+        if not _dense_like(x):
+            x = x.contiguous()
+        n, c, h, w = x.shape
+        mask = torch.empty_like(x, dtype=torch.uint8)            # preserves x's memory format
+        count = torch.empty(1, dtype=torch.int32, device=x.device)
+        rng = dropblock_rng(x.device)
+        st = [int(v) for v in x.stride()]
+        if seeds is None:
+            sd = torch.empty_like(mask)
+            check(lib.ppy_dropblock_mask(ptr(sd), ptr(mask), n, c, h, w, st[0], st[1], st[2], st[3], int(block_size),
+                                         dropblock_gamma(h, block_size, keep_prob), ptr(rng), ptr(count), stream_ptr()), 'dropblock_mask')
+        else:
+            sd = torch.empty_like(mask)
+            sd.copy_(seeds.to(torch.uint8))
+            check(lib.ppy_dropblock_mask_from_seeds(ptr(sd), ptr(mask), n, c, h, w, st[0], st[1], st[2], st[3], ptr(rng), ptr(count),
+                                                    stream_ptr()), 'dropblock_mask_from_seeds')
+        y = torch.empty_like(x)
+        code = PPY_BF16 if x.dtype == torch.bfloat16 else PPY_F32
+        check(lib.ppy_dropblock_apply(ptr(x), ptr(y), ptr(mask), ptr(count), x.numel(), code, stream_ptr()), 'dropblock_apply')
+        ctx.save_for_backward(mask, count)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mask, count = ctx.saved_tensors
+        if dy.stride() != mask.stride():
+            dy = dy.contiguous(memory_format=torch.channels_last) if mask.is_contiguous(memory_format=torch.channels_last) and not mask.is_contiguous() else dy.contiguous()
+        dx = torch.empty_like(dy)
+        code = PPY_BF16 if dy.dtype == torch.bfloat16 else PPY_F32
+        check(lib.ppy_dropblock_apply(ptr(dy), ptr(dx), ptr(mask), ptr(count), dy.numel(), code, stream_ptr()), 'dropblock_apply')
+        return dx, None, None, None
+
+
+def drop_block(x, block_size=3, keep_prob=0.9, seeds=None):
+    """DropBlock.__call__ in training mode (reference model/custom_layers.py:303-342); differentiable.  ``seeds``: optional
+    0/1 tensor of x's shape replacing the Bernoulli draw (parity tests inject the reference's own draw)."""
+    return _DropBlockFn.apply(x, block_size, keep_prob, seeds)
+
+
+# ------------------------------------------------------------------------------------------------
 # head post-processing
 # ------------------------------------------------------------------------------------------------
 def iou_aware_score(output, an_num, num_classes, factor):

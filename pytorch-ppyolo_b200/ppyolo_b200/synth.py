@@ -75,6 +75,11 @@ def images(batch, size, seed=1):
     return torch.randn((batch, 3, size, size), generator=_gen(seed, 'images'))
 
 
+def images_u8(batch, size, seed=1):
+    """Resized uint8 RGB batches [N,S,S,3] (what ``Decode.process_image_u8`` produces)."""
+    return torch.randint(0, 256, (batch, size, size, 3), generator=_gen(seed, 'images_u8'), dtype=torch.uint8)
+
+
 def im_sizes(batch, h=480, w=640):
     return torch.tensor([[float(h), float(w)]] * batch, dtype=torch.float32)
 

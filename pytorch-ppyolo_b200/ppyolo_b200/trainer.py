@@ -1,11 +1,16 @@
-"""Data-parallel training step (reference train.py:264-285 setup, :427-442 loop body).
+"""Data-parallel training step (reference train.py:264-285 setup, :427-442 loop body, :460-478 checkpoints).
 
 One process per GPU; every rank runs forward + backward on its own shard of the batch; the ONE exchange step per
 iteration is the gradient all-reduce(sum)/world of the trainable (head) parameters -- a single flat fp32 bucket
-(92.6 MB for ppyolo_2x) reduced by NCCL over NVLink -- followed by a fused SGD-momentum kernel that reads the reduced
-bucket in place.  BatchNorm statistics, DropBlock RNG and data sharding stay per rank; the learning
-rate follows the reference's warm-up + piecewise decay and is NOT rescaled by the world size, like the reference."""
+(92.6 MB for ppyolo_2x) reduced by NCCL over NVLink.  Autograd accumulates every gradient DIRECTLY into its slice of
+that bucket (``p.grad`` is a view of it: no pack copies), and the whole optimizer step -- torch.optim.SGD momentum update
+with the reference's per-layer lr / weight-decay groups, plus the ExponentialMovingAverage of the new weights
+(model/EMA.py:31-45, which the reference round-trips through host memory every step) -- is ONE kernel launch
+(``ppy_sgd_ema_multi``) reading the reduced bucket in place.  BatchNorm statistics, DropBlock RNG and data sharding stay
+per rank; initial parameters / buffers are broadcast from rank 0; the learning rate follows the
+reference's warm-up + piecewise decay and is NOT rescaled by the world size, like the reference."""
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -27,7 +32,7 @@ def calc_lr(iter_id, cfg):
 
 
 class GradientBucket(object):
-    """Flat fp32 view of a list of gradients: pack -> all_reduce(sum) -> per-parameter views (device agnostic)."""
+    """Flat fp32 buffer holding every gradient: per-parameter views, all_reduce(sum) over the ranks (device agnostic)."""
 
     def __init__(self, params):
         self.params = list(params)
@@ -42,12 +47,19 @@ class GradientBucket(object):
     def view(self, i):
         return self.flat[self.offsets[i]:self.offsets[i + 1]]
 
-    def pack(self):
+    def bind_grads(self):
+        """Make every ``p.grad`` a view of the bucket, so backward accumulates straight into it."""
         for i, p in enumerate(self.params):
+            p.grad = self.view(i).view_as(p)
+
+    def pack(self):
+        """Copy gradients that live elsewhere (a caller replaced ``p.grad``) into the bucket; bound views cost nothing."""
+        for i, p in enumerate(self.params):
+            v = self.view(i)
             if p.grad is None:
-                self.view(i).zero_()
-            else:
-                self.view(i).copy_(p.grad.reshape(-1))
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad.reshape(-1))
 
     def all_reduce(self):
         """Sum over ranks; returns the factor the consumer must apply (1/world)."""
@@ -62,9 +74,10 @@ class GradientBucket(object):
 
 
 class Trainer(object):
-    def __init__(self, model, cfg, graph=None):
+    def __init__(self, model, cfg, graph=None, ema=None):
         """``graph``: replay the frozen-backbone forward and the head forward + losses + backward as CUDA graphs (one set per
-        input shape); None = keep the model's ``train_graph`` setting."""
+        input shape); None = keep the model's ``train_graph`` setting.  ``ema``: keep the reference's exponential moving average of
+        the trainable weights (None = ``cfg.use_ema``), updated inside the optimizer kernel."""
         self.model, self.cfg = model, cfg
         if graph is not None:
             model.train_graph = bool(graph)
@@ -75,32 +88,141 @@ class Trainer(object):
         model.add_param_group(groups, self.base_lr, self.base_wd)        # per-tensor groups, reference custom_layers.py:167-241
         self.groups = groups
         self.params = [g['params'][0] for g in groups]
+        rank, world = parallel.world()
+        if world > 1:                      # replicas must start from the same weights and statistics
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, 0)
         self.bucket = GradientBucket(self.params)
-        self.momentum_bufs = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+        dev = self.bucket.flat.device
+        self.momentum_flat = torch.zeros_like(self.bucket.flat)
+        self.momentum_bufs = [self.momentum_flat[self.bucket.offsets[i]:self.bucket.offsets[i + 1]].view_as(p)
+                              for i, p in enumerate(self.params)]
         self.iter_id = 0
+        self.ema = None
+        use_ema = getattr(cfg, 'use_ema', False) if ema is None else ema
+        self._cuda = dev.type == 'cuda'
+        if self._cuda:
+            self._offsets_dev = torch.tensor(self.bucket.offsets, dtype=torch.int64, device=dev)
+            self._lr_mult = torch.tensor([g['base_lr'] / self.base_lr for g in groups], dtype=torch.float32, device=dev)
+            self._wd = torch.tensor([g['weight_decay'] for g in groups], dtype=torch.float32, device=dev)
+            self._ptr_key, self._ptr_table = None, None
+            if use_ema:
+                from model.EMA import ExponentialMovingAverage
+                self.ema = ExponentialMovingAverage(model, cfg.ema_decay)
+                self.ema.register()
+                at = {id(p): self.ema._offsets[i] for i, p in enumerate(self.ema._params)}
+                self._shadow_offsets = torch.tensor([at[id(p)] for p in self.params], dtype=torch.int64, device=dev)
+        self._events = []
+
+    # ------------------------------------------------------------------ one iteration
+    def _pointer_table(self):
+        ptrs = [p.data_ptr() for p in self.params]
+        if self._ptr_key != ptrs:                                  # EMA.apply()/restore() rebind param.data
+            self._ptr_key, self._ptr_table = ptrs, torch.tensor(ptrs, dtype=torch.int64, device=self.bucket.flat.device)
+        return self._ptr_table
 
     def step(self, images, gt_bbox, gt_class, gt_score, targets):
         from ._lib import lib, check
         from . import ops
+        if not self._cuda:
+            raise RuntimeError('ppyolo_b200: the training step needs CUDA parameters (no CPU fallback)')
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        self.bucket.flat.zero_()
+        self.bucket.bind_grads()
         losses = self.model(images, None, False, gt_bbox, gt_class, gt_score, targets)
         total = sum(losses.values())
-        for p in self.params:
-            p.grad = None
         total.backward()
-        self.bucket.pack()
+        self.bucket.pack()                                         # no-op for the bound views
+        ev[1].record()
         grad_scale = self.bucket.all_reduce()
+        ev[2].record()
         lr = calc_lr(self.iter_id, self.cfg)
         first = 1 if self.iter_id == 0 else 0
-        for i, (g, p) in enumerate(zip(self.groups, self.params)):
-            if not p.is_cuda:
-                raise RuntimeError('ppyolo_b200: the fused SGD kernel needs CUDA parameters')
-            group_lr = lr * g['base_lr'] / self.base_lr
-            gv = self.bucket.view(i)
-            check(lib.ppy_sgd_momentum(ops.ptr(p.data), ctypes.c_void_p(gv.data_ptr()), ops.ptr(self.momentum_bufs[i]), p.numel(),
-                                       float(group_lr), float(self.momentum), float(g['weight_decay']), float(grad_scale), first,
-                                       ops.stream_ptr()), 'sgd_momentum')
-        for p in self.params:                 # the kernel wrote through raw pointers: move torch's version counters too
-            torch._C._increment_version(p)
+        shadow, sh_off, decay = None, None, 0.0
+        if self.ema is not None:
+            import numpy as np
+            step = self.ema._update_step
+            decay = min(self.ema._decay, (1 + step) / (10 + step)) if self.ema._thres_steps else self.ema._decay
+            shadow, sh_off = self.ema._shadow_flat, self._shadow_offsets
+            d32, omd32 = float(np.float32(decay)), float(np.float32(1 - decay))
+        else:
+            d32, omd32 = 0.0, 0.0
+        check(lib.ppy_sgd_ema_multi(ops.ptr(self._pointer_table()), ops.ptr(self.bucket.flat), ops.ptr(self.momentum_flat), ops.ptr(shadow),
+                                    ops.ptr(self._offsets_dev), ops.ptr(sh_off), ops.ptr(self._lr_mult), ops.ptr(self._wd), len(self.params),
+                                    float(lr), float(self.momentum), float(grad_scale), first, d32, omd32, ops.stream_ptr()), 'sgd_ema_multi')
+        ev[3].record()
+        if self.ema is not None:
+            self.ema._update_step += 1
+        with torch.no_grad():
+            for p in self.params:                 # the kernel wrote through raw pointers: move torch's version counters too
+                torch._C._increment_version(p)
         self.iter_id += 1
         self.model.invalidate_engines_for_weights()
+        self._events.append(ev)
+        if len(self._events) > 64:
+            self._events.pop(0)
         return {k: v.detach() for k, v in losses.items()}
+
+    def timing_summary(self, last=10):
+        """Mean CUDA-event times of the last steps: forward+backward / gradient all-reduce / optimizer(+EMA) kernel."""
+        torch.cuda.synchronize()
+        evs = self._events[-last:]
+        if not evs:
+            return {}
+        mean = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in evs) / len(evs)
+        ar = mean(1, 2)
+        return {'fwd_bwd_ms': mean(0, 1), 'allreduce_ms': ar, 'optimizer_ema_ms': mean(2, 3), 'allreduce_overlap_fraction': 0.0,
+                'allreduce_note': 'one NCCL all-reduce of the flat bucket after the (single CUDA graph) backward; not overlapped',
+                'ema': self.ema is not None}
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Optimizer + EMA state next to the model weights (the reference saves the weights only, train.py:460-478, so a resumed
+        run restarts momentum and EMA from scratch)."""
+        sd = {'iter_id': self.iter_id, 'momentum_flat': self.momentum_flat.clone(),
+              'param_shapes': [tuple(p.shape) for p in self.params]}
+        if self.ema is not None:
+            sd['ema_shadow_flat'] = self.ema._shadow_flat.clone()
+            sd['ema_update_step'] = self.ema._update_step
+            sd['ema_names'] = list(self.ema._names)
+        return sd
+
+    def load_state_dict(self, sd):
+        if [tuple(s) for s in sd['param_shapes']] != [tuple(p.shape) for p in self.params]:
+            raise ValueError('trainer checkpoint does not match the trainable parameters of this model')
+        self.iter_id = int(sd['iter_id'])
+        self.momentum_flat.copy_(sd['momentum_flat'])
+        if self.ema is not None and 'ema_shadow_flat' in sd:
+            if list(sd['ema_names']) != list(self.ema._names):
+                raise ValueError('EMA checkpoint tensor names differ')
+            self.ema._shadow_flat.copy_(sd['ema_shadow_flat'])
+            self.ema._update_step = int(sd['ema_update_step'])
+
+    def save_checkpoint(self, directory, keep=10):
+        """``step%08d.pt`` = model.state_dict() exactly like the reference (train.py:462-463; resume = iteration parsed from the
+        file name, :255-261) + ``step%08d.opt.pt`` with the optimizer / EMA state; keeps the newest ``keep`` (train.py:464-478)."""
+        os.makedirs(directory, exist_ok=True)
+        path = os.path.join(directory, 'step%.8d.pt' % self.iter_id)
+        torch.save(self.model.state_dict(), path)
+        torch.save(self.state_dict(), path[:-3] + '.opt.pt')
+        names = sorted(f for f in os.listdir(directory) if f.startswith('step') and f.endswith('.pt') and not f.endswith('.opt.pt'))
+        for old in names[:-keep] if keep > 0 else []:
+            for f in (old, old[:-3] + '.opt.pt'):
+                try:
+                    os.remove(os.path.join(directory, f))
+                except OSError:
+                    pass
+        return path
+
+    def load_checkpoint(self, path):
+        self.model.load_state_dict(torch.load(path, map_location=self.bucket.flat.device))
+        opt = path[:-3] + '.opt.pt'
+        if os.path.exists(opt):
+            self.load_state_dict(torch.load(opt, map_location=self.bucket.flat.device))
+        else:                                   # a reference-style checkpoint: iteration from the file name (train.py:258-260)
+            base = os.path.basename(path)
+            if base.startswith('step') and base[4:12].isdigit():
+                self.iter_id = int(base[4:12])
+        return self.iter_id

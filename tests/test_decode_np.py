@@ -65,3 +65,21 @@ def test_detect_image_and_batch_on_gpu():
     if len(scores):
         np.testing.assert_allclose(out_scores[0], scores, rtol=2e-2, atol=2e-3)
         assert out_boxes[0].shape[1] == 4 and out_classes[0].dtype == np.int32
+
+
+def test_process_image_u8_plus_table_equals_process_image():
+    """The uint8 fast path splits process_image in two: cv2 steps on the host (process_image_u8), NormalizeImage + Permute as a
+    3 x 256 table applied on the GPU.  Table(process_image_u8(img)) must equal process_image(img) bit for bit."""
+    import numpy as np
+    from ppyolo_b200.engine import normalize_lut
+    from model.decode_np import Decode
+    import config as cfgs
+    cfg = cfgs.PPYOLO_r18vd_Config()
+    d = Decode(None, ['c%d' % i for i in range(80)], False, cfg, for_test=True)
+    img = np.random.RandomState(7).randint(0, 256, (240, 320, 3)).astype(np.uint8)
+    want, im_size = d.process_image(img.copy())
+    u8, im_size2 = d.process_image_u8(img.copy())
+    assert u8.dtype == np.uint8 and u8.shape == (1, d.target_size, d.target_size, 3) and np.array_equal(im_size, im_size2)
+    lut = normalize_lut([float(v) for v in d.mean], [float(v) for v in d.std], d.is_scale)
+    got = np.stack([lut[c][u8[0, :, :, c]] for c in range(3)], 0)[None]
+    assert np.array_equal(got, want)

@@ -211,3 +211,45 @@ def test_graphed_training_step_matches_eager():
         assert float((a - b).norm()) <= 2e-2 * float(a.norm()) + 1e-6, n
     for k in se:
         np.testing.assert_allclose(sg[k].cpu().numpy(), se[k].cpu().numpy(), rtol=2e-3, atol=1e-5, err_msg=k)
+
+
+def test_trainer_fused_ema_checkpoint_and_eval_refresh(tmp_path):
+    """Trainer with the EMA fused into the optimizer kernel: (1) the shadow equals a stand-alone ExponentialMovingAverage
+    (model/EMA.py semantics) updated after every step; (2) save_checkpoint / load_checkpoint restore weights, momentum, EMA and the
+    iteration; (3) after training, eager module-level eval sees the NEW weights (packed-weight cache refreshed: ADVICE r1) and
+    agrees with a freshly built engine."""
+    from model.EMA import ExponentialMovingAverage
+    from ppyolo_b200.trainer import Trainer
+    model, cfg = build_train_model('r18vd')
+    x, gb, gc, gs, targets = train_inputs(cfg)
+    trainer = Trainer(model, cfg, ema=True)
+    ref_ema = ExponentialMovingAverage(model, cfg.ema_decay)
+    ref_ema.register()
+    trainer.iter_id = 2000                                  # past lr = 0 of the first warm-up step
+    for _ in range(3):
+        trainer.step(x, gb, gc, gs, targets)
+        ref_ema.update()
+    assert torch.equal(trainer.ema._shadow_flat, ref_ema._shadow_flat)
+    assert trainer.ema._update_step == 3
+    path = trainer.save_checkpoint(str(tmp_path))
+    w_before = [p.detach().clone() for p in trainer.params]
+    mom_before = trainer.momentum_flat.clone()
+    trainer.step(x, gb, gc, gs, targets)                    # move on, then restore
+    assert not torch.equal(trainer.momentum_flat, mom_before)
+    it = trainer.load_checkpoint(path)
+    assert it == 2003 and torch.equal(trainer.momentum_flat, mom_before)
+    for a, b in zip(w_before, trainer.params):
+        assert torch.equal(a, b.detach())
+    assert torch.equal(trainer.ema._shadow_flat, ref_ema._shadow_flat)
+    # eval after training: module-level path (packs weights lazily) vs a fresh engine, both must see the trained weights
+    model.eval()
+    model.head.set_dropblock(True)
+    model.precision = 'fp32'
+    im = synth.im_sizes(x.shape[0]).to(DEV)
+    model.use_engine = True
+    model(x, im)
+    outs_engine = [o.clone() for o in model.engine(x.shape[0], x.shape[2], x.shape[3]).head_outputs_nchw()]
+    model.use_engine = False
+    outs_eager = model.head._get_outputs(model.backbone(x))
+    for a, b in zip(outs_engine, outs_eager):
+        np.testing.assert_allclose(a.cpu().numpy(), b.detach().cpu().numpy(), rtol=0, atol=1e-4 * float(a.abs().max()))
