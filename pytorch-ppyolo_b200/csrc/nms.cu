@@ -25,7 +25,16 @@ namespace ppy {
 namespace {
 
 constexpr int kCap = kNmsKeyCap;      // max collected candidates per image (keys in shared memory)
-constexpr int kMaxN = 1024;           // max boxes entering the n x n stage
+constexpr int kMaxN = 4000;           // max boxes entering the n x n stage (per-box arrays live in dynamic shared memory: 227 KB cap)
+constexpr int kMinN = 1024;           // smallest per-box array size allocated
+// dynamic shared memory of nms_matrix_kernel: kCap keys, then the per-box arrays for `nmax` boxes (41 bytes per box)
+inline int matrix_smem_bytes(int nmax) { return kCap * 8 + nmax * (16 + 4 * 4 + 2 * 2 + 1) + 64; }
+inline int matrix_nmax(int nms_top_k) {
+  int want = nms_top_k > 0 ? nms_top_k : kMaxN;        // <= 0 ("all candidates", model/matrix_nms.py:120-125): up to kMaxN
+  int n = kMinN;
+  while (n < want && n < kMaxN) n <<= 1;
+  return n < kMaxN ? n : kMaxN;
+}
 constexpr int kScanThreads = 256;
 constexpr int kMatrixThreads = 1024;
 
@@ -220,16 +229,17 @@ __global__ void __launch_bounds__(kMatrixThreads)
 nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classes, const unsigned int* __restrict__ count,
                   const unsigned long long* __restrict__ keys, int key_stride, const unsigned int* __restrict__ hist,
                   unsigned int thr_bits, int shift, int nms_top_k, int keep_top_k, float post_thr,
-                  int use_gaussian, float sigma, float* __restrict__ out, int* __restrict__ counts) {
+                  int use_gaussian, float sigma, float* __restrict__ out, int* __restrict__ counts, int nmax) {
   extern __shared__ unsigned long long s_keys[];           // kCap keys, later reused for the other sorts
-  __shared__ float4 s_box[kMaxN];
-  __shared__ float s_score[kMaxN];
-  __shared__ int s_label[kMaxN];
-  __shared__ float s_comp[kMaxN];
-  __shared__ float s_new[kMaxN];
-  __shared__ unsigned short s_order[kMaxN];   // box indices grouped by label (ascending index inside a label)
-  __shared__ unsigned short s_gstart[kMaxN];  // first position of the label group a position belongs to
-  __shared__ unsigned char s_odd[kMaxN];      // box whose IoU can be NaN/inf (area not a positive finite number)
+  // per-box arrays for up to nmax boxes, carved from the dynamic allocation behind the keys
+  float4* s_box = reinterpret_cast<float4*>(s_keys + kCap);
+  float* s_score = reinterpret_cast<float*>(s_box + nmax);
+  int* s_label = reinterpret_cast<int*>(s_score + nmax);
+  float* s_comp = reinterpret_cast<float*>(s_label + nmax);
+  float* s_new = s_comp + nmax;
+  unsigned short* s_order = reinterpret_cast<unsigned short*>(s_new + nmax);    // box indices grouped by label (ascending index inside a label)
+  unsigned short* s_gstart = s_order + nmax;                                      // first position of the label group a position belongs to
+  unsigned char* s_odd = reinterpret_cast<unsigned char*>(s_gstart + nmax);       // box whose IoU can be NaN/inf (area not positive finite)
   __shared__ unsigned int s_part[33];
   __shared__ int s_nan_from;   // largest i with NaN compensate (poisons every column j <= i), -1 if none
   __shared__ int s_kept;
@@ -273,7 +283,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   bitonic_sort_desc(s_keys, len);
   int n = m;
   if (nms_top_k > 0 && n > nms_top_k) n = nms_top_k;
-  if (n > kMaxN) { if (tid == 0) counts[img] = -3; return; }
+  if (n > nmax) { if (tid == 0) counts[img] = -3; return; }
   if (tid == 0) { s_nan_from = -1; s_kept = 0; s_any_odd = 0; }
   __syncthreads();
   const float4* gb = reinterpret_cast<const float4*>(boxes) + (long long)img * num_boxes;
@@ -528,15 +538,16 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
   }
   if ((rc = check_launch())) return rc;
   static bool attr_set = false;
-  const int smem = kCap * (int)sizeof(unsigned long long);
+  const int nmax = matrix_nmax(nms_top_k);
+  const int smem = matrix_smem_bytes(nmax);
   if (!attr_set) {
-    rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, matrix_smem_bytes(kMaxN)));
     if (rc) return rc;
     attr_set = true;
   }
   nms_matrix_kernel<<<n, kMatrixThreads, smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, kCap, nullptr, 0u, 0,
                                                      nms_top_k, keep_top_k, post_threshold, use_gaussian, gaussian_sigma,
-                                                     out, counts);
+                                                     out, counts, nmax);
   return check_launch();
 }
 
@@ -567,15 +578,16 @@ int ppy_matrix_nms_candidates(const float* boxes, int n, int num_boxes, int num_
   PPY_REQUIRE((long long)num_boxes * num_classes < 0xFFFFFFFFll);
   const CandSink c = cand_carve(workspace, n, cap, score_threshold);
   static bool attr_set = false;
-  const int smem = kCap * (int)sizeof(unsigned long long);
+  const int nmax = matrix_nmax(nms_top_k);
+  const int smem = matrix_smem_bytes(nmax);
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, matrix_smem_bytes(kMaxN)));
     if (rc) return rc;
     attr_set = true;
   }
   nms_matrix_kernel<<<n, kMatrixThreads, smem, as_stream(s)>>>(boxes, num_boxes, num_classes, c.count, c.keys, cap, c.hist,
                                                                c.thr_bits, c.shift, nms_top_k, keep_top_k, post_threshold,
-                                                               use_gaussian, gaussian_sigma, out, counts);
+                                                               use_gaussian, gaussian_sigma, out, counts, nmax);
   return check_launch();
 }
 

@@ -549,7 +549,7 @@ def split_predictions(out, counts_host):
     for i, c in enumerate(counts_host):
         if c < 0:
             raise _lib.KernelError('matrix_nms: candidate overflow on image %d (code %d): more than 8192 scores tie '
-                                   'at the top-k cutoff, nms_top_k<=0 with more than 1024 candidates, or (sparse '
+                                   'at the top-k cutoff, nms_top_k<=0 with more than 4000 candidates, or (sparse '
                                    'post-processing) more scores above score_threshold than the candidate list holds -- '
                                    "set model.postprocess_impl = 'dense'" % (i, c))
         preds.append(out[i, :c] if c > 0 else torch.full((1, 6), -1.0, device=out.device))

@@ -76,6 +76,19 @@ def test_nms_c5_batched_vs_oracle():
             assert_preds_close(got[i].cpu().numpy(), want, rtol=2e-6 if gauss else 2e-7, atol=0)
 
 
+@pytest.mark.parametrize('nb,topk,gauss', [(400, 3000, False), (400, 2000, True), (200, -1, False), (330, 4000, False)])
+def test_nms_beyond_1024_candidates_vs_oracle(nb, topk, gauss):
+    """More than 1024 boxes in the n x n stage (per-box arrays in dynamic shared memory, up to 4000) and nms_top_k = -1 ("all
+    candidates", model/matrix_nms.py:120-125): labels / order exact, scores 2e-7 (linear) / 2e-6 (gaussian) against the oracle."""
+    from model.matrix_nms import matrix_nms
+    b, s = synth.nms_inputs(nb, 80, seed=nb + 7)
+    cand = int((s > 0.01).sum())
+    assert cand > 1024 and (topk > 0 or cand <= 4000)
+    out = matrix_nms(b.to(DEV), s.to(DEV), 0.01, 0.01, topk, 100, use_gaussian=gauss, gaussian_sigma=2.0)
+    want = ref.matrix_nms(b.numpy(), s.numpy(), 0.01, 0.01, topk, 100, use_gaussian=gauss, gaussian_sigma=2.0)
+    assert_preds_close(out.cpu().numpy(), want, rtol=2e-6 if gauss else 2e-7, atol=0)
+
+
 def test_nms_properties_full_size():
     """Size-independent properties at the bench size (22743 boxes x 80, bs 8): sorted scores, idempotent
     re-run, labels in range, all boxes are input boxes."""
