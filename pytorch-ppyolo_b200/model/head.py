@@ -147,11 +147,10 @@ class YOLOv3Head(torch.nn.Module):
         return outputs
 
     def get_loss(self, input, gt_box, gt_label, gt_score, targets):
-        outputs = self._get_outputs(input)
-        if self.yolo_loss is None:
-            raise NotImplementedError('training losses are not built yet (SURVEY.md 8f rank 2)')
-        return self.yolo_loss(outputs, gt_box, gt_label, gt_score, targets, self.anchors, self.anchor_masks,
-                              self.mask_anchors, self.num_classes)
+        """Reference model/head.py:400-422.  The module-level operators of ``_get_outputs`` run kernels on detached tensors, so the
+        losses are computed on the differentiable evaluation of the head instead (same values, gradients for every head
+        parameter) -- never a silently non-differentiable dict."""
+        return self.get_loss_autograd(input, gt_box, gt_label, gt_score, targets)
 
     def get_loss_autograd(self, body_feats, gt_box, gt_label, gt_score, targets):
         """get_loss (reference :400-422) with the head evaluated as differentiable tensor code."""

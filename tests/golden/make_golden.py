@@ -273,7 +273,47 @@ def gen_train():
     save('train', **arrays)
 
 
+def gen_train_c4():
+    """BASELINE config C4 at its FULL shape: ppyolo_2x 608x608, bs 8, one training forward+backward of the reference (frozen
+    backbone in train mode, DropBlock disabled for determinism) -> the six losses and gradient probes."""
+    from config import select_loss
+    spec = importlib.util.spec_from_file_location('targets', os.path.join(REPO, 'pytorch-ppyolo_b200', 'ppyolo_b200', 'targets.py'))
+    tg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tg)
+    torch.set_num_threads(8)
+    cfg = PPYOLO_2x_Config()
+    size, batch = 608, 8
+    iou_loss = select_loss(cfg.iou_loss_type)(**cfg.iou_loss)
+    iou_aware = select_loss(cfg.iou_aware_loss_type)(**cfg.iou_aware_loss)
+    yolo = select_loss(cfg.yolo_loss_type)(iou_loss=iou_loss, iou_aware_loss=iou_aware, **cfg.yolo_loss)
+    head_kw = dict(cfg.head); head_kw['drop_block'] = False
+    backbone = select_backbone(cfg.backbone_type)(**cfg.backbone)
+    head = select_head(cfg.head_type)(yolo_loss=yolo, is_train=True, nms_cfg=cfg.nms_cfg, **head_kw)
+    model = PPYOLO(backbone, head)
+    synth.randomize_(model, seed=0)
+    model.train()
+    backbone.freeze()
+    x = synth.images(batch, size, seed=20)
+    gt_bbox, gt_class, gt_score = tg.synthetic_ground_truth(batch, seed=30)
+    targets = tg.gt2yolo_target(gt_bbox, gt_class, gt_score, h=size, w=size, **cfg.gt2YoloTarget)
+    losses = model(x, None, False, torch.from_numpy(gt_bbox), torch.from_numpy(gt_class), torch.from_numpy(gt_score),
+                   [torch.from_numpy(t) for t in targets])
+    sum(losses.values()).backward()
+    arrays = {k: v.detach() for k, v in losses.items()}
+    arrays['out0_bias_grad'] = head.yolo_output_convs[0].conv.bias.grad
+    arrays['out2_bias_grad'] = head.yolo_output_convs[2].conv.bias.grad
+    w = head.detection_blocks[0].layers[1].conv.weight.grad
+    arrays['blk0_w_gradabs'] = np.array([float(w.double().abs().sum())])
+    arrays['stem_running_mean'] = model.state_dict()['backbone.stage1_conv1_1.bn.running_mean']
+    print('   train C4:', {k: round(float(v.detach()), 4) for k, v in losses.items()})
+    save('train_c4', **arrays)
+    torch.set_num_threads(1)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'train_c4':
+        gen_train_c4()
+        sys.exit(0)
     gen_train()
     gen_losses()
     gen_nms()
