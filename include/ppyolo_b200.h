@@ -122,6 +122,22 @@ typedef struct ppy_conv_params {
   long long y_plane;
   long long res_plane;
   int* overflow;
+  /* --- PPY_F16X2 path, plain 1x1 stride-1 convs only: a SECOND K source.  K blocks [cin/64, cin/64 + x2_kb) of the GEMM are
+   * 64-channel blocks of the pair tensor x2 ([n,ho,wo,*], the output's pixel grid); the packed weight rows are
+   * k_pad = cin + 64*x2_kb long.  Two uses (model/resnet_vd.py:44-56, :75-86 -- the bottleneck's `conv3(y) + shortcut`):
+   *   x2_tiled = 0  K-concatenation: x2 channels [0, 64*x2_kb) -- conv3 and the projection shortcut conv4 as ONE GEMM
+   *                 [W3*s3 | W4*s4] . [y ; x] (both norms' scales folded into the weight rows by the caller);
+   *   x2_tiled = 1  the identity shortcut added BY THE TENSOR CORE: for the N tile starting at column n0 the blocks are x2
+   *                 channels [n0, n0 + 64*x2_kb) and the weight block holds chan_scale[co] (a power of two: exact) on the
+   *                 diagonal, so the residual arrives through the deep TMA operand pipeline instead of the epilogue's
+   *                 latency-exposed loads; requires 64*x2_kb == the kernel's N tile (256 when cout % 256 == 0 and
+   *                 k_pad <= 512, else 128) and the lo plane of those weight blocks to be zero (it is not even loaded).
+   * x2_kb = 0: off.  Mutually exclusive with `residual`. */
+  const void* x2;
+  int x2_ld;
+  long long x2_plane;
+  int x2_kb;
+  int x2_tiled;
 } ppy_conv_params;
 
 /* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)

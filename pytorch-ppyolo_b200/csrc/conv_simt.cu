@@ -212,7 +212,7 @@ int ppy_conv_f32(const ppy_conv_params* p, ppy_stream_t s) {
   int ho, wo;
   int rc = validate_conv(p, 4, &ho, &wo);
   if (rc) return rc;
-  if (p->accumulate || p->split_k > 1 || p->wgrad_taps > 1) return PPY_ERR_UNSUPPORTED;   // tcgen05 path only
+  if (p->accumulate || p->split_k > 1 || p->wgrad_taps > 1 || p->x2_kb > 0) return PPY_ERR_UNSUPPORTED;   // tcgen05 path only
   PPY_REQUIRE(p->out_dtype == PPY_F32);
   const long long M = (long long)p->n * ho * wo;
   dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(p->cout, BN));

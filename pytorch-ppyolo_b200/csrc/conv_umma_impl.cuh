@@ -490,6 +490,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     {
       constexpr uint32_t tx_bytes = (Cfg::kBStageBytes + (mode_is_tma(MODE) ? A_STAGE : 0)) * (CTA2 ? 2 : 1);
       const int kb_per_tap = p.cin / BLOCK_K;
+      // second K source (split mode, 1x1 convs; see ppy_conv_params.x2): K blocks >= kb_x2 read x2 through the maps tmap_y (hi
+      // plane) / tmap_r (lo plane), which the slab epilogue leaves unused
+      const int kb_x2 = (SPLIT && MODE == MODE_TMA_A) ? num_kb - p.x2_kb : num_kb;
+      const bool x2_ident = SPLIT && MODE == MODE_TMA_A && p.x2_tiled != 0;      // identity blocks: their lo weight plane is zero
       int g = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
@@ -514,7 +518,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           if (elect_one()) {                     // the whole warp walks the ring (uniform control flow), one lane issues
             // CTA pairs: both CTAs' bytes are counted on the leader's barrier, which the leader arms for the whole pair
             const uint32_t bar = CTA2 ? map_to_cta(full_bar(s), 0) : full_bar(s);
-            if (!CTA2 || cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), tx_bytes);
+            const bool second = kb >= kb_x2, skip_blo = second && x2_ident;
+            if (!CTA2 || cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), tx_bytes - (skip_blo ? (uint32_t)B_PLANE * (CTA2 ? 2u : 1u) : 0u));
             constexpr bool by_tap = MODE == MODE_TMA_PATCH || MODE == MODE_TMA_IM2COL;
             const int tap = by_tap ? kb / kb_per_tap : 0, c0 = by_tap ? (kb % kb_per_tap) * BLOCK_K : 0;
 #pragma unroll
@@ -522,7 +527,12 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               const CUtensorMap* ma = pl ? &tmap_a2 : &tmap_a;
               const uint32_t a_dst = smem_a + s * A_STAGE + pl * A_TILE, b_dst = smem_b + s * Cfg::kBStageBytes + pl * B_PLANE;
               const int nrow = n0 + pl * p.cout_pad;
-              if (MODE == MODE_TMA_A) { if (CTA2) tma2_load_2d(a_dst, ma, bar, kb * BLOCK_K, m0); else tma_load_2d(a_dst, ma, bar, kb * BLOCK_K, m0); }
+              if (MODE == MODE_TMA_A) {
+                const CUtensorMap* m1 = (SPLIT && second) ? (pl ? &tmap_r : &tmap_y) : ma;
+                const int col = (SPLIT && second) ? (kb - kb_x2) * BLOCK_K + (x2_ident ? u.nt * BN : 0) : kb * BLOCK_K;
+                if (CTA2) tma2_load_2d(a_dst, m1, bar, col, m0); else tma_load_2d(a_dst, m1, bar, col, m0);
+                if (pl == 1 && skip_blo) continue;       // identity block: no lo weight tile
+              }
               if (MODE == MODE_TMA_PATCH) {
                 // one tap x 64 channels of the 16x8 patch; the halo (negative / beyond-edge coordinates) is zero-filled by TMA
                 if (CTA2) tma2_load_4d(a_dst, ma, bar, c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
@@ -558,6 +568,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     if (cta_rank == 0) {
       constexpr uint32_t idesc = make_idesc(CTA2 ? 2 * BLOCK_M : BLOCK_M, BN);
       constexpr int CH = CHUNKED ? chunk_kb(MODE) : (1 << 28);
+      const int kb_ident = (SPLIT && MODE == MODE_TMA_A && p.x2_tiled) ? num_kb - p.x2_kb : num_kb;   // identity blocks: b_lo == 0
       int g = 0, it = 0;                         // it: uses of the accumulator buffers = tiles (CHUNKED: K chunks)
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
@@ -577,6 +588,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           constexpr int COMBOS = SPLIT ? 3 : 1;
 #pragma unroll
           for (int cb = 0; cb < COMBOS; ++cb) {
+          if (SPLIT && cb == 1 && kb >= kb_ident) continue;
           const uint32_t a_pl = a_addr + (cb == 2 ? A_TILE : 0), b_pl = b_addr + (cb == 1 ? B_PLANE : 0);
           if (MODE == MODE_TMA_SLAB) {           // three taps per stage: tap ky reads the slab one pixel row (1024 bytes) further down
 #pragma unroll
@@ -1181,6 +1193,13 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   tmap_y = tmap_b;
   tmap_r = tmap_b;
+  if (SPLIT && MODE == MODE_TMA_A && p->x2_kb > 0) {      // second K source: hi plane -> tmap_y, lo plane -> tmap_r
+    const uint64_t c2 = p->x2_tiled ? (uint64_t)p->cout : (uint64_t)p->x2_kb * BLOCK_K;
+    rc = encode_2d(enc, &tmap_y, p->x2, c2, (uint64_t)M, (uint64_t)p->x2_ld * 2, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    rc = encode_2d(enc, &tmap_r, reinterpret_cast<const uint16_t*>(p->x2) + p->x2_plane, c2, (uint64_t)M, (uint64_t)p->x2_ld * 2, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+  }
   if (EPI == EPI_TMA) {
     rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH, p->out_dtype == PPY_F32);
     if (rc) return rc;
@@ -1250,7 +1269,19 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     if (p->accumulate) return PPY_ERR_UNSUPPORTED;
     static const bool no_pair = knob_off("PPY_NO_CTA2");
     const bool pair = mode_is_tma(MODE) && !no_pair && (long long)p->n * ho * wo > BLOCK_M;
-    if (p->k_pad / BLOCK_K <= chunk_kb(MODE)) {    // the whole K is one chunk (K <= 256): no register stage, BLOCK_N up to 256
+    if constexpr (MODE == MODE_TMA_A) {
+      if (p->x2_kb > 0 && p->x2_tiled) {     // identity blocks: the N tile is fixed by their width; up to 8 K blocks in one accumulator
+        const int kbt = p->k_pad / BLOCK_K;
+        if (p->x2_kb == 4 && c % 256 == 0 && kbt <= 8)
+          return pair ? launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB>(p, ho, wo, st);
+        if (p->x2_kb == 2 && c % 128 == 0) {
+          if (kbt <= 8) return pair ? launch<128, MODE, EPI_SLAB, false, true>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB>(p, ho, wo, st);
+          return pair ? launch<128, MODE, EPI_SLAB, false, true, true>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB, false, false, true>(p, ho, wo, st);
+        }
+        return PPY_ERR_UNSUPPORTED;
+      }
+    }
+    if (p->k_pad / BLOCK_K <= (p->x2_kb > 0 ? 6 : chunk_kb(MODE))) {    // the whole K is one chunk (K <= 256): no register stage, BLOCK_N up to 256
       if (c <= 32) return launch<32, MODE, EPI_SLAB>(p, ho, wo, st);
       if (c <= 64) return launch<64, MODE, EPI_SLAB>(p, ho, wo, st);
       if constexpr (mode_is_tma(MODE)) {
@@ -1338,8 +1369,14 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
     PPY_REQUIRE(p->x_plane > 0 && (p->x_plane * 2) % 16 == 0 && !p->accumulate && !p->coord_w);
     if (p->out_dtype == PPY_F16X2) PPY_REQUIRE(p->y_plane > 0);
     if (p->residual) PPY_REQUIRE(p->out_dtype == PPY_F16X2 && p->res_plane > 0);
+    if (p->x2_kb > 0) {
+      PPY_REQUIRE(p->x2 && !p->residual && !p->offset_mask && p->kh == 1 && p->stride == 1 && p->pad == 0 && p->cin % BLOCK_K == 0);
+      PPY_REQUIRE(p->k_pad == p->cin + p->x2_kb * BLOCK_K && p->x2_plane > 0 && (p->x2_plane * 2) % 16 == 0);
+      PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->x2) & 15) == 0 && (p->x2_ld * 2) % 16 == 0);
+      PPY_REQUIRE(p->x2_ld >= (p->x2_tiled ? p->cout : p->x2_kb * BLOCK_K));
+    }
   } else {
-    PPY_REQUIRE(p->out_dtype != PPY_F16X2);
+    PPY_REQUIRE(p->out_dtype != PPY_F16X2 && p->x2_kb == 0);
   }
   if (p->offset_mask) PPY_REQUIRE(p->cin % BLOCK_K == 0 && (long long)p->n * p->h * p->w * p->x_ld < 0x7FFFFFFFll);
   PPY_REQUIRE((long long)p->n * ho * wo < 0x7FFFFFFFll);
@@ -1360,7 +1397,7 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
     return dispatch<MODE_DCN>(p, ho, wo, as_stream(s));
   }
   const bool plain_1x1 = p->kh == 1 && p->stride == 1 && p->pad == 0 && p->cin % BLOCK_K == 0 &&
-                         p->k_pad == p->cin;
+                         p->k_pad == p->cin + p->x2_kb * BLOCK_K;
   if (plain_1x1) return dispatch<MODE_TMA_A>(p, ho, wo, as_stream(s));
   // 3x3 stride-1: A tiles as 16x8 pixel patches fetched by 4-D TMA, when the patch grid wastes < 15% of the tiles
   const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&

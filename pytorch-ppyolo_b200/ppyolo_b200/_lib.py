@@ -12,7 +12,7 @@ c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_lon
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
 
 PPY_F32, PPY_BF16, PPY_F16X2 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
 
 
@@ -32,6 +32,7 @@ class ConvParams(ctypes.Structure):
         ('accumulate', c_int), ('split_k', c_int), ('wgrad_taps', c_int), ('wgrad_pitch', c_int), ('wgrad_tap_stride', c_int),
         ('coord_w', c_void_p),
         ('x_plane', c_ll), ('y_plane', c_ll), ('res_plane', c_ll), ('overflow', c_void_p),
+        ('x2', c_void_p), ('x2_ld', c_int), ('x2_plane', c_ll), ('x2_kb', c_int), ('x2_tiled', c_int),
     ]
 
 

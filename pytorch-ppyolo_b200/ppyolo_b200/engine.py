@@ -476,6 +476,70 @@ class InferenceEngine(object):
         return self._conv(name, x, unit.conv.weight.detach(), scale, shift, unit.stride, act, residual=residual,
                           dst=dst, coord=coord, upsample=upsample, out_code=out_code)
 
+    def _dual_ok(self, conv3, y, sc_unit, sc_in):
+        """`conv3(y) + shortcut` of a bottleneck as ONE pair GEMM with a second K source (ppy_conv_params.x2)?"""
+        from model.custom_layers import DCNv2
+        if self.code != PPY_F16X2 or self.train_bn or not getattr(self.model, 'fuse_shortcut', True):
+            return False
+        units = [conv3] + ([sc_unit] if sc_unit is not None else [])
+        for u in units:
+            if (isinstance(u.conv, DCNv2) or u.conv.weight.shape[-1] != 1 or u.stride != 1 or u.conv.weight.shape[1] % 64 or
+                    u.act_name is not None):
+                return False
+        if y.c != conv3.conv.weight.shape[1] or sc_in.n != y.n or sc_in.h != y.h or sc_in.w != y.w:
+            return False
+        if sc_unit is None:
+            return sc_in.c == conv3.filters and ops.ident_tile(conv3.filters, y.c) is not None
+        return sc_in.c == sc_unit.conv.weight.shape[1]
+
+    def _conv_dual(self, name, conv3, y, sc_in, sc_unit=None, act=0, dst=None):
+        """act(norm3(conv3(y)) + shortcut) as one launch of the pair kernel: the shortcut is a second K source -- the projection
+        conv4 K-concatenated (both folded norm scales multiplied into the weight rows), or the identity shortcut as identity
+        weight blocks so the tensor core does the residual add and the residual travels through the TMA operand pipeline
+        (reference model/resnet_vd.py:44-56, :75-86).  Returns None when the packer declines (tiny weights): caller falls back."""
+        cout, cin = conv3.filters, y.c
+        s3, b3 = conv3.folded_scale_shift()
+        w3 = conv3.conv.weight.detach()
+        if sc_unit is not None:
+            s4, b4 = sc_unit.folded_scale_shift()
+            res = ops.pack_weight_pair_dual(w3, s3, sc_unit.conv.weight.detach(), s4)
+            shift = b3 + b4
+            k_alg = cin + sc_in.c
+        else:
+            res = ops.pack_weight_pair_dual(w3, s3, ident_bn=ops.ident_tile(cout, cin))
+            shift = b3
+            k_alg = cin
+        if res is None:
+            return None
+        packed, k_pad, cout_pad, chan_scale = res
+        self._keep(packed)
+        if dst is None:
+            dst = TensorRef(self._new(y.n, y.h, y.w, ops.round_up(cout, 8)), c=cout)
+        # accumulator = act_scale * chan_scale * (true value - shift); pair outputs are stored times act_scale
+        scale = self._keep((1.0 / chan_scale).contiguous())
+        shift = self._keep((shift.float() * self.act_scale).contiguous())
+        p = ConvParams()
+        p.x, p.x_ld, p.x_plane = y.ptr, y.ld, y.plane
+        p.n, p.h, p.w, p.cin = y.n, y.h, y.w, cin
+        p.weight = packed.data_ptr()
+        p.cout, p.kh, p.kw, p.stride, p.pad = cout, 1, 1, 1, 0
+        p.k_pad, p.cout_pad = k_pad, cout_pad
+        p.scale, p.shift = scale.data_ptr(), shift.data_ptr()
+        p.act = act
+        p.y, p.y_ld, p.out_dtype, p.y_plane = dst.ptr, dst.ld, PPY_F16X2, dst.plane
+        p.x2, p.x2_ld, p.x2_plane = sc_in.ptr, sc_in.ld, sc_in.plane
+        p.x2_kb, p.x2_tiled = (k_pad - cin) // 64, 0 if sc_unit is not None else 1
+        p.overflow = self.overflow.data_ptr()
+        self._keep(p)
+        ref = ctypes.byref(p)
+        self._add(name, lambda: check(lib.ppy_conv_f16x2(ref, ops.stream_ptr()), name))
+        m = y.n * y.h * y.w
+        flops = 2 * m * cout * k_alg
+        self.conv_flops += flops
+        nbytes = m * (cin + sc_in.c) * y.esz + packed.numel() * packed.element_size() + m * cout * dst.esz
+        self.step_info[name] = {'flops': flops, 'bytes': nbytes, 'm': m, 'n': cout, 'k': k_alg}
+        return dst
+
     def _pool_into_conv_ok(self, unit, x):
         """AvgPool2d(2,2) + 1x1 conv of the vd shortcut (model/resnet_vd.py:29-33) as ONE 2x2 / stride-2 conv with the weight
         replicated over the window and divided by 4 (exact in bf16): the input is read once instead of pooled, written and
@@ -503,18 +567,30 @@ class InferenceEngine(object):
         from model.resnet_vd import ConvBlock, IdentityBlock, BasicBlock
         relu = _lib.ACT_RELU
         if isinstance(blk, ConvBlock):
-            if blk.is_first:
+            y = self._unit(name + '.conv1', blk.conv1, x)
+            y = self._unit(name + '.conv2', blk.conv2, y)
+            if self.code == PPY_F16X2 and not self.train_bn:
+                # pair path: conv3 and the projection shortcut conv4 as one GEMM over [y ; shortcut input] (no shortcut tensor)
+                sc_in = x if blk.is_first else self._avgpool(x)
+                if self._dual_ok(blk.conv3, y, blk.conv4, sc_in):
+                    out = self._conv_dual(name + '.conv3', blk.conv3, y, sc_in, blk.conv4, relu, dst)
+                    if out is not None:
+                        return out
+                sc = self._unit(name + '.conv4', blk.conv4, sc_in)
+            elif blk.is_first:
                 sc = self._unit(name + '.conv4', blk.conv4, x)
             elif self._pool_into_conv_ok(blk.conv4, x):
                 sc = self._unit_avgpooled(name + '.conv4', blk.conv4, x)
             else:
                 sc = self._unit(name + '.conv4', blk.conv4, self._avgpool(x))
-            y = self._unit(name + '.conv1', blk.conv1, x)
-            y = self._unit(name + '.conv2', blk.conv2, y)
             return self._unit(name + '.conv3', blk.conv3, y, residual=sc, act=relu, dst=dst)
         if isinstance(blk, IdentityBlock):
             y = self._unit(name + '.conv1', blk.conv1, x)
             y = self._unit(name + '.conv2', blk.conv2, y)
+            if self._dual_ok(blk.conv3, y, None, x):
+                out = self._conv_dual(name + '.conv3', blk.conv3, y, x, None, relu, dst)
+                if out is not None:
+                    return out
             return self._unit(name + '.conv3', blk.conv3, y, residual=x, act=relu, dst=dst)
         if isinstance(blk, BasicBlock):
             sc = x

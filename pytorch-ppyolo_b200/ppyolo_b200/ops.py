@@ -139,6 +139,90 @@ def pack_weight_pair(weight, c_begin=0, c_count=None):
     return packed, cin_pad, k_pad, cout_pad, chan_scale.contiguous()
 
 
+def ident_tile(cout, cin):
+    """N tile of ppy_conv_f16x2 for a 1x1 conv whose identity shortcut runs as K blocks (ppy_conv_params.x2_tiled): 256 when the
+    whole K (cin + 256) fits one accumulator (<= 8 blocks), else 128; None = shape not supported."""
+    if cin % 64:
+        return None
+    if cout % 256 == 0 and cin // 64 + 4 <= 8:
+        return 256
+    return 128 if cout % 128 == 0 else None
+
+
+def pack_weight_pair_dual(w1, scale1, w2=None, scale2=None, ident_bn=None):
+    """Packed PPY_F16X2 weight [2, cout_pad, cin + extra] of a 1x1 conv with a second K source (ppy_conv_params.x2).
+
+    ``w2`` given: K-concatenation [w1 * scale1 | w2 * scale2] (two 1x1 convs with their folded norm scales, one GEMM).
+    ``ident_bn`` given: identity shortcut -- ``ident_bn`` extra columns per row holding ``chan_scale[co]`` at column
+    ``co % ident_bn`` (a power of two, exact in fp16, lo part zero).  Rows are multiplied by the power of two ``chan_scale``
+    that brings the largest entry into [2^13, 2^14) (identity mode: capped at 2^15 so the diagonal stays representable).
+    Returns (packed, k_pad, cout_pad, chan_scale) or None when a channel's weights are too small for the cap."""
+    _cuda(w1, 'weight')
+    cout, cin = w1.shape[0], w1.shape[1]
+    assert w1.shape[2] == 1 and w1.shape[3] == 1 and cin % 64 == 0
+    wa = w1.detach().float().reshape(cout, cin) * scale1.detach().float().view(-1, 1)
+    if w2 is not None:
+        wb = w2.detach().float().reshape(cout, -1) * scale2.detach().float().view(-1, 1)
+        assert wb.shape[1] % 64 == 0
+        amax = torch.cat([wa, wb], 1).abs().amax(dim=1)
+        _, ex = torch.frexp(amax)
+        chan_scale = torch.where(amax > 0, torch.ldexp(torch.ones_like(amax), (14 - ex).clamp(-30, 40)), torch.ones_like(amax))
+    else:
+        amax = wa.abs().amax(dim=1)
+        _, ex = torch.frexp(amax)
+        chan_scale = torch.where(amax > 0, torch.ldexp(torch.ones_like(amax), (14 - ex).clamp(-14, 15)), torch.ones_like(amax))
+        if bool(((amax * chan_scale < 1.0) & (amax > 0)).any()):
+            return None
+        wb = torch.zeros((cout, ident_bn), dtype=torch.float32, device=w1.device)
+        idx = torch.arange(cout, device=w1.device)
+        wb[idx, idx % ident_bn] = 1.0
+    w = (torch.cat([wa, wb], 1) * chan_scale.view(-1, 1)).contiguous()
+    k_pad = w.shape[1]
+    cout_pad = round_up(cout, 32)
+    packed = torch.empty((2, cout_pad, k_pad), dtype=torch.float16, device=w1.device)
+    check(lib.ppy_pack_conv_weight(ptr(w), cout, k_pad, 1, 1, 0, k_pad, ptr(packed), cout_pad, k_pad, k_pad, PPY_F16X2, stream_ptr()),
+          'pack_conv_weight')
+    return packed, k_pad, cout_pad, chan_scale.contiguous()
+
+
+def conv_pair_dual(x, w1, scale1, shift1, x2, w2=None, scale2=None, shift2=None, act=0, overflow=None):
+    """1x1 conv of the f16x2 path with a second K source (stand-alone wrapper; the engine builds the same parameters):
+    ``w2`` given -> act(scale1*conv(x, w1) + shift1 + scale2*conv(x2, w2) + shift2) as one GEMM; ``w2`` None -> x2 is the
+    identity shortcut, act(scale1*conv(x, w1) + shift1 + x2) with the add done by the tensor core."""
+    _cuda(x, 'input')
+    cout, cin = w1.shape[0], w1.shape[1]
+    bn = None
+    if w2 is None:
+        bn = ident_tile(cout, cin)
+        if bn is None:
+            raise ValueError('identity K blocks need cin %% 64 == 0 and cout %% 128 == 0')
+    res = pack_weight_pair_dual(w1, scale1, w2, scale2, bn)
+    if res is None:
+        raise ValueError('weights too small for the identity-block scaling')
+    packed, k_pad, cout_pad, cs = res
+    _, n, h, w, ld = x.shape
+    ldo = round_up(cout, 8)
+    out = torch.zeros((2, n, h, w, ldo), dtype=torch.float16, device=x.device)
+    sc = (1.0 / cs).contiguous()
+    sh = _f32(shift1).to(x.device)
+    if shift2 is not None:
+        sh = (sh + _f32(shift2).to(x.device)).contiguous()
+    p = ConvParams()
+    p.x, p.x_ld, p.x_plane = x.data_ptr(), ld, x.stride(0)
+    p.n, p.h, p.w, p.cin = n, h, w, cin
+    p.weight = packed.data_ptr()
+    p.cout, p.kh, p.kw, p.stride, p.pad = cout, 1, 1, 1, 0
+    p.k_pad, p.cout_pad = k_pad, cout_pad
+    p.scale, p.shift = sc.data_ptr(), sh.data_ptr()
+    p.act = act
+    p.y, p.y_ld, p.out_dtype, p.y_plane = out.data_ptr(), ldo, PPY_F16X2, out.stride(0)
+    p.x2, p.x2_ld, p.x2_plane = x2.data_ptr(), x2.shape[-1], x2.stride(0)
+    p.x2_kb, p.x2_tiled = (k_pad - cin) // 64, 1 if w2 is None else 0
+    p.overflow = overflow.data_ptr() if overflow is not None else None
+    check(lib.ppy_conv_f16x2(ctypes.byref(p), stream_ptr()), 'conv_f16x2')
+    return out
+
+
 def split_pair(x_nhwc):
     """NHWC fp32 tensor -> PPY_F16X2 tensor [2, N, H, W, C] (hi plane, lo plane)."""
     _cuda(x_nhwc)

@@ -118,6 +118,60 @@ def test_pair_conv_epilogue_variants():
           F.conv2d(x.double(), w5.double()) * scale[:13].double().view(1, -1, 1, 1) + shift[:13].double().view(1, -1, 1, 1), 'cout 13 fp32')
 
 
+DUAL_SHAPES = [  # n, cin, cout, hw, c2 (None = identity shortcut)        kernel path
+    (2, 64, 256, 19, None),     # identity, N tile 256, 1 + 4 K blocks (stage-2 conv3)
+    (1, 128, 512, 30, None),    # identity, 2 + 4 blocks, two N tiles
+    (2, 256, 1024, 19, None),   # identity, 4 + 4 blocks (stage-4 conv3)
+    (1, 512, 2048, 19, None),   # identity, N tile 128, K-chunked (stage-5 conv3)
+    (1, 320, 384, 17, None),    # identity, N tile 128 (cout % 256 != 0), 5 + 2 blocks in one accumulator
+    (3, 64, 128, 11, None),     # identity, N tile 128, rows off the tile
+    (2, 64, 256, 19, 64),       # concat: conv3 + conv4 of stage2_0 (K = 64 + 64)
+    (1, 128, 512, 24, 256),     # concat, 6 K blocks in one accumulator (stage3_0)
+    (1, 512, 2048, 10, 1024),   # concat, K-chunked (stage5_0)
+]
+
+
+@pytest.mark.parametrize('n,cin,cout,hw,c2', DUAL_SHAPES)
+def test_pair_conv_second_k_source(n, cin, cout, hw, c2):
+    """Second K source of the 1x1 pair conv (ppy_conv_params.x2): the bottleneck's `conv3(y) + shortcut` -- identity shortcut
+    added by the tensor core through identity weight blocks, or the projection shortcut conv4 K-concatenated -- against fp64."""
+    o = ops()
+    g = torch.Generator().manual_seed(cin * 13 + cout + hw + (c2 or 0))
+    x = torch.randn((n, cin, hw, hw), generator=g)
+    w1 = torch.randn((cout, cin, 1, 1), generator=g) / cin ** 0.5
+    s1, b1 = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    y1 = F.conv2d(x.double(), w1.double()) * s1.double().view(1, -1, 1, 1) + b1.double().view(1, -1, 1, 1)
+    if c2 is None:
+        r = torch.randn((n, cout, hw, hw), generator=g) * 2.0
+        want = torch.relu(y1 + r.double())
+        got = o.conv_pair_dual(to_pair(x), w1.to(DEV), s1.to(DEV), b1.to(DEV), to_pair(r), act=1)
+    else:
+        x2 = torch.randn((n, c2, hw, hw), generator=g)
+        w2 = torch.randn((cout, c2, 1, 1), generator=g) / c2 ** 0.5
+        s2, b2 = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+        want = torch.relu(y1 + F.conv2d(x2.double(), w2.double()) * s2.double().view(1, -1, 1, 1) + b2.double().view(1, -1, 1, 1))
+        got = o.conv_pair_dual(to_pair(x), w1.to(DEV), s1.to(DEV), b1.to(DEV), to_pair(x2), w2.to(DEV), s2.to(DEV), b2.to(DEV), act=1)
+    check(from_pair(got, cout), want, 'second K source %s' % ((n, cin, cout, hw, c2),))
+
+
+def test_pair_conv_identity_blocks_small_weights():
+    """Identity blocks with channel weight scales spread over 2^-12 .. 2^6: chan_scale is capped at 2^15 (the diagonal must be an
+    fp16 number); a channel whose weights are too small for the cap makes the packer decline (the engine then keeps the
+    epilogue residual)."""
+    o = ops()
+    g = torch.Generator().manual_seed(21)
+    n, cin, cout, hw = 1, 64, 256, 16
+    x = torch.randn((n, cin, hw, hw), generator=g)
+    mag = torch.ldexp(torch.ones(cout), torch.randint(-12, 7, (cout,), generator=g))
+    w1 = torch.randn((cout, cin, 1, 1), generator=g) / 8.0 * mag.view(-1, 1, 1, 1)
+    one, zero = torch.ones(cout), torch.zeros(cout)
+    r = torch.randn((n, cout, hw, hw), generator=g)
+    want = F.conv2d(x.double(), w1.double()) + r.double()
+    got = o.conv_pair_dual(to_pair(x), w1.to(DEV), one.to(DEV), zero.to(DEV), to_pair(r), act=0)
+    check(from_pair(got, cout), want, 'identity blocks, spread weight scales')
+    assert o.pack_weight_pair_dual((w1 * 1e-7).to(DEV), one.to(DEV), ident_bn=256) is None
+
+
 def test_pair_conv_small_and_large_magnitudes():
     """Activations of scale 1e-3 and 1e3, weights of scale 1e-4: the per-channel weight scaling keeps hi and lo parts of the
     weights normal at any magnitude.  Activations of scale 1e-3 have their lo parts in the fp16 subnormal range (absolute floor
