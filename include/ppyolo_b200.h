@@ -138,6 +138,13 @@ typedef struct ppy_conv_params {
   long long x2_plane;
   int x2_kb;
   int x2_tiled;
+  /* x2_row_mod > 0 (x2_tiled = 0; also 3x3 stride-1 pad-1 convs): x2 is BATCH-INVARIANT -- one image's ho*wo = x2_row_mod rows,
+   * repeated so that the buffer holds x2_rows >= x2_row_mod + 127 rows (a 128-row tile starting anywhere inside an image reads
+   * contiguous rows).  This is how CoordConv (model/custom_layers.py:256-272) enters the pair path: the two coordinate channels
+   * (for a 3x3 conv: their zero-padded values at the 9 taps, 18 columns) are one extra 64-wide K block against the coordinate
+   * columns of the weight, instead of a per-pixel fp32 bias map read by the epilogue. */
+  int x2_row_mod;
+  int x2_rows;
 } ppy_conv_params;
 
 /* Stem conv1_1 fused with the NCHW->NHWC change: NCHW fp32 images -> conv 3x3/s2/p1 (3 -> 32, model/resnet_vd.py:100)

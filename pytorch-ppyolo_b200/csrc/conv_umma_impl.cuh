@@ -492,7 +492,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       const int kb_per_tap = p.cin / BLOCK_K;
       // second K source (split mode, 1x1 convs; see ppy_conv_params.x2): K blocks >= kb_x2 read x2 through the maps tmap_y (hi
       // plane) / tmap_r (lo plane), which the slab epilogue leaves unused
-      const int kb_x2 = (SPLIT && MODE == MODE_TMA_A) ? num_kb - p.x2_kb : num_kb;
+      constexpr bool X2_MODE = SPLIT && (MODE == MODE_TMA_A || MODE == MODE_TMA_IM2COL || MODE == MODE_TMA_PATCH);
+      const int kb_x2 = X2_MODE ? num_kb - p.x2_kb : num_kb;
       const bool x2_ident = SPLIT && MODE == MODE_TMA_A && p.x2_tiled != 0;      // identity blocks: their lo weight plane is zero
       int g = 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
@@ -527,12 +528,19 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               const CUtensorMap* ma = pl ? &tmap_a2 : &tmap_a;
               const uint32_t a_dst = smem_a + s * A_STAGE + pl * A_TILE, b_dst = smem_b + s * Cfg::kBStageBytes + pl * B_PLANE;
               const int nrow = n0 + pl * p.cout_pad;
-              if (MODE == MODE_TMA_A) {
-                const CUtensorMap* m1 = (SPLIT && second) ? (pl ? &tmap_r : &tmap_y) : ma;
-                const int col = (SPLIT && second) ? (kb - kb_x2) * BLOCK_K + (x2_ident ? u.nt * BN : 0) : kb * BLOCK_K;
-                if (CTA2) tma2_load_2d(a_dst, m1, bar, col, m0); else tma_load_2d(a_dst, m1, bar, col, m0);
+              if (X2_MODE && second) {                  // block of the second K source: maps tmap_y (hi plane) / tmap_r (lo plane)
+                const CUtensorMap* m2 = pl ? &tmap_r : &tmap_y;
+                const int col = (kb - kb_x2) * BLOCK_K + (x2_ident ? u.nt * BN : 0);
+                if (MODE == MODE_TMA_PATCH) {           // (batch-invariant sources have one image)
+                  const int img2 = p.x2_row_mod ? 0 : img;
+                  if (CTA2) tma2_load_4d(a_dst, m2, bar, col, px0, py0, img2); else tma_load_4d(a_dst, m2, bar, col, px0, py0, img2);
+                } else {
+                  const int row = p.x2_row_mod ? m0 % p.x2_row_mod : m0;
+                  if (CTA2) tma2_load_2d(a_dst, m2, bar, col, row); else tma_load_2d(a_dst, m2, bar, col, row);
+                }
                 if (pl == 1 && skip_blo) continue;       // identity block: no lo weight tile
-              }
+              } else {
+              if (MODE == MODE_TMA_A) { if (CTA2) tma2_load_2d(a_dst, ma, bar, kb * BLOCK_K, m0); else tma_load_2d(a_dst, ma, bar, kb * BLOCK_K, m0); }
               if (MODE == MODE_TMA_PATCH) {
                 // one tap x 64 channels of the 16x8 patch; the halo (negative / beyond-edge coordinates) is zero-filled by TMA
                 if (CTA2) tma2_load_4d(a_dst, ma, bar, c0, px0 + tap % 3 - 1, py0 + tap / 3 - 1, img);
@@ -541,6 +549,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               if (MODE == MODE_TMA_IM2COL) {
                 if (CTA2) tma2_load_im2col(a_dst, ma, bar, c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
                 else tma_load_im2col(a_dst, ma, bar, c0, px0, py0, img, (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+              }
               }
               if (MODE == MODE_TMA_SLAB) {           // iteration kb = (channel block, kx): the slab and the weight tiles of its three taps
                 const int cb = kb / 3, kx = kb % 3;
@@ -1193,12 +1202,27 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   }
   tmap_y = tmap_b;
   tmap_r = tmap_b;
-  if (SPLIT && MODE == MODE_TMA_A && p->x2_kb > 0) {      // second K source: hi plane -> tmap_y, lo plane -> tmap_r
+  if (SPLIT && p->x2_kb > 0) {      // second K source: hi plane -> tmap_y, lo plane -> tmap_r
+    if (!(MODE == MODE_TMA_A || MODE == MODE_TMA_IM2COL || MODE == MODE_TMA_PATCH)) return PPY_ERR_UNSUPPORTED;
     const uint64_t c2 = p->x2_tiled ? (uint64_t)p->cout : (uint64_t)p->x2_kb * BLOCK_K;
-    rc = encode_2d(enc, &tmap_y, p->x2, c2, (uint64_t)M, (uint64_t)p->x2_ld * 2, BLOCK_K, BLOCK_M);
-    if (rc) return rc;
-    rc = encode_2d(enc, &tmap_r, reinterpret_cast<const uint16_t*>(p->x2) + p->x2_plane, c2, (uint64_t)M, (uint64_t)p->x2_ld * 2, BLOCK_K, BLOCK_M);
-    if (rc) return rc;
+    // x2_row_mod > 0: a batch-invariant source of x2_row_mod rows per image, stored x2_rows >= x2_row_mod + 127 rows long
+    const uint64_t rows2 = p->x2_row_mod ? (uint64_t)p->x2_rows : (uint64_t)M;
+    for (int pl = 0; pl < 2; ++pl) {
+      const void* b2 = reinterpret_cast<const uint16_t*>(p->x2) + (pl ? p->x2_plane : 0);
+      CUtensorMap* m2 = pl ? &tmap_r : &tmap_y;
+      if (MODE == MODE_TMA_PATCH) {
+        const cuuint64_t dims[4] = {(cuuint64_t)c2, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)(p->x2_row_mod ? 1 : p->n)};
+        const cuuint64_t strides[3] = {(cuuint64_t)p->x2_ld * 2, (cuuint64_t)wo * p->x2_ld * 2, (cuuint64_t)ho * wo * p->x2_ld * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)PW, (cuuint32_t)PH, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = enc(m2, OPERAND_DT, 4, const_cast<void*>(b2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
+      } else {
+        rc = encode_2d(enc, m2, b2, c2, rows2, (uint64_t)p->x2_ld * 2, BLOCK_K, BLOCK_M);
+        if (rc) return rc;
+      }
+    }
   }
   if (EPI == EPI_TMA) {
     rc = encode_tile_map(enc, &tmap_y, p->y, p->y_ld, p->cout, p, ho, wo, mode_is_patchy(MODE), PW, PH, p->out_dtype == PPY_F32);
@@ -1370,8 +1394,10 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
     if (p->out_dtype == PPY_F16X2) PPY_REQUIRE(p->y_plane > 0);
     if (p->residual) PPY_REQUIRE(p->out_dtype == PPY_F16X2 && p->res_plane > 0);
     if (p->x2_kb > 0) {
-      PPY_REQUIRE(p->x2 && !p->residual && !p->offset_mask && p->kh == 1 && p->stride == 1 && p->pad == 0 && p->cin % BLOCK_K == 0);
-      PPY_REQUIRE(p->k_pad == p->cin + p->x2_kb * BLOCK_K && p->x2_plane > 0 && (p->x2_plane * 2) % 16 == 0);
+      PPY_REQUIRE(p->x2 && !p->residual && !p->offset_mask && p->stride == 1 && p->cin % BLOCK_K == 0);
+      PPY_REQUIRE(p->kh == 1 || (!p->x2_tiled && p->kh == 3 && p->pad == 1));
+      PPY_REQUIRE(p->k_pad == p->kh * p->kw * p->cin + p->x2_kb * BLOCK_K && p->x2_plane > 0 && (p->x2_plane * 2) % 16 == 0);
+      if (p->x2_row_mod) PPY_REQUIRE(p->x2_row_mod == ho * wo && p->x2_rows >= p->x2_row_mod + BLOCK_M - 1 && !p->x2_tiled);
       PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->x2) & 15) == 0 && (p->x2_ld * 2) % 16 == 0);
       PPY_REQUIRE(p->x2_ld >= (p->x2_tiled ? p->cout : p->x2_kb * BLOCK_K));
     }
@@ -1400,20 +1426,21 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
                          p->k_pad == p->cin + p->x2_kb * BLOCK_K;
   if (plain_1x1) return dispatch<MODE_TMA_A>(p, ho, wo, as_stream(s));
   // 3x3 stride-1: A tiles as 16x8 pixel patches fetched by 4-D TMA, when the patch grid wastes < 15% of the tiles
-  const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin &&
+  const bool patchable = p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin % BLOCK_K == 0 && p->k_pad == 9 * p->cin + p->x2_kb * BLOCK_K &&
                          (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
   static const bool no_patch = knob_off("PPY_NO_PATCH"), no_slab = knob_off("PPY_NO_SLAB"), no_im2col = knob_off("PPY_NO_IM2COL");
   if (patchable && !p->accumulate && !no_patch) {
     auto grid_eff = [&](int pw, int ph) { return (double)ho * wo / ((double)ceil_div(ho, ph) * ph * ceil_div(wo, pw) * pw); };
-    if (p->cout > 32 && p->cout <= 128 && grid_eff(patch_w(MODE_TMA_SLAB), patch_h(MODE_TMA_SLAB)) >= 0.85 && !no_slab)
+    if (p->cout > 32 && p->cout <= 128 && grid_eff(patch_w(MODE_TMA_SLAB), patch_h(MODE_TMA_SLAB)) >= 0.85 && !no_slab && p->x2_kb == 0)
       return dispatch_slab(p, ho, wo, as_stream(s));
     if (grid_eff(patch_w(MODE_TMA_PATCH), patch_h(MODE_TMA_PATCH)) >= 0.85) return dispatch<MODE_TMA_PATCH>(p, ho, wo, as_stream(s));
   }
   // any other k x k conv over whole 64-channel blocks: im2col-mode TMA (stride and zero padding done by the copy engine)
-  const bool im2col_ok = p->cin % BLOCK_K == 0 && p->k_pad == p->kh * p->kw * p->cin && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
+  const bool im2col_ok = p->cin % BLOCK_K == 0 && p->k_pad == p->kh * p->kw * p->cin + p->x2_kb * BLOCK_K && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
                          (p->x_ld * 2) % 16 == 0 && p->pad <= 8 && p->kh <= 8 && p->kw <= 8 && p->stride <= 8 &&
                          p->wgrad_taps <= 1 && get_encode_im2col_fn() != nullptr && !no_im2col;
   if (im2col_ok) return dispatch<MODE_TMA_IM2COL>(p, ho, wo, as_stream(s));
+  if (p->x2_kb > 0) return PPY_ERR_UNSUPPORTED;
   return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }
 

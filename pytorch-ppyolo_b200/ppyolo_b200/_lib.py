@@ -32,7 +32,7 @@ class ConvParams(ctypes.Structure):
         ('accumulate', c_int), ('split_k', c_int), ('wgrad_taps', c_int), ('wgrad_pitch', c_int), ('wgrad_tap_stride', c_int),
         ('coord_w', c_void_p),
         ('x_plane', c_ll), ('y_plane', c_ll), ('res_plane', c_ll), ('overflow', c_void_p),
-        ('x2', c_void_p), ('x2_ld', c_int), ('x2_plane', c_ll), ('x2_kb', c_int), ('x2_tiled', c_int),
+        ('x2', c_void_p), ('x2_ld', c_int), ('x2_plane', c_ll), ('x2_kb', c_int), ('x2_tiled', c_int), ('x2_row_mod', c_int), ('x2_rows', c_int),
     ]
 
 

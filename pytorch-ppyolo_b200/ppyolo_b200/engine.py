@@ -233,8 +233,21 @@ class InferenceEngine(object):
         pad = (k - 1) // 2
         pair = self.code == PPY_F16X2
         chan_scale = None
+        # pair path: CoordConv's two channels enter as ONE extra K block from a batch-invariant second source (ppy_conv_params.x2)
+        # instead of a per-pixel fp32 bias map in the epilogue (1x1 convs, and the 3x3 convs that run the patch / im2col loaders)
+        coord_x2 = (pair and coord and stride == 1 and c_main % 64 == 0 and x.c == c_main and offset_mask is None and residual is None and
+                    (k == 1 or (k == 3 and cout > 128)) and x.h > 1 and x.w > 1 and getattr(self.model, 'coord_as_k', True))
+        x2 = None
         if pair:
-            packed, cin_pad, k_pad, cout_pad, chan_scale = ops.pack_weight_pair(weight, 0, c_main)
+            wc = weight.detach().float()[:, c_main:c_main + 2] if coord_x2 else None
+            packed, cin_pad, k_pad, cout_pad, chan_scale = ops.pack_weight_pair(
+                weight, 0, c_main, amax_with=wc.abs().amax(dim=(1, 2, 3)) if coord_x2 else None)
+            if coord_x2:
+                extra = torch.zeros((cout, 64), dtype=torch.float32, device=self.dev)
+                extra[:, :2 * k * k] = wc.permute(0, 2, 3, 1).reshape(cout, 2 * k * k)        # column 2*tap + {0: x, 1: y}
+                packed = ops.append_weight_block(packed, cout, extra * chan_scale.view(-1, 1))
+                k_pad += 64
+                x2 = self._keep(ops.coord_source(x.h, x.w, k, self.act_scale, self.dev))
         else:
             packed, cin_pad, k_pad, cout_pad = ops.pack_weight(weight, self.code, c_begin=0, c_count=c_main)
         self._keep(packed)
@@ -249,7 +262,7 @@ class InferenceEngine(object):
         # for the TMA epilogue); a 3x3 conv needs the per-pixel map (zero padding breaks the rank-2 structure at the borders)
         coord_vec = (coord and k == 1 and stride == 1 and self.code == PPY_BF16 and out_code == PPY_BF16 and not upsample and
                      cout >= 64 and cout % 8 == 0 and k_pad <= (512 if cout % 256 == 0 else 1152) and x.h > 1 and x.w > 1)
-        bias_map = self._coord_bias_map(weight, c_main, x.h, x.w) if (coord and not coord_vec) else None
+        bias_map = self._coord_bias_map(weight, c_main, x.h, x.w) if (coord and not coord_vec and not coord_x2) else None
         if pair:
             # the accumulator holds act_scale * chan_scale * (true pre-norm value): x is stored scaled by act_scale, every weight
             # row by chan_scale (both powers of two, so all of this is exact).  Pair outputs are stored scaled by act_scale again
@@ -286,6 +299,9 @@ class InferenceEngine(object):
             p.x_plane, p.y_plane = x.plane, dst.plane
             p.res_plane = residual.plane if residual is not None else 0
             p.overflow = self.overflow.data_ptr()
+            if x2 is not None:
+                p.x2, p.x2_ld, p.x2_plane = x2.data_ptr(), 64, x2.stride(0)
+                p.x2_kb, p.x2_tiled, p.x2_row_mod, p.x2_rows = 1, 0, x.h * x.w, x2.shape[1]
         # split_k: few output tiles and a long K (the DCN offset conv): K splits added atomically into the zeroed fp32 output
         split_k = split_k and self.code == PPY_BF16 and out_code == PPY_F32 and act == 0 and residual is None and not coord
         p.accumulate = 1 if split_k else 0

@@ -115,7 +115,47 @@ def pack_weight(weight, code, c_begin=0, c_count=None, cache=True):
     return result
 
 
-def pack_weight_pair(weight, c_begin=0, c_count=None):
+def split_halves(t):
+    """fp32 tensor -> (hi, lo) fp16 tensors with t = hi + lo to 2^-22 (torch ops; used for small host-built operands)."""
+    hi = t.to(torch.float16)
+    return hi, (t - hi.float()).to(torch.float16)
+
+
+def coord_source(h, w, k, act_scale, device):
+    """Batch-invariant second K source that carries CoordConv's two channels (model/custom_layers.py:256-272) into a k x k
+    stride-1 conv of the pair path: pair tensor [2, rows, 64] with, per output pixel, the x / y coordinate each tap reads (zero
+    where the tap falls into the padding) in columns 2*tap, 2*tap + 1.  rows = the image's h*w pixels repeated until any
+    128-row tile that starts inside the image is contiguous.  Values are multiplied by ``act_scale`` like every pair activation."""
+    xs = torch.arange(0, w, dtype=torch.float32, device=device) / (w - 1) * 2.0 - 1
+    ys = torch.arange(0, h, dtype=torch.float32, device=device) / (h - 1) * 2.0 - 1
+    src = torch.zeros((h, w, 64), dtype=torch.float32, device=device)
+    r = (k - 1) // 2
+    for ky in range(k):
+        for kx in range(k):
+            t = ky * k + kx
+            y0, y1 = max(0, r - ky), min(h, h + r - ky)          # output rows whose tap row (oy + ky - r) is inside
+            x0, x1 = max(0, r - kx), min(w, w + r - kx)
+            src[y0:y1, x0:x1, 2 * t] = xs[x0 + kx - r:x1 + kx - r].view(1, -1)
+            src[y0:y1, x0:x1, 2 * t + 1] = ys[y0 + ky - r:y1 + ky - r].view(-1, 1)
+    src = src.reshape(h * w, 64) * act_scale
+    reps = (h * w + 127 + h * w - 1) // (h * w)
+    src = src.repeat(reps, 1)
+    hi, lo = split_halves(src)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def append_weight_block(packed, cout, extra):
+    """[2, cout_pad, k_pad] packed pair weight + ``extra`` [cout, 64] fp32 (already multiplied by chan_scale) -> packed
+    [2, cout_pad, k_pad + 64]."""
+    _, cout_pad, k_pad = packed.shape
+    out = torch.zeros((2, cout_pad, k_pad + 64), dtype=torch.float16, device=packed.device)
+    out[:, :, :k_pad] = packed
+    hi, lo = split_halves(extra.float())
+    out[0, :cout, k_pad:], out[1, :cout, k_pad:] = hi, lo
+    return out.contiguous()
+
+
+def pack_weight_pair(weight, c_begin=0, c_count=None, amax_with=None):
     """OIHW fp32 -> PPY_F16X2 packing [2, cout_pad, k_pad] fp16 (hi plane, lo plane) for ppy_conv_f16x2.
 
     Every output channel is first multiplied by a power of two ``chan_scale[co]`` that brings its largest weight into
@@ -130,6 +170,8 @@ def pack_weight_pair(weight, c_begin=0, c_count=None):
     cout_pad = round_up(cout, 32)
     w32 = weight.detach().float()
     amax = w32[:, c_begin:c_begin + c_count].abs().amax(dim=(1, 2, 3))
+    if amax_with is not None:                       # further weights of the same rows that will share chan_scale
+        amax = torch.maximum(amax, amax_with.float())
     _, ex = torch.frexp(amax)                       # amax = m * 2^ex, m in [0.5, 1)
     chan_scale = torch.where(amax > 0, torch.ldexp(torch.ones_like(amax), (14 - ex).clamp(-30, 40)), torch.ones_like(amax))
     w32 = (w32 * chan_scale.view(-1, 1, 1, 1)).contiguous()
@@ -276,14 +318,24 @@ def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, res
 
 
 def conv_pair(x, weight, scale, shift, stride=1, pad=0, act=0, residual=None, bias_map=None, out_f32=False,
-              upsample2x=False, offset_mask=None, c_count=None, overflow=None):
+              upsample2x=False, offset_mask=None, c_count=None, overflow=None, coord=False):
     """One fused conv of the fp32-grade tensor-core path (ppy_conv_f16x2): ``x`` / ``residual`` are PPY_F16X2 tensors
     [2, N, H, W, ld] (fp16 hi | lo planes), ``weight`` the OIHW fp32 tensor (its first ``c_count`` input channels are
     used).  Returns a pair tensor [2, N, Ho, Wo, ld_out], or an NHWC fp32 tensor with ``out_f32``."""
     _cuda(x, 'input')
     assert x.dtype == torch.float16 and x.dim() == 5 and x.shape[0] == 2
     cout, cin_total, k, _ = weight.shape
-    packed, cin_pad, k_pad, cout_pad, cs = pack_weight_pair(weight, 0, c_count)
+    x2 = None
+    if coord:        # the weight's channels [c_count, c_count + 2) are CoordConv's: one extra K block from a batch-invariant source
+        wc = weight.detach().float()[:, c_count:c_count + 2]
+        packed, cin_pad, k_pad, cout_pad, cs = pack_weight_pair(weight, 0, c_count, amax_with=wc.abs().amax(dim=(1, 2, 3)))
+        extra = torch.zeros((cout, 64), dtype=torch.float32, device=x.device)
+        extra[:, :2 * k * k] = wc.permute(0, 2, 3, 1).reshape(cout, 2 * k * k)
+        packed = append_weight_block(packed, cout, extra * cs.view(-1, 1))
+        k_pad += 64
+        x2 = coord_source(x.shape[2], x.shape[3], k, 1.0, x.device)
+    else:
+        packed, cin_pad, k_pad, cout_pad, cs = pack_weight_pair(weight, 0, c_count)
     _, n, h, w, ld = x.shape
     ho = (h + 2 * pad - k) // stride + 1
     wo = (w + 2 * pad - k) // stride + 1
@@ -315,6 +367,9 @@ def conv_pair(x, weight, scale, shift, stride=1, pad=0, act=0, residual=None, bi
     p.offset_mask = offset_mask.data_ptr() if offset_mask is not None else None
     p.om_ld = offset_mask.shape[-1] if offset_mask is not None else 0
     p.overflow = overflow.data_ptr() if overflow is not None else None
+    if x2 is not None:
+        p.x2, p.x2_ld, p.x2_plane = x2.data_ptr(), 64, x2.stride(0)
+        p.x2_kb, p.x2_tiled, p.x2_row_mod, p.x2_rows = 1, 0, h * w, x2.shape[1]
     check(lib.ppy_conv_f16x2(ctypes.byref(p), stream_ptr()), 'conv_f16x2')
     return out
 

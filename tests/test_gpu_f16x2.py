@@ -154,6 +154,28 @@ def test_pair_conv_second_k_source(n, cin, cout, hw, c2):
     check(from_pair(got, cout), want, 'second K source %s' % ((n, cin, cout, hw, c2),))
 
 
+@pytest.mark.parametrize('n,cin,cout,k,hw', [(2, 128, 128, 1, 19),     # tma_a, one K chunk
+                                              (1, 512, 256, 1, 38),     # tma_a, K-chunked
+                                              (3, 64, 96, 1, 7),        # image smaller than a tile: rows wrap several times
+                                              (2, 128, 256, 3, 32),     # patch loader (4-D box of the coordinate source)
+                                              (2, 256, 512, 3, 19),     # im2col loader
+                                              (1, 64, 256, 3, 5)])      # im2col, tiny map
+def test_pair_conv_coordconv_as_k_block(n, cin, cout, k, hw):
+    """CoordConv (model/custom_layers.py:256-272) + k x k conv on the pair path: the two coordinate channels are one extra K block
+    from a batch-invariant second source; against fp64 of conv(cat([x, xs, ys]))."""
+    o = ops()
+    g = torch.Generator().manual_seed(cin + cout * 3 + k * 7 + hw)
+    x = torch.randn((n, cin, hw, hw), generator=g)
+    w = torch.randn((cout, cin + 2, k, k), generator=g) / (cin * k * k) ** 0.5
+    w[:, cin:] *= 3.0                       # coordinate weights larger than the rest: they share the row scaling
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    xs = torch.arange(hw, dtype=torch.float32) / (hw - 1) * 2.0 - 1
+    xc = torch.cat([x, xs.view(1, 1, 1, hw).expand(n, 1, hw, hw), xs.view(1, 1, hw, 1).expand(n, 1, hw, hw)], 1)
+    want = act64(F.conv2d(xc.double(), w.double(), padding=(k - 1) // 2) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1), 2)
+    y = o.conv_pair(to_pair(x), w.to(DEV), scale.to(DEV), shift.to(DEV), 1, (k - 1) // 2, 2, c_count=cin, coord=True)
+    check(from_pair(y, cout), want, 'coordconv as K block %s' % ((n, cin, cout, k, hw),))
+
+
 def test_pair_conv_identity_blocks_small_weights():
     """Identity blocks with channel weight scales spread over 2^-12 .. 2^6: chan_scale is capped at 2^15 (the diagonal must be an
     fp16 number); a channel whose weights are too small for the cap makes the packer decline (the engine then keeps the
