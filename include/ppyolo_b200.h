@@ -301,6 +301,46 @@ int ppy_matrix_nms_candidates(const float* boxes, int n, int num_boxes, int num_
                               float post_threshold, int nms_top_k, int keep_top_k, int use_gaussian, float gaussian_sigma,
                               float* out, int* counts, void* workspace, int cap, ppy_stream_t s);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training: fused fine-grained YOLOv3 loss for one output scale (model/losses.py:121-356 _get_fine_grained_loss + _calc_obj_loss,
+ * model/iou_losses.py IouLoss :15-191, IouAwareLoss :194-246) and the target assignment of the data pipeline
+ * (tools/transform.py:1318-1421 Gt2YoloTargetSingle).
+ *   out     [n, a*(5|6+C), size, size] fp32 NCHW raw head output (iou_aware: the first `a` channels are the IoU logits)
+ *   target  [n, a, 6+C, size, size] fp32 (tx, ty, tw, th, tscale, tobj, one-hot class)
+ *   gt_box  [n, g, 4] fp32 normalised (cx, cy, w, h), 16-byte aligned (zero rows = padding)
+ *   anchors_host: 2*a floats (w, h in pixels) of this scale's anchors, HOST pointer
+ * forward: ADDS this scale's six losses (xy, wh, obj, cls, iou, iou_aware; each the batch mean of per-image sums) to
+ * losses[6] (device; zero it before the first scale) and writes the no-object mask [n, a, size, size] the backward needs.
+ * workspace: ppy_yolo_loss_workspace_bytes() bytes, 16-byte aligned, its first 4 bytes zero before the first use.
+ * backward: grad_out[n, a*(5|6+C), size, size] = d(sum_k grad_losses[k] * loss_k)/d(out); grad_losses is a DEVICE pointer to 6
+ * floats (no host synchronisation; CUDA-graph capturable).  ciou_term is not supported (no config enables it). */
+int ppy_yolo_loss_workspace_bytes(int n, int a, int size);
+int ppy_yolo_loss_forward(const float* out, const float* target, const float* gt_box, int n, int a, int num_classes, int size, int g,
+                          const float* anchors_host, int stride, double scale_x_y, float ignore_thresh, int iou_aware, int has_iou_loss,
+                          float iou_loss_weight, int loss_square, float iou_aware_weight, int match_score, float* noobj_mask,
+                          void* workspace, float* losses, ppy_stream_t s);
+int ppy_yolo_loss_backward(const float* out, const float* target, int n, int a, int num_classes, int size, const float* anchors_host,
+                           int stride, double scale_x_y, int iou_aware, int has_iou_loss, float iou_loss_weight, int loss_square,
+                           float iou_aware_weight, const float* noobj_mask, const float* grad_losses, float* grad_out, ppy_stream_t s);
+/* target [n, mask_len, 6+C, img_h/downsample, img_w/downsample] for one scale from padded ground truth: gt_bbox [n, g, 4]
+ * normalised (cx, cy, w, h), gt_class [n, g] int32, gt_score [n, g]; anchors_host = all 2*num_anchors anchor sizes (ints, pixels),
+ * mask_host = this scale's anchor indices (HOST pointers).  Sequential over a sample's boxes like the reference: later boxes
+ * overwrite earlier ones in the same cell, class bits accumulate. */
+int ppy_gt2yolo_target(const float* gt_bbox, const int* gt_class, const float* gt_score, int n, int g, const int* anchors_host,
+                       int num_anchors, const int* mask_host, int mask_len, int num_classes, int img_h, int img_w, int downsample,
+                       float iou_thresh, float* target, ppy_stream_t s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pre-processing: ResizeImage of the eval / test pipeline (tools/transform.py:923-1018 with interp = cv2.INTER_CUBIC,
+ * model/decode_np.py:125-134) + decodeImage's BGR -> RGB, for a batch of differently sized uint8 images in one launch.
+ *   src   packed source images (each tightly packed HWC uint8, 3 channels), DEVICE memory
+ *   meta  [n][3] int64, DEVICE: {byte offset of image i in src, height, width}
+ *   dst   [n, dsize, dsize, 3] uint8 -- the input format of ppy_stem_conv3x3s2_u8
+ * Arithmetic: OpenCV's own 8-bit bicubic resize restated operation by operation (fixed-point horizontal pass, float vertical
+ * pass, round-to-nearest-even): bit-identical to cv2.resize wherever OpenCV runs its own code (builds without Intel IPP, or
+ * cv2.ipp.setUseIPP(False)); IPP-enabled wheels differ from that by +-1 on ~3 % of the pixels. */
+int ppy_resize_cubic_u8_batch(const uint8_t* src, const long long* meta, int n, uint8_t* dst, int dsize, int swap_rb, ppy_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -383,3 +383,43 @@ def ema_update(shadow, params, decay, update_step, thres_steps=True):
     ``decay * old + (1 - decay) * new`` with a Python-float decay keeps float32 arrays float32 (numpy weak scalars)."""
     d = min(decay, (1 + update_step) / (10 + update_step)) if thres_steps else decay
     return [np.asarray(d * s + (1 - d) * np.asarray(p, dtype=np.float32), dtype=np.float32) for s, p in zip(shadow, params)], d
+
+
+# ----------------------------------------------------------------------------------------------
+# pre-processing: the resize of model/decode_np.py:125-134 (cv2.resize(..., interpolation=cv2.INTER_CUBIC) of a uint8 image)
+# ----------------------------------------------------------------------------------------------
+def _cubic_axis(ssize, dsize):
+    """Per destination index: the 4 clamped source indices and 16-bit fixed-point weights of OpenCV's bicubic resize
+    (third-party dependency of the reference: opencv-python, imgproc/src/resize.cpp resizeGeneric_ / interpolateCubic,
+    A = -0.75; float32 arithmetic in OpenCV's operation order, weights * 2048 rounded to nearest-even)."""
+    f32 = np.float32
+    scale = 1.0 / (float(dsize) / float(ssize))                       # cv2.resize(fx = dsize / ssize): scale = 1 / fx (double)
+    f = ((np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5).astype(f32)
+    s = np.floor(f).astype(np.int64)
+    x = (f - s.astype(f32)).astype(f32)
+    a = f32(-0.75)
+    one = f32(1)
+    c0 = ((a * (x + one) - f32(5) * a) * (x + one) + f32(8) * a) * (x + one) - f32(4) * a
+    c1 = ((a + f32(2)) * x - (a + f32(3))) * x * x + one
+    c2 = ((a + f32(2)) * (one - x) - (a + f32(3))) * (one - x) * (one - x) + one
+    c3 = one - c0 - c1 - c2
+    w = np.clip(np.rint(np.stack([c0, c1, c2, c3], 1).astype(f32) * f32(2048)), -32768, 32767).astype(np.int32)
+    idx = np.clip(s[:, None] - 1 + np.arange(4)[None, :], 0, ssize - 1)
+    return idx, w
+
+
+def resize_cubic_u8(img, size):
+    """cv2.resize(img, None, None, fx=size/w, fy=size/h, interpolation=cv2.INTER_CUBIC) for an HWC uint8 image as OpenCV's own
+    code computes it (HResizeCubic in 32-bit integers, VResizeCubicVec_32s8u in float32 with separately rounded products and
+    sums -- the baseline code path has no fused multiply-add -- then round-to-nearest-even and saturation)."""
+    h, w, _ = img.shape
+    xi, xw = _cubic_axis(w, size)
+    yi, yw = _cubic_axis(h, size)
+    hor = np.einsum('hdkc,dk->hdc', img.astype(np.int32)[:, xi, :], xw)               # [h, size, c] int32
+    scale = np.float32(1.0 / (2048.0 * 2048.0))
+    b = yw.astype(np.float32) * scale                                                # [size, 4]
+    rows = hor[yi].astype(np.float32)                                                # [size, 4, size, c]
+    acc = rows[:, 3] * b[:, 3, None, None]
+    for k in (2, 1, 0):
+        acc = (rows[:, k] * b[:, k, None, None]).astype(np.float32) + acc
+    return np.clip(np.rint(acc), 0, 255).astype(np.uint8)

@@ -46,6 +46,23 @@ __global__ void dropblock_seeds_kernel(uint8_t* __restrict__ seeds, Shape4 s, fl
   const long long total = (long long)s.n * s.c * s.h * s.w;
   const unsigned long long seed = rng[0], offset = rng[1];
   if (blockIdx.x == 0 && threadIdx.x == 0) *count = 0u;
+  if (s.sc == 1 && s.c > 1) {
+    // channels_last storage: walk the STORAGE order (channel fastest) so the byte stores coalesce; every element still takes
+    // word (i & 3) of the Philox call of its logical index i / 4 -- four times the RNG work, the same numbers
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+      long long t = j;
+      const int ch = (int)(t % s.c); t /= s.c;
+      const int x = (int)(t % s.w); t /= s.w;
+      const int y = (int)(t % s.h);
+      const long long img = t / s.h;
+      const long long i = ((img * s.c + ch) * s.h + y) * s.w + x;
+      uint32_t r[4];
+      philox4x32_10((unsigned long long)(i >> 2), offset, seed, r);
+      const float u = (float)(r[i & 3] >> 8) * (1.0f / 16777216.0f);
+      seeds[img * s.sn + ch * s.sc + y * s.sh + x * s.sw] = u < gamma ? 1 : 0;
+    }
+    return;
+  }
   for (long long call = (long long)blockIdx.x * blockDim.x + threadIdx.x; call * 4 < total; call += (long long)gridDim.x * blockDim.x) {
     uint32_t r[4];
     philox4x32_10((unsigned long long)call, offset, seed, r);
@@ -66,10 +83,17 @@ __global__ void dropblock_mask_kernel(const uint8_t* __restrict__ seeds, uint8_t
   unsigned int kept = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long t = i;
-    const int x = (int)(t % s.w); t /= s.w;
-    const int y = (int)(t % s.h); t /= s.h;
-    const int ch = (int)(t % s.c);
-    const long long base = (t / s.c) * s.sn + ch * s.sc;
+    int x, y, ch;
+    if (s.sc == 1 && s.c > 1) {          // channels_last storage: channel fastest, so a warp's byte loads / stores coalesce
+      ch = (int)(t % s.c); t /= s.c;
+      x = (int)(t % s.w); t /= s.w;
+      y = (int)(t % s.h); t /= s.h;
+    } else {
+      x = (int)(t % s.w); t /= s.w;
+      y = (int)(t % s.h); t /= s.h;
+      ch = (int)(t % s.c); t /= s.c;
+    }
+    const long long base = t * s.sn + ch * s.sc;
     int hit = 0;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {

@@ -69,7 +69,37 @@ class YOLOv3Loss(object):
         self.downsample, self.scale_x_y, self.match_score = downsample, scale_x_y, match_score
 
     def __call__(self, outputs, gt_box, gt_label, gt_score, targets, anchors, anchor_masks, mask_anchors, num_classes):
+        if outputs[0].is_cuda and self.use_kernel and self._kernel_supported(gt_box, mask_anchors):
+            return self._fused_loss(outputs, targets, gt_box, num_classes, mask_anchors)
         return self._get_fine_grained_loss(outputs, targets, gt_box, num_classes, mask_anchors, self._ignore_thresh)
+
+    use_kernel = True      # CUDA tensors: fused forward/backward loss kernels (csrc/loss.cu); False = the tensor code below
+
+    def _kernel_supported(self, gt_box, mask_anchors):
+        from model.iou_losses import IouLoss, IouAwareLoss
+        il, al = self._iou_loss, self._iou_aware_loss
+        if il is not None and (type(il) is not IouLoss or il.ciou_term):
+            return False
+        if al is not None and type(al) is not IouAwareLoss:
+            return False
+        return gt_box.shape[1] <= 128 and all(len(a) // 2 <= 8 for a in mask_anchors)
+
+    def _fused_loss(self, outputs, targets, gt_box, num_classes, mask_anchors):
+        """Same dict as ``_get_fine_grained_loss`` from one forward launch per scale (and one backward launch per scale through
+        autograd): model/losses.py:121-356 + model/iou_losses.py in csrc/loss.cu."""
+        from ppyolo_b200 import ops
+        assert len(outputs) == len(targets), "YOLOv3 output layer number not equal target number"
+        il, al = self._iou_loss, self._iou_aware_loss
+        scales = []
+        for i, anchors in enumerate(mask_anchors):
+            sxy = self.scale_x_y if not isinstance(self.scale_x_y, Sequence) else self.scale_x_y[i]
+            scales.append(dict(anchors=list(anchors), stride=self.downsample[i], scale_x_y=float(sxy)))
+        vec = ops.yolo_loss_fused(outputs, targets, gt_box, scales, num_classes, self._ignore_thresh, al is not None, il is not None,
+                                  il._loss_weight if il is not None else 0.0, il.loss_square if il is not None else True,
+                                  al._loss_weight if al is not None else 0.0, self.match_score)
+        keys = ['loss_xy', 'loss_wh', 'loss_obj', 'loss_cls'] + (['loss_iou'] if il is not None else []) + \
+               (['loss_iou_aware'] if al is not None else [])
+        return {k: vec[ops.LOSS_NAMES.index(k)] for k in keys}
 
     def _get_fine_grained_loss(self, outputs, targets, gt_box, num_classes, mask_anchors, ignore_thresh, eps=1.e-10):
         assert len(outputs) == len(targets), "YOLOv3 output layer number not equal target number"

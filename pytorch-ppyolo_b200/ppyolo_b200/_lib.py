@@ -92,6 +92,15 @@ SIGNATURES = {
     'ppy_matrix_nms_batched_hist': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_int, c_int,
                                             c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'ppy_pairwise_iou': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'ppy_resize_cubic_u8_batch': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    'ppy_yolo_loss_workspace_bytes': (c_int, [c_int, c_int, c_int]),
+    'ppy_yolo_loss_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int,
+                                      ctypes.c_double, c_float, c_int, c_int, c_float, c_int, c_float, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    'ppy_yolo_loss_backward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, ctypes.c_double,
+                                       c_int, c_int, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ppy_gt2yolo_target': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int),
+                                   c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     'ppy_matrix_nms_workspace_bytes': (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
     'ppy_nms_candidate_workspace_bytes': (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
     'ppy_nms_candidates_reset': (c_int, [c_void_p, c_int, c_int, c_void_p]),

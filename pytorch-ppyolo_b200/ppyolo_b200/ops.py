@@ -571,6 +571,136 @@ def drop_block(x, block_size=3, keep_prob=0.9, seeds=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# pre-processing
+# ------------------------------------------------------------------------------------------------
+def pack_images(images, pinned=True):
+    """List of HWC uint8 3-channel images (any sizes) -> (blob uint8 [total bytes], meta int64 [N, 3] = offset, h, w) host tensors
+    (pinned for an asynchronous upload)."""
+    metas, total = [], 0
+    for im in images:
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise ValueError('pack_images: HWC uint8 images with 3 channels expected, got %s %s' % (im.dtype, im.shape))
+        metas.append((total, im.shape[0], im.shape[1]))
+        total += (im.size + 15) // 16 * 16
+    blob = torch.empty(total, dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
+    view = blob.numpy()
+    for (off, h, w), im in zip(metas, images):
+        view[off:off + im.size] = np.ascontiguousarray(im).reshape(-1)
+    meta = torch.tensor(metas, dtype=torch.int64)
+    if pinned and torch.cuda.is_available():
+        meta = meta.pin_memory()
+    return blob, meta
+
+
+def resize_cubic_u8(blob, meta, size, swap_rb=True, out=None):
+    """cv2.resize(img, fx=size/w, fy=size/h, interpolation=cv2.INTER_CUBIC) (+ BGR->RGB) of every packed image on the GPU:
+    device ``blob`` / ``meta`` from ``pack_images`` -> uint8 [N, size, size, 3]."""
+    _cuda(blob, 'image blob')
+    _cuda(meta, 'image meta')
+    n = meta.shape[0]
+    if out is None:
+        out = torch.empty((n, size, size, 3), dtype=torch.uint8, device=blob.device)
+    check(lib.ppy_resize_cubic_u8_batch(ptr(blob), ptr(meta), n, ptr(out), int(size), 1 if swap_rb else 0, stream_ptr()), 'resize_cubic_u8')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# training: fused loss + target assignment
+# ------------------------------------------------------------------------------------------------
+LOSS_NAMES = ('loss_xy', 'loss_wh', 'loss_obj', 'loss_cls', 'loss_iou', 'loss_iou_aware')
+
+
+class _YoloLossFn(torch.autograd.Function):
+    """All scales of the fine-grained YOLOv3 loss (reference model/losses.py:121-356) on the fused kernels: forward = one launch
+    per scale adding into a 6-vector of losses, backward = one launch per scale writing d(sum_k g_k loss_k)/d(output)."""
+
+    @staticmethod
+    def forward(ctx, meta, gt_box, *tensors):
+        ns = len(meta['scales'])
+        outs = [t.detach().float().contiguous() for t in tensors[:ns]]
+        tgts = [t.detach().float().contiguous() for t in tensors[ns:]]
+        gt = gt_box.detach().float().contiguous()
+        dev = outs[0].device
+        losses = torch.zeros(6, dtype=torch.float32, device=dev)
+        masks = []
+        for o, t, sc in zip(outs, tgts, meta['scales']):
+            n, _, size, _ = o.shape
+            anchors = np.ascontiguousarray(np.asarray(sc['anchors'], dtype=np.float32).reshape(-1))
+            a = anchors.size // 2
+            per = 5 + meta['num_classes'] + (1 if meta['iou_aware'] else 0)
+            if o.shape[1] != a * per or tuple(t.shape) != (n, a, 6 + meta['num_classes'], size, size):
+                raise ValueError('yolo_loss: output %s / target %s do not match %d anchors x %d channels' % (tuple(o.shape), tuple(t.shape), a, per))
+            noobj = torch.empty((n, a, size, size), dtype=torch.float32, device=dev)
+            ws = torch.zeros(int(lib.ppy_yolo_loss_workspace_bytes(n, a, size)), dtype=torch.uint8, device=dev)
+            check(lib.ppy_yolo_loss_forward(ptr(o), ptr(t), ptr(gt), n, a, meta['num_classes'], size, gt.shape[1],
+                                            anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(sc['stride']), float(sc['scale_x_y']),
+                                            float(meta['ignore_thresh']), 1 if meta['iou_aware'] else 0, 1 if meta['has_iou_loss'] else 0,
+                                            float(meta['iou_w']), 1 if meta['loss_square'] else 0, float(meta['aware_w']),
+                                            1 if meta['match_score'] else 0, ptr(noobj), ptr(ws), ptr(losses), stream_ptr()), 'yolo_loss_forward')
+            masks.append(noobj)
+        ctx.meta = meta
+        ctx.save_for_backward(*(outs + tgts + masks))
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        meta = ctx.meta
+        ns = len(meta['scales'])
+        saved = ctx.saved_tensors
+        outs, tgts, masks = saved[:ns], saved[ns:2 * ns], saved[2 * ns:]
+        g = g.detach().float().contiguous()
+        grads = []
+        for o, t, m, sc in zip(outs, tgts, masks, meta['scales']):
+            n, _, size, _ = o.shape
+            anchors = np.ascontiguousarray(np.asarray(sc['anchors'], dtype=np.float32).reshape(-1))
+            a = anchors.size // 2
+            go = torch.empty_like(o)
+            check(lib.ppy_yolo_loss_backward(ptr(o), ptr(t), n, a, meta['num_classes'], size,
+                                             anchors.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), int(sc['stride']), float(sc['scale_x_y']),
+                                             1 if meta['iou_aware'] else 0, 1 if meta['has_iou_loss'] else 0, float(meta['iou_w']),
+                                             1 if meta['loss_square'] else 0, float(meta['aware_w']), ptr(m), ptr(g), ptr(go), stream_ptr()),
+                  'yolo_loss_backward')
+            grads.append(go)
+        return (None, None) + tuple(grads) + (None,) * ns
+
+
+def yolo_loss_fused(outputs, targets, gt_box, scales, num_classes, ignore_thresh, iou_aware, has_iou_loss, iou_w, loss_square, aware_w,
+                    match_score):
+    """Six-vector (LOSS_NAMES order) of the fine-grained YOLOv3 loss summed over ``outputs`` (raw head outputs, NCHW) -- fused
+    forward/backward kernels, differentiable w.r.t. the outputs.  ``scales``: per output dict(anchors=[w0,h0,...], stride, scale_x_y)."""
+    for t in list(outputs) + list(targets) + [gt_box]:
+        _cuda(t, 'yolo_loss input')
+    meta = dict(scales=list(scales), num_classes=int(num_classes), ignore_thresh=ignore_thresh, iou_aware=bool(iou_aware),
+                has_iou_loss=bool(has_iou_loss), iou_w=iou_w, loss_square=bool(loss_square), aware_w=aware_w, match_score=bool(match_score))
+    return _YoloLossFn.apply(meta, gt_box, *(list(outputs) + list(targets)))
+
+
+def gt2yolo_target_gpu(gt_bbox, gt_class, gt_score, anchors, anchor_masks, downsample_ratios, num_classes, h, w, iou_thresh=1.):
+    """Gt2YoloTargetSingle (reference tools/transform.py:1318-1421) for a whole padded batch on the GPU: gt_bbox [N,G,4] normalised
+    (cx,cy,w,h), gt_class [N,G] int, gt_score [N,G] (device tensors) -> list of [N, A, 6+C, h/s, w/s] fp32 device tensors."""
+    _cuda(gt_bbox, 'gt_bbox')
+    gb = gt_bbox.detach().float().contiguous()
+    gc = gt_class.detach().to(torch.int32).contiguous()
+    gs = gt_score.detach().float().contiguous()
+    n, g = gb.shape[0], gb.shape[1]
+    flat = np.ascontiguousarray(np.asarray(anchors, dtype=np.int32).reshape(-1))
+    if not np.array_equal(flat, np.asarray(anchors).reshape(-1)):
+        raise ValueError('gt2yolo_target_gpu: anchors must be whole pixels (the reference configs use ints)')
+    out = []
+    for mask, ratio in zip(anchor_masks, downsample_ratios):
+        m = np.ascontiguousarray(np.asarray(mask, dtype=np.int32))
+        gh_, gw_ = int(h / ratio), int(w / ratio)
+        if gh_ * ratio != h or gw_ * ratio != w:
+            raise ValueError('gt2yolo_target_gpu: image size must be a multiple of the downsample ratio')
+        t = torch.empty((n, len(mask), 6 + num_classes, gh_, gw_), dtype=torch.float32, device=gb.device)
+        check(lib.ppy_gt2yolo_target(ptr(gb), ptr(gc), ptr(gs), n, g, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), flat.size // 2,
+                                     m.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), m.size, int(num_classes), int(h), int(w), int(ratio),
+                                     float(iou_thresh), ptr(t), stream_ptr()), 'gt2yolo_target')
+        out.append(t)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # head post-processing
 # ------------------------------------------------------------------------------------------------
 def iou_aware_score(output, an_num, num_classes, factor):

@@ -13,8 +13,11 @@ def gt2yolo_target(gt_bbox, gt_class, gt_score, anchors, anchor_masks, downsampl
                    iou_thresh=1.):
     """gt_bbox [N,G,4] normalised (cx,cy,w,h); gt_class [N,G] int; gt_score [N,G] -> list of float32
     [N, A, 6+C, H/s, W/s] = (tx, ty, tw, th, 2 - gw*gh, score, one-hot class)."""
+    anchors_py = [[v for v in a] for a in anchors]          # python numbers, like the reference's config lists
     anchors = np.asarray(anchors, dtype=np.float64)
     an_w, an_h = anchors[:, 0] / w, anchors[:, 1] / h
+    gt_bbox = np.asarray(gt_bbox, dtype=np.float32)
+    gt_score = np.asarray(gt_score, dtype=np.float32)
     n = gt_bbox.shape[0]
     targets = []
     for mask, ratio in zip(anchor_masks, downsample_ratios):
@@ -22,8 +25,8 @@ def gt2yolo_target(gt_bbox, gt_class, gt_score, anchors, anchor_masks, downsampl
         tgt = np.zeros((n, len(mask), 6 + num_classes, gh_, gw_), dtype=np.float32)
         for b in range(n):
             for g in range(gt_bbox.shape[1]):
-                gx, gy, bw, bh = (float(v) for v in gt_bbox[b, g])
-                score = float(gt_score[b, g])
+                gx, gy, bw, bh = gt_bbox[b, g]          # np.float32 scalars: the arithmetic below is float32 like the reference's
+                score = gt_score[b, g]
                 if bw <= 0. or bh <= 0. or score <= 0.:
                     continue
                 ious = _wh_iou(bw, bh, an_w, an_h)
@@ -37,8 +40,8 @@ def gt2yolo_target(gt_bbox, gt_class, gt_score, anchors, anchor_masks, downsampl
                     t = tgt[b, slot]
                     t[0, gj, gi] = gx * gw_ - gi
                     t[1, gj, gi] = gy * gh_ - gj
-                    t[2, gj, gi] = np.log(bw * w / anchors[an_idx][0])
-                    t[3, gj, gi] = np.log(bh * h / anchors[an_idx][1])
+                    t[2, gj, gi] = np.log(bw * w / anchors_py[an_idx][0])
+                    t[3, gj, gi] = np.log(bh * h / anchors_py[an_idx][1])
                     t[4, gj, gi] = 2.0 - bw * bh
                     t[5, gj, gi] = score
                     t[6 + cls, gj, gi] = 1.

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=10); ap.add_argument('--warmup', type=int, default=3)
 ap.add_argument('--precision', default='fp32'); ap.add_argument('--size', type=int, default=608)
 ap.add_argument('--batch', type=int, default=8); ap.add_argument('--arch', default='r50vd')
+ap.add_argument('--profile', type=int, default=0, help='also print the top-N kernels of 3 steps (torch.profiler, CUDA time)')
 a = ap.parse_args()
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
 torch.cuda.set_device(local)
@@ -63,5 +64,21 @@ if rank == 0:
                                  'backbone_precision': a.precision, 'trainable_params': int(sum(p.numel() for p in trainer.params)),
                                  'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'head_convs': model.train_head_impl or ('kernels (tcgen05 fwd/dgrad/wgrad)' if a.precision == 'bf16' else 'aten (TF32)')},
                       'losses': {k: float(v) for k, v in losses.items()}}), flush=True)
+if a.profile and rank == 0:
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(3):
+            trainer.step(x, gb, gc, gs, targets)
+        torch.cuda.synchronize()
+    rows = {}
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            r = rows.setdefault(ev.name, [0.0, 0])
+            r[0] += ev.device_time / 3e3
+            r[1] += 1
+    total = sum(r[0] for r in rows.values())
+    print('profile: %.3f ms of kernels per step, %d distinct kernels' % (total, len(rows)))
+    for name, (ms_k, cnt) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:a.profile]:
+        print('  %8.3f ms  %5d x  %s' % (ms_k, cnt // 3, name[:150]))
 if world > 1:
     dist.destroy_process_group()
