@@ -51,6 +51,13 @@
 #ifndef PPY_UMMA_SPLIT
 #define PPY_UMMA_SPLIT 0
 #endif
+// PPY_UMMA_K32 == 1 (third compilation, split mode only: ppy_conv_f16x2_k32): K blocks of 32 elements -- 64-byte operand rows in
+// the SWIZZLE_64B layout -- for the 3x3 convs with 32 input channels (stem conv1_2 / conv1_3): one K block is exactly one tap, so
+// no MAC multiplies a structural zero (the pixel-pair reinterpretation that feeds those layers to the 64-wide kernel wastes half).
+// Only the slab loader is dispatched in that build.
+#ifndef PPY_UMMA_K32
+#define PPY_UMMA_K32 0
+#endif
 
 namespace ppy {
 
@@ -62,7 +69,10 @@ namespace {
 constexpr bool SPLIT = PPY_UMMA_SPLIT != 0;       // fp16 hi/lo pair operands, three MMA groups per K block
 constexpr int PLANES = SPLIT ? 2 : 1;
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr bool K32 = PPY_UMMA_K32 != 0;
+constexpr int BLOCK_K = K32 ? 32 : 64;            // 16-bit elements of one operand row = one swizzle row (128 bytes; K32: 64 bytes)
+constexpr int ROW_BYTES = BLOCK_K * 2;
+constexpr int ATOM_BYTES = 8 * ROW_BYTES;         // swizzle atom: 8 rows (SBO of the shared-memory descriptors)
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int EPI_WARPS = 8;                      // two warps per TMEM lane quarter, alternating sub-tiles
 constexpr int PRODUCER_WARP0 = EPI_WARPS;
@@ -91,7 +101,7 @@ __host__ __device__ constexpr bool mode_is_patchy(int mode) { return mode == MOD
 __host__ __device__ constexpr int patch_w(int mode) { return mode == MODE_TMA_SLAB ? 8 : 16; }
 __host__ __device__ constexpr int patch_h(int mode) { return mode == MODE_TMA_SLAB ? 16 : 8; }
 constexpr int SLAB_ROWS = 18;                     // patch_h + 2 halo rows
-constexpr int SLAB_BYTES = SLAB_ROWS * 8 * 128;   // 18 rows x 8 pixels x 64 bf16
+constexpr int SLAB_BYTES = SLAB_ROWS * 8 * ROW_BYTES;   // 18 rows x 8 pixels x one operand row
 constexpr int SUB = 32;                           // epilogue sub-tile columns (= one tcgen05.ld.x32)
 constexpr int ST_LD = SUB;                        // floats per staged row; 16-byte chunks XOR-swizzled by (row & 7)
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * ST_LD * 4;
@@ -137,6 +147,9 @@ template <int BN, int MODE, int EPI, bool CTA2 = false> struct TileCfg {
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (SPLIT ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// shared-memory operand descriptor of this build's swizzle (K-major; 128-byte rows / SWIZZLE_128B, or 64-byte rows / SWIZZLE_64B)
+__device__ __forceinline__ uint64_t mk_desc(uint32_t smem_addr) { return K32 ? make_smem_desc_sw64(smem_addr) : make_smem_desc(smem_addr); }
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
@@ -301,12 +314,18 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   const uint32_t stg_off = S * (A_STAGE + Cfg::kBStageBytes);
   // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], res_full[8 warps][2], then the TMEM base slot
   const uint32_t bars = smem_base + stg_off + Cfg::kEpiBytes;
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + Cfg::kEpiBytes + (2 * S + 4 + 2 * EPI_WARPS) * 8);
+  // Accumulator buffers in TMEM: two (tile i drains while tile i+1 is multiplied); K-chunked tiles use four, so the MMA issuer can
+  // run up to four chunks ahead while the epilogue warps are still busy with the previous tile's coalesced pass (with two, layers
+  // with few chunks per tile -- K = 1152 -- stalled the tensor pipe for ~25 % of the time)
+  constexpr int NBUF = CHUNKED ? 4 : 2;
+  constexpr int TMEM_COLS = NBUF * BN < 32 ? 32 : NBUF * BN;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + stg_off + Cfg::kEpiBytes + (2 * S + 8 + 2 * EPI_WARPS) * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * S + a); };
-  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto res_full_bar = [&](int w, int b) { return bars + 8u * (2 * S + 4 + 2 * w + b); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * S + 4 + a); };
+  auto res_full_bar = [&](int w, int b) { return bars + 8u * (2 * S + 8 + 2 * w + b); };
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler: role branches are not divergent
@@ -327,18 +346,19 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   if (tid == 0) {
     const uint32_t full_count = mode_is_tma(MODE) ? 1u : (uint32_t)(BLOCK_M + 1);
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), full_count); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NBUF; ++a) {
       // TMA epilogue at BLOCK_N 64 (one column group): the two warps of a TMEM lane quarter take alternate tiles, so each
       // accumulator buffer is drained by four warps
-      constexpr uint32_t drainers = (EPI == EPI_TMA && BN == GROUP_COLS) ? EPI_WARPS / 2 : EPI_WARPS;
+      // (the slab epilogue at BLOCK_N 32 -- one sub-tile per tile -- does the same)
+      constexpr uint32_t drainers = ((EPI == EPI_TMA && BN == GROUP_COLS) || (EPI == EPI_SLAB && BN == SUB && !CHUNKED && !ACC)) ? EPI_WARPS / 2 : EPI_WARPS;
       mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), CTA2 ? 2 * drainers : drainers);
     }
     for (int w = 0; w < EPI_WARPS; ++w) { mbar_init(res_full_bar(w, 0), 1); mbar_init(res_full_bar(w, 1), 1); }
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {
-    if (CTA2) tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
-    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), Cfg::kTmemCols);
+    if (CTA2) tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), TMEM_COLS);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), TMEM_COLS);
   }
   tc_fence_before();
   if (CTA2) cluster_sync_all(); else __syncthreads();      // pair: the peer's barriers are initialised before anything targets them
@@ -582,8 +602,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
         for (int kc0 = u.kb0; kc0 < u.kb1; kc0 += CH, ++it) {
-        const int acc = it & 1;
-        mbar_wait(tmem_empty_bar(acc), ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        const int acc = it % NBUF;
+        mbar_wait(tmem_empty_bar(acc), ((it / NBUF) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         const int kc1 = (u.kb1 - kc0 > CH) ? kc0 + CH : u.kb1;
@@ -604,7 +624,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / 16; ++k) {
-                const uint64_t da = make_smem_desc(a_pl + ky * 1024 + k * 32), db = make_smem_desc(b_pl + ky * Cfg::kBTileBytes + k * 32);
+                const uint64_t da = mk_desc(a_pl + ky * ATOM_BYTES + k * 32), db = mk_desc(b_pl + ky * Cfg::kBTileBytes + k * 32);
                 if (CTA2) umma2_bf16(d_tmem, da, db, idesc, ((kb - kc0) | cb | ky | k) ? 1u : 0u);
                 else umma_bf16(d_tmem, da, db, idesc, ((kb - kc0) | cb | ky | k) ? 1u : 0u);
               }
@@ -612,8 +632,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
           } else {
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            if (CTA2) umma2_bf16(d_tmem, make_smem_desc(a_pl + k * 32), make_smem_desc(b_pl + k * 32), idesc, ((kb - kc0) | cb | k) ? 1u : 0u);
-            else umma_bf16(d_tmem, make_smem_desc(a_pl + k * 32), make_smem_desc(b_pl + k * 32), idesc, ((kb - kc0) | cb | k) ? 1u : 0u);
+            if (CTA2) umma2_bf16(d_tmem, mk_desc(a_pl + k * 32), mk_desc(b_pl + k * 32), idesc, ((kb - kc0) | cb | k) ? 1u : 0u);
+            else umma_bf16(d_tmem, mk_desc(a_pl + k * 32), mk_desc(b_pl + k * 32), idesc, ((kb - kc0) | cb | k) ? 1u : 0u);
           }
           }
           }
@@ -804,6 +824,11 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
     const bool has_res = p.residual != nullptr;
     constexpr int NSUB = BN / SUB;               // sub-tiles per tile
     constexpr int MY_SUBS = (NSUB + 1) / 2;      // upper bound of sub-tiles per warp
+    // BLOCK_N 32 (one sub-tile per tile): the two warps of a TMEM lane quarter take alternate TILES -- warp half h drains
+    // accumulator buffer h -- so all eight warps work (these layers are epilogue-bound: tiny N, short K)
+    constexpr bool ALT = NSUB == 1 && !CHUNKED && !ACC;
+    const int sub0 = ALT ? 0 : half;
+    const int my_first = ALT ? tile_first + half * tile_step : tile_first, my_step = ALT ? 2 * tile_step : tile_step;
     auto row_to_m = [&](int mt, int r) -> int {  // output pixel index of tile row r, -1 if outside
       if (mode_is_patchy(MODE)) {
         const int y = ((mt / pw_tiles) % ph_tiles) * PH + r / PW, xq = (mt % pw_tiles) * PW + r % PW;
@@ -829,15 +854,15 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         }
       }
     };
-    prefetch_residual(tile_first);
+    prefetch_residual(my_first);
     const uint32_t empty_rank0 = CTA2 ? map_to_cta(tmem_empty_bar(0), 0) : 0u;      // the leader's MMA thread waits for both epilogues
-    int it = 0;
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step, it += CHUNKED ? 0 : 1) {    // (CHUNKED: `it` counts K chunks)
+    int it = ALT ? half : 0;
+    for (int tile = my_first; tile < num_tiles; tile += my_step, it += CHUNKED ? 0 : (ALT ? 2 : 1)) {    // (CHUNKED: `it` counts K chunks)
       const int acc = it & 1;
       const Unit u = decode_unit<ACC>(tile, num_m_tiles, num_n_tiles, num_splits, num_kb);
       const int n0 = u.nt * BN;
       const int mt = CTA2 ? 2 * u.mt + cta_rank : u.mt;
-      prefetch_residual(tile + tile_step);
+      prefetch_residual(tile + my_step);
       int mrow[4];
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) mrow[ps] = row_to_m(mt, quarter * 32 + ps * 8 + rsub);
@@ -857,7 +882,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       };
       // residual of the first sub-tile is requested before the accumulator is even ready
       uint4 rv[4], rv2[SPLIT ? 4 : 1];
-      if (!CHUNKED) load_res(half, rv, rv2);       // (CHUNKED: after the K-chunk drain, whose loop wants the registers)
+      if (!CHUNKED) load_res(sub0, rv, rv2);       // (CHUNKED: after the K-chunk drain, whose loop wants the registers)
       uint32_t v[32];
       // split mode: this warp's (up to two) 32-column sub-tiles accumulate in registers over the K chunks of the tile
       uint32_t racc0[CHUNKED ? 32 : 1], racc1[CHUNKED ? 32 : 1];
@@ -865,8 +890,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         constexpr int CH = chunk_kb(MODE);
         const int nchunks = (num_kb + CH - 1) / CH;
         for (int c = 0; c < nchunks; ++c, ++it) {
-          const int accb = it & 1;
-          mbar_wait(tmem_full_bar(accb), (it >> 1) & 1);
+          const int accb = it % NBUF;
+          mbar_wait(tmem_full_bar(accb), (it / NBUF) & 1);
           tc_fence_after();
           const uint32_t t_rowc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(accb * BN);
           // one sub-tile at a time through the same 32 staging registers (both at once would not fit next to the 64 sums)
@@ -890,10 +915,10 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
       tc_fence_after();
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      if (!CHUNKED && half < NSUB) tmem_ld32_nowait(t_row + (uint32_t)(half * SUB), v);
+      if (!CHUNKED && sub0 < NSUB) tmem_ld32_nowait(t_row + (uint32_t)(sub0 * SUB), v);
 #pragma unroll 1
       for (int k = 0; k < MY_SUBS; ++k) {
-        const int cc = half + 2 * k;
+        const int cc = sub0 + 2 * k;
         if (cc >= NSUB) break;
         // bf16: the next sub-tile's residual is requested one sub-tile ahead; split mode (twice the registers per residual)
         // requests it right after this sub-tile's has been consumed
@@ -1013,7 +1038,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
         }
         __syncwarp();                            // slab is rewritten by the next sub-tile
       }
-      if (!CHUNKED && half >= NSUB) {            // BN == 32: the second warp of a quarter has no sub-tile, still releases
+      if (!CHUNKED && !ALT && half >= NSUB) {    // BN == 32 with partial sums: the second warp of a quarter has no sub-tile, still releases
         tc_fence_before();
         if (lane == 0) { if (CTA2) mbar_arrive_cluster(empty_rank0 + 8u * acc); else mbar_arrive(tmem_empty_bar(acc)); }
       }
@@ -1023,8 +1048,8 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
   tc_fence_before();
   if (CTA2) cluster_sync_all(); else __syncthreads();       // pair: nobody leaves while the peer may still touch its smem / TMEM
   if (warp == MMA_WARP) {
-    if (CTA2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
-    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTA2) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -1083,6 +1108,7 @@ int num_sms() {
 }
 
 constexpr CUtensorMapDataType OPERAND_DT = SPLIT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+constexpr CUtensorMapSwizzle OPERAND_SWIZZLE = K32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
 
 int encode_2d(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
               uint32_t box_inner, uint32_t box_outer, CUtensorMapDataType dt = OPERAND_DT) {
@@ -1091,7 +1117,7 @@ int encode_2d(EncodeTiledFn enc, CUtensorMap* map, const void* base, uint64_t in
   const cuuint32_t box[2] = {box_inner, box_outer};
   const cuuint32_t estr[2] = {1, 1};
   CUresult cr = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, OPERAND_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
   return PPY_OK;
@@ -1104,7 +1130,7 @@ int encode_patch_4d(EncodeTiledFn enc, CUtensorMap* map, const ppy_conv_params* 
   const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(map, OPERAND_DT, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, OPERAND_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
   return PPY_OK;
@@ -1121,7 +1147,7 @@ int encode_im2col_4d(CUtensorMap* map, const ppy_conv_params* p, const void* bas
   const int upper[2] = {p->pad - (p->kw - 1), p->pad - (p->kh - 1)};
   const cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
   CUresult cr = enc(map, OPERAND_DT, 4, const_cast<void*>(base), dims, strides, lower, upper, (cuuint32_t)BLOCK_K,
-                    (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, OPERAND_SWIZZLE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
   // drivers up to CUDA 13.1 set a descriptor bit for tensors under 128 KB that im2col loads then mishandle (same fix-up as CUTLASS)
@@ -1144,7 +1170,7 @@ int encode_tile_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int l
   const cuuint32_t box[4] = {box_cols, (cuuint32_t)box_w, (cuuint32_t)(BOX_ROWS / box_w), 1};   // one warp's 32 tile rows
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, OPERAND_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
   return PPY_OK;
@@ -1216,7 +1242,7 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
         const cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)PW, (cuuint32_t)PH, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult cr = enc(m2, OPERAND_DT, 4, const_cast<void*>(b2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          OPERAND_SWIZZLE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
       } else {
         rc = encode_2d(enc, m2, b2, c2, rows2, (uint64_t)p->x2_ld * 2, BLOCK_K, BLOCK_M);
@@ -1346,11 +1372,17 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 }
 
 // 3x3 stride-1 convs with 64..128 output channels (the stem and the stage-2/3 bottleneck 3x3s): slab stages, CTA pairs
+template <int UNUSED = 0>     // (a template so that `if constexpr` discards the branches of the other builds)
 int dispatch_slab(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
   static const bool no_pair = knob_off("PPY_NO_CTA2");
   const bool tma_epi = tma_epilogue_ok(p);
   const bool pair = !no_pair && p->n * ceil_div(ho, patch_h(MODE_TMA_SLAB)) * ceil_div(wo, patch_w(MODE_TMA_SLAB)) > 1;
-  if constexpr (SPLIT) {     // (3x3: always more than one K chunk)
+  if constexpr (SPLIT && K32) {     // cin = 32: three slab stages (54 MMAs) = one accumulator, no register stage
+    if (p->cin != BLOCK_K) return PPY_ERR_UNSUPPORTED;
+    if (p->cout <= 32) return launch<32, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
+    if (p->cout <= 64) return pair ? launch<64, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
+    return pair ? launch<128, MODE_TMA_SLAB, EPI_SLAB, false, true>(p, ho, wo, st) : launch<128, MODE_TMA_SLAB, EPI_SLAB>(p, ho, wo, st);
+  } else if constexpr (SPLIT) {     // (3x3: always more than one K chunk)
     if (p->cout <= 64) return pair ? launch<64, MODE_TMA_SLAB, EPI_SLAB, false, true, true>(p, ho, wo, st) : launch<64, MODE_TMA_SLAB, EPI_SLAB, false, false, true>(p, ho, wo, st);
     if (pair) return launch<128, MODE_TMA_SLAB, EPI_SLAB, false, true, true>(p, ho, wo, st);
     return dispatch<MODE_TMA_IM2COL>(p, ho, wo, st);            // single-tile problem: a 128-wide slab stage pair does not fit twice
@@ -1370,7 +1402,25 @@ int dispatch_slab(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
 extern "C" {
 using namespace ppy;
 
-#if !PPY_UMMA_SPLIT
+#if PPY_UMMA_K32
+int ppy_conv_bf16_supported(void);
+
+// 3x3 stride-1 pad-1 convs with 32 input channels on pair operands (called by ppy_conv_f16x2)
+int ppy_conv_f16x2_k32(const ppy_conv_params* p, ppy_stream_t s) {
+  int ho, wo;
+  int rc = validate_conv(p, 2, &ho, &wo);
+  if (rc) return rc;
+  PPY_REQUIRE(SPLIT && p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin == BLOCK_K && p->k_pad % 64 == 0 && p->k_pad >= 9 * BLOCK_K);
+  PPY_REQUIRE(p->out_dtype == PPY_F16X2 || p->out_dtype == PPY_F32);
+  PPY_REQUIRE(p->x_plane > 0 && (p->x_plane * 2) % 16 == 0 && !p->accumulate && !p->coord_w && !p->offset_mask && p->x2_kb == 0);
+  if (p->out_dtype == PPY_F16X2) PPY_REQUIRE(p->y_plane > 0);
+  if (p->residual) PPY_REQUIRE(p->out_dtype == PPY_F16X2 && p->res_plane > 0);
+  PPY_REQUIRE((long long)p->n * ho * wo < 0x7FFFFFFFll && p->cout <= 128 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0);
+  PPY_REQUIRE((reinterpret_cast<uintptr_t>(p->scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->shift) & 15) == 0);
+  if (p->act == PPY_ACT_MISH || !ppy_conv_bf16_supported()) return PPY_ERR_UNSUPPORTED;
+  return dispatch_slab(p, ho, wo, as_stream(s));
+}
+#elif !PPY_UMMA_SPLIT
 int ppy_conv_bf16_supported(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -1381,9 +1431,11 @@ int ppy_conv_bf16_supported(void) {
 int ppy_conv_bf16(const ppy_conv_params* p, ppy_stream_t s) {
 #else
 int ppy_conv_bf16_supported(void);
+int ppy_conv_f16x2_k32(const ppy_conv_params* p, ppy_stream_t s);
 
 int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
 #endif
+#if !PPY_UMMA_K32
   int ho, wo;
   int rc = validate_conv(p, 2, &ho, &wo);
   if (rc) return rc;
@@ -1422,6 +1474,13 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
     if (rc2 != 1) return rc2;
     return dispatch<MODE_DCN>(p, ho, wo, as_stream(s));
   }
+#if PPY_UMMA_SPLIT
+  if (p->kh == 3 && p->stride == 1 && p->pad == 1 && p->cin == 32 && p->cout <= 128 && p->x2_kb == 0 && !knob_off("PPY_NO_K32")) {
+    // 32 input channels: one tap = one 32-element K block in the SWIZZLE_64B build (no structural zeros)
+    const double eff = (double)ho * wo / ((double)ceil_div(ho, patch_h(MODE_TMA_SLAB)) * patch_h(MODE_TMA_SLAB) * ceil_div(wo, patch_w(MODE_TMA_SLAB)) * patch_w(MODE_TMA_SLAB));
+    if (eff >= 0.85 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0) return ppy_conv_f16x2_k32(p, s);
+  }
+#endif
   const bool plain_1x1 = p->kh == 1 && p->stride == 1 && p->pad == 0 && p->cin % BLOCK_K == 0 &&
                          p->k_pad == p->cin + p->x2_kb * BLOCK_K;
   if (plain_1x1) return dispatch<MODE_TMA_A>(p, ho, wo, as_stream(s));
@@ -1443,5 +1502,6 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s) {
   if (p->x2_kb > 0) return PPY_ERR_UNSUPPORTED;
   return dispatch<MODE_GATHER>(p, ho, wo, as_stream(s));
 }
+#endif
 
 }  // extern "C"

@@ -87,6 +87,51 @@ __global__ void __launch_bounds__(256) pool_pair_kernel(const __half* __restrict
   }
 }
 
+// MaxPool 3x3 / stride 2 / pad 1, second version: one thread = one 8-channel vector of TWO vertically adjacent output pixels.
+// The five input rows they share are read once (15 positions x 2 planes instead of 18 per output), coordinates are clamped to
+// the image instead of tested (a clamped position always lies inside the window, so the maximum is unchanged): branch-free, all
+// 30 loads of a thread in flight together.
+__global__ void __launch_bounds__(256) maxpool_pair2_kernel(const __half* __restrict__ x, int x_ld, long long x_plane, __half* __restrict__ y,
+                                                            int y_ld, long long y_plane, int n, int h, int w, int c, int ho, int wo) {
+  const int cv = c >> 3, ho2 = (ho + 1) >> 1;
+  const unsigned total = (unsigned)(n * ho2 * wo * cv);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = (int)(i % (unsigned)cv);
+    unsigned p = i / (unsigned)cv;
+    const int ox = (int)(p % (unsigned)wo); p /= (unsigned)wo;
+    const int oy = 2 * (int)(p % (unsigned)ho2);
+    const int img = (int)(p / (unsigned)ho2);
+    const __half* base = x + (long long)img * h * w * x_ld + v * 8;
+    int xs[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { const int t = ox * 2 + d - 1; xs[d] = t < 0 ? 0 : (t >= w ? w - 1 : t); }
+    float rmax[5][8];                      // horizontal 3-max of input rows 2*oy - 1 .. 2*oy + 3
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      int yy = oy * 2 + r - 1;
+      yy = yy < 0 ? 0 : (yy >= h ? h - 1 : yy);
+      float a[8], b[8], cc[8];
+      const __half* row = base + (long long)yy * w * x_ld;
+      load_pair8(row + (long long)xs[0] * x_ld, x_plane, a);
+      load_pair8(row + (long long)xs[1] * x_ld, x_plane, b);
+      load_pair8(row + (long long)xs[2] * x_ld, x_plane, cc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rmax[r][k] = fmaxf(fmaxf(a[k], b[k]), cc[k]);
+    }
+    float o0[8], o1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // output row oy: input rows 2oy-1..2oy+1 = r 0..2; output row oy+1: input rows 2oy+1..2oy+3 = r 2..4.  Rows clamped at the
+      // bottom repeat row h-1, which is inside the window of output row oy+1 whenever that row exists.
+      o0[k] = fmaxf(fmaxf(rmax[0][k], rmax[1][k]), rmax[2][k]);
+      o1[k] = fmaxf(fmaxf(rmax[2][k], rmax[3][k]), rmax[4][k]);
+    }
+    __half* dst = y + (((long long)img * ho + oy) * wo + ox) * y_ld + v * 8;
+    store_pair8(dst, y_plane, o0);
+    if (oy + 1 < ho) store_pair8(dst + (long long)wo * y_ld, y_plane, o1);
+  }
+}
+
 // SPP (model/custom_layers.py:275-290), separable + cascaded like spp_separable_kernel: maxpool9 = maxpool5(maxpool5(x)),
 // maxpool13 = maxpool5(maxpool9), each 5x5 as a row pass and a column pass over fp32 values in shared memory.
 // One CTA = one image x SPPP_VECS 8-channel vectors.
@@ -193,8 +238,9 @@ int ppy_maxpool3x3s2_f16x2(const void* x, int x_ld, long long x_plane, void* y, 
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   const long long total = (long long)n * ho * wo * (c / 8);
   PPY_REQUIRE(total < 0x7FFFFFFFll);
-  pool_pair_kernel<0><<<grid_for(total, 256), 256, 0, as_stream(s)>>>((const __half*)x, x_ld, x_plane, (__half*)y, y_ld, y_plane, n, h, w,
-                                                                       c, ho, wo);
+  const long long total2 = (long long)n * ((ho + 1) / 2) * wo * (c / 8);
+  maxpool_pair2_kernel<<<grid_for(total2, 256), 256, 0, as_stream(s)>>>((const __half*)x, x_ld, x_plane, (__half*)y, y_ld, y_plane, n, h, w,
+                                                                         c, ho, wo);
   return check_launch();
 }
 

@@ -170,5 +170,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// The same for 64-byte operand rows: SWIZZLE_64B (layout type 4), 8-row groups 512 bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
 }  // namespace
 }  // namespace ppy

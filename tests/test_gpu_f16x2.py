@@ -73,6 +73,10 @@ SHAPES = [  # n, cin, cout, k, stride, hw          kernel mode
     (1, 128, 256, 3, 2, 20),    # im2col stride 2
     (2, 512, 27, 3, 1, 19),     # BLOCK_N 32 (DCN offset conv shape)
     (1, 64, 32, 3, 1, 8),       # single tile
+    (2, 32, 32, 3, 1, 32),      # 32-element K blocks (SWIZZLE_64B build), BLOCK_N 32 (stem conv1_2)
+    (1, 32, 64, 3, 1, 48),      # 32-element K blocks, BLOCK_N 64, CTA pair (stem conv1_3)
+    (3, 32, 128, 3, 1, 40),     # 32-element K blocks, BLOCK_N 128
+    (1, 32, 48, 3, 1, 19),      # cin 32 on a map the slab grid wastes: gather mode
     (2, 8, 16, 3, 1, 9),        # gather mode (cin < 64)
     (1, 24, 40, 1, 1, 7),       # gather mode 1x1
 ]
