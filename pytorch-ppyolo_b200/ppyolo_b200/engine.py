@@ -668,7 +668,8 @@ class InferenceEngine(object):
         x = x0
         for u, nm in stem_units:
             # (pair path: these layers run the 32-element-K-block build of the kernel instead -- no structural zeros)
-            pairable = (self.code == PPY_BF16 and not self.train_bn and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
+            pairs_ok = self.code == PPY_BF16 or (self.code == PPY_F16X2 and u.conv.weight.shape[0] < getattr(self.model, 'k32_min_cout', 64))
+            pairable = (pairs_ok and not self.train_bn and not hasattr(u.conv, 'dcn_weight') and u.stride == 1 and
                         tuple(u.conv.weight.shape[1:]) == (32, 3, 3) and x.c == 32 and x.ld == 32 and x.c_off == 0 and
                         x.w % 2 == 0 and u.conv.weight.shape[0] % 8 == 0 and u.conv.bias is None)
             x = self._unit_pixel_pairs('stem.' + nm, u, x) if pairable else self._unit('stem.' + nm, u, x)
