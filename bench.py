@@ -401,6 +401,56 @@ def time_e2e(eng, x_host, im_host, steps, warmup, dd, dev):
     return ms, h2d, d2h
 
 
+def time_e2e_raw(eng, blobs, metas, im_host, steps, warmup, dd, dev):
+    """End to end from the ORIGINAL images: packed uint8 BGR images of the camera / file size in pinned host
+    memory -> one upload -> batched bicubic resize + BGR->RGB kernel straight into the engine's uint8 input slot -> forward ->
+    detections back.  The host does no image processing at all."""
+    from ppyolo_b200 import ops
+    main = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream(device=dev)
+    while len(eng.input_slots) < 2:
+        eng.add_input_slot()
+    blob_dev = [torch.empty_like(b, device=dev) for b in blobs]
+    meta_dev = [m.to(dev) for m in metas]
+    out_host = [torch.empty((eng.n, eng.keep_top_k, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    cnt_host = [torch.empty((eng.n + 1,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    stage_im = [torch.empty_like(eng.im_size) for _ in range(2)]
+    ready, consumed, done = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
+
+    def loop(n_steps):
+        for b in range(2):
+            consumed[b].record(main)
+        for step in range(n_steps):
+            b = step % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                blob_dev[b].copy_(blobs[b], non_blocking=True)
+                stage_im[b].copy_(im_host[b], non_blocking=True)
+                ready[b].record(copy_stream)
+            main.wait_event(ready[b])
+            ops.resize_cubic_u8(blob_dev[b], meta_dev[b], eng.h, swap_rb=True, out=eng.input_slots[b])
+            eng.im_size.copy_(stage_im[b], non_blocking=True)
+            eng.launch(slot=b)
+            consumed[b].record(main)
+            out_host[b].copy_(eng.nms_out, non_blocking=True)
+            cnt_host[b].copy_(eng._flags, non_blocking=True)
+            done[b].record(main)
+            if step >= 1:
+                done[1 - b].synchronize()
+                _ = int(cnt_host[1 - b][0])
+        done[(n_steps - 1) % 2].synchronize()
+
+    loop(max(2, warmup))
+    dd.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(main)
+    loop(steps)
+    s1.record(main)
+    dd.barrier()
+    ms = dd.max(s0.elapsed_time(s1)) / steps
+    return ms, blobs[0].numel() + metas[0].numel() * 8 + im_host[0].numel() * 4
+
+
 def conv_family_roofline(eng, precision, steps, ms_step, local_rank):
     """Roofline of the dominant kernel family (tcgen05 implicit-GEMM conv, all launches of one step), rank 0."""
     peaks, peak_src = measured_peaks()
@@ -442,6 +492,14 @@ def conv_family_roofline(eng, precision, steps, ms_step, local_rank):
                 'timing': 'CUDA events around %d replays of a CUDA graph holding the %d conv launches of one step' % (steps, conv_launches),
                 'kernel_ms_per_step_eager_events': conv_ms_eager, 'achieved_eager_events': eng.conv_flops / (conv_ms_eager * 1e-3) / 1e12,
                 'traffic_note': 'see profiles/ (ncu launch list of this round) for DRAM bytes per launch'}
+    # DRAM bytes of the same launches from the committed ncu launch list of this round (profiles/, tools/summarize_launches.py)
+    tpath = os.path.join(REPO, 'profiles', 'r02_conv_family_traffic_%s.json' % precision)
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f)
+        roofline['traffic'] = t['dram_bytes']
+        roofline['traffic_note'] = ('dram__bytes_read.sum + dram__bytes_write.sum over the %d conv launches of one step, ncu launch list '
+                                    'profiles/r02_ncu_launches_%s.csv; algorithmic minimum = min_bytes_per_step' % (t['launches'], precision))
     os.makedirs(os.path.join(REPO, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(REPO, 'gpurun_out', 'per_op_ms_%s.json' % precision), 'w') as f:
         json.dump({'ops': ops_t, 'total_ms': sum(t for _, t in ops_t), 'graph_ms_per_step': ms_step, 'info': eng.step_info}, f, indent=1)
@@ -513,7 +571,13 @@ def run_ours(args, rank, world, local_rank):
     eng_u8 = model.engine(BATCH, SIZE, SIZE, input_u8=True)
     e2e_ms, h2d, d2h = time_e2e(eng_u8, u8_host, im_host, args.steps, args.warmup, dd, dev)
     e2e_f32_ms, h2d_f32, _ = time_e2e(eng, x_host, im_host, args.steps, args.warmup, dd, dev)
-    del eng_u8
+    # the same from the ORIGINAL images: 480x640 BGR uint8 frames packed in pinned memory, resized on the GPU (csrc/preprocess.cu)
+    from ppyolo_b200 import ops
+    import numpy as np
+    raw_rng = np.random.RandomState(100 + rank)
+    packed = [ops.pack_images([raw_rng.randint(0, 256, (480, 640, 3)).astype(np.uint8) for _ in range(BATCH)]) for _ in range(2)]
+    e2e_raw_ms, h2d_raw = time_e2e_raw(eng_u8, [p[0] for p in packed], [p[1] for p in packed], im_host, args.steps, args.warmup, dd, dev)
+    del eng_u8, packed
 
     # ---- the bf16 mode beside it (labelled, with its drift from the headline mode's detections on the same batch)
     modes = {}
@@ -563,7 +627,9 @@ def run_ours(args, rank, world, local_rank):
             'clocks': clocks, 'gpu_launches': eng.launches_per_run * args.steps * world,
             'e2e': {'value': world * BATCH / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms, 'h2d_bytes_per_step': world * h2d,
                     'd2h_bytes_per_step': world * d2h, 'input': 'resized uint8 HWC batch (normalise + permute fused into the stem kernel)',
-                    'float_chw_upload': {'value': world * BATCH / (e2e_f32_ms * 1e-3), 'ms_per_step': e2e_f32_ms, 'h2d_bytes_per_step': world * h2d_f32}},
+                    'float_chw_upload': {'value': world * BATCH / (e2e_f32_ms * 1e-3), 'ms_per_step': e2e_f32_ms, 'h2d_bytes_per_step': world * h2d_f32},
+                    'from_original_images': {'value': world * BATCH / (e2e_raw_ms * 1e-3), 'ms_per_step': e2e_raw_ms, 'h2d_bytes_per_step': world * h2d_raw,
+                                             'input': '480x640 BGR uint8 frames, bicubic resize + BGR->RGB on the GPU (no host image processing)'}},
             'roofline': roofline, 'cpu_baseline': cpu, 'torch_gpu_baseline': tgb, 'precision_modes': modes, 'train': train,
             'matrix_nms': matrix_nms_isolation(dev, world == 1 and not args.no_cpu_baseline and not args.quick),
             'loaded_library': _lib.LIB_PATH}

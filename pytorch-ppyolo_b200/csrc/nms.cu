@@ -41,13 +41,20 @@ constexpr int kMatrixThreads = 1024;
 struct Workspace {
   unsigned int* hist;     // [n][kBins]
   unsigned int* count;    // [n] collected keys
+  int* cutoff;            // [n] bin holding the nms_top_k-th best score
+  unsigned int* done;     // [n] histogram CTAs finished (the last one derives the cutoff)
   unsigned long long* keys;  // [n][kCap]
 };
 
+__device__ int find_cutoff_bin(const unsigned int* __restrict__ gh, int want, unsigned int* sh, unsigned int* part);
+
 __global__ void __launch_bounds__(kScanThreads)
 nms_hist_kernel(const float* __restrict__ scores, long long per_image, long long chunk, float thr,
-                unsigned int thr_bits, int shift, unsigned int* __restrict__ hist) {
+                unsigned int thr_bits, int shift, unsigned int* __restrict__ hist, int want, int* __restrict__ cutoff,
+                unsigned int* __restrict__ done) {
   __shared__ unsigned int sh[kBins];
+  __shared__ unsigned int part[33];
+  __shared__ bool last;
   for (int i = threadIdx.x; i < kBins; i += kScanThreads) sh[i] = 0;
   __syncthreads();
   const int img = blockIdx.y;
@@ -58,12 +65,20 @@ nms_hist_kernel(const float* __restrict__ scores, long long per_image, long long
   if (vec) {
     const float4* b4 = reinterpret_cast<const float4*>(base);
     long long hi4 = hi / 4;
-    for (long long i = lo / 4 + threadIdx.x; i < hi4; i += kScanThreads) {
-      float4 v = __ldg(b4 + i);
-      if (v.x > thr) atomicAdd(&sh[score_bin(v.x, thr_bits, shift)], 1u);
-      if (v.y > thr) atomicAdd(&sh[score_bin(v.y, thr_bits, shift)], 1u);
-      if (v.z > thr) atomicAdd(&sh[score_bin(v.z, thr_bits, shift)], 1u);
-      if (v.w > thr) atomicAdd(&sh[score_bin(v.w, thr_bits, shift)], 1u);
+    for (long long i0 = lo / 4 + threadIdx.x; i0 < hi4; i0 += 4 * kScanThreads) {      // four independent loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * kScanThreads;
+        v[u] = i < hi4 ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (v[u].x > thr) atomicAdd(&sh[score_bin(v[u].x, thr_bits, shift)], 1u);
+        if (v[u].y > thr) atomicAdd(&sh[score_bin(v[u].y, thr_bits, shift)], 1u);
+        if (v[u].z > thr) atomicAdd(&sh[score_bin(v[u].z, thr_bits, shift)], 1u);
+        if (v[u].w > thr) atomicAdd(&sh[score_bin(v[u].w, thr_bits, shift)], 1u);
+      }
     }
     lo = hi4 * 4;  // scalar tail (only the last chunk can have one)
   }
@@ -75,6 +90,23 @@ nms_hist_kernel(const float* __restrict__ scores, long long per_image, long long
   unsigned int* gh = hist + (long long)img * kBins;
   for (int i = threadIdx.x; i < kBins; i += kScanThreads)
     if (sh[i]) atomicAdd(&gh[i], sh[i]);
+  // the last CTA of the image to get here derives the cutoff bin once, for every CTA of the collect pass
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(done + img, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int cut = find_cutoff_bin(gh, want, sh, part);
+  if (threadIdx.x == 0) cutoff[img] = cut;
+}
+
+// The same for a histogram somebody else filled (the decode kernels of the whole-network path): one CTA per image.
+__global__ void __launch_bounds__(kScanThreads) nms_cutoff_kernel(const unsigned int* __restrict__ hist, int want, int* __restrict__ cutoff) {
+  __shared__ unsigned int sh[kBins];
+  __shared__ unsigned int part[33];
+  const int cut = find_cutoff_bin(hist + (long long)blockIdx.x * kBins, want, sh, part);
+  if (threadIdx.x == 0) cutoff[blockIdx.x] = cut;
 }
 
 // Cutoff bin: the largest bin b such that count(bins >= b) >= want; 0 if fewer candidates than `want`.
@@ -85,7 +117,7 @@ __device__ int find_cutoff_bin(const unsigned int* __restrict__ gh, int want, un
   unsigned int local = 0;
   for (int k = 0; k < per; ++k) {
     int bin = kBins - 1 - (threadIdx.x * per + k);
-    unsigned int v = gh[bin];
+    unsigned int v = __ldcg(gh + bin);          // L2 read: other CTAs of this launch may have just added to it
     sh[bin] = v;
     local += v;
   }
@@ -125,12 +157,10 @@ __device__ int find_cutoff_bin(const unsigned int* __restrict__ gh, int want, un
 
 __global__ void __launch_bounds__(kScanThreads)
 nms_collect_kernel(const float* __restrict__ scores, long long per_image, long long chunk, float thr,
-                   unsigned int thr_bits, int shift, int want, const unsigned int* __restrict__ hist, unsigned int* __restrict__ count,
+                   unsigned int thr_bits, int shift, const int* __restrict__ cutoff, unsigned int* __restrict__ count,
                    unsigned long long* __restrict__ keys) {
-  __shared__ unsigned int sh[kBins];
-  __shared__ unsigned int part[33];
   const int img = blockIdx.y;
-  const int cut = find_cutoff_bin(hist + (long long)img * kBins, want, sh, part);
+  const int cut = cutoff[img];
   const float* base = scores + (long long)img * per_image;
   unsigned long long* out = keys + (long long)img * kCap;
   unsigned int* cnt = count + img;
@@ -147,9 +177,18 @@ nms_collect_kernel(const float* __restrict__ scores, long long per_image, long l
   if (vec) {
     const float4* b4 = reinterpret_cast<const float4*>(base);
     long long hi4 = hi / 4;
-    for (long long i = lo / 4 + threadIdx.x; i < hi4; i += kScanThreads) {
-      float4 v = __ldg(b4 + i);
-      emit(v.x, 4 * i); emit(v.y, 4 * i + 1); emit(v.z, 4 * i + 2); emit(v.w, 4 * i + 3);
+    for (long long i0 = lo / 4 + threadIdx.x; i0 < hi4; i0 += 4 * kScanThreads) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * kScanThreads;
+        v[u] = i < hi4 ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + (long long)u * kScanThreads;
+        emit(v[u].x, 4 * i); emit(v[u].y, 4 * i + 1); emit(v[u].z, 4 * i + 2); emit(v[u].w, 4 * i + 3);
+      }
     }
     lo = hi4 * 4;
   }
@@ -162,12 +201,10 @@ nms_collect_kernel(const float* __restrict__ scores, long long per_image, long l
 // load per thread).  Same keys as nms_collect_kernel.  Needs num_classes % 4 == 0.
 __global__ void __launch_bounds__(kScanThreads)
 nms_collect_pruned_kernel(const float* __restrict__ scores, const float* __restrict__ conf, int num_boxes, int num_classes,
-                          float thr, unsigned int thr_bits, int shift, int want,
-                          const unsigned int* __restrict__ hist, unsigned int* __restrict__ count, unsigned long long* __restrict__ keys) {
-  __shared__ unsigned int sh[kBins];
-  __shared__ unsigned int part[33];
+                          float thr, unsigned int thr_bits, int shift, const int* __restrict__ cutoff,
+                          unsigned int* __restrict__ count, unsigned long long* __restrict__ keys) {
   const int img = blockIdx.y;
-  const int cut = find_cutoff_bin(hist + (long long)img * kBins, want, sh, part);
+  const int cut = cutoff[img];
   const float4* sc = reinterpret_cast<const float4*>(scores + (long long)img * num_boxes * num_classes);
   const float* cf = conf + (long long)img * num_boxes;
   unsigned long long* out = keys + (long long)img * kCap;
@@ -190,10 +227,68 @@ nms_collect_pruned_kernel(const float* __restrict__ scores, const float* __restr
   }
 }
 
-// descending bitonic sort of `len` (power of two) 64-bit keys in shared memory
+// descending bitonic sort of `len` (power of two) 64-bit keys in shared memory.
+// The network is latency-bound (145 dependent stages for the kernel's three sorts), so every stage whose partner distance is
+// <= 32 runs in REGISTERS: a warp owns 64 consecutive keys, lane l holds keys l and l + 32; distance 32 is a compare-exchange
+// inside the thread, distances 16..1 are shuffles.  Merge sizes 2..64 never touch shared memory; for larger sizes only the
+// distances >= 64 are shared-memory stages with a CTA barrier (10 for 1024 keys), followed by one register phase.
+__device__ __forceinline__ unsigned long long key_pick(unsigned long long x, unsigned long long y, bool want_max) {
+  return want_max ? (x > y ? x : y) : (x < y ? x : y);
+}
+// distances 16..1 (or from `first` down) of merge size `size` on this lane's two keys (indices i0, i0 + 32)
+__device__ __forceinline__ void bitonic_shuffle_steps(unsigned long long& a, unsigned long long& b, int i0, int size, int first) {
+  const int lane = threadIdx.x & 31;
+  const bool desc = (i0 & size) == 0;       // (i0 and i0 + 32 share that bit for every size >= 64; for smaller sizes see the caller)
+  for (int stride = first; stride > 0; stride >>= 1) {
+    const unsigned long long pa = __shfl_xor_sync(0xffffffffu, a, stride), pb = __shfl_xor_sync(0xffffffffu, b, stride);
+    const bool lo = (lane & stride) == 0;    // this lane holds the lower index of the pair
+    a = key_pick(a, pa, lo == desc);
+    b = key_pick(b, pb, lo == desc);
+  }
+}
 __device__ void bitonic_sort_desc(unsigned long long* k, int len) {
-  for (int size = 2; size <= len; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+  __syncthreads();
+  if (len < 64) {                            // tiny lists: plain shared-memory network
+    for (int size = 2; size <= len; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
+          int lo = 2 * t - (t & (stride - 1));
+          int hi = lo + stride;
+          bool desc = ((lo & size) == 0);
+          unsigned long long a = k[lo], b = k[hi];
+          if ((a < b) == desc) { k[lo] = b; k[hi] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // merge sizes 2 .. 64, all in registers
+  for (int base = warp * 64; base < len; base += nw * 64) {
+    const int i0 = base + lane;
+    unsigned long long a = k[i0], b = k[i0 + 32];
+    for (int size = 2; size <= 32; size <<= 1) {
+      // (sizes < 64: keys l and l + 32 differ in bit 5 only, so (i & size) is the same for both when size <= 16; for size == 32
+      // it differs: handled by flipping the direction of b)
+      const bool da = (i0 & size) == 0, db = ((i0 + 32) & size) == 0;
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const unsigned long long pa = __shfl_xor_sync(0xffffffffu, a, stride), pb = __shfl_xor_sync(0xffffffffu, b, stride);
+        const bool lo = (lane & stride) == 0;
+        a = key_pick(a, pa, lo == da);
+        b = key_pick(b, pb, lo == db);
+      }
+    }
+    {                                        // size 64: distance 32 inside the thread, then 16..1
+      const bool desc = (i0 & 64) == 0;
+      const unsigned long long mx = a > b ? a : b, mn = a > b ? b : a;
+      a = desc ? mx : mn; b = desc ? mn : mx;
+      bitonic_shuffle_steps(a, b, i0, 64, 16);
+    }
+    k[i0] = a; k[i0 + 32] = b;
+  }
+  for (int size = 128; size <= len; size <<= 1) {
+    for (int stride = size >> 1; stride >= 64; stride >>= 1) {
       __syncthreads();
       for (int t = threadIdx.x; t < (len >> 1); t += blockDim.x) {
         int lo = 2 * t - (t & (stride - 1));
@@ -202,6 +297,16 @@ __device__ void bitonic_sort_desc(unsigned long long* k, int len) {
         unsigned long long a = k[lo], b = k[hi];
         if ((a < b) == desc) { k[lo] = b; k[hi] = a; }
       }
+    }
+    __syncthreads();
+    for (int base = warp * 64; base < len; base += nw * 64) {
+      const int i0 = base + lane;
+      unsigned long long a = k[i0], b = k[i0 + 32];
+      const bool desc = (i0 & size) == 0;
+      const unsigned long long mx = a > b ? a : b, mn = a > b ? b : a;
+      a = desc ? mx : mn; b = desc ? mn : mx;
+      bitonic_shuffle_steps(a, b, i0, size, 16);
+      k[i0] = a; k[i0 + 32] = b;
     }
   }
   __syncthreads();
@@ -244,6 +349,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   __shared__ int s_nan_from;   // largest i with NaN compensate (poisons every column j <= i), -1 if none
   __shared__ int s_kept;
   __shared__ int s_any_odd;
+  __shared__ int s_maxgrp;     // longest same-label prefix a column has to scan
   __shared__ unsigned int s_m;
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMatrixThreads >> 5;
@@ -284,7 +390,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   int n = m;
   if (nms_top_k > 0 && n > nms_top_k) n = nms_top_k;
   if (n > nmax) { if (tid == 0) counts[img] = -3; return; }
-  if (tid == 0) { s_nan_from = -1; s_kept = 0; s_any_odd = 0; }
+  if (tid == 0) { s_nan_from = -1; s_kept = 0; s_any_odd = 0; s_maxgrp = 0; }
   __syncthreads();
   const float4* gb = reinterpret_cast<const float4*>(boxes) + (long long)img * num_boxes;
   for (int i = tid; i < n; i += kMatrixThreads) {
@@ -316,8 +422,47 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
       int q = p;
       while (q > 0 && s_label[s_order[q - 1]] == lp) --q;
       s_gstart[p] = (unsigned short)q;
+      if (p - q > 32) atomicMax(&s_maxgrp, p - q);
     }
     __syncthreads();
+    if (s_maxgrp == 0) {
+      // every label group is short (<= 33 boxes): one THREAD per column walks its prefix -- no shuffle reductions, all columns
+      // at once (the warp-per-column form below costs ~450 dependent cycles per column and 16 columns per warp)
+      for (int p = tid; p < n; p += kMatrixThreads) {
+        const int j = s_order[p];
+        const float4 bj = s_box[j];
+        float mx = 0.f;
+        for (int q = s_gstart[p]; q < p; ++q) {
+          const float4 bi = s_box[s_order[q]];
+          const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+          if (iw <= 0.f || ih <= 0.f) continue;
+          mx = fmaxf(mx, box_iou(bi, bj));
+        }
+        s_comp[j] = mx;
+      }
+      __syncthreads();
+      for (int p = tid; p < n; p += kMatrixThreads) {
+        const int j = s_order[p];
+        const float4 bj = s_box[j];
+        float mn = j > 0 ? 1.f : CUDART_INF_F;
+        for (int q = s_gstart[p]; q < p; ++q) {
+          const int i = s_order[q];
+          const float4 bi = s_box[i];
+          const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+          if (iw <= 0.f || ih <= 0.f) continue;
+          const float d = box_iou(bi, bj);
+          const float c = s_comp[i];
+          float e;
+          if (use_gaussian) e = __fdiv_rn(expf(__fmul_rn(neg_sigma, __fmul_rn(d, d))), expf(__fmul_rn(neg_sigma, __fmul_rn(c, c))));
+          else e = __fdiv_rn(__fsub_rn(1.f, d), __fsub_rn(1.f, c));
+          mn = nan_min(mn, e);
+        }
+        const float cj = s_comp[j];
+        const float self = use_gaussian ? __fdiv_rn(1.f, expf(__fmul_rn(neg_sigma, __fmul_rn(cj, cj)))) : __fdiv_rn(1.f, __fsub_rn(1.f, cj));
+        mn = nan_min(mn, self);
+        s_new[j] = __fmul_rn(s_score[j], mn);
+      }
+    } else {
     for (int p = wid; p < n; p += nwarps) {
       const int j = s_order[p];
       const float4 bj = s_box[j];
@@ -355,6 +500,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
         mn = nan_min(mn, self);
         s_new[j] = __fmul_rn(s_score[j], mn);
       }
+    }
     }
   } else {
   // compensate[j] = max_i (iou*same)[i][j] over the strict upper triangle (matrix_nms.py:67-78); warp per column
@@ -465,13 +611,15 @@ Workspace carve(void* ws, int n) {
   w.hist = reinterpret_cast<unsigned int*>(p);
   p += sizeof(unsigned int) * (size_t)n * kBins;
   w.count = reinterpret_cast<unsigned int*>(p);
-  p += ((sizeof(unsigned int) * (size_t)n + 255) / 256) * 256;
+  w.cutoff = reinterpret_cast<int*>(w.count + n);
+  w.done = w.count + 2 * n;
+  p += cand_count_bytes(n);
   w.keys = reinterpret_cast<unsigned long long*>(p);
   return w;
 }
 
 size_t workspace_bytes(int n, int num_boxes) {
-  return sizeof(unsigned int) * (size_t)n * kBins + ((sizeof(unsigned int) * (size_t)n + 255) / 256) * 256 +
+  return sizeof(unsigned int) * (size_t)n * kBins + cand_count_bytes(n) +
          sizeof(unsigned long long) * (size_t)n * kCap + sizeof(float) * (size_t)n * num_boxes;
 }
 
@@ -509,9 +657,9 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
   int shift;
   score_binning(score_threshold, &thr_bits, &shift);
   const long long per_image = (long long)num_boxes * num_classes;
-  // enough CTAs to saturate HBM: ~4 per SM over the whole batch, each CTA >= 16K scores, chunk % 4 == 0
+  // enough CTAs to saturate HBM: ~4 per SM over the whole batch, each CTA >= 4K scores (four 16-byte loads per thread), chunk % 4 == 0
   long long gx = ceil_div(148 * 4, n);
-  long long max_gx = ceil_div(per_image, 16384);
+  long long max_gx = ceil_div(per_image, 4096);
   if (gx > max_gx) gx = max_gx;
   if (gx < 1) gx = 1;
   long long chunk = ceil_div(ceil_div(per_image, gx), 4) * 4;
@@ -519,7 +667,10 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
   dim3 grid((unsigned)gx, (unsigned)n);
   int want = nms_top_k > 0 ? nms_top_k : kCap + 1;   // <=0: take everything (cutoff bin 0)
   if (!have_hist) {
-    nms_hist_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.hist);
+    nms_hist_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.hist, want, w.cutoff, w.done);
+    if ((rc = check_launch())) return rc;
+  } else {
+    nms_cutoff_kernel<<<n, kScanThreads, 0, st>>>(w.hist, want, w.cutoff);
     if ((rc = check_launch())) return rc;
   }
   if (have_hist && num_classes % 4 == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0) {
@@ -531,9 +682,9 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
     if (cx < 1) cx = 1;
     dim3 cgrid((unsigned)cx, (unsigned)n);
     nms_collect_pruned_kernel<<<cgrid, kScanThreads, 0, st>>>(scores, conf, num_boxes, num_classes, score_threshold, thr_bits, shift,
-                                                              want, w.hist, w.count, w.keys);
+                                                              w.cutoff, w.count, w.keys);
   } else {
-    nms_collect_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, want, w.hist,
+    nms_collect_kernel<<<grid, kScanThreads, 0, st>>>(scores, per_image, chunk, score_threshold, thr_bits, shift, w.cutoff,
                                                       w.count, w.keys);
   }
   if ((rc = check_launch())) return rc;

@@ -6,7 +6,7 @@
 // Every candidate is also counted in a per-image histogram of its score, binned on
 // (float_bits - bits(threshold)) >> shift, from which the NMS kernel derives the bin holding the nms_top_k-th score.
 //
-// Workspace layout (n images): hist[n][kBins] u32 | count[n] u32 (padded to 256 B) | keys[n][cap] u64
+// Workspace layout (n images): hist[n][kBins] u32 | count[n] u32, cutoff[n] i32, done[n] u32 (padded to 256 B) | keys[n][cap] u64
 // (dense Matrix-NMS workspace: cap = kNmsKeyCap, followed by conf[n][num_boxes] fp32 = objectness per box)
 #pragma once
 #include <string.h>
@@ -45,7 +45,9 @@ inline void score_binning(float score_threshold, unsigned int* thr_bits, int* sh
   *shift = sh;
 }
 
-inline size_t cand_count_bytes(int n) { return ((sizeof(unsigned int) * (size_t)n + 255) / 256) * 256; }
+// count[n] u32 | cutoff[n] i32 (bin holding the nms_top_k-th score, written by the cutoff stage) | done[n] u32 (CTAs of the
+// histogram pass that have flushed), padded to 256 B -- zeroed together with the histogram
+inline size_t cand_count_bytes(int n) { return ((3 * sizeof(unsigned int) * (size_t)n + 255) / 256) * 256; }
 inline size_t cand_workspace_bytes(int n, int cap) {
   return sizeof(unsigned int) * (size_t)n * kBins + cand_count_bytes(n) + sizeof(unsigned long long) * (size_t)n * cap;
 }

@@ -1,5 +1,7 @@
-"""ncu launch-list CSV (one eager step) -> compact per-launch table with plan-step names and kernel shares."""
-import csv, sys, collections
+"""ncu launch-list CSV (one eager step) -> compact per-launch table with plan-step names and kernel shares.
+Optional third argument: path of a JSON summary of the conv kernel family (DRAM bytes and time share of one step) that bench.py
+reports as `roofline.traffic`."""
+import csv, json, sys, collections
 path, names_path = sys.argv[1], sys.argv[2]
 rows = list(csv.reader(open(path)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
@@ -33,3 +35,12 @@ print()
 print('total %.1f us (cold-cache, serialised ncu replay: compare shares, not absolutes)' % (tot / 1e3))
 for f, t in fam.most_common():
     print('  %-28s %.1f us  %.1f%%' % (f, t / 1e3, 100 * t / tot))
+
+if len(sys.argv) > 3:
+    conv = [m for m in per.values() if 'conv_umma_kernel' in m['name'] or 'dcn_umma_kernel' in m['name']]
+    t_conv = sum(m['gpu__time_duration.sum'] for m in conv)
+    json.dump({'kernel_family': 'conv_umma_kernel + dcn_umma_kernel launches of one eager step (ncu, --clock-control none)',
+               'launches': len(conv), 'dram_bytes_read': sum(m['dram__bytes_read.sum'] for m in conv),
+               'dram_bytes_write': sum(m['dram__bytes_write.sum'] for m in conv),
+               'dram_bytes': sum(m['dram__bytes_read.sum'] + m['dram__bytes_write.sum'] for m in conv),
+               'time_share_of_step': t_conv / tot, 'source_csv': path}, open(sys.argv[3], 'w'), indent=1)
