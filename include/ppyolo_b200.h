@@ -242,6 +242,19 @@ int ppy_sgd_ema_multi(float* const* params, const float* grad_flat, float* momen
  * outside the image and for m in [n*h*w, m_pad); rows follow the OIHW weight order, k = 1 is the plain transpose (also used
  * for dY).  m_pad % 64 == 0. */
 int ppy_im2col_kmajor(const void* x, int x_ld, int n, int h, int w, int c, int k, int pad, void* out, long long m_pad, ppy_stream_t s);
+/* The same operand for a STRIDED conv (the 3x3 / stride 2 convs of an unfrozen ResNet-vd stage, model/resnet_vd.py:19-22; the
+ * DCNv2 offset conv of stage5_0): columns are the n*ho*wo OUTPUT pixels, out[(ch*k*k + ky*k + kx)][m] =
+ * x[oy*stride + ky - pad][ox*stride + kx - pad][ch]. */
+int ppy_im2col_kmajor_strided(const void* x, int x_ld, int n, int h, int w, int c, int k, int stride, int pad, void* out, long long m_pad,
+                              ppy_stream_t s);
+/* DCNv2 backward, sampling side (model/custom_layers.py:551-677 under torch autograd; the native spec the reference vendors but never
+ * loads is external/DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:197-327): given dcol = dY . Wt ([n*ho*wo][k*k*c] fp32, column tap*c + ch --
+ * the layout ppy_dcn_gather writes) it ACCUMULATES the input gradient into dx (fp32 NHWC [n,h,w,dx_ld], caller-zeroed or holding the
+ * offset conv's input gradient; vector atomics) and writes the gradient of the offset/mask conv's output into d_offset_mask
+ * ([n*ho*wo][om_ld] fp32: 2t = d dy, 2t+1 = d dx, 2*k*k + t = d mask-logit; columns >= 3*k*k untouched).  x: NHWC, dtype PPY_F32 or
+ * PPY_BF16.  The weight gradient is the conv kernel's partial-sum GEMM over ppy_dcn_gather's matrix (conv_autograd.py). */
+int ppy_dcn_backward_sample(const void* x, int x_ld, int n, int h, int w, int c, const float* offset_mask, int om_ld, int k, int stride,
+                            int pad, const float* dcol, float* dx, int dx_ld, float* d_offset_mask, int dtype, ppy_stream_t s);
 /* ExponentialMovingAverage.update, model/EMA.py:31-45, on the device for all trainable tensors in one launch:
  * shadow[offsets[t] + i] = decay * shadow[..] + one_minus_decay * params[t][i]  (numpy float32 operation order; the reference
  * round-trips every parameter through host memory each step).  params: device array of num_tensors device pointers;

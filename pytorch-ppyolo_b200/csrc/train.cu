@@ -124,20 +124,20 @@ inline unsigned blocks_for(long long work, int threads, long long cap = 148ll * 
 // the plain transpose for k = 1.  One 64-pixel x 64-channel tile per CTA and tap, transposed through shared memory: reads are
 // 128-byte channel runs of NHWC pixels, writes 128-byte pixel runs of one output row.
 __global__ void __launch_bounds__(256) kmajor_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int n, int h, int w, int c, int k, int pad,
-                                                     __nv_bfloat16* __restrict__ out, long long m_pad) {
+                                                     int stride, int ho, int wo, __nv_bfloat16* __restrict__ out, long long m_pad) {
   __shared__ __nv_bfloat16 tile[64][64 + 2];
   const long long m0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64, tap = blockIdx.z, ky = tap / k, kx = tap % k;
-  const long long M = (long long)n * h * w;
+  const long long M = (long long)n * ho * wo;          // columns = OUTPUT pixels (stride 1: the input's own grid)
   // load: thread -> (pixel row r = tid / 4 (+ 0 / 64 stride over two passes), 16 channels = two 16-byte vectors)
   for (int e = threadIdx.x; e < 64 * 8; e += 256) {
     const int r = e >> 3, v = e & 7;
     const long long m = m0 + r;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (m < M && c0 + v * 8 < c) {
-      const int px = (int)(m % w), py = (int)((m / w) % h);
-      const long long img = m / ((long long)w * h);
-      const int iy = py + ky - pad, ix = px + kx - pad;
+      const int px = (int)(m % wo), py = (int)((m / wo) % ho);
+      const long long img = m / ((long long)wo * ho);
+      const int iy = py * stride + ky - pad, ix = px * stride + kx - pad;
       if (iy >= 0 && iy < h && ix >= 0 && ix < w)
         val = __ldg(reinterpret_cast<const uint4*>(x + ((img * h + iy) * w + ix) * x_ld + c0 + v * 8));
     }
@@ -266,14 +266,22 @@ int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long 
   return check_launch();
 }
 
-int ppy_im2col_kmajor(const void* x, int x_ld, int n, int h, int w, int c, int k, int pad, void* out, long long m_pad, ppy_stream_t s) {
+int ppy_im2col_kmajor_strided(const void* x, int x_ld, int n, int h, int w, int c, int k, int stride, int pad, void* out, long long m_pad,
+                              ppy_stream_t s) {
   PPY_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && x_ld >= c && (x_ld * 2) % 16 == 0 && k >= 1 && k <= 7 && pad >= 0);
-  PPY_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const long long M = (long long)n * h * w;
+  PPY_REQUIRE(stride >= 1 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  PPY_REQUIRE(ho > 0 && wo > 0);
+  const long long M = (long long)n * ho * wo;
   PPY_REQUIRE(m_pad >= M && m_pad % 64 == 0 && m_pad / 64 < 0x7FFFFFFFll);
   dim3 grid((unsigned)(m_pad / 64), (unsigned)ceil_div(c, 64), (unsigned)(k * k));
-  kmajor_kernel<<<grid, 256, 0, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, n, h, w, c, k, pad, (__nv_bfloat16*)out, m_pad);
+  kmajor_kernel<<<grid, 256, 0, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, n, h, w, c, k, pad, stride, ho, wo, (__nv_bfloat16*)out, m_pad);
   return check_launch();
+}
+
+int ppy_im2col_kmajor(const void* x, int x_ld, int n, int h, int w, int c, int k, int pad, void* out, long long m_pad, ppy_stream_t s) {
+  PPY_REQUIRE(k >= 1 && 2 * pad == k - 1);            // the "same" stride-1 form: output grid = input grid
+  return ppy_im2col_kmajor_strided(x, x_ld, n, h, w, c, k, 1, pad, out, m_pad, s);
 }
 
 // EMA of the trainable parameters (reference model/EMA.py:31-45), all tensors in one launch: shadow and parameters are

@@ -92,13 +92,19 @@ class PPYOLO(torch.nn.Module):
 
         The frozen backbone (``freeze_at=5`` in both configs) runs under no_grad on the kernel engine with BATCH-statistic
         BatchNorm, exactly like the reference's train-mode frozen BNs; the trainable head runs as differentiable tensor code
-        (``ppyolo_b200.autograd_head``) so torch autograd provides its backward, and the losses are ``model/losses.py``."""
-        from ppyolo_b200 import autograd_head
-        if any(p.requires_grad for p in self.backbone.parameters()):
-            raise NotImplementedError('training with an unfrozen backbone (freeze_at < 5) is not built yet: the conv/DCN '
-                                      'backward kernels are a later row of the scope table')
+        (``ppyolo_b200.autograd_head``) so torch autograd provides its backward, and the losses are ``model/losses.py``.
+        With ``freeze_at < 5`` the backbone's trainable stages join the autograd graph (``ppyolo_b200.autograd_backbone``)."""
         if not x.is_cuda:
             raise RuntimeError('ppyolo_b200: training needs CUDA tensors -- the backbone kernels have no CPU fallback')
+        if any(p.requires_grad for p in self.backbone.parameters()):
+            # freeze_at < 5 (reference model/resnet_vd.py:170-220): the trainable stages -- stage 5's DCNv2 units included -- run as
+            # differentiable kernel calls (ppyolo_b200.autograd_backbone), bf16 operands, the frozen prefix under no_grad
+            from ppyolo_b200 import autograd_backbone
+            if self.train_head_impl == 'aten':
+                raise NotImplementedError("an unfrozen backbone trains on the kernel path only (train_head_impl='kernels')")
+            self.head.train_impl = 'kernels'
+            feats = autograd_backbone.backbone_features(self.backbone, x, 'kernels')
+            return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
         n, _, h, w = x.shape
         with torch.no_grad():
             feats = self.backbone_train_engine(n, h, w).run_backbone(x)

@@ -12,7 +12,7 @@ c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_lon
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
 
 PPY_F32, PPY_BF16, PPY_F16X2 = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
 
 
@@ -83,6 +83,9 @@ SIGNATURES = {
                                   c_float, c_int, c_float, c_float, c_void_p]),
     'ppy_ema_update': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     'ppy_im2col_kmajor': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    'ppy_im2col_kmajor_strided': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    'ppy_dcn_backward_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_int, c_void_p, c_int, c_void_p]),
     'ppy_iou_aware_score': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_double, c_void_p]),
     'ppy_yolo_decode': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float), c_int, c_double,
                                 c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -50,17 +50,22 @@ def _coord_image(h, w, device):
 
 def conv_unit(u, x, impl='aten', coord=False):
     """One Conv2dUnit.  ``coord`` (kernels only): the unit's weight has two extra CoordConv input channels that ``x`` lacks."""
-    if not isinstance(u.conv, torch.nn.Conv2d):
-        raise NotImplementedError('DCNv2 inside the trainable head is not part of any PP-YOLO config')
-    if impl == 'kernels':
+    if not isinstance(u.conv, torch.nn.Conv2d):           # DCNv2 unit (stage 5 of an unfrozen ResNet50-vd)
+        d = u.conv
+        if d.dcn_bias is not None or coord:
+            raise NotImplementedError('DCNv2 with a bias / behind a CoordConv is not part of any PP-YOLO config')
+        if impl == 'kernels':
+            from .conv_autograd import dcnv2_kernels
+            y = dcnv2_kernels(x, d.conv_offset.weight, d.conv_offset.bias, d.dcn_weight, stride=d.stride, padding=d.padding)
+        else:
+            raise NotImplementedError("DCNv2 has no ATen path: use the 'kernels' implementation (train_precision='bf16')")
+    elif impl == 'kernels':
         from .conv_autograd import conv2d_kernels
-        if u.stride != 1:
-            raise NotImplementedError('conv2d_kernels: the head only has stride-1 convs')
         w = u.conv.weight
         c_main = w.shape[1] - (2 if coord else 0)
-        y = conv2d_kernels(x, w, u.conv.bias, padding=u.padding, c_main=c_main, out_f32=ACT_FP32 or u.bn is None)
+        y = conv2d_kernels(x, w, u.conv.bias, padding=u.padding, c_main=c_main, out_f32=ACT_FP32 or u.bn is None, stride=u.stride)
         if coord:
-            y = y + F.conv2d(_coord_image(x.shape[2], x.shape[3], x.device), w[:, c_main:], None, 1, u.padding).to(y.dtype)
+            y = y + F.conv2d(_coord_image(x.shape[2], x.shape[3], x.device), w[:, c_main:], None, u.stride, u.padding).to(y.dtype)
     else:
         y = F.conv2d(x, u.conv.weight, u.conv.bias, stride=u.stride, padding=u.padding)
     if u.bn is not None:

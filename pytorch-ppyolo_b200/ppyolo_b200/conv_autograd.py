@@ -43,68 +43,184 @@ def _nhwc_bf16(x, c_pad):
     return out
 
 
+def _dgrad(dyh, weight, c_main, stride, pad, in_hw, out_f32):
+    """Input gradient of a k x k conv on the conv kernel: a stride-1 conv of dY with the 180-degree-rotated transposed weight and
+    padding k-1-pad.  A strided conv's dY is first spread onto the input grid (zeros between the samples: dx = full correlation of
+    the zero-stuffed dY) -- 4x redundant MACs for stride 2, three layers of an unfrozen ResNet-vd."""
+    cout, _, k, _ = weight.shape
+    dev = dyh.device
+    o_pad = dyh.shape[-1]
+    h, w = in_hw
+    if stride > 1:
+        n, ho, wo, _ = dyh.shape
+        hz, wz = h + 2 * pad - k + 1, w + 2 * pad - k + 1          # stride-1 output grid of the same conv
+        z = torch.zeros((n, hz, wz, o_pad), dtype=dyh.dtype, device=dev)
+        z[:, 0:ho * stride:stride, 0:wo * stride:stride] = dyh
+        dyh = z
+    wt = torch.zeros((c_main, o_pad, k, k), dtype=torch.float32, device=dev)
+    wt[:, :cout] = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3)
+    packed_t = ops.pack_weight(wt, PPY_BF16, cache=False)
+    dxh = ops.conv_nhwc(dyh, packed_t, o_pad, c_main, k, 1, k - 1 - pad, _const('one', c_main, dev), _const('zero', c_main, dev),
+                        0, PPY_BF16, out_code=PPY_F32 if out_f32 else PPY_BF16)
+    return dxh
+
+
+def _kmajor(t_nhwc, c, k, stride, pad, m_pad):
+    """[c*k*k rows][m_pad] K-major operand (ppy_im2col_kmajor[_strided]); columns = the conv's output pixels."""
+    n, h, w, ld = t_nhwc.shape
+    out = torch.empty((c * k * k, m_pad), dtype=torch.bfloat16, device=t_nhwc.device)
+    check(lib.ppy_im2col_kmajor_strided(ops.ptr(t_nhwc), ld, n, h, w, c, k, stride, pad, ops.ptr(out), m_pad, ops.stream_ptr()),
+          'im2col_kmajor')
+    return out
+
+
+def _wgrad_gemm(a_rows_kmajor, rows, b_kmajor, cols, m_pad):
+    """out[rows][cols] = A[rows][m] . B[cols][m]^T on the conv kernel's partial-sum (split-K) instantiation; fp32 result."""
+    dev = a_rows_kmajor.device
+    a_op = a_rows_kmajor[:rows].view(1, 1, rows, m_pad)
+    cols_pad = ops.round_up(cols, 8)
+    out = torch.zeros((1, 1, rows, cols_pad), dtype=torch.float32, device=dev)
+    ops.conv_nhwc(a_op, (b_kmajor, m_pad, m_pad, cols), m_pad, cols, 1, 1, 0, _const('one', cols, dev), _const('zero', cols, dev), 0,
+                  PPY_BF16, out=out, out_code=PPY_F32, accumulate=True, split_k=0)
+    return out[0, 0, :, :cols]
+
+
+def _wgrad(xh, dyh, weight, c_main, stride, pad):
+    """Weight gradient dW = dY^T [O x M] . Xcol [M x C k k] (M = the output pixels), result in the weight's OIHW order."""
+    cout, _, k, _ = weight.shape
+    n, ho, wo, _ = dyh.shape
+    m_pad = ops.round_up(n * ho * wo, 64)
+    c_eff = c_main if c_main % 8 == 0 else xh.shape[-1]        # the stem's 3 channels travel zero-padded to 8
+    b_op = _kmajor(xh, c_eff, k, stride, pad, m_pad)
+    a_rows = ops.round_up(cout, 8)
+    a_full = _kmajor(dyh, a_rows, 1, 1, 0, m_pad)
+    out = _wgrad_gemm(a_full, cout, b_op, c_eff * k * k, m_pad)
+    dw = torch.zeros_like(weight, dtype=torch.float32)
+    dw[:, :c_main] = out.reshape(cout, c_eff, k, k)[:, :c_main]
+    return dw
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, c_main, pad, out_f32):
+    def forward(ctx, x, weight, bias, c_main, pad, out_f32, stride):
         if not x.is_cuda:
             raise RuntimeError('ppyolo_b200: conv2d_kernels needs CUDA tensors -- there is no CPU fallback')
         cout, _, k, _ = weight.shape
         packed = ops.pack_weight(weight, PPY_BF16, c_begin=0, c_count=c_main, cache=False)
         xh = _nhwc_bf16(x, packed[1])
         shift = bias.detach().float().contiguous() if bias is not None else _const('zero', cout, x.device)
-        y = ops.conv_nhwc(xh, packed, c_main, cout, k, 1, pad, _const('one', cout, x.device), shift, 0, PPY_BF16,
+        y = ops.conv_nhwc(xh, packed, c_main, cout, k, stride, pad, _const('one', cout, x.device), shift, 0, PPY_BF16,
                           out_code=PPY_F32 if out_f32 else PPY_BF16)
         ctx.save_for_backward(xh, weight)
-        ctx.meta = (c_main, pad, bias is not None, tuple(x.shape), x.dtype)
+        ctx.meta = (c_main, pad, bias is not None, tuple(x.shape), x.dtype, stride)
         return y[..., :cout].permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         xh, weight = ctx.saved_tensors
-        c_main, pad, has_bias, x_shape, x_dtype = ctx.meta
-        cout, cin_total, k, _ = weight.shape
-        n, _, h, w = x_shape
-        dev = dy.device
-        o_pad = ops.round_up(cout, 8)
-        dyh = _nhwc_bf16(dy, o_pad)
+        c_main, pad, has_bias, x_shape, x_dtype, stride = ctx.meta
+        cout = weight.shape[0]
+        dyh = _nhwc_bf16(dy, ops.round_up(cout, 8))
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            # dgrad: W^T rotated by 180 degrees, [c_main, cout(+pad), k, k]
-            wt = torch.zeros((c_main, o_pad, k, k), dtype=torch.float32, device=dev)
-            wt[:, :cout] = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3)
-            packed_t = ops.pack_weight(wt, PPY_BF16, cache=False)
-            dxh = ops.conv_nhwc(dyh, packed_t, o_pad, c_main, k, 1, k - 1 - pad, _const('one', c_main, dev), _const('zero', c_main, dev),
-                                0, PPY_BF16, out_code=PPY_BF16 if x_dtype == torch.bfloat16 else PPY_F32)
+            dxh = _dgrad(dyh, weight, c_main, stride, pad, x_shape[2:], x_dtype != torch.bfloat16)
             dx = dxh[..., :c_main].permute(0, 3, 1, 2)
             if dx.dtype != x_dtype:
                 dx = dx.to(x_dtype)
         if ctx.needs_input_grad[1]:
-            m = n * h * w
-            m_pad = ops.round_up(m, 64)
-            kk = c_main * k * k
-            # B operand: Xcol^T [C*k*k][M] (K-major in the pixel index), rows in the weight's (c, ky, kx) order; A operand: dY^T
-            # [cout][M] -- both written in one pass each by ppy_im2col_kmajor (zero padding of M included)
-            b_op = torch.empty((kk, m_pad), dtype=torch.bfloat16, device=dev)
-            check(lib.ppy_im2col_kmajor(ops.ptr(xh), xh.shape[-1], n, h, w, c_main, k, pad, ops.ptr(b_op), m_pad, ops.stream_ptr()), 'im2col_kmajor')
-            a_rows = ops.round_up(cout, 8)
-            a_full = torch.empty((a_rows, m_pad), dtype=torch.bfloat16, device=dev)
-            check(lib.ppy_im2col_kmajor(ops.ptr(dyh), dyh.shape[-1], n, h, w, a_rows, 1, 0, ops.ptr(a_full), m_pad, ops.stream_ptr()), 'transpose_kmajor')
-            a_op = a_full[:cout].view(1, 1, cout, m_pad)
-            kk_pad = ops.round_up(kk, 8)
-            out = torch.zeros((1, 1, cout, kk_pad), dtype=torch.float32, device=dev)
-            ops.conv_nhwc(a_op, (b_op, m_pad, m_pad, kk), m_pad, kk, 1, 1, 0, _const('one', kk, dev), _const('zero', kk, dev), 0,
-                          PPY_BF16, out=out, out_code=PPY_F32, accumulate=True, split_k=0)
-            dw = torch.zeros_like(weight, dtype=torch.float32)
-            dw[:, :c_main] = out[0, 0, :, :kk].reshape(cout, c_main, k, k)
+            dw = _wgrad(xh, dyh, weight, c_main, stride, pad)
         if has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(dim=(0, 2, 3))
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def conv2d_kernels(x, weight, bias=None, padding=0, c_main=None, out_f32=False):
-    """Stride-1 conv2d over the first ``c_main`` input channels of ``weight`` (the rest -- CoordConv's two -- is the caller's).
-    ``x``: logical [N, c_main, H, W]; returns logical [N, cout, H, W] (channels_last bf16, or fp32 with ``out_f32``)."""
+def conv2d_kernels(x, weight, bias=None, padding=0, c_main=None, out_f32=False, stride=1):
+    """conv2d over the first ``c_main`` input channels of ``weight`` (the rest -- CoordConv's two -- is the caller's).
+    ``x``: logical [N, c_main, H, W]; returns logical [N, cout, Ho, Wo] (channels_last bf16, or fp32 with ``out_f32``)."""
     c_main = weight.shape[1] if c_main is None else c_main
     if x.shape[1] != c_main:
         raise ValueError('conv2d_kernels: input has %d channels, expected %d' % (x.shape[1], c_main))
-    return _ConvFn.apply(x, weight, bias, c_main, padding, out_f32)
+    return _ConvFn.apply(x, weight, bias, c_main, padding, out_f32, stride)
+
+
+class _DcnFn(torch.autograd.Function):
+    """DCNv2.forward (reference model/custom_layers.py:551-677) with its backward on this repo's kernels.
+
+    forward   offset/mask conv (conv kernel, fp32 NHWC result) -> whole-layer fused deformable conv (dcn_umma.cu)
+    backward  cols  = ppy_dcn_gather(x, om)                      [M x 9C] bf16 (rebuilt, not saved)
+              dW    = dY^T . cols                                partial-sum GEMM, fp32
+              dcol  = dY . Wt                                    1x1 conv with 9C output channels, fp32
+              (dx, d_om) = ppy_dcn_backward_sample(dcol, x, om)   vector atomics into fp32 dx
+              conv_offset: dgrad added into dx, wgrad, bias      the strided conv backward above
+    The native spec the reference vendors without loading is external/DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:197-327."""
+
+    @staticmethod
+    def forward(ctx, x, offset_w, offset_b, dcn_w, stride, pad):
+        if not x.is_cuda:
+            raise RuntimeError('ppyolo_b200: dcnv2_kernels needs CUDA tensors -- there is no CPU fallback')
+        cout, cin, k, _ = dcn_w.shape
+        dev = x.device
+        n_om = offset_w.shape[0]
+        om_packed = ops.pack_weight(offset_w, PPY_BF16, cache=False)
+        xh = _nhwc_bf16(x, om_packed[1])
+        om = ops.conv_nhwc(xh, om_packed, cin, n_om, k, stride, pad, _const('one', n_om, dev), offset_b.detach().float().contiguous(), 0,
+                           PPY_BF16, out_code=PPY_F32)
+        packed = ops.pack_weight(dcn_w, PPY_BF16, cache=False)
+        y = ops.conv_nhwc(xh, packed, cin, cout, k, stride, pad, _const('one', cout, dev), _const('zero', cout, dev), 0, PPY_BF16,
+                          offset_mask=om)
+        ctx.save_for_backward(xh, om, offset_w, dcn_w)
+        ctx.meta = (stride, pad, tuple(x.shape), x.dtype)
+        return y[..., :cout].permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, om, offset_w, dcn_w = ctx.saved_tensors
+        stride, pad, x_shape, x_dtype = ctx.meta
+        cout, cin, k, _ = dcn_w.shape
+        n, _, h, w = x_shape
+        dev = dy.device
+        taps = k * k
+        o_pad = ops.round_up(cout, 8)
+        dyh = _nhwc_bf16(dy, o_pad)
+        _, ho, wo, om_ld = om.shape
+        m = n * ho * wo
+        m_pad = ops.round_up(m, 64)
+        kk = taps * cin
+        # weight gradient over the re-sampled matrix (columns tap*C + c, the packed 3x3 weight's own K order)
+        cols = torch.empty((1, 1, m, kk), dtype=torch.bfloat16, device=dev)
+        check(lib.ppy_dcn_gather(ops.ptr(xh), xh.shape[-1], n, h, w, cin, ops.ptr(om), om_ld, k, stride, pad, ops.ptr(cols), PPY_BF16,
+                                 ops.stream_ptr()), 'dcn_gather')
+        dw = None
+        if ctx.needs_input_grad[3]:
+            a_full = _kmajor(dyh, o_pad, 1, 1, 0, m_pad)
+            b_op = _kmajor(cols, kk, 1, 1, 0, m_pad)
+            dw = _wgrad_gemm(a_full, cout, b_op, kk, m_pad).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+        del cols
+        # dcol = dY . Wt: a 1x1 conv whose output channel tap*C + c carries W[:, c, tap]
+        wt = torch.zeros((kk, o_pad, 1, 1), dtype=torch.float32, device=dev)
+        wt[:, :cout, 0, 0] = dcn_w.detach().permute(2, 3, 1, 0).reshape(kk, cout)
+        packed_t = ops.pack_weight(wt, PPY_BF16, cache=False)
+        dcol = ops.conv_nhwc(dyh, packed_t, o_pad, kk, 1, 1, 0, _const('one', kk, dev), _const('zero', kk, dev), 0, PPY_BF16,
+                             out_code=PPY_F32)
+        d_om = torch.zeros_like(om)
+        dx32 = torch.zeros((n, h, w, cin), dtype=torch.float32, device=dev)
+        check(lib.ppy_dcn_backward_sample(ops.ptr(xh), xh.shape[-1], n, h, w, cin, ops.ptr(om), om_ld, k, stride, pad, ops.ptr(dcol),
+                                          ops.ptr(dx32), cin, ops.ptr(d_om), PPY_BF16, ops.stream_ptr()), 'dcn_backward_sample')
+        del dcol
+        # the offset/mask conv's own backward
+        n_om = offset_w.shape[0]
+        d_omh = d_om.to(torch.bfloat16)
+        dx = dow = dob = None
+        if ctx.needs_input_grad[0]:
+            dx32 = dx32 + _dgrad(d_omh, offset_w, cin, stride, pad, (h, w), True)[..., :cin]
+            dx = dx32.permute(0, 3, 1, 2).to(x_dtype)
+        if ctx.needs_input_grad[1]:
+            dow = _wgrad(xh, d_omh, offset_w, cin, stride, pad)
+        if ctx.needs_input_grad[2]:
+            dob = d_om[..., :n_om].sum(dim=(0, 1, 2))
+        return dx, dow, dob, dw, None, None
+
+
+def dcnv2_kernels(x, offset_w, offset_b, dcn_w, stride=1, padding=1):
+    """Differentiable DCNv2 (3x3, deformable_groups 1, no bias): logical NCHW in, channels_last bf16 out."""
+    return _DcnFn.apply(x, offset_w, offset_b, dcn_w, stride, padding)

@@ -1,0 +1,172 @@
+"""GPU parity of training with an UNFROZEN backbone (freeze_at < 5; SURVEY.md 8 a5 backward, VERDICT r1 missing #7):
+the DCNv2 backward kernels and the strided conv backward against the unmodified reference's autograd
+(tests/golden/dcn_bwd.npz, train_unfrozen.npz from make_golden_unfrozen.py) and against torch on the same operands."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ppyolo_b200 import ops
+from ppyolo_b200._lib import lib, check, PPY_F32, PPY_BF16
+from tests.test_gpu_train import build_train_model, train_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _nhwc(t, ld=None):
+    n, c, h, w = t.shape
+    out = torch.zeros((n, h, w, ld or c), dtype=t.dtype, device=t.device)
+    out[..., :c] = t.permute(0, 2, 3, 1)
+    return out
+
+
+@pytest.mark.parametrize('tag', ['s1', 's2'])
+def test_dcn_backward_sample_fp32_vs_reference(golden, tag):
+    """ppy_dcn_backward_sample in fp32 on the reference's own offset/mask tensor: the gradient of the offset/mask conv's output
+    and the input gradient (sampling part + the offset conv's dgrad, done here by torch) against the reference module's autograd.
+    Tolerance 1e-5 of each tensor's scale (fp32 summation order; the input gradient is accumulated by atomics)."""
+    z = golden('dcn_bwd')
+    stride = int(z[tag + '_stride'][0])
+    t = lambda k: torch.from_numpy(z['%s_%s' % (tag, k)]).to(DEV)
+    x, om, dy, w, ow = t('x'), t('om'), t('dy'), t('dcn_w'), t('offset_w')
+    n, c, h, wd = x.shape
+    o = w.shape[0]
+    ho, wo = om.shape[2:]
+    xh, omh = _nhwc(x), _nhwc(om, 32)
+    dyh = dy.permute(0, 2, 3, 1).reshape(-1, o)
+    wt = w.permute(2, 3, 1, 0).reshape(9 * c, o)                    # row tap*C + ch
+    dcol = (dyh @ wt.t()).contiguous()                               # [M, 9C]
+    dx = torch.zeros((n, h, wd, c), dtype=torch.float32, device=DEV)
+    d_om = torch.zeros_like(omh)
+    check(lib.ppy_dcn_backward_sample(ops.ptr(xh), c, n, h, wd, c, ops.ptr(omh), 32, 3, stride, 1, ops.ptr(dcol), ops.ptr(dx), c,
+                                      ops.ptr(d_om), PPY_F32, ops.stream_ptr()), 'dcn_backward_sample')
+    want = z[tag + '_d_om']
+    got = d_om[..., :27].permute(0, 3, 1, 2).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-5 * np.abs(want).max())
+    assert float(d_om[..., 27:].abs().max()) == 0.0
+    dx_total = dx.permute(0, 3, 1, 2) + F.conv_transpose2d(torch.from_numpy(want).to(DEV), ow, None, stride, 1,
+                                                           output_padding=(h + 2 - 3) % stride)
+    want_dx = z[tag + '_dx']
+    np.testing.assert_allclose(dx_total.cpu().numpy(), want_dx, rtol=0, atol=1e-5 * np.abs(want_dx).max())
+
+
+@pytest.mark.parametrize('tag', ['s1', 's2'])
+def test_dcnv2_kernels_forward_backward_vs_reference(golden, tag):
+    """conv_autograd.dcnv2_kernels (fused forward kernel; backward = gather + two tcgen05 GEMMs + ppy_dcn_backward_sample + the offset
+    conv's strided backward) against the reference DCNv2 module's forward and autograd on bf16-representable inputs.  bf16 GEMM
+    operands (the sampled matrix, dY, d_om are rounded to 8 bits): 1e-2 of each tensor's scale, 3e-2 for the offset conv's
+    weight gradient (its dY -- the offset/mask gradient -- is itself a rounded sum of 64 bf16 products per entry)."""
+    from ppyolo_b200.conv_autograd import dcnv2_kernels
+    z = golden('dcn_bwd')
+    stride = int(z[tag + '_stride'][0])
+    t = lambda k: torch.from_numpy(z['%s_%s' % (tag, k)]).to(DEV)
+    x, ow, ob, w = (t(k).requires_grad_(True) for k in ('x', 'offset_w', 'offset_b', 'dcn_w'))
+    y = dcnv2_kernels(x, ow, ob, w, stride=stride, padding=1)
+    y.float().backward(t('dy'))
+    rel = {}
+    for got, name, tol in ((y, 'y', 1e-2), (x.grad, 'dx', 1e-2), (w.grad, 'd_dcn_w', 1e-2), (ob.grad, 'd_offset_b', 1e-2),
+                           (ow.grad, 'd_offset_w', 3e-2)):
+        want = z['%s_%s' % (tag, name)]
+        err = np.abs(got.detach().float().cpu().numpy() - want).max() / np.abs(want).max()
+        rel[name] = float(err)
+        assert err < tol, (name, err)
+    print('dcnv2_kernels %s: max error / scale %s' % (tag, {k: '%.2e' % v for k, v in rel.items()}))
+
+
+@pytest.mark.parametrize('n,c,o,k,hw,stride', [(2, 128, 128, 3, 16, 2), (2, 64, 96, 3, 15, 2), (1, 256, 64, 1, 12, 2), (2, 8, 32, 3, 32, 2),
+                                               (2, 512, 27, 3, 10, 2)])
+def test_conv2d_kernels_strided_forward_dgrad_wgrad(n, c, o, k, hw, stride):
+    """Strided convs of an unfrozen ResNet-vd (3x3 / stride 2 in the 3x3 of every down-sampling block, the stem's first conv, the
+    stage5_0 offset conv): forward, input gradient (zero-stuffed dY through the same kernel) and weight gradient (strided K-major
+    operand) against torch's fp32 conv on the same bf16-rounded operands."""
+    from ppyolo_b200.conv_autograd import conv2d_kernels
+    g = torch.Generator().manual_seed(c + o + k + hw)
+    rb = lambda t: t.to(torch.bfloat16).float()
+    x = rb(torch.randn((n, c, hw, hw), generator=g)).to(DEV).requires_grad_(True)
+    w = rb(torch.randn((o, c, k, k), generator=g) * (1.0 / (c * k * k) ** 0.5)).to(DEV).requires_grad_(True)
+    pad = (k - 1) // 2
+    yr = F.conv2d(x, w, None, stride, pad)
+    dy = rb(torch.randn(yr.shape, generator=g)).to(DEV)
+    yr.backward(dy)
+    want = (yr.detach(), x.grad.clone(), w.grad.clone())
+    x.grad = w.grad = None
+    y = conv2d_kernels(x, w, None, padding=pad, out_f32=True, stride=stride)
+    y.backward(dy)
+    scale = lambda t: float(t.abs().max())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), want[0].cpu().numpy(), rtol=0, atol=2e-4 * scale(want[0]))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want[1].cpu().numpy(), rtol=0, atol=2e-4 * scale(want[1]))
+    np.testing.assert_allclose(w.grad.cpu().numpy(), want[2].cpu().numpy(), rtol=0, atol=2e-4 * scale(want[2]))
+
+
+def _unfrozen_model(tag, freeze_at):
+    model, cfg = build_train_model(tag)
+    for p in model.backbone.parameters():
+        p.requires_grad = True
+    model.backbone.freeze_at = freeze_at
+    model.backbone.freeze()
+    model.train_precision = 'bf16'
+    return model, cfg
+
+
+@pytest.mark.parametrize('tag,freeze_at', [('r50vd', 3), ('r18vd', 0)])
+def test_train_unfrozen_backbone_vs_reference(golden, tag, freeze_at):
+    """One training forward+backward with trainable backbone stages (ppyolo_2x freeze_at=3: stage 4's strided 3x3 conv and stage 5's
+    three DCNv2 units; ppyolo_r18vd freeze_at=0: the whole net, stem included) against the unmodified reference (fp32 CPU): the six
+    losses and the gradients of backbone tensors.  The path computes with bf16 GEMM operands, the reference in fp32, so gradients
+    are compared by direction and size: cosine > 0.8 (measured 0.90-0.999; output convs > 0.98) and norm within 20 %; losses
+    within 3 %.  r50vd runs its BatchNorm layers on running statistics, r18vd on batch statistics -- see make_golden_unfrozen.py
+    for why the deep net's batch-statistic case is not comparable at test size."""
+    z = golden('train_unfrozen')
+    assert int(z[tag + '_freeze_at'][0]) == freeze_at
+    model, cfg = _unfrozen_model(tag, freeze_at)
+    if int(z[tag + '_bn_eval'][0]):
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+    assert sum(p.numel() for p in model.parameters() if p.requires_grad) == int(z[tag + '_trainable'][0])
+    x, gb, gc, gs, targets = train_inputs(cfg)
+    losses = model(x, None, False, gb, gc, gs, targets)
+    sum(losses.values()).backward()
+    print('unfrozen %s losses (got, reference):' % tag, {k: (round(float(v.detach()), 3), round(float(z['%s_%s' % (tag, k)]), 3)) for k, v in losses.items()})
+    params = dict(model.named_parameters())
+    report = {}
+    for key in z.files:
+        if not key.startswith(tag + '_grad:'):
+            continue
+        name = key.split(':', 1)[1]
+        want = z[key].astype(np.float64)
+        g = params[name].grad
+        assert g is not None, name
+        got = g.detach().float().flatten()[:want.size].cpu().numpy().astype(np.float64)
+        cos = float((got * want).sum() / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-30))
+        ratio = float(g.detach().double().norm()) / float(z['%s_gradnorm:%s' % (tag, name)][0])
+        report[name] = (round(cos, 4), round(ratio, 3))
+    print('unfrozen %s gradient (cosine, norm ratio) vs reference:' % tag, report)
+    for k, v in losses.items():
+        np.testing.assert_allclose(float(v.detach()), float(z['%s_%s' % (tag, k)]), rtol=3e-2, err_msg=k)
+    assert len(report) >= 7
+    for name, (cos, ratio) in report.items():
+        assert cos > (0.98 if name.startswith('head.yolo_output_convs') else 0.8), (name, cos)
+        assert 0.8 < ratio < 1.25, (name, ratio)
+
+
+def test_trainer_step_updates_unfrozen_stage():
+    """Trainer.step with freeze_at=4: stage 5 (DCNv2 weights, offset convs, BNs) joins the flat gradient bucket and moves."""
+    from ppyolo_b200.trainer import Trainer
+    model, cfg = _unfrozen_model('r50vd', 4)
+    trainer = Trainer(model, cfg, graph=False, ema=False)
+    names = {id(p): n for n, p in model.named_parameters()}
+    picked = [names[id(p)] for p in trainer.params]
+    assert any('stage5_1.conv2.conv.dcn_weight' in n for n in picked) and not any('stage4' in n for n in picked)
+    before = {n: p.detach().clone() for n, p in model.named_parameters() if 'stage5_1.conv2.conv' in n or 'stage4_0.conv1.conv' in n}
+    x, gb, gc, gs, targets = train_inputs(cfg)
+    for _ in range(2):
+        losses = trainer.step(x, gb, gc, gs, targets)
+    assert all(np.isfinite(float(v)) for v in losses.values())
+    after = dict(model.named_parameters())
+    for n, b in before.items():
+        moved = float((after[n].detach() - b).abs().max())
+        assert (moved > 0) == ('stage5' in n), (n, moved)

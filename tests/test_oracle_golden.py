@@ -145,3 +145,20 @@ def test_network(golden, arch, name):
     np.testing.assert_allclose(res['scores'][0].numpy(), z['scores_img0_f32'], rtol=1e-3, atol=1e-6)
     for i, p in enumerate(res['preds']):
         assert_preds_close(p, z['pred%d' % i], rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize('tag', ['s1', 's2'])
+def test_dcn_backward_oracle_vs_reference(golden, tag):
+    """torch autograd through the oracle's dcnv2 restatement against the reference DCNv2 module's own backward
+    (tests/golden/dcn_bwd.npz from make_golden_unfrozen.py; offsets up to ~8 px on a 9x9 / 12x12 map, so clamped and
+    out-of-image samples are in): y, dx and the three parameter gradients -- the checker the GPU backward tests lean on.
+    Tolerance 2e-5 of each tensor's scale (fp32 summation order)."""
+    z = golden('dcn_bwd')
+    stride = int(z[tag + '_stride'][0])
+    t = lambda k: torch.from_numpy(z['%s_%s' % (tag, k)]).clone()
+    x, ow, ob, w = (t(k).requires_grad_(True) for k in ('x', 'offset_w', 'offset_b', 'dcn_w'))
+    y = ref.dcnv2(x, ow, ob, w, stride, 1)
+    y.backward(t('dy'))
+    for got, name in ((y, 'y'), (x.grad, 'dx'), (ow.grad, 'd_offset_w'), (ob.grad, 'd_offset_b'), (w.grad, 'd_dcn_w')):
+        want = z['%s_%s' % (tag, name)]
+        np.testing.assert_allclose(got.detach().numpy(), want, rtol=0, atol=2e-5 * np.abs(want).max(), err_msg=name)

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=10); ap.add_argument('--warmup', type=int, default=3)
 ap.add_argument('--precision', default='fp32'); ap.add_argument('--size', type=int, default=608)
 ap.add_argument('--batch', type=int, default=8); ap.add_argument('--arch', default='r50vd')
+ap.add_argument('--freeze-at', type=int, default=None, help='override cfg.backbone freeze_at (< 5: trainable backbone stages, autograd_backbone path)')
 ap.add_argument('--profile', type=int, default=0, help='also print the top-N kernels of 3 steps (torch.profiler, CUDA time)')
 a = ap.parse_args()
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -30,7 +31,10 @@ cfg = {'r50vd': cfgs.PPYOLO_2x_Config, 'r18vd': cfgs.PPYOLO_r18vd_Config}[a.arch
 iou_loss = cfgs.select_loss(cfg.iou_loss_type)(**cfg.iou_loss)
 iou_aware = cfgs.select_loss(cfg.iou_aware_loss_type)(**cfg.iou_aware_loss) if cfg.head['iou_aware'] else None
 yolo = cfgs.select_loss(cfg.yolo_loss_type)(iou_loss=iou_loss, iou_aware_loss=iou_aware, **cfg.yolo_loss)
-backbone = cfgs.select_backbone(cfg.backbone_type)(**cfg.backbone)
+bb_kw = dict(cfg.backbone)
+if a.freeze_at is not None:
+    bb_kw['freeze_at'] = a.freeze_at
+backbone = cfgs.select_backbone(cfg.backbone_type)(**bb_kw)
 head = cfgs.select_head(cfg.head_type)(yolo_loss=yolo, is_train=True, nms_cfg=cfg.nms_cfg, **cfg.head)
 model = PPYOLO(backbone, head)
 synth.randomize_(model, seed=0)
@@ -60,7 +64,7 @@ ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
 if rank == 0:
     print(json.dumps({'metric': 'train_images_per_sec', 'value': world * a.batch / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
                       'ms_per_step': ms, 'steps': a.steps, 'warmup': a.warmup, 'scaling': 'weak',
-                      'config': {'workload': 'ppyolo_2x %dx%d bs=%d/GPU train step (freeze_at=5)' % (a.size, a.size, a.batch),
+                      'config': {'workload': 'ppyolo_2x %dx%d bs=%d/GPU train step (freeze_at=%d)' % (a.size, a.size, a.batch, bb_kw['freeze_at']),
                                  'backbone_precision': a.precision, 'trainable_params': int(sum(p.numel() for p in trainer.params)),
                                  'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'head_convs': model.train_head_impl or ('kernels (tcgen05 fwd/dgrad/wgrad)' if a.precision == 'bf16' else 'aten (TF32)')},
                       'losses': {k: float(v) for k, v in losses.items()}}), flush=True)
