@@ -103,6 +103,8 @@ class PPYOLO(torch.nn.Module):
             if self.train_head_impl == 'aten':
                 raise NotImplementedError("an unfrozen backbone trains on the kernel path only (train_head_impl='kernels')")
             self.head.train_impl = 'kernels'
+            if self.train_graph:
+                return self._graphed_head_loss([x], gt_box, gt_label, gt_score, targets, full=True)
             feats = autograd_backbone.backbone_features(self.backbone, x, 'kernels')
             return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
         n, _, h, w = x.shape
@@ -113,36 +115,45 @@ class PPYOLO(torch.nn.Module):
             return self._graphed_head_loss(feats, gt_box, gt_label, gt_score, targets)
         return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
 
-    def _graphed_head_loss(self, feats, gt_box, gt_label, gt_score, targets):
+    def _graphed_head_loss(self, feats, gt_box, gt_label, gt_score, targets, full=False):
         """Head forward + the six losses (and, through autograd, their backward) replayed as CUDA graphs: the step is
         launch-bound (hundreds of small loss / BatchNorm / activation kernels), the graphs remove the launches.  One pair of
         graphs per input shape (``torch.cuda.make_graphed_callables``); BatchNorm buffers are restored after the capture's
-        warm-up passes so capturing does not advance the running statistics."""
+        warm-up passes so capturing does not advance the running statistics.  ``full``: ``feats`` is ``[x]`` and the graphs hold
+        the differentiable backbone (``freeze_at < 5``) as well."""
         head = self.head
-        key = (tuple(tuple(f.shape) for f in feats), tuple(gt_box.shape), tuple(tuple(t.shape) for t in targets), head.train_impl)
+        key = (bool(full), tuple(tuple(f.shape) for f in feats), tuple(gt_box.shape), tuple(tuple(t.shape) for t in targets), head.train_impl)
         entry = self._graphed_heads.get(key)
         if entry is None:
             n_feats, n_targets = len(feats), len(targets)
+            backbone = self.backbone
 
             class HeadLoss(torch.nn.Module):
                 def __init__(self, head):
                     super().__init__()
                     self.head = head
+                    if full:
+                        self.backbone = backbone
 
                 def forward(self, *args):
                     fs, rest = list(args[:n_feats]), args[n_feats:]
                     gb, gl, gs = rest[0], rest[1], rest[2]
                     tg = list(rest[3:3 + n_targets])
+                    if full:
+                        from ppyolo_b200 import autograd_backbone
+                        fs = autograd_backbone.backbone_features(self.backbone, fs[0], 'kernels')
                     losses = self.head.get_loss_autograd(fs, gb, gl, gs, tg)
                     return tuple(losses[k] for k in sorted(losses))
 
             wrapper = HeadLoss(head)
             sample = tuple(f.detach().clone() for f in feats) + (gt_box.clone(), gt_label.clone(), gt_score.clone()) + \
                 tuple(t.clone() for t in targets)
-            saved = {k: v.clone() for k, v in head.state_dict().items() if 'running_' in k or 'num_batches_tracked' in k}
-            names = sorted(head.get_loss_autograd([f.detach() for f in feats], gt_box, gt_label, gt_score, targets))
+            saved = {k: v.clone() for k, v in wrapper.state_dict().items() if 'running_' in k or 'num_batches_tracked' in k}
+            yl = head.yolo_loss
+            names = sorted(['loss_xy', 'loss_wh', 'loss_obj', 'loss_cls'] + (['loss_iou'] if yl._iou_loss is not None else []) +
+                           (['loss_iou_aware'] if yl._iou_aware_loss is not None else []))
             graphed = torch.cuda.make_graphed_callables(wrapper, sample, allow_unused_input=True)
-            head.load_state_dict(saved, strict=False)
+            wrapper.load_state_dict(saved, strict=False)
             entry = (graphed, names)
             self._graphed_heads[key] = entry
         graphed, names = entry

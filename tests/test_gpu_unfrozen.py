@@ -170,3 +170,35 @@ def test_trainer_step_updates_unfrozen_stage():
     for n, b in before.items():
         moved = float((after[n].detach() - b).abs().max())
         assert (moved > 0) == ('stage5' in n), (n, moved)
+
+
+def test_graphed_unfrozen_step_matches_eager():
+    """model.train_graph with freeze_at=4: the differentiable backbone + head + losses + backward replayed as CUDA graphs give the
+    eager step's losses and gradients (same kernels, same order; the DCN input gradient is accumulated by atomics: 1e-3 of scale),
+    twice in a row, without advancing the BatchNorm running statistics during capture."""
+    ref_model, cfg = _unfrozen_model('r50vd', 4)
+    x, gb, gc, gs, targets = train_inputs(cfg)
+    losses = ref_model(x, None, False, gb, gc, gs, targets)
+    sum(losses.values()).backward()
+    want = {k: float(v.detach()) for k, v in losses.items()}
+    want_g = {n: p.grad.detach().clone() for n, p in ref_model.named_parameters() if p.grad is not None}
+    want_rm = ref_model.state_dict()['backbone.stage5_2.conv3.bn.running_mean'].clone()
+    model, cfg = _unfrozen_model('r50vd', 4)
+    model.train_graph = True
+    for it in range(2):
+        for p in model.parameters():
+            p.grad = None
+        losses = model(x, None, False, gb, gc, gs, targets)
+        sum(losses.values()).backward()
+        for k, v in losses.items():
+            np.testing.assert_allclose(float(v.detach()), want[k], rtol=2e-3, err_msg=k)
+        if it == 0:
+            np.testing.assert_allclose(model.state_dict()['backbone.stage5_2.conv3.bn.running_mean'].cpu().numpy(), want_rm.cpu().numpy(),
+                                       rtol=1e-3, atol=1e-5)
+    got_g = {n: p.grad for n, p in model.named_parameters() if p.grad is not None}
+    assert set(got_g) == set(want_g)
+    for n in ('backbone.stage5_1.conv2.conv.dcn_weight', 'backbone.stage5_0.conv2.conv.conv_offset.weight', 'backbone.stage5_0.conv1.conv.weight',
+              'head.yolo_output_convs.1.conv.weight'):
+        a, b = want_g[n].float(), got_g[n].float()
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > 0.995, (n, cos)
