@@ -32,6 +32,7 @@ class PPYOLO(torch.nn.Module):
         self.normalize = None         # dict(mean, std, is_scale) of the uint8 input path; None = the configs' ImageNet values
         self.use_engine = True
         self._engines = {}
+        self._mish = None             # cached: does any Conv2dUnit use Mish (module structure is static)
 
     def engine(self, batch, height, width, input_u8=False):
         from ppyolo_b200.engine import InferenceEngine
@@ -42,6 +43,14 @@ class PPYOLO(torch.nn.Module):
             self._engines[key] = eng
             self._weights_seen = self._weights_fingerprint()
         return eng
+
+    def _has_mish(self):
+        """Mish units (defined by the reference, used by neither config) run module by module: the engine's fused epilogues
+        carry none / relu / leaky only."""
+        if self._mish is None:
+            from model.custom_layers import Conv2dUnit
+            self._mish = any(isinstance(m, Conv2dUnit) and m.act_name == 'mish' for m in self.modules())
+        return self._mish
 
     def invalidate_engines(self):
         """Drop compiled plans and packed-weight caches (call after mutating weights in place)."""
@@ -76,7 +85,7 @@ class PPYOLO(torch.nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def forward(self, x, im_size, eval=True, gt_box=None, gt_label=None, gt_score=None, targets=None):
-        if eval and self.use_engine and not self.training and x.is_cuda:
+        if eval and self.use_engine and not self.training and x.is_cuda and not self._has_mish():
             if x.dtype == torch.uint8:       # resized uint8 RGB batch [N, H, W, 3]: normalisation + permute inside the stem kernel
                 n, h, w, _ = x.shape
                 return self.engine(n, h, w, input_u8=True).run(x, im_size)

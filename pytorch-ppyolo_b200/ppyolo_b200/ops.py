@@ -307,13 +307,18 @@ def conv_nhwc(x, packed, cin, cout, k, stride, pad, scale, shift, act, code, res
     p.accumulate, p.split_k = (1 if accumulate else 0), split_k      # partial sums are ADDED into a caller-zeroed fp32 `out`
     p.residual = residual.data_ptr() if residual is not None else None
     p.res_ld = residual.shape[-1] if residual is not None else 0
-    p.act = act
+    # Mish (reference model/custom_layers.py:37-43; no PP-YOLO config uses it): the tcgen05 epilogue's activation is a slope
+    # select, so on that path the conv leaves the pre-activation and ppy_activation finishes it in place
+    mish_pass = act == _lib.ACT_MISH and code == PPY_BF16
+    p.act = 0 if mish_pass else act
     p.y, p.y_ld, p.out_dtype = out.data_ptr(), out.shape[-1], out_code
     p.upsample2x = 1 if upsample2x else 0
     p.offset_mask = offset_mask.data_ptr() if offset_mask is not None else None
     p.om_ld = offset_mask.shape[-1] if offset_mask is not None else 0
     fn = lib.ppy_conv_bf16 if code == PPY_BF16 else lib.ppy_conv_f32
     check(fn(ctypes.byref(p), stream_ptr()), 'conv_bf16' if code == PPY_BF16 else 'conv_f32')
+    if mish_pass:
+        check(lib.ppy_activation(out.data_ptr(), out.numel(), _lib.ACT_MISH, out_code, stream_ptr()), 'activation')
     return out
 
 

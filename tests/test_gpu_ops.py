@@ -272,6 +272,29 @@ def test_conv_units_golden(golden, precision):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_conv_unit_mish(precision):
+    """Conv2dUnit(act='mish') (reference model/custom_layers.py:37-43, :131-132): conv + folded BN + x*tanh(softplus(x)) against
+    torch fp32 -- in the SIMT epilogue for fp32, conv kernel + ppy_activation pass on the tcgen05 path.  1e-4 / 3e-2 of scale."""
+    from model.custom_layers import Conv2dUnit
+    o = ops()
+    o.set_precision(precision)
+    try:
+        u = Conv2dUnit(64, 96, 3, stride=1, bn=1, act='mish')
+        synth.randomize_(u, seed=35)
+        u = u.to(DEV).eval()
+        x = torch.randn((2, 64, 12, 12), generator=torch.Generator().manual_seed(5)).to(DEV)
+        y = u(x)
+        c = lambda t: t.detach().cpu()                  # reference on the CPU: cuDNN would use TF32
+        t = torch.nn.functional.conv2d(c(x), c(u.conv.weight), None, 1, 1)
+        t = torch.nn.functional.batch_norm(t, c(u.bn.running_mean), c(u.bn.running_var), c(u.bn.weight), c(u.bn.bias), False, 0.1, u.bn.eps)
+        want = t * torch.tanh(torch.nn.functional.softplus(t))
+        tol = 1e-4 if precision == 'fp32' else 3e-2
+        np.testing.assert_allclose(y.cpu().numpy(), want.detach().cpu().numpy(), rtol=0, atol=tol * scale_of(want.detach().cpu().numpy()))
+    finally:
+        o.set_precision('fp32')
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 @pytest.mark.parametrize('tag,stride', [('dcn_s1', 1), ('dcn_s2', 2)])
 def test_dcn_golden(golden, precision, tag, stride):
     from model.custom_layers import Conv2dUnit
