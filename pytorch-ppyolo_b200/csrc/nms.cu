@@ -36,7 +36,11 @@ inline int matrix_nmax(int nms_top_k) {
   return n < kMaxN ? n : kMaxN;
 }
 constexpr int kScanThreads = 256;
-constexpr int kMatrixThreads = 1024;
+constexpr int kMatrixThreads = 1024;   // launch bound; the launch uses matrix_threads()
+// CTA size of nms_matrix_kernel: its sorts are barrier-bound (ncu source view: half the kernel's samples sit at the bitonic network's
+// CTA barriers) and 1024 keys are 512 compare-exchange pairs per stage -- 16 warps arrive at a barrier sooner than 32 (C5 at bs 1:
+// 41.4 -> 39.4 us; 256 threads: 43.5).  Lists beyond 1024 boxes keep 1024 threads.
+inline int matrix_threads(int nmax) { return nmax > 1024 ? 1024 : 512; }
 
 struct Workspace {
   unsigned int* hist;     // [n][kBins]
@@ -352,7 +356,8 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   __shared__ int s_maxgrp;     // longest same-label prefix a column has to scan
   __shared__ unsigned int s_m;
   const int img = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = kMatrixThreads >> 5;
+  const int nthreads = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = nthreads >> 5;
   const unsigned int total = count[img];
   float* my_out = out + (long long)img * keep_top_k * 6;
   if (total > (unsigned)key_stride) {   // candidate list overflowed -- flagged, see DESIGN.md
@@ -367,7 +372,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     const int cut = find_cutoff_bin(hist + (long long)img * kBins, want, reinterpret_cast<unsigned int*>(s_keys), s_part);
     if (tid == 0) s_m = 0;
     __syncthreads();
-    for (unsigned int i = tid; i < total; i += kMatrixThreads) {
+    for (unsigned int i = tid; i < total; i += nthreads) {
       const unsigned long long k = gk[i];
       if (score_bin(__uint_as_float((unsigned int)(k >> 32)), thr_bits, shift) >= cut) {
         const unsigned int slot = atomicAdd(&s_m, 1u);
@@ -382,10 +387,10 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     m = (int)s_m;
   } else {
     m = (int)total;
-    for (int i = tid; i < m; i += kMatrixThreads) s_keys[i] = gk[i];
+    for (int i = tid; i < m; i += nthreads) s_keys[i] = gk[i];
   }
   int len = 1; while (len < m) len <<= 1;
-  for (int i = m + tid; i < len; i += kMatrixThreads) s_keys[i] = 0ull;
+  for (int i = m + tid; i < len; i += nthreads) s_keys[i] = 0ull;
   bitonic_sort_desc(s_keys, len);
   int n = m;
   if (nms_top_k > 0 && n > nms_top_k) n = nms_top_k;
@@ -393,7 +398,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   if (tid == 0) { s_nan_from = -1; s_kept = 0; s_any_odd = 0; s_maxgrp = 0; }
   __syncthreads();
   const float4* gb = reinterpret_cast<const float4*>(boxes) + (long long)img * num_boxes;
-  for (int i = tid; i < n; i += kMatrixThreads) {
+  for (int i = tid; i < n; i += nthreads) {
     unsigned long long k = s_keys[i];
     unsigned int flat = 0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull);
     s_score[i] = __uint_as_float((unsigned int)(k >> 32));
@@ -412,12 +417,12 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     // contribute exactly +0 to compensate and a factor >= 1 to the decay min, so only same-label pairs matter.
     // Group the boxes by label (sort of (label, index)) and let each warp walk just its column's group prefix.
     int len2 = 1; while (len2 < n) len2 <<= 1;
-    for (int i = tid; i < len2; i += kMatrixThreads)
+    for (int i = tid; i < len2; i += nthreads)
       s_keys[i] = i < n ? (((unsigned long long)(0xFFFFFFFFu - (unsigned int)s_label[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i)) : 0ull;
     bitonic_sort_desc(s_keys, len2);
-    for (int p = tid; p < n; p += kMatrixThreads) s_order[p] = (unsigned short)(0xFFFFFFFFu - (unsigned int)(s_keys[p] & 0xFFFFFFFFull));
+    for (int p = tid; p < n; p += nthreads) s_order[p] = (unsigned short)(0xFFFFFFFFu - (unsigned int)(s_keys[p] & 0xFFFFFFFFull));
     __syncthreads();
-    for (int p = tid; p < n; p += kMatrixThreads) {
+    for (int p = tid; p < n; p += nthreads) {
       const int lp = s_label[s_order[p]];
       int q = p;
       while (q > 0 && s_label[s_order[q - 1]] == lp) --q;
@@ -428,7 +433,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
     if (s_maxgrp == 0) {
       // every label group is short (<= 33 boxes): one THREAD per column walks its prefix -- no shuffle reductions, all columns
       // at once (the warp-per-column form below costs ~450 dependent cycles per column and 16 columns per warp)
-      for (int p = tid; p < n; p += kMatrixThreads) {
+      for (int p = tid; p < n; p += nthreads) {
         const int j = s_order[p];
         const float4 bj = s_box[j];
         float mx = 0.f;
@@ -441,7 +446,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
         s_comp[j] = mx;
       }
       __syncthreads();
-      for (int p = tid; p < n; p += kMatrixThreads) {
+      for (int p = tid; p < n; p += nthreads) {
         const int j = s_order[p];
         const float4 bj = s_box[j];
         float mn = j > 0 ? 1.f : CUDART_INF_F;
@@ -572,7 +577,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   __syncthreads();
   // post threshold (>=, NaN fails; :132) then stable descending sort by decayed score (:140-145)
   int len3 = 1; while (len3 < n) len3 <<= 1;
-  for (int i = tid; i < len3; i += kMatrixThreads) {
+  for (int i = tid; i < len3; i += nthreads) {
     unsigned long long k = 0ull;
     if (i < n) {
       float v = s_new[i];
@@ -589,7 +594,7 @@ nms_matrix_kernel(const float* __restrict__ boxes, int num_boxes, int num_classe
   bitonic_sort_desc(s_keys, len3);
   int kept = s_kept;
   if (kept > keep_top_k) kept = keep_top_k;
-  for (int r = tid; r < kept; r += kMatrixThreads) {
+  for (int r = tid; r < kept; r += nthreads) {
     int i = (int)(0xFFFFFFFFu - (unsigned int)(s_keys[r] & 0xFFFFFFFFull));
     float4 b = s_box[i];
     float* row = my_out + r * 6;
@@ -696,7 +701,7 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
     if (rc) return rc;
     attr_set = true;
   }
-  nms_matrix_kernel<<<n, kMatrixThreads, smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, kCap, nullptr, 0u, 0,
+  nms_matrix_kernel<<<n, matrix_threads(nmax), smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, kCap, nullptr, 0u, 0,
                                                      nms_top_k, keep_top_k, post_threshold, use_gaussian, gaussian_sigma,
                                                      out, counts, nmax);
   return check_launch();
@@ -736,7 +741,7 @@ int ppy_matrix_nms_candidates(const float* boxes, int n, int num_boxes, int num_
     if (rc) return rc;
     attr_set = true;
   }
-  nms_matrix_kernel<<<n, kMatrixThreads, smem, as_stream(s)>>>(boxes, num_boxes, num_classes, c.count, c.keys, cap, c.hist,
+  nms_matrix_kernel<<<n, matrix_threads(nmax), smem, as_stream(s)>>>(boxes, num_boxes, num_classes, c.count, c.keys, cap, c.hist,
                                                                c.thr_bits, c.shift, nms_top_k, keep_top_k, post_threshold,
                                                                use_gaussian, gaussian_sigma, out, counts, nmax);
   return check_launch();
