@@ -16,6 +16,20 @@ inline int check_cuda(cudaError_t e) {
 }
 inline int check_launch() { count_launch(); return check_cuda(cudaGetLastError()); }
 
+// cudaFuncSetAttribute is per device: `static DeviceOnce once; if (once.first()) { set attribute }` runs once for every device this
+// process launches on (a bool would only cover the first one).
+struct DeviceOnce {
+  unsigned long long seen[2] = {0ull, 0ull};       // up to 128 devices; benign race: at worst the attribute is set twice
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen[dev >> 6] & bit) return false;
+    seen[dev >> 6] |= bit;
+    return true;
+  }
+};
+
 inline cudaStream_t as_stream(ppy_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 inline int dtype_size(int dt) { return dt == PPY_BF16 ? 2 : 4; }

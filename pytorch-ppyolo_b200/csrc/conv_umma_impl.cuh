@@ -1258,11 +1258,10 @@ int launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
       if (rc) return rc;
     }
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     rc = check_cuda(cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, EPI, ACC, CTA2, CHUNKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     if (rc) return rc;
-    attr_done = true;
   }
   const int pw_tiles = (int)ceil_div(wo, PW), ph_tiles = (int)ceil_div(ho, PH);
   int num_m_tiles = mode_is_patchy(MODE) ? p->n * pw_tiles * ph_tiles : (int)ceil_div(M, BLOCK_M);

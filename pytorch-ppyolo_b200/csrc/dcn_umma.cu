@@ -378,11 +378,10 @@ int dcn_launch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { g_last_cuda_error = (int)cr; return PPY_ERR_CUDA; }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     int rc = check_cuda(cudaFuncSetAttribute(dcn_umma_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     if (rc) return rc;
-    attr_done = true;
   }
   const long long M = (long long)p->n * ho * wo;
   const long long pairs = ceil_div(M, 2 * DB_M);

@@ -693,13 +693,12 @@ static int matrix_nms_dense(const float* boxes, const float* scores, int n, int 
                                                       w.count, w.keys);
   }
   if ((rc = check_launch())) return rc;
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
   const int nmax = matrix_nmax(nms_top_k);
   const int smem = matrix_smem_bytes(nmax);
-  if (!attr_set) {
+  if (attr_once.first()) {
     rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, matrix_smem_bytes(kMaxN)));
     if (rc) return rc;
-    attr_set = true;
   }
   nms_matrix_kernel<<<n, matrix_threads(nmax), smem, st>>>(boxes, num_boxes, num_classes, w.count, w.keys, kCap, nullptr, 0u, 0,
                                                      nms_top_k, keep_top_k, post_threshold, use_gaussian, gaussian_sigma,
@@ -733,13 +732,12 @@ int ppy_matrix_nms_candidates(const float* boxes, int n, int num_boxes, int num_
   PPY_REQUIRE(nms_top_k <= kMaxN);
   PPY_REQUIRE((long long)num_boxes * num_classes < 0xFFFFFFFFll);
   const CandSink c = cand_carve(workspace, n, cap, score_threshold);
-  static bool attr_set = false;
+  static DeviceOnce attr_once;
   const int nmax = matrix_nmax(nms_top_k);
   const int smem = matrix_smem_bytes(nmax);
-  if (!attr_set) {
+  if (attr_once.first()) {
     int rc = check_cuda(cudaFuncSetAttribute(nms_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, matrix_smem_bytes(kMaxN)));
     if (rc) return rc;
-    attr_set = true;
   }
   nms_matrix_kernel<<<n, matrix_threads(nmax), smem, as_stream(s)>>>(boxes, num_boxes, num_classes, c.count, c.keys, cap, c.hist,
                                                                c.thr_bits, c.shift, nms_top_k, keep_top_k, post_threshold,

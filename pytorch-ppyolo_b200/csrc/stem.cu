@@ -340,10 +340,9 @@ extern "C" int ppy_stem_conv3x3s2(const float* x_nchw, int n, int h, int w, cons
       up.scale[co] = scale_host[co];
       up.shift[co] = shift_host[co];
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
       if (check_cuda(cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem))) return PPY_ERR_CUDA;
-      attr_set = true;
     }
     const int tiles = n * tiles_x * tiles_y;
     static const int per_sm = getenv("PPY_STEM_CTAS") ? atoi(getenv("PPY_STEM_CTAS")) : 4;   // measured: 3 -> 96.6, 4 -> 90.5, 5 -> 110.2 us (bs 32 x 608^2)

@@ -131,7 +131,13 @@ class PPYOLO(torch.nn.Module):
         warm-up passes so capturing does not advance the running statistics.  ``full``: ``feats`` is ``[x]`` and the graphs hold
         the differentiable backbone (``freeze_at < 5``) as well."""
         head = self.head
-        key = (bool(full), tuple(tuple(f.shape) for f in feats), tuple(gt_box.shape), tuple(tuple(t.shape) for t in targets), head.train_impl)
+        from model.custom_layers import DropBlock
+        # everything the captured kernels depend on besides the tensors: shapes, conv implementation, BatchNorm mode of every unit
+        # (batch vs running statistics) and the DropBlock switches -- toggling one of them must not replay a stale graph
+        mods = list(head.modules()) + (list(self.backbone.modules()) if full else [])
+        modes = tuple(m.training for m in mods if isinstance(m, torch.nn.BatchNorm2d)) + \
+            tuple(bool(m.is_test) for m in mods if isinstance(m, DropBlock))
+        key = (bool(full), tuple(tuple(f.shape) for f in feats), tuple(gt_box.shape), tuple(tuple(t.shape) for t in targets), head.train_impl, modes)
         entry = self._graphed_heads.get(key)
         if entry is None:
             n_feats, n_targets = len(feats), len(targets)
