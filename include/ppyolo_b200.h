@@ -205,7 +205,8 @@ int ppy_conv_f16x2(const ppy_conv_params* p, ppy_stream_t s);
  * training side (train.py:427-442; frozen-backbone BNs run on BATCH statistics, custom_layers.py:122)
  * ---------------------------------------------------------------------------------------------- */
 /* Per-channel batch statistics of an NHWC tensor -> folded scale = gamma/sqrt(var+eps), shift = beta - mean*scale;
- * running_mean/var (optional) updated in place with torch's momentum / unbiased-variance rule. workspace: 2*c doubles. */
+ * running_mean/var (optional) updated in place with torch's momentum / unbiased-variance rule (one launch: the last block to
+ * finish finalizes). workspace: 2*c + 1 doubles (sums, sums of squares, block counter); zeroed by the call. */
 int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                        double* workspace, ppy_stream_t s);

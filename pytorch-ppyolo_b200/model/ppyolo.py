@@ -117,9 +117,9 @@ class PPYOLO(torch.nn.Module):
             feats = autograd_backbone.backbone_features(self.backbone, x, 'kernels')
             return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)
         n, _, h, w = x.shape
-        with torch.no_grad():
-            feats = self.backbone_train_engine(n, h, w).run_backbone(x)
         self.head.train_impl = self.train_head_impl or ('kernels' if self.train_precision == 'bf16' else 'aten')
+        with torch.no_grad():      # the kernel head reads the engine's bf16 NHWC feature buffers as they are
+            feats = self.backbone_train_engine(n, h, w).run_backbone(x, native=self.head.train_impl == 'kernels')
         if self.train_graph:
             return self._graphed_head_loss(feats, gt_box, gt_label, gt_score, targets)
         return self.head.get_loss_autograd(feats, gt_box, gt_label, gt_score, targets)

@@ -11,7 +11,7 @@ like in the head.  The frozen prefix (stem and stages below ``freeze_at``) runs 
 import torch
 import torch.nn.functional as F
 
-from .autograd_head import conv_unit, ACT_FP32
+from .autograd_head import conv_unit, flush_bn_counters, ACT_FP32
 
 
 def _block(blk, x, impl):
@@ -61,4 +61,5 @@ def backbone_features(backbone, x, impl='kernels'):
                 x = _block(blk, x, impl)
         if stage in backbone.feature_maps:
             outs.append(x)
+    flush_bn_counters()
     return outs

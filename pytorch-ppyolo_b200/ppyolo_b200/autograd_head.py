@@ -73,7 +73,7 @@ def conv_unit(u, x, impl='aten', coord=False):
         y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
                          0.1 if bn.momentum is None else bn.momentum, bn.eps)
         if bn.training:
-            bn.num_batches_tracked += 1
+            _PENDING_BN.append(bn)                  # counters advance in one multi-tensor launch (flush_bn_counters)
     if u.act_name == 'relu':
         y = F.relu(y)
     elif u.act_name == 'leaky':
@@ -81,6 +81,17 @@ def conv_unit(u, x, impl='aten', coord=False):
     elif u.act_name == 'mish':
         y = y * torch.tanh(F.softplus(y))
     return y
+
+
+_PENDING_BN = []
+
+
+def flush_bn_counters():
+    """``num_batches_tracked += 1`` of every train-mode BatchNorm evaluated since the last flush -- one ``_foreach_add_`` instead
+    of one tiny kernel (and CUDA-graph node) per layer."""
+    if _PENDING_BN:
+        torch._foreach_add_([bn.num_batches_tracked for bn in _PENDING_BN], 1)
+        del _PENDING_BN[:]
 
 
 def _run_layers(layers, x, impl='aten'):
@@ -118,4 +129,5 @@ def head_outputs(head, body_feats, impl='aten'):
         outputs.append(conv_unit(head.yolo_output_convs[i], tip, impl).float())
         if i < n_out - 1:
             route = F.interpolate(conv_unit(head.upsample_layers[2 * i], route, impl), scale_factor=2, mode='nearest')
+    flush_bn_counters()
     return outputs

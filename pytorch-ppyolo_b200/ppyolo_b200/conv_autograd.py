@@ -57,8 +57,11 @@ def _dgrad(dyh, weight, c_main, stride, pad, in_hw, out_f32):
         z = torch.zeros((n, hz, wz, o_pad), dtype=dyh.dtype, device=dev)
         z[:, 0:ho * stride:stride, 0:wo * stride:stride] = dyh
         dyh = z
-    wt = torch.zeros((c_main, o_pad, k, k), dtype=torch.float32, device=dev)
-    wt[:, :cout] = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3)
+    if o_pad == cout:                                          # no padded output channels to zero: one flip + one transposing copy
+        wt = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3).contiguous()
+    else:
+        wt = torch.zeros((c_main, o_pad, k, k), dtype=torch.float32, device=dev)
+        wt[:, :cout] = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3)
     packed_t = ops.pack_weight(wt, PPY_BF16, cache=False)
     dxh = ops.conv_nhwc(dyh, packed_t, o_pad, c_main, k, 1, k - 1 - pad, _const('one', c_main, dev), _const('zero', c_main, dev),
                         0, PPY_BF16, out_code=PPY_F32 if out_f32 else PPY_BF16)
@@ -95,6 +98,8 @@ def _wgrad(xh, dyh, weight, c_main, stride, pad):
     a_rows = ops.round_up(cout, 8)
     a_full = _kmajor(dyh, a_rows, 1, 1, 0, m_pad)
     out = _wgrad_gemm(a_full, cout, b_op, c_eff * k * k, m_pad)
+    if c_eff == weight.shape[1]:                               # the GEMM result IS the gradient (a view when its rows are unpadded)
+        return out.reshape(cout, c_eff, k, k)
     dw = torch.zeros_like(weight, dtype=torch.float32)
     dw[:, :c_main] = out.reshape(cout, c_eff, k, k)[:, :c_main]
     return dw

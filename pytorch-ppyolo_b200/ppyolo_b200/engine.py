@@ -454,7 +454,7 @@ class InferenceEngine(object):
             dst = TensorRef(self._new(raw.n, raw.h, raw.w, ops.round_up(cout, 8)), c=cout)
         scale = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
         shift = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
-        ws = self._keep(torch.empty(2 * cout, dtype=torch.float64, device=self.dev))
+        ws = self._keep(torch.empty(2 * cout + 1, dtype=torch.float64, device=self.dev))
         rows = raw.n * raw.h * raw.w
         momentum = 0.1 if bn.momentum is None else float(bn.momentum)
         a1 = (ctypes.c_void_p(raw.ptr), raw.ld, rows, cout, raw.code, ops.ptr(bn.weight.data), ops.ptr(bn.bias.data), float(bn.eps),
@@ -871,13 +871,16 @@ class InferenceEngine(object):
         """Raw head outputs of the last run as NCHW fp32 tensors (parity tests)."""
         return [ops.from_nhwc(o.t, o.c) for o in self.head_outs]
 
-    def run_backbone(self, x):
-        """Backbone forward only (``backbone_only`` engines): list of NCHW fp32 feature maps (fresh tensors)."""
+    def run_backbone(self, x, native=False):
+        """Backbone forward only (``backbone_only`` engines): list of NCHW fp32 feature maps (fresh tensors).  ``native`` (bf16 /
+        fp32 engines): logical NCHW VIEWS of the engine's own NHWC buffers instead (channels_last, the engine's dtype; valid until
+        the next run) -- what the kernel head of the training step consumes without a layout or dtype round trip."""
         self.x_in.copy_(x, non_blocking=True)
         self.launch()
-        if self.train_bn:
-            for bn in self.bn_modules:
-                bn.num_batches_tracked += 1
+        if self.train_bn and self.bn_modules:
+            torch._foreach_add_([bn.num_batches_tracked for bn in self.bn_modules], 1)      # one launch for all counters
+        if native and not any(f.pair for f in self.feats):
+            return [f.t[..., f.c_off:f.c_off + f.c].permute(0, 3, 1, 2) for f in self.feats]
         return self.feature_maps_nchw()
 
     def feature_maps_nchw(self):
