@@ -32,6 +32,7 @@ print('# SASS opcode histogram per kernel of %s (cuobjdump -sass, sm_100a)' % os
 print('# tcgen05.mma -> UTCHMMA[.2CTA]; tcgen05.ld -> LDTM; TMA -> UTMALDG / UTMASTG; tcgen05.commit -> UTCBAR; mbarrier -> SYNCS\n')
 for name, c in kernels.items():
     dn = demangle(name)
+    dn = dn.replace('(anonymous namespace)::', '').replace('void ', '')
     dn = re.sub(r'\(.*', '', dn)
     groups = collections.OrderedDict()
     for op, n in sorted(c.items()):
