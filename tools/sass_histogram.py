@@ -13,7 +13,7 @@ import sys
 REPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(REPO, 'pytorch-ppyolo_b200', 'ppyolo_b200', 'libppyolo_b200.so')
 KEYS = ('UTCHMMA', 'UTCQMMA', 'UTCMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UBLKCP', 'UTCBAR', 'UTCATOM', 'SYNCS', 'LDGSTS', 'HMMA',
-        'FFMA', 'LDG', 'STG', 'LDS', 'STS', 'RED', 'ATOM', 'MUFU', 'SHFL', 'BAR', 'UCGABAR', 'ELECT', 'LDL', 'STL')
+        'FFMA', 'LDG', 'STG', 'LDS', 'STS', 'REDG', 'RED', 'ATOMG', 'ATOMS', 'ATOM', 'MUFU', 'SHFL', 'BAR', 'UCGABAR', 'ELECT', 'LDL', 'STL')
 sass = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
 demangle = lambda n: subprocess.run(['c++filt', n], capture_output=True, text=True).stdout.strip()
 kernels = collections.OrderedDict()
@@ -40,7 +40,7 @@ for name, c in kernels.items():
             continue
         for k in KEYS:
             if op == k or op.startswith(k + '.'):
-                detail = op if k in ('UTCHMMA', 'UTMALDG', 'UTMASTG', 'UTCBAR', 'LDTM', 'UTCQMMA') else k
+                detail = op if k in ('UTCHMMA', 'UTMALDG', 'UTMASTG', 'UTCBAR', 'LDTM', 'UTCQMMA') else ('REDG.F32x4' if 'F32x4' in op else k)
                 groups[detail] = groups.get(detail, 0) + n
                 break
     print('%s   [%d instructions]' % (dn, c['_total']))
