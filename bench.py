@@ -532,12 +532,23 @@ def train_record(args, rank, world, local_rank, dd, dev):
     dd.barrier()
     ms = dd.max(e0.elapsed_time(e1)) / steps
     rec = {'workload': 'ppyolo_2x 608x608 bs=8/GPU train step (freeze_at=5: frozen backbone fwd with batch-stat BN, head fwd+bwd, 6 losses, '
-                       'gradient all-reduce, fused SGD)', 'value': world * bs / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+                       'gradient exchange + SGD + EMA)', 'value': world * bs / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
            'warmup': warmup, 'n_gpus': world, 'scaling': 'weak', 'backbone_precision': 'bf16',
            'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'trainable_params': int(sum(p.numel() for p in trainer.params)),
            'losses': {k: float(v) for k, v in losses.items()}}
     if hasattr(trainer, 'timing_summary'):
-        rec.update(trainer.timing_summary())
+        ts = trainer.timing_summary()
+        if world > 1:
+            # the exchange step rendezvouses the ranks, so its event time on a rank includes waiting for the slowest one: report the
+            # fastest rank's view (the work itself) next to this rank's
+            import torch.distributed as dist
+            for key in ('allreduce_ms', 'exchange_optimizer_ms'):
+                if ts.get(key) is not None:
+                    t = torch.tensor([ts[key]], dtype=torch.float32, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    ts[key + '_rank0_incl_wait'] = ts[key]
+                    ts[key] = float(t.item())
+        rec.update(ts)
     del trainer, model
     torch.cuda.empty_cache()
     return rec

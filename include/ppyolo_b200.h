@@ -238,6 +238,21 @@ int ppy_sgd_momentum(float* param, const float* grad, float* momentum_buf, long 
 int ppy_sgd_ema_multi(float* const* params, const float* grad_flat, float* momentum_flat, float* shadow_flat, const long long* offsets,
                       const long long* shadow_offsets, const float* lr_mult, const float* weight_decay, int num_tensors, float lr,
                       float momentum, float grad_scale, int first_step, float ema_decay, float ema_one_minus_decay, ppy_stream_t s);
+/* The exchange step of data-parallel training (train.py:437-442 with replicas) as ONE kernel per rank over NVLink /
+ * NVSwitch peer memory: all-reduce(sum) of the flat fp32 gradient bucket + the ppy_sgd_ema_multi update.  The bucket of every rank
+ * lives in symmetric memory: grad_local = this rank's mapping, grad_peers = DEVICE array [world] of every rank's bucket as mapped
+ * into this process, grad_multicast = the NVLS multicast address of all of them (NULL when the box has none: the kernel then sums /
+ * stores through grad_peers).  signal_pads = DEVICE array [world] of zero-initialised uint32 pads in peer memory (words
+ * [pad_slot, pad_slot + world) are used); seq must grow by one per call on every rank (barrier sequence); done = TWO zeroed device
+ * uint32 (CTA counter; error word, set to 1 when a barrier wait gave up after 10 s because a peer never arrived).  Every rank must make the same call (same seq) on its own device: the kernels rendezvous on the pads -- rank r reduces
+ * slice r with multimem.ld_reduce (the switch adds) and multimem.st (the switch replicates), then all ranks run the optimizer on
+ * the reduced bucket.  total_padded: bucket length in floats, multiple of 4 (tail zero); remaining arguments as ppy_sgd_ema_multi.
+ * Cooperative launch (one CTA per SM); PPY_ERR_UNSUPPORTED if the device cannot. */
+int ppy_allreduce_sgd_ema(float* grad_local, float* grad_multicast, float* const* grad_peers, unsigned int* const* signal_pads,
+                          int pad_slot, int rank, int world, unsigned int seq, unsigned int* done, long long total_padded,
+                          float* const* params, float* momentum_flat, float* shadow_flat, const long long* offsets,
+                          const long long* shadow_offsets, const float* lr_mult, const float* weight_decay, int num_tensors, float lr,
+                          float momentum, float grad_scale, int first_step, float ema_decay, float ema_one_minus_decay, ppy_stream_t s);
 /* K-major operand of the weight-gradient GEMM of a k x k stride-1 conv (training step, conv_autograd.py): NHWC bf16 x
  * [n,h,w,c] -> out [c*k*k rows][m_pad] bf16 with out[(ch*k*k + ky*k + kx)][m] = x[pixel m shifted by (ky-pad, kx-pad)][ch], zero
  * outside the image and for m in [n*h*w, m_pad); rows follow the OIHW weight order, k = 1 is the plain transpose (also used

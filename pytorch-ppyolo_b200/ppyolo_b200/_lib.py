@@ -12,7 +12,7 @@ c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_lon
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
 
 PPY_F32, PPY_BF16, PPY_F16X2 = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
 
 
@@ -81,6 +81,9 @@ SIGNATURES = {
     'ppy_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     'ppy_sgd_ema_multi': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
                                   c_float, c_int, c_float, c_float, c_void_p]),
+    'ppy_allreduce_sgd_ema': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_uint, c_void_p, c_ll,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float,
+                                      c_float, c_int, c_float, c_float, c_void_p]),
     'ppy_ema_update': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     'ppy_im2col_kmajor': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     'ppy_im2col_kmajor_strided': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),

@@ -6,7 +6,10 @@ iteration is the gradient all-reduce(sum)/world of the trainable (head) paramete
 that bucket (``p.grad`` is a view of it: no pack copies), and the whole optimizer step -- torch.optim.SGD momentum update
 with the reference's per-layer lr / weight-decay groups, plus the ExponentialMovingAverage of the new weights
 (model/EMA.py:31-45, which the reference round-trips through host memory every step) -- is ONE kernel launch
-(``ppy_sgd_ema_multi``) reading the reduced bucket in place.  BatchNorm statistics, DropBlock RNG and data sharding stay
+(``ppy_sgd_ema_multi``) reading the reduced bucket in place.  When the ranks of a node can map each other's buckets (symmetric
+memory), the all-reduce itself moves INTO that launch (``ppy_allreduce_sgd_ema``, csrc/allreduce_sgd.cu): barrier on peer signal
+pads, in-switch reduction of each rank's slice (``multimem.ld_reduce`` / ``multimem.st`` over NVSwitch, or P2P loads / stores),
+barrier, optimizer -- NCCL then only carries the rendezvous.  BatchNorm statistics, DropBlock RNG and data sharding stay
 per rank; initial parameters / buffers are broadcast from rank 0; the learning rate follows the
 reference's warm-up + piecewise decay and is NOT rescaled by the world size, like the reference."""
 import ctypes
@@ -43,6 +46,12 @@ class GradientBucket(object):
         self.offsets = [0]
         for s in self.sizes:
             self.offsets.append(self.offsets[-1] + s)
+
+    def rebase(self, storage):
+        """Move the bucket into caller-provided storage (symmetric memory mapped into every peer): same length, same views."""
+        assert storage.numel() >= self.flat.numel() and storage.dtype == torch.float32
+        storage[:self.flat.numel()].copy_(self.flat)
+        self.flat = storage[:self.flat.numel()]
 
     def view(self, i):
         return self.flat[self.offsets[i]:self.offsets[i + 1]]
@@ -114,6 +123,44 @@ class Trainer(object):
                 at = {id(p): self.ema._offsets[i] for i, p in enumerate(self.ema._params)}
                 self._shadow_offsets = torch.tensor([at[id(p)] for p in self.params], dtype=torch.int64, device=dev)
         self._events = []
+        # the exchange step as ONE kernel over NVLink peer memory (csrc/allreduce_sgd.cu) when the ranks can map each other's
+        # gradient buckets; NCCL all-reduce + the optimizer kernel otherwise (PPY_PEER_ALLREDUCE=0 forces that)
+        self._peer, self.exchange_impl = None, 'nccl all-reduce + optimizer kernel' if world > 1 else 'single rank: optimizer kernel'
+        if world > 1 and self._cuda and os.environ.get('PPY_PEER_ALLREDUCE', '1') != '0':
+            self._setup_peer_exchange(rank, world)
+
+    def _setup_peer_exchange(self, rank, world):
+        """Put the gradient bucket into symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every
+        rank of the node, NVLS multicast address when the switch offers one) and keep the peer pointer tables for the kernel.  All
+        ranks switch together or not at all."""
+        dev = self.bucket.flat.device
+        state, err = None, ''
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            total = self.bucket.flat.numel()
+            padded = (total + 4 * world - 1) // (4 * world) * (4 * world)
+            store = symm_mem.empty(padded, dtype=torch.float32, device=dev)
+            store.zero_()
+            hdl = symm_mem.rendezvous(store, dist.group.WORLD)
+            if hdl.world_size != world or hdl.rank != rank or hdl.signal_pad_size < 4 * (self.PAD_SLOT + world):
+                raise RuntimeError('symmetric memory handle does not match the process group')
+            mc = 0 if os.environ.get('PPY_PEER_NO_MULTICAST') else int(hdl.multicast_ptr or 0)      # knob: exercise the P2P form on an NVLS box
+            state = {'store': store, 'hdl': hdl, 'padded': padded, 'multicast': mc,
+                     'peers': int(hdl.buffer_ptrs_dev), 'pads': int(hdl.signal_pad_ptrs_dev),
+                     'done': torch.zeros(2, dtype=torch.int32, device=dev)}
+        except Exception as exc:                # no symmetric memory on this box / torch build: NCCL path
+            err = '%s: %s' % (type(exc).__name__, str(exc)[:120])
+        ok = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            self.bucket.rebase(state['store'])
+            self._peer = state
+            self.exchange_impl = 'one kernel per rank over peer memory: %s all-reduce + SGD + EMA (csrc/allreduce_sgd.cu)' % (
+                'NVLS multimem.ld_reduce / multimem.st' if state['multicast'] else 'P2P load / store')
+        elif err:
+            self.exchange_impl += ' (peer-memory kernel unavailable: %s)' % err
+
+    PAD_SLOT = 2048          # first uint32 word of the signal pads this trainer uses (torch's own barriers use the low channels)
 
     # ------------------------------------------------------------------ one iteration
     def _pointer_table(self):
@@ -136,7 +183,7 @@ class Trainer(object):
         total.backward()
         self.bucket.pack()                                         # no-op for the bound views
         ev[1].record()
-        grad_scale = self.bucket.all_reduce()
+        grad_scale = 1.0 / parallel.world()[1] if self._peer is not None else self.bucket.all_reduce()
         ev[2].record()
         lr = calc_lr(self.iter_id, self.cfg)
         first = 1 if self.iter_id == 0 else 0
@@ -149,9 +196,19 @@ class Trainer(object):
             d32, omd32 = float(np.float32(decay)), float(np.float32(1 - decay))
         else:
             d32, omd32 = 0.0, 0.0
-        check(lib.ppy_sgd_ema_multi(ops.ptr(self._pointer_table()), ops.ptr(self.bucket.flat), ops.ptr(self.momentum_flat), ops.ptr(shadow),
-                                    ops.ptr(self._offsets_dev), ops.ptr(sh_off), ops.ptr(self._lr_mult), ops.ptr(self._wd), len(self.params),
-                                    float(lr), float(self.momentum), float(grad_scale), first, d32, omd32, ops.stream_ptr()), 'sgd_ema_multi')
+        if self._peer is not None:
+            pe = self._peer
+            rank, world = parallel.world()
+            check(lib.ppy_allreduce_sgd_ema(ops.ptr(self.bucket.flat), ctypes.c_void_p(pe['multicast'] or None), ctypes.c_void_p(pe['peers']),
+                                            ctypes.c_void_p(pe['pads']), self.PAD_SLOT, rank, world, self.iter_id + 1, ops.ptr(pe['done']),
+                                            pe['padded'], ops.ptr(self._pointer_table()), ops.ptr(self.momentum_flat), ops.ptr(shadow),
+                                            ops.ptr(self._offsets_dev), ops.ptr(sh_off), ops.ptr(self._lr_mult), ops.ptr(self._wd),
+                                            len(self.params), float(lr), float(self.momentum), float(grad_scale), first, d32, omd32,
+                                            ops.stream_ptr()), 'allreduce_sgd_ema')
+        else:
+            check(lib.ppy_sgd_ema_multi(ops.ptr(self._pointer_table()), ops.ptr(self.bucket.flat), ops.ptr(self.momentum_flat), ops.ptr(shadow),
+                                        ops.ptr(self._offsets_dev), ops.ptr(sh_off), ops.ptr(self._lr_mult), ops.ptr(self._wd), len(self.params),
+                                        float(lr), float(self.momentum), float(grad_scale), first, d32, omd32, ops.stream_ptr()), 'sgd_ema_multi')
         ev[3].record()
         if self.ema is not None:
             self.ema._update_step += 1
@@ -168,19 +225,33 @@ class Trainer(object):
     def timing_summary(self, last=10):
         """Mean CUDA-event times of the last steps: forward+backward / gradient all-reduce / optimizer(+EMA) kernel."""
         torch.cuda.synchronize()
+        self.check_exchange()
         evs = self._events[-last:]
         if not evs:
             return {}
         mean = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in evs) / len(evs)
         ar = mean(1, 2)
-        return {'fwd_bwd_ms': mean(0, 1), 'allreduce_ms': ar, 'optimizer_ema_ms': mean(2, 3), 'allreduce_overlap_fraction': 0.0,
-                'allreduce_note': 'one NCCL all-reduce of the flat bucket after the (single CUDA graph) backward; not overlapped',
-                'ema': self.ema is not None}
+        out = {'fwd_bwd_ms': mean(0, 1), 'allreduce_ms': ar, 'optimizer_ema_ms': mean(2, 3), 'allreduce_overlap_fraction': 0.0,
+               'exchange_impl': self.exchange_impl, 'ema': self.ema is not None}
+        if self._peer is not None:
+            out['allreduce_ms'] = None
+            out['exchange_optimizer_ms'] = out.pop('optimizer_ema_ms')
+            out['allreduce_note'] = ('the all-reduce runs INSIDE the optimizer launch (barrier on peer signal pads, in-switch reduction of '
+                                     "the rank's slice, barrier, optimizer): exchange_optimizer_ms is all-reduce + SGD + EMA")
+        else:
+            out['allreduce_note'] = 'one NCCL all-reduce of the flat bucket after the (single CUDA graph) backward; not overlapped'
+        return out
+
+    def check_exchange(self):
+        """Raise if a barrier of the peer-memory exchange kernel ever timed out (a rank did not make the matching call)."""
+        if self._peer is not None and int(self._peer['done'][1].item()) != 0:
+            raise RuntimeError('ppyolo_b200: the peer-memory gradient exchange timed out waiting for a rank; parameters are not in sync')
 
     # ------------------------------------------------------------------ checkpoint / resume
     def state_dict(self):
         """Optimizer + EMA state next to the model weights (the reference saves the weights only, train.py:460-478, so a resumed
         run restarts momentum and EMA from scratch)."""
+        self.check_exchange()
         sd = {'iter_id': self.iter_id, 'momentum_flat': self.momentum_flat.clone(),
               'param_shapes': [tuple(p.shape) for p in self.params]}
         if self.ema is not None:

@@ -61,6 +61,7 @@ if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
+sys.stderr.write('rank %d timing %s\n' % (rank, json.dumps({k: v for k, v in trainer.timing_summary(8).items() if 'note' not in k})))
 if rank == 0:
     print(json.dumps({'metric': 'train_images_per_sec', 'value': world * a.batch / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
                       'ms_per_step': ms, 'steps': a.steps, 'warmup': a.warmup, 'scaling': 'weak',
