@@ -609,6 +609,17 @@ def run_ours(args, rank, world, local_rank):
         del eng_b
         model.precision = args.precision
 
+    # ---- the north_star's second resolution: the same net and batch at 320x320 (device-resident, CUDA-graph replay)
+    shape320 = None
+    if not args.quick:
+        eng_3 = model.engine(BATCH, 320, 320)
+        eng_3.x_in.copy_(synth.images(BATCH, 320, seed=40 + rank))
+        eng_3.im_size.copy_(im_host[0])
+        ms_3, _ = time_engine(eng_3, args.steps, args.warmup, dd)
+        shape320 = {'workload': 'ppyolo_2x 320x320 bs=%d/GPU inference' % BATCH, 'value': world * BATCH / (ms_3 * 1e-3), 'unit': UNIT,
+                    'ms_per_step': ms_3, 'conv_gflop_per_image': eng_3.conv_flops / BATCH / 1e9}
+        del eng_3
+
     # ---- strong scaling: the SAME 32 images split over the ranks, 32 / N per GPU -- the harder number (small M:
     # tile quantisation); N > 1 only, N = 1 is the headline itself
     strong = None
@@ -654,7 +665,7 @@ def run_ours(args, rank, world, local_rank):
                     'float_chw_upload': {'value': world * BATCH / (e2e_f32_ms * 1e-3), 'ms_per_step': e2e_f32_ms, 'h2d_bytes_per_step': world * h2d_f32},
                     'from_original_images': {'value': world * BATCH / (e2e_raw_ms * 1e-3), 'ms_per_step': e2e_raw_ms, 'h2d_bytes_per_step': world * h2d_raw,
                                              'input': '480x640 BGR uint8 frames, bicubic resize + BGR->RGB on the GPU (no host image processing)'}},
-            'roofline': roofline, 'cpu_baseline': cpu, 'torch_gpu_baseline': tgb, 'precision_modes': modes, 'strong_scaling': strong, 'train': train,
+            'roofline': roofline, 'cpu_baseline': cpu, 'torch_gpu_baseline': tgb, 'precision_modes': modes, 'shape_320': shape320, 'strong_scaling': strong, 'train': train,
             'matrix_nms': matrix_nms_isolation(dev, world == 1 and not args.no_cpu_baseline and not args.quick),
             'loaded_library': _lib.LIB_PATH}
     print(json.dumps(line), flush=True)
