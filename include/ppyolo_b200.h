@@ -58,6 +58,10 @@ int ppy_maxpool3x3s2(const void* x, int x_ld, void* y, int y_ld, int n, int h, i
 int ppy_avgpool2x2(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
 /* SPP, model/custom_layers.py:275-290: y[..., 0:c]=x, [c:2c]=maxpool5, [2c:3c]=maxpool9, [3c:4c]=maxpool13. */
 int ppy_spp(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
+/* Backward of ppy_spp (training head): dx = dy[..., 0:c] + the three max-pools' gradients routed to each window's arg-max (torch
+ * max_pool2d semantics: the first maximum in row-major window order).  x: the forward input, dy: [n,h,w,>=4c]; c % 32 == 0. */
+int ppy_spp_backward(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int n, int h, int w, int c, int dtype,
+                     ppy_stream_t s);
 /* nearest x2 upsample (model/head.py:362) written into a channel slice: y is [n,2h,2w,*]. */
 int ppy_upsample2x(const void* x, int x_ld, void* y, int y_ld, int n, int h, int w, int c, int dtype, ppy_stream_t s);
 /* strided channel-slice copy (concat), rows = n*h*w pixels. */

@@ -12,7 +12,7 @@ c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_lon
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
 
 PPY_F32, PPY_BF16, PPY_F16X2 = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
 
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     'ppy_maxpool3x3s2': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_avgpool2x2': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_spp': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'ppy_spp_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_upsample2x': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_copy_channels': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p]),
     'ppy_coord_channels': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

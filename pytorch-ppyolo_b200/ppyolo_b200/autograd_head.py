@@ -83,6 +83,45 @@ def conv_unit(u, x, impl='aten', coord=False):
     return y
 
 
+class _SppFn(torch.autograd.Function):
+    """SPP (reference model/custom_layers.py:275-290) on the library's kernels for the training head: forward = ppy_spp (three
+    cascaded 5x5 max-pools + concat in one launch), backward = ppy_spp_backward (arg-max routing in shared memory, torch's
+    first-maximum rule) -- ATen's NHWC max-pool kernels took 1.2 ms per step for these 19x19 maps."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import ops
+        from ._lib import lib, check, PPY_BF16, PPY_F32
+        n, c, h, w = x.shape
+        xh = x.permute(0, 2, 3, 1)
+        if not xh.is_contiguous():
+            xh = xh.contiguous()
+        code = PPY_BF16 if x.dtype == torch.bfloat16 else PPY_F32
+        y = torch.empty((n, h, w, 4 * c), dtype=x.dtype, device=x.device)
+        check(lib.ppy_spp(ops.ptr(xh), c, ops.ptr(y), 4 * c, n, h, w, c, code, ops.stream_ptr()), 'spp')
+        ctx.save_for_backward(xh)
+        ctx.code = code
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        from ._lib import lib, check
+        xh, = ctx.saved_tensors
+        n, h, w, c = xh.shape
+        dyh = dy.permute(0, 2, 3, 1)
+        if not dyh.is_contiguous() or dyh.dtype != xh.dtype:
+            dyh = dyh.to(xh.dtype).contiguous()
+        dx = torch.empty_like(xh)
+        check(lib.ppy_spp_backward(ops.ptr(xh), c, ops.ptr(dyh), 4 * c, ops.ptr(dx), c, n, h, w, c, ctx.code, ops.stream_ptr()), 'spp_backward')
+        return dx.permute(0, 3, 1, 2)
+
+
+def spp_kernels_ok(x):
+    return x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.shape[1] % 32 == 0 and \
+        x.shape[2] * x.shape[3] * 32 * (4 + x.element_size()) <= 200 * 1024
+
+
 _PENDING_BN = []
 
 
@@ -106,7 +145,10 @@ def _run_layers(layers, x, impl='aten'):
             x = conv_unit(ly, x, impl, pending_coord)
             pending_coord = False
         elif isinstance(ly, SPP):
-            x = torch.cat([x] + [F.max_pool2d(x, k, 1, k // 2) for k in (5, 9, 13)], dim=1)
+            if impl == 'kernels' and ly.seq == 'asc' and spp_kernels_ok(x):
+                x = _SppFn.apply(x)
+            else:
+                x = torch.cat([x] + [F.max_pool2d(x, k, 1, k // 2) for k in (5, 9, 13)], dim=1)
         elif isinstance(ly, DropBlock):
             x = x if ly.is_test else drop_block(x, ly.block_size, ly.keep_prob)
         else:
