@@ -32,6 +32,7 @@ class PPYOLO(torch.nn.Module):
         self.normalize = None         # dict(mean, std, is_scale) of the uint8 input path; None = the configs' ImageNet values
         self.use_engine = True
         self._engines = {}
+        self._mode_mods = {}
         self._mish = None             # cached: does any Conv2dUnit use Mish (module structure is static)
 
     def engine(self, batch, height, width, input_u8=False):
@@ -134,9 +135,12 @@ class PPYOLO(torch.nn.Module):
         from model.custom_layers import DropBlock
         # everything the captured kernels depend on besides the tensors: shapes, conv implementation, BatchNorm mode of every unit
         # (batch vs running statistics) and the DropBlock switches -- toggling one of them must not replay a stale graph
-        mods = list(head.modules()) + (list(self.backbone.modules()) if full else [])
-        modes = tuple(m.training for m in mods if isinstance(m, torch.nn.BatchNorm2d)) + \
-            tuple(bool(m.is_test) for m in mods if isinstance(m, DropBlock))
+        cached = self._mode_mods.get(bool(full))
+        if cached is None:                       # the module tree is static: walk it once
+            mods = list(head.modules()) + (list(self.backbone.modules()) if full else [])
+            cached = ([m for m in mods if isinstance(m, torch.nn.BatchNorm2d)], [m for m in mods if isinstance(m, DropBlock)])
+            self._mode_mods[bool(full)] = cached
+        modes = tuple(m.training for m in cached[0]) + tuple(bool(m.is_test) for m in cached[1])
         key = (bool(full), tuple(tuple(f.shape) for f in feats), tuple(gt_box.shape), tuple(tuple(t.shape) for t in targets), head.train_impl, modes)
         entry = self._graphed_heads.get(key)
         if entry is None:

@@ -174,13 +174,18 @@ class Trainer(object):
         from . import ops
         if not self._cuda:
             raise RuntimeError('ppyolo_b200: the training step needs CUDA parameters (no CPU fallback)')
+        import time
+        tc = [time.perf_counter()]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         self.bucket.flat.zero_()
         self.bucket.bind_grads()
+        tc.append(time.perf_counter())
         losses = self.model(images, None, False, gt_bbox, gt_class, gt_score, targets)
+        tc.append(time.perf_counter())
         total = sum(losses.values())
         total.backward()
+        tc.append(time.perf_counter())
         self.bucket.pack()                                         # no-op for the bound views
         ev[1].record()
         grad_scale = 1.0 / parallel.world()[1] if self._peer is not None else self.bucket.all_reduce()
@@ -213,10 +218,14 @@ class Trainer(object):
         if self.ema is not None:
             self.ema._update_step += 1
         with torch.no_grad():
-            for p in self.params:                 # the kernel wrote through raw pointers: move torch's version counters too
-                torch._C._increment_version(p)
+            # the kernel wrote through raw pointers: move torch's version counters too.  ONE call with the list -- the binding
+            # takes an iterable of tensors, and handing it a single tensor makes it iterate over (unbind) that tensor's rows:
+            # 16 ms of host time per step, the whole difference between a host-bound and a GPU-bound iteration
+            torch._C._increment_version(self.params)
         self.iter_id += 1
         self.model.invalidate_engines_for_weights()
+        tc.append(time.perf_counter())
+        self.host_ms = [(b - a) * 1e3 for a, b in zip(tc[:-1], tc[1:])]     # host time: zero+bind / forward / backward / exchange+tail
         self._events.append(ev)
         if len(self._events) > 64:
             self._events.pop(0)

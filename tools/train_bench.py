@@ -54,17 +54,20 @@ if world > 1:
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+t_cpu = time.perf_counter()
 for _ in range(a.steps):
     losses = trainer.step(x, gb, gc, gs, targets)
+t_cpu = (time.perf_counter() - t_cpu) / a.steps * 1e3          # host time to ENQUEUE a step (no sync inside)
 e1.record()
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
+sys.stderr.write('rank %d host ms per phase (zero+bind, forward, backward, exchange+tail): %s\n' % (rank, [round(v, 2) for v in trainer.host_ms]))
 sys.stderr.write('rank %d timing %s\n' % (rank, json.dumps({k: v for k, v in trainer.timing_summary(8).items() if 'note' not in k})))
 if rank == 0:
     print(json.dumps({'metric': 'train_images_per_sec', 'value': world * a.batch / (ms * 1e-3), 'unit': 'images/s', 'n_gpus': world,
-                      'ms_per_step': ms, 'steps': a.steps, 'warmup': a.warmup, 'scaling': 'weak',
+                      'ms_per_step': ms, 'cpu_enqueue_ms_per_step': t_cpu, 'steps': a.steps, 'warmup': a.warmup, 'scaling': 'weak',
                       'config': {'workload': 'ppyolo_2x %dx%d bs=%d/GPU train step (freeze_at=%d)' % (a.size, a.size, a.batch, bb_kw['freeze_at']),
                                  'backbone_precision': a.precision, 'trainable_params': int(sum(p.numel() for p in trainer.params)),
                                  'allreduce_bytes': int(trainer.bucket.flat.numel() * 4), 'head_convs': model.train_head_impl or ('kernels (tcgen05 fwd/dgrad/wgrad)' if a.precision == 'bf16' else 'aten (TF32)')},
