@@ -7,6 +7,7 @@
 //   bn_finalize   mean / biased var -> folded scale, shift; running stats <- (1-m)*running + m*(mean, unbiased var)
 //   scale_shift   y = act(x*scale[c] + shift[c] (+ residual)), 16-byte channel vectors
 //   sgd_momentum  g' = g*grad_scale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ppy {
@@ -261,7 +262,9 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
   const int rl = 256 / lc;
   const int gx = (int)ceil_div(cv, lc);
   long long gy = ceil_div(rows, (long long)rl * 8);    // >= 8 rows per row-lane
-  const long long cap = ceil_div(148ll * 8, gx);
+  // two CTAs per SM at most: every CTA ends with 2 fp64 atomics per channel on the same addresses, and with 8 CTAs per SM those
+  // serialised atomics cost more than the loads (55 backbone layers of a bs-8 step: 1.58 -> 1.14 ms; 1 per SM: the same)
+  const long long cap = ceil_div(148ll * 2, gx);
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
   dim3 grid((unsigned)gx, (unsigned)gy);
