@@ -248,7 +248,7 @@ int ppy_sgd_ema_multi(float* const* params, const float* grad_flat, float* momen
  * into this process, grad_multicast = the NVLS multicast address of all of them (NULL when the box has none: the kernel then sums /
  * stores through grad_peers).  signal_pads = DEVICE array [world] of zero-initialised uint32 pads in peer memory (words
  * [pad_slot, pad_slot + world) are used); seq must grow by one per call on every rank (barrier sequence); done = TWO zeroed device
- * uint32 (CTA counter; error word, set to 1 when a barrier wait gave up after 10 s because a peer never arrived).  Every rank must make the same call (same seq) on its own device: the kernels rendezvous on the pads -- rank r reduces
+ * uint32 (CTA counter; error word, set to 1 when a barrier wait gave up after 3 s because a peer never arrived).  Every rank must make the same call (same seq) on its own device: the kernels rendezvous on the pads -- rank r reduces
  * slice r with multimem.ld_reduce (the switch adds) and multimem.st (the switch replicates), then all ranks run the optimizer on
  * the reduced bucket.  total_padded: bucket length in floats, multiple of 4 (tail zero); remaining arguments as ppy_sgd_ema_multi.
  * Cooperative launch (one CTA per SM); PPY_ERR_UNSUPPORTED if the device cannot. */

@@ -63,9 +63,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 // thread 0 of every CTA waits until every rank has published `value` in this rank's pad.  A peer that never arrives (its process
-// died, it skipped the call) must not hang the GPU: after kWaitTimeoutNs the wait gives up and raises the error word behind the
+// died, it skipped the call) must not hang the GPU: after kWaitTimeoutNs (3 s) the wait gives up and raises the error word behind the
 // `done` counter (done[1]), which the host checks (Trainer.timing_summary / state_dict); the step's results are then invalid.
-constexpr unsigned long long kWaitTimeoutNs = 10ull * 1000 * 1000 * 1000;
+constexpr unsigned long long kWaitTimeoutNs = 3ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void wait_all(const PeerStep& a, unsigned int value) {
   if (threadIdx.x == 0) {
     const unsigned int* mine = a.pads[a.rank] + a.pad_slot;

@@ -223,6 +223,11 @@ class Trainer(object):
             # 16 ms of host time per step, the whole difference between a host-bound and a GPU-bound iteration
             torch._C._increment_version(self.params)
         self.iter_id += 1
+        if self._peer is not None and not self._peer.get('checked'):
+            # first step through the peer-memory kernel: make sure every rank arrived at its barriers before trusting the path
+            torch.cuda.synchronize()
+            self._peer['checked'] = True
+            self.check_exchange()
         self.model.invalidate_engines_for_weights()
         tc.append(time.perf_counter())
         self.host_ms = [(b - a) * 1e3 for a, b in zip(tc[:-1], tc[1:])]     # host time: zero+bind / forward / backward / exchange+tail
