@@ -167,7 +167,7 @@ def cpu_reference_rate(steps, warmup, batch=CPU_SAMPLE_BATCH, arch=ARCH, size=SI
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 6)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 50)), max(1, min(args.warmup, 3))      # ~0.8 s per 4-image step: K = 20, W = 5 is ~20 s
     torch.set_num_threads(host_threads())          # torchrun pins OMP_NUM_THREADS=1; the reference arm may use every host core
     rate, ms, cores = cpu_reference_rate(steps, warmup)
     sample = ('%d forward(s) of %d images 608x608 (a slice of the 32-image batch), backbone+head+decode+MatrixNMS, torch CPU '
