@@ -2,7 +2,8 @@
 import json, sys
 d = json.load(open(sys.argv[1] if len(sys.argv) > 1 else 'gpurun_out/per_op_ms.json'))
 peaks = json.load(open('MEASURED_PEAKS.json'))
-pf, pb = peaks['bf16_tflops_sustained'] * 1e12, peaks['hbm_gbs'] * 1e9
+mma_per_mac = 3.0 if 'f16x2' in (sys.argv[1] if len(sys.argv) > 1 else '') else 1.0      # the pair path issues three MMAs per algorithmic MAC
+pf, pb = peaks['bf16_tflops_sustained'] * 1e12 / mma_per_mac, peaks['hbm_gbs'] * 1e9
 rows, lost_total = [], 0.0
 for name, ms in d['ops']:
     info = d.get('info', {}).get(name)
