@@ -42,10 +42,20 @@ def drop_block(x, block_size, keep_prob):
 ACT_FP32 = False
 
 
+_COORD_IMAGES = {}
+
+
 def _coord_image(h, w, device):
-    xs = torch.arange(w, dtype=torch.float32, device=device) / (w - 1) * 2.0 - 1
-    ys = torch.arange(h, dtype=torch.float32, device=device) / (h - 1) * 2.0 - 1
-    return torch.stack([xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w)]).unsqueeze(0)       # [1, 2, h, w]
+    """[1, 2, h, w] CoordConv channels (x then y in [-1, 1]); constant per map size, so built once (a dozen tiny arange / mul / add
+    launches per use otherwise -- ~100 graph nodes of the training step)."""
+    key = (h, w, str(device))
+    img = _COORD_IMAGES.get(key)
+    if img is None:
+        xs = torch.arange(w, dtype=torch.float32, device=device) / (w - 1) * 2.0 - 1
+        ys = torch.arange(h, dtype=torch.float32, device=device) / (h - 1) * 2.0 - 1
+        img = torch.stack([xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w)]).unsqueeze(0).contiguous()
+        _COORD_IMAGES[key] = img
+    return img
 
 
 def conv_unit(u, x, impl='aten', coord=False):
