@@ -13,10 +13,10 @@ for r in data:
     per.setdefault(int(r[ix['ID']]), {'name': r[ix['Kernel Name']]})[r[ix['Metric Name']]] = float(r[ix['Metric Value']].replace(',', ''))
 names = open(names_path).read().split('\n')
 # dense post-processing: every decode step is two launches (anchor math, then the streaming score kernel with the fused
-# score histogram), matrix_nms is collect + matrix (its memset is not a kernel)
+# score histogram), matrix_nms is cutoff + collect + matrix (its memset is not a kernel)
 plan = []
 for n in names:
-    if n == 'matrix_nms': plan += [n + ':collect', n + ':matrix']
+    if n == 'matrix_nms': plan += [n + ':cutoff', n + ':collect', n + ':matrix']
     elif n.startswith('decode'): plan += [n + ':anchors', n + ':scores']
     else: plan.append(n)
 tot = sum(m['gpu__time_duration.sum'] for m in per.values())
