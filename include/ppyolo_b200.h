@@ -108,7 +108,8 @@ typedef struct ppy_conv_params {
    * a 1x1 "conv" whose rows are the conv's output channels (x = dY transposed, [cout][pixels]), whose packed "weight" is
    * the transposed zero-bordered input ([cin][pixels]) and whose K runs over the pixels; wgrad_taps=9 repeats the GEMM per
    * tap with the B operand read at flat pixel offset (ky-1)*wgrad_pitch + (kx-1) and the result written to columns
-   * [tap*wgrad_tap_stride, ..).  (Kernel instantiation only: no host wrapper uses it yet; the head's backward is ATen's.) */
+   * [tap*wgrad_tap_stride, ..).  (Kernel instantiation only, NOT validated: a round-2c attempt to drive it from bordered transposes faulted on the device; the
+   * training step uses wgrad_taps = 0 with the K-major im2col operand of ppy_im2col_kmajor.) */
   int accumulate;
   int split_k;
   int wgrad_taps;
