@@ -73,8 +73,10 @@ def conv_unit(u, x, impl='aten', coord=False):
         from .conv_autograd import conv2d_kernels
         w = u.conv.weight
         c_main = w.shape[1] - (2 if coord else 0)
-        y = conv2d_kernels(x, w, u.conv.bias, padding=u.padding, c_main=c_main, out_f32=ACT_FP32 or u.bn is None, stride=u.stride)
-        if coord:
+        fold = coord and u.stride == 1 and c_main % 8 == 0           # CoordConv inside the conv function (bias map + extra wgrad columns)
+        y = conv2d_kernels(x, w, u.conv.bias, padding=u.padding, c_main=c_main, out_f32=ACT_FP32 or u.bn is None, stride=u.stride,
+                           coord=fold)
+        if coord and not fold:
             y = y + F.conv2d(_coord_image(x.shape[2], x.shape[3], x.device), w[:, c_main:], None, u.stride, u.padding).to(y.dtype)
     else:
         y = F.conv2d(x, u.conv.weight, u.conv.bias, stride=u.stride, padding=u.padding)

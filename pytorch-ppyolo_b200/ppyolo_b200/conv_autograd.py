@@ -88,16 +88,58 @@ def _wgrad_gemm(a_rows_kmajor, rows, b_kmajor, cols, m_pad):
     return out[0, 0, :, :cols]
 
 
-def _wgrad(xh, dyh, weight, c_main, stride, pad):
-    """Weight gradient dW = dY^T [O x M] . Xcol [M x C k k] (M = the output pixels), result in the weight's OIHW order."""
+_COORD = {}
+
+
+def coord_cols(h, w, k, pad, device):
+    """im2col of CoordConv's two channels (model/custom_layers.py:256-272: x in [-1, 1] along W, then y along H; zero padding like
+    any input channel) for a k x k stride-1 conv: fp32 [h*w, 2*k*k], columns in the weight's (channel, ky, kx) order.  Constant per
+    map size: built once."""
+    key = ('cols', h, w, k, pad, str(device))
+    t = _COORD.get(key)
+    if t is None:
+        xs = torch.arange(w, dtype=torch.float32, device=device) / (w - 1) * 2.0 - 1
+        ys = torch.arange(h, dtype=torch.float32, device=device) / (h - 1) * 2.0 - 1
+        img = torch.stack([xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w)]).unsqueeze(0)
+        t = torch.nn.functional.unfold(img, k, padding=pad)[0].t().contiguous()                  # [h*w, 2*k*k]
+        _COORD[key] = t
+    return t
+
+
+def _coord_rows_kmajor(n, h, w, k, pad, m_pad, device):
+    """The same columns as the K-major bf16 operand of the weight-gradient GEMM: [8-padded 2*k*k rows][m_pad], tiled over the batch."""
+    key = ('rows', n, h, w, k, pad, m_pad, str(device))
+    t = _COORD.get(key)
+    if t is None:
+        cols = coord_cols(h, w, k, pad, device)                                                # [h*w, 2kk]
+        rows = ops.round_up(cols.shape[1], 8)
+        t = torch.zeros((rows, m_pad), dtype=torch.bfloat16, device=device)
+        t[:cols.shape[1], :n * h * w] = cols.t().repeat(1, n).to(torch.bfloat16)
+        _COORD[key] = t
+    return t
+
+
+def _wgrad(xh, dyh, weight, c_main, stride, pad, coord=False):
+    """Weight gradient dW = dY^T [O x M] . Xcol [M x C k k] (M = the output pixels), result in the weight's OIHW order.  ``coord``:
+    the weight's channels [c_main, c_main + 2) are CoordConv's -- their constant im2col columns join the GEMM's B operand, so the
+    same launch yields their gradient."""
     cout, _, k, _ = weight.shape
     n, ho, wo, _ = dyh.shape
     m_pad = ops.round_up(n * ho * wo, 64)
     c_eff = c_main if c_main % 8 == 0 else xh.shape[-1]        # the stem's 3 channels travel zero-padded to 8
-    b_op = _kmajor(xh, c_eff, k, stride, pad, m_pad)
+    kk = c_eff * k * k
     a_rows = ops.round_up(cout, 8)
     a_full = _kmajor(dyh, a_rows, 1, 1, 0, m_pad)
-    out = _wgrad_gemm(a_full, cout, b_op, c_eff * k * k, m_pad)
+    if coord:
+        crow = _coord_rows_kmajor(n, ho, wo, k, pad, m_pad, xh.device)
+        b_op = torch.empty((kk + crow.shape[0], m_pad), dtype=torch.bfloat16, device=xh.device)
+        check(lib.ppy_im2col_kmajor_strided(ops.ptr(xh), xh.shape[-1], n, xh.shape[1], xh.shape[2], c_eff, k, stride, pad, ops.ptr(b_op), m_pad,
+                                            ops.stream_ptr()), 'im2col_kmajor')
+        b_op[kk:].copy_(crow)
+        out = _wgrad_gemm(a_full, cout, b_op, kk + 2 * k * k, m_pad)
+        return out.reshape(cout, c_main + 2, k, k) if c_eff == c_main else None
+    b_op = _kmajor(xh, c_eff, k, stride, pad, m_pad)
+    out = _wgrad_gemm(a_full, cout, b_op, kk, m_pad)
     if c_eff == weight.shape[1]:                               # the GEMM result IS the gradient (a view when its rows are unpadded)
         return out.reshape(cout, c_eff, k, k)
     dw = torch.zeros_like(weight, dtype=torch.float32)
@@ -107,23 +149,29 @@ def _wgrad(xh, dyh, weight, c_main, stride, pad):
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, c_main, pad, out_f32, stride):
+    def forward(ctx, x, weight, bias, c_main, pad, out_f32, stride, coord):
         if not x.is_cuda:
             raise RuntimeError('ppyolo_b200: conv2d_kernels needs CUDA tensors -- there is no CPU fallback')
         cout, _, k, _ = weight.shape
         packed = ops.pack_weight(weight, PPY_BF16, c_begin=0, c_count=c_main, cache=False)
         xh = _nhwc_bf16(x, packed[1])
         shift = bias.detach().float().contiguous() if bias is not None else _const('zero', cout, x.device)
+        bias_map = None
+        if coord:
+            # CoordConv's two channels (the weight's last two) contribute a batch-invariant per-pixel term: one small fp32 matmul of
+            # their constant im2col columns, added to the accumulator by the conv's epilogue (`bias_map`) -- no concat, no extra pass
+            wc = weight.detach()[:, c_main:c_main + 2].reshape(cout, 2 * k * k).float()
+            bias_map = torch.matmul(coord_cols(x.shape[2], x.shape[3], k, pad, x.device), wc.t()).contiguous()       # [h*w, cout]
         y = ops.conv_nhwc(xh, packed, c_main, cout, k, stride, pad, _const('one', cout, x.device), shift, 0, PPY_BF16,
-                          out_code=PPY_F32 if out_f32 else PPY_BF16)
+                          out_code=PPY_F32 if out_f32 else PPY_BF16, bias_map=bias_map)
         ctx.save_for_backward(xh, weight)
-        ctx.meta = (c_main, pad, bias is not None, tuple(x.shape), x.dtype, stride)
+        ctx.meta = (c_main, pad, bias is not None, tuple(x.shape), x.dtype, stride, coord)
         return y[..., :cout].permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         xh, weight = ctx.saved_tensors
-        c_main, pad, has_bias, x_shape, x_dtype, stride = ctx.meta
+        c_main, pad, has_bias, x_shape, x_dtype, stride, coord = ctx.meta
         cout = weight.shape[0]
         dyh = _nhwc_bf16(dy, ops.round_up(cout, 8))
         dx = dw = db = None
@@ -133,19 +181,23 @@ class _ConvFn(torch.autograd.Function):
             if dx.dtype != x_dtype:
                 dx = dx.to(x_dtype)
         if ctx.needs_input_grad[1]:
-            dw = _wgrad(xh, dyh, weight, c_main, stride, pad)
+            dw = _wgrad(xh, dyh, weight, c_main, stride, pad, coord)
         if has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(dim=(0, 2, 3))
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv2d_kernels(x, weight, bias=None, padding=0, c_main=None, out_f32=False, stride=1):
-    """conv2d over the first ``c_main`` input channels of ``weight`` (the rest -- CoordConv's two -- is the caller's).
+def conv2d_kernels(x, weight, bias=None, padding=0, c_main=None, out_f32=False, stride=1, coord=False):
+    """conv2d over the first ``c_main`` input channels of ``weight``.  ``coord``: the weight has exactly two more input channels,
+    CoordConv's (x then y coordinate), which ``x`` does not carry -- their contribution and their weight gradient are computed
+    inside (stride 1, c_main % 8 == 0); without ``coord`` extra weight channels are the caller's business and get a zero gradient.
     ``x``: logical [N, c_main, H, W]; returns logical [N, cout, Ho, Wo] (channels_last bf16, or fp32 with ``out_f32``)."""
     c_main = weight.shape[1] if c_main is None else c_main
     if x.shape[1] != c_main:
         raise ValueError('conv2d_kernels: input has %d channels, expected %d' % (x.shape[1], c_main))
-    return _ConvFn.apply(x, weight, bias, c_main, padding, out_f32, stride)
+    if coord and (stride != 1 or c_main % 8 != 0 or weight.shape[1] != c_main + 2):
+        raise ValueError('conv2d_kernels: coord needs stride 1, c_main % 8 == 0 and exactly two extra weight channels')
+    return _ConvFn.apply(x, weight, bias, c_main, padding, out_f32, stride, coord)
 
 
 class _DcnFn(torch.autograd.Function):
