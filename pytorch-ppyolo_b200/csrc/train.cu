@@ -8,6 +8,7 @@
 //   scale_shift   y = act(x*scale[c] + shift[c] (+ residual)), 16-byte channel vectors
 //   sgd_momentum  g' = g*grad_scale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace ppy {
@@ -99,6 +100,114 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   if (!last) return;
   __threadfence();
   for (int ch = threadIdx.x; ch < c; ch += 256) bn_finalize_channel(sums, rows, c, ch, fin);
+}
+
+// Train-mode BatchNorm of one layer in ONE cooperative launch: batch statistics, finalize, running-stat update and the
+// normalise + activation (+ residual) pass.  The backbone of a training step has 55 of these layers; as four graph nodes each
+// (memset, statistics, finalize-in-last-block, apply) their launch ramps and tails cost more than their bytes (the launches move
+// 1..280 MB).  Phase 1 = bn_stats_kernel's reduction (fp32 partials, fp64 atomics per CTA); grid-wide barrier; phase 2: every
+// CTA derives scale / shift for all channels into shared memory and streams its share of the tensor (second read: mostly L2 hits,
+// the conv has just written it).  The workspace is ZERO on entry and left zero on exit (the last CTA to have read the sums clears
+// them): no memset node.  c <= kBnFusedMaxC.
+constexpr int kBnFusedMaxC = 2048;
+template <typename T, int LC>
+__global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, long long rows,
+                                                             int c, double* __restrict__ sums, BnFinal fin, const T* __restrict__ res,
+                                                             int res_ld, int act, int gx) {
+  constexpr int V = VecT<T>::N;
+  constexpr int RL = 256 / LC;
+  __shared__ float red[2][256][V];
+  __shared__ float s_scale[kBnFusedMaxC], s_shift[kBnFusedMaxC];
+  const int bx = blockIdx.x % gx, by = blockIdx.x / gx, gy = gridDim.x / gx;      // 1-D grid (cooperative), viewed as gx x gy
+  const int vl = threadIdx.x % LC, rl = threadIdx.x / LC;
+  const int vec = bx * LC + vl;
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  if (vec * V < c && by < gy) {
+    const long long step = (long long)gy * RL;
+    const T* col = x + vec * V;
+    for (long long r0 = (long long)by * RL + rl; r0 < rows; r0 += 4 * step) {
+      float v[4][V];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * step;
+        if (r < rows) ldv<T>(col + r * x_ld, v[u]);
+        else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[u][k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < V; ++k) { s[k] += v[u][k]; q[k] += v[u][k] * v[u][k]; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red[0][threadIdx.x][k] = s[k]; red[1][threadIdx.x][k] = q[k]; }
+  __syncthreads();
+  if (rl == 0 && vec * V < c && by < gy) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      double ds = 0.0, dq = 0.0;
+      for (int j = 0; j < RL; ++j) { ds += red[0][j * LC + vl][k]; dq += red[1][j * LC + vl][k]; }
+      atomicAdd(&sums[vec * V + k], ds);
+      atomicAdd(&sums[c + vec * V + k], dq);
+    }
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  // ---- phase 2: scale / shift of every channel (block 0 also publishes them and moves the running statistics)
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    const double mean = __ldcg(sums + ch) / (double)rows;
+    double var = __ldcg(sums + c + ch) / (double)rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = rsqrtf((float)var + fin.eps) * (fin.gamma ? fin.gamma[ch] : 1.f);
+    const float sh = (fin.beta ? fin.beta[ch] : 0.f) - (float)mean * inv;
+    s_scale[ch] = inv; s_shift[ch] = sh;
+    if (blockIdx.x == 0) {
+      fin.scale[ch] = inv; fin.shift[ch] = sh;
+      if (fin.running_mean) fin.running_mean[ch] = (1.f - fin.momentum) * fin.running_mean[ch] + fin.momentum * (float)mean;
+      if (fin.running_var) {
+        const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+        fin.running_var[ch] = (1.f - fin.momentum) * fin.running_var[ch] + fin.momentum * (float)unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  // the last CTA to have read the sums clears them (and the counter) for the next launch
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(sums + 2 * c);
+    last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    for (int i = threadIdx.x; i < 2 * c + 1; i += 256) sums[i] = 0.0;
+  }
+  const int cv = c / V;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int v = (int)(i % cv);
+    const long long r = i / cv;
+    float a[V];
+    ldv<T>(x + r * x_ld + v * V, a);
+    if (res) {
+      float b[V];
+      ldv<T>(res + r * res_ld + v * V, b);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] = a[k] * s_scale[v * V + k] + s_shift[v * V + k] + b[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] = a[k] * s_scale[v * V + k] + s_shift[v * V + k];
+    }
+    uint4 raw;
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int k = 0; k < V; ++k) e[k] = from_f<T>(apply_act(a[k], act));
+    *reinterpret_cast<uint4*>(y + r * y_ld + v * V) = raw;
+  }
 }
 
 template <typename T>
@@ -229,6 +338,32 @@ __global__ void __launch_bounds__(256) sgd_ema_multi_kernel(float* const* __rest
   }
 }
 
+template <typename T, int LC>
+static int launch_bn_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, double* ws, const BnFinal& fin, const void* res,
+                           int res_ld, int act, int gx, cudaStream_t st) {
+  int dev = 0, sms = 0, per_sm = 0;
+  int rc = check_cuda(cudaGetDevice(&dev));
+  if (rc) return rc;
+  if ((rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)))) return rc;
+  if ((rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_train_fused_kernel<T, LC>, 256, 0)))) return rc;
+  if (per_sm < 1) return PPY_ERR_UNSUPPORTED;
+  if (per_sm > 4) per_sm = 4;
+  const int rl = 256 / LC;
+  long long gy = ceil_div(rows, (long long)rl * 8);
+  const long long cap = (long long)sms * per_sm / gx;          // every CTA resident (grid barrier)
+  if (cap < 1) return PPY_ERR_UNSUPPORTED;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  const T* xp = (const T*)x; T* yp = (T*)y; const T* rp = (const T*)res;
+  BnFinal f = fin;
+  void* args[] = {(void*)&xp, (void*)&x_ld, (void*)&yp, (void*)&y_ld, (void*)&rows, (void*)&c, (void*)&ws, (void*)&f, (void*)&rp,
+                  (void*)&res_ld, (void*)&act, (void*)&gx};
+  rc = check_cuda(cudaLaunchCooperativeKernel((const void*)bn_train_fused_kernel<T, LC>, dim3((unsigned)(gx * gy)), dim3(256), args, 0, st));
+  if (rc) return rc;
+  count_launch();
+  return PPY_OK;
+}
+
 }  // namespace
 }  // namespace ppy
 
@@ -277,6 +412,31 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
 #undef PPY_BN_LC
 #undef PPY_BN
   return check_launch();
+}
+
+int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
+                       float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                       const void* residual, int res_ld, int act, double* workspace /* 2*c + 1 doubles, ZERO on entry, zero on exit */,
+                       ppy_stream_t s) {
+  PPY_REQUIRE(x && y && scale && shift && workspace && rows > 0 && c > 0 && c <= kBnFusedMaxC && x_ld >= c && y_ld >= c);
+  PPY_REQUIRE(dtype == PPY_BF16 || dtype == PPY_F32);
+  const int v = 16 / dtype_size(dtype);
+  PPY_REQUIRE(c % v == 0 && x_ld % v == 0 && y_ld % v == 0 && (!residual || res_ld % v == 0));
+  PPY_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual)) & 15) == 0);
+  PPY_REQUIRE(act >= PPY_ACT_NONE && act <= PPY_ACT_MISH);
+  const int cv = c / v;
+  int lc = 32;
+  while (lc > 1 && lc / 2 >= cv) lc >>= 1;
+  const int gx = (int)ceil_div(cv, lc);
+  const BnFinal fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift};
+  cudaStream_t st = as_stream(s);
+#define PPY_BNF(T, LC) return launch_bn_fused<T, LC>(x, x_ld, y, y_ld, rows, c, workspace, fin, residual, res_ld, act, gx, st)
+#define PPY_BNF_LC(T) do { switch (lc) { case 32: PPY_BNF(T, 32); case 16: PPY_BNF(T, 16); case 8: PPY_BNF(T, 8); case 4: PPY_BNF(T, 4); \
+                                        case 2: PPY_BNF(T, 2); default: PPY_BNF(T, 1); } } while (0)
+  if (dtype == PPY_BF16) PPY_BNF_LC(__nv_bfloat16);
+  PPY_BNF_LC(float);
+#undef PPY_BNF_LC
+#undef PPY_BNF
 }
 
 int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* scale,

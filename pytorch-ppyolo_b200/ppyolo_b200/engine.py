@@ -17,6 +17,7 @@ Reference path being replaced: model/ppyolo.py:19-22 -> model/resnet_vd.py:132-1
 model/head.py:424-469.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -454,7 +455,7 @@ class InferenceEngine(object):
             dst = TensorRef(self._new(raw.n, raw.h, raw.w, ops.round_up(cout, 8)), c=cout)
         scale = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
         shift = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
-        ws = self._keep(torch.empty(2 * cout + 1, dtype=torch.float64, device=self.dev))
+        ws = self._keep(torch.zeros(2 * cout + 1, dtype=torch.float64, device=self.dev))
         rows = raw.n * raw.h * raw.w
         momentum = 0.1 if bn.momentum is None else float(bn.momentum)
         a1 = (ctypes.c_void_p(raw.ptr), raw.ld, rows, cout, raw.code, ops.ptr(bn.weight.data), ops.ptr(bn.bias.data), float(bn.eps),
@@ -462,8 +463,16 @@ class InferenceEngine(object):
         a2 = (ctypes.c_void_p(raw.ptr), raw.ld, ctypes.c_void_p(dst.ptr), dst.ld, rows, cout, raw.code, ops.ptr(scale), ops.ptr(shift),
               ctypes.c_void_p(residual.ptr) if residual is not None else ctypes.c_void_p(0),
               residual.ld if residual is not None else 0, act)
-        self._add(name + '.bn_stats', lambda: check(lib.ppy_bn_batch_stats(*a1, ops.stream_ptr()), name + '.bn_stats'))
-        self._add(name + '.bn_apply', lambda: check(lib.ppy_scale_shift_act(*a2, ops.stream_ptr()), name + '.bn_apply'))
+        if cout <= 2048 and not os.environ.get('PPY_NO_BN_FUSED'):
+            # statistics + normalise + activation (+ residual) as ONE cooperative launch (workspace self-cleaning: no memset node)
+            a3 = (ctypes.c_void_p(raw.ptr), raw.ld, ctypes.c_void_p(dst.ptr), dst.ld, rows, cout, raw.code, ops.ptr(bn.weight.data),
+                  ops.ptr(bn.bias.data), float(bn.eps), momentum, ops.ptr(bn.running_mean), ops.ptr(bn.running_var), ops.ptr(scale),
+                  ops.ptr(shift), ctypes.c_void_p(residual.ptr) if residual is not None else ctypes.c_void_p(0),
+                  residual.ld if residual is not None else 0, act, ops.ptr(ws))
+            self._add(name + '.bn_fused', lambda: check(lib.ppy_bn_train_fused(*a3, ops.stream_ptr()), name + '.bn_fused'))
+        else:
+            self._add(name + '.bn_stats', lambda: check(lib.ppy_bn_batch_stats(*a1, ops.stream_ptr()), name + '.bn_stats'))
+            self._add(name + '.bn_apply', lambda: check(lib.ppy_scale_shift_act(*a2, ops.stream_ptr()), name + '.bn_apply'))
         self.bn_modules.append(bn)
         return dst
 
