@@ -218,10 +218,11 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
 /* ppy_bn_batch_stats + ppy_scale_shift_act of one layer in ONE cooperative launch (statistics, grid barrier, normalise +
  * activation + residual; the second read of x mostly hits L2): the train-mode BatchNorm of a frozen-backbone layer as one graph node
  * instead of four.  scale / shift receive the folded parameters as before.  workspace: 2*c + 1 doubles that are ZERO on entry; the
- * call leaves them zero (no memset).  c <= 2048; PPY_ERR_UNSUPPORTED when the device cannot launch cooperatively. */
+ * call leaves them zero (no memset).  save_mean / save_invstd (optional, [c]): the batch mean and 1/sqrt(var + eps) a BatchNorm
+ * backward needs.  c <= 2048; PPY_ERR_UNSUPPORTED when the device cannot launch cooperatively. */
 int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                       const void* residual, int res_ld, int act, double* workspace, ppy_stream_t s);
+                       const void* residual, int res_ld, int act, double* workspace, float* save_mean, float* save_invstd, ppy_stream_t s);
 /* y = act(x*scale[c] + shift[c] (+ residual)) on NHWC rows. */
 int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* scale,
                         const float* shift, const void* residual, int res_ld, int act, ppy_stream_t s);

@@ -30,6 +30,7 @@ __device__ __forceinline__ void ldv(const T* p, float (&v)[VecT<T>::N]) {
 // finish (device counter behind the sums) turns the totals into folded scale / shift and updates the running statistics.
 struct BnFinal {
   const float* gamma; const float* beta; float eps, momentum; float* running_mean; float* running_var; float* scale; float* shift;
+  float* save_mean; float* save_invstd;      // optional: batch mean / 1/sqrt(var + eps) for a BatchNorm backward
 };
 
 __device__ __forceinline__ void bn_finalize_channel(const double* __restrict__ sums, long long rows, int c, int ch, const BnFinal& f) {
@@ -168,6 +169,8 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
     s_scale[ch] = inv; s_shift[ch] = sh;
     if (blockIdx.x == 0) {
       fin.scale[ch] = inv; fin.shift[ch] = sh;
+      if (fin.save_mean) fin.save_mean[ch] = (float)mean;
+      if (fin.save_invstd) fin.save_invstd[ch] = rsqrtf((float)var + fin.eps);
       if (fin.running_mean) fin.running_mean[ch] = (1.f - fin.momentum) * fin.running_mean[ch] + fin.momentum * (float)mean;
       if (fin.running_var) {
         const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
@@ -403,7 +406,7 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  const BnFinal fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift};
+  const BnFinal fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, nullptr, nullptr};
 #define PPY_BN(T, LC) bn_stats_kernel<T, LC><<<grid, 256, 0, st>>>((const T*)x, x_ld, rows, c, workspace, fin)
 #define PPY_BN_LC(T) do { switch (lc) { case 32: PPY_BN(T, 32); break; case 16: PPY_BN(T, 16); break; case 8: PPY_BN(T, 8); break; \
                                        case 4: PPY_BN(T, 4); break; case 2: PPY_BN(T, 2); break; default: PPY_BN(T, 1); } } while (0)
@@ -417,7 +420,7 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
 int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                        const void* residual, int res_ld, int act, double* workspace /* 2*c + 1 doubles, ZERO on entry, zero on exit */,
-                       ppy_stream_t s) {
+                       float* save_mean, float* save_invstd, ppy_stream_t s) {
   PPY_REQUIRE(x && y && scale && shift && workspace && rows > 0 && c > 0 && c <= kBnFusedMaxC && x_ld >= c && y_ld >= c);
   PPY_REQUIRE(dtype == PPY_BF16 || dtype == PPY_F32);
   const int v = 16 / dtype_size(dtype);
@@ -428,7 +431,7 @@ int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long row
   int lc = 32;
   while (lc > 1 && lc / 2 >= cv) lc >>= 1;
   const int gx = (int)ceil_div(cv, lc);
-  const BnFinal fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift};
+  const BnFinal fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean, save_invstd};
   cudaStream_t st = as_stream(s);
 #define PPY_BNF(T, LC) return launch_bn_fused<T, LC>(x, x_ld, y, y_ld, rows, c, workspace, fin, residual, res_ld, act, gx, st)
 #define PPY_BNF_LC(T) do { switch (lc) { case 32: PPY_BNF(T, 32); case 16: PPY_BNF(T, 16); case 8: PPY_BNF(T, 8); case 4: PPY_BNF(T, 4); \

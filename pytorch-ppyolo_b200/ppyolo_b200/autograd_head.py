@@ -15,6 +15,8 @@ The head is the only trainable part under the reference's default ``freeze_at=5`
 Semantics follow the reference:
 DetectionBlock.__call__ model/head.py:223-231, _get_outputs :381-398, CoordConv / SPP / DropBlock
 model/custom_layers.py:256-342, BatchNorm in whatever mode the module is in (train: batch statistics)."""
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -82,10 +84,14 @@ def conv_unit(u, x, impl='aten', coord=False):
         y = F.conv2d(x, u.conv.weight, u.conv.bias, stride=u.stride, padding=u.padding)
     if u.bn is not None:
         bn = u.bn
-        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training,
-                         0.1 if bn.momentum is None else bn.momentum, bn.eps)
+        momentum = 0.1 if bn.momentum is None else bn.momentum
         if bn.training:
             _PENDING_BN.append(bn)                  # counters advance in one multi-tensor launch (flush_bn_counters)
+        if (impl == 'kernels' and BN_KERNELS and bn.training and y.is_cuda and y.dtype in (torch.bfloat16, torch.float32)
+                and u.act_name in (None, 'relu', 'leaky') and y.shape[1] % 8 == 0 and y.shape[1] <= 2048):
+            return _BnActFn.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, momentum, bn.eps,
+                                  {None: 0, 'relu': 1, 'leaky': 2}[u.act_name])
+        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, momentum, bn.eps)
     if u.act_name == 'relu':
         y = F.relu(y)
     elif u.act_name == 'leaky':
@@ -127,6 +133,63 @@ class _SppFn(torch.autograd.Function):
         dx = torch.empty_like(xh)
         check(lib.ppy_spp_backward(ops.ptr(xh), c, ops.ptr(dyh), 4 * c, ops.ptr(dx), c, n, h, w, c, ctx.code, ops.stream_ptr()), 'spp_backward')
         return dx.permute(0, 3, 1, 2)
+
+
+class _BnActFn(torch.autograd.Function):
+    """Train-mode BatchNorm2d + activation of a head Conv2dUnit: forward = ONE cooperative launch (ppy_bn_train_fused: batch
+    statistics, running-stat update, normalise + relu / leaky) instead of ATen's statistics + transform + activation kernels;
+    backward = ATen's activation and batch-norm backward on the saved batch mean / inverse std."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, act_code):
+        from . import ops
+        from ._lib import lib, check, PPY_BF16, PPY_F32
+        n, c, h, w = x.shape
+        xh = x.permute(0, 2, 3, 1)
+        if not xh.is_contiguous():
+            xh = xh.contiguous()
+        code = PPY_BF16 if x.dtype == torch.bfloat16 else PPY_F32
+        dev = x.device
+        y = torch.empty_like(xh)
+        scale, shift = torch.empty(c, dtype=torch.float32, device=dev), torch.empty(c, dtype=torch.float32, device=dev)
+        mean, invstd = torch.empty(c, dtype=torch.float32, device=dev), torch.empty(c, dtype=torch.float32, device=dev)
+        ws = _bn_workspace(c, dev)
+        check(lib.ppy_bn_train_fused(ops.ptr(xh), c, ops.ptr(y), c, n * h * w, c, code, ops.ptr(weight.detach()), ops.ptr(bias.detach()),
+                                     float(eps), float(momentum), ops.ptr(running_mean), ops.ptr(running_var), ops.ptr(scale), ops.ptr(shift),
+                                     None, 0, act_code, ops.ptr(ws), ops.ptr(mean), ops.ptr(invstd), ops.stream_ptr()), 'bn_train_fused')
+        ctx.save_for_backward(xh, y, weight, mean, invstd)
+        ctx.meta = (act_code, float(eps))
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, y, weight, mean, invstd = ctx.saved_tensors
+        act_code, eps = ctx.meta
+        x = xh.permute(0, 3, 1, 2)
+        g = dy
+        if act_code == 1:
+            g = torch.where(y.permute(0, 3, 1, 2) > 0, dy, torch.zeros((), dtype=dy.dtype, device=dy.device))
+        elif act_code == 2:
+            g = torch.ops.aten.leaky_relu_backward(dy, y.permute(0, 3, 1, 2), 0.1, True)
+        dx, dw, db = torch.ops.aten.native_batch_norm_backward(g, x, weight, None, None, mean, invstd, True, eps, [True, True, True])
+        return dx, dw, db, None, None, None, None, None
+
+
+_BN_WS = {}
+
+
+def _bn_workspace(c, device):
+    """Self-cleaning statistics workspace of ppy_bn_train_fused (zero on entry, zero on exit): one per channel count and device
+    -- launches on one stream run one after the other."""
+    key = (c, str(device))
+    ws = _BN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(2 * c + 1, dtype=torch.float64, device=device)
+        _BN_WS[key] = ws
+    return ws
+
+
+BN_KERNELS = os.environ.get('PPY_HEAD_BN_KERNELS', '1') != '0'
 
 
 def spp_kernels_ok(x):

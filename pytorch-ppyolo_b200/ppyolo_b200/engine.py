@@ -468,7 +468,7 @@ class InferenceEngine(object):
             a3 = (ctypes.c_void_p(raw.ptr), raw.ld, ctypes.c_void_p(dst.ptr), dst.ld, rows, cout, raw.code, ops.ptr(bn.weight.data),
                   ops.ptr(bn.bias.data), float(bn.eps), momentum, ops.ptr(bn.running_mean), ops.ptr(bn.running_var), ops.ptr(scale),
                   ops.ptr(shift), ctypes.c_void_p(residual.ptr) if residual is not None else ctypes.c_void_p(0),
-                  residual.ld if residual is not None else 0, act, ops.ptr(ws))
+                  residual.ld if residual is not None else 0, act, ops.ptr(ws), ctypes.c_void_p(0), ctypes.c_void_p(0))
             self._add(name + '.bn_fused', lambda: check(lib.ppy_bn_train_fused(*a3, ops.stream_ptr()), name + '.bn_fused'))
         else:
             self._add(name + '.bn_stats', lambda: check(lib.ppy_bn_batch_stats(*a1, ops.stream_ptr()), name + '.bn_stats'))
