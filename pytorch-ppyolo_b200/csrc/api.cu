@@ -10,7 +10,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" {
 
-int ppy_abi_version(void) { return 9; }
+int ppy_abi_version(void) { return 10; }
 
 const char* ppy_status_string(int status) {
   switch (status) {

@@ -299,44 +299,61 @@ __global__ void __launch_bounds__(256) spp_separable_kernel(const T* __restrict_
 
 // SPP backward (training head): dx = dy[:, 0:c] + sum over the three pools of dy routed to each window's arg-max -- torch's
 // max_pool2d backward: the FIRST maximum in row-major window order takes the gradient.  One CTA per (image, 32 channels): the input
-// tile and an fp32 gradient tile live in shared memory, every (pixel, channel) item scans its 5x5 / 9x9 / 13x13 windows there and adds
-// its three gradients with shared-memory atomics (lane = channel: conflict-free), the tile is written once -- no global atomics.
+// tile and an fp32 gradient tile live in shared memory.  The arg-max search is separable: per pool, a row pass leaves every pixel's
+// first maximum of its horizontal window (value + column), a column pass scans those rows top to bottom with a strict '>' -- the
+// first row holding the window maximum, and inside it the first column: exactly the row-major first maximum, for 2(2r+1) reads per
+// item instead of (2r+1)^2 -- and adds the item's gradient with a shared-memory atomic (lane = channel: conflict-free); the tile is
+// written once, no global atomics.
 constexpr int SPPB_C = 32;    // channels per CTA
 template <typename T>
-__global__ void __launch_bounds__(256) spp_backward_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, int dy_ld,
+__global__ void __launch_bounds__(1024) spp_backward_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, int dy_ld,
                                                            T* __restrict__ dx, int dx_ld, int h, int w, int c) {
   extern __shared__ float sppb_smem[];
   const int hw = h * w;
+  const int items = hw * SPPB_C;
   float* gs = sppb_smem;                                         // [hw][SPPB_C] gradient tile
-  T* xs = reinterpret_cast<T*>(sppb_smem + hw * SPPB_C);         // [hw][SPPB_C] input tile
+  T* xs = reinterpret_cast<T*>(gs + items);                      // [hw][SPPB_C] input tile
+  T* rv = xs + items;                                            // [hw][SPPB_C] row-pass maximum (one of the inputs: exact in T)
+  unsigned char* ra = reinterpret_cast<unsigned char*>(rv + items);   // [hw][SPPB_C] row-pass arg-max column
   const int img = blockIdx.y, c0 = blockIdx.x * SPPB_C;
   const T* xi = x + (long long)img * hw * x_ld + c0;
   const T* dyi = dy + (long long)img * hw * dy_ld + c0;
-  const int items = hw * SPPB_C;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int pix = i / SPPB_C, ch = i % SPPB_C;
     xs[i] = xi[(long long)pix * x_ld + ch];
     gs[i] = to_f<T>(dyi[(long long)pix * dy_ld + ch]);            // identity branch of the concat
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int pix = i / SPPB_C, ch = i % SPPB_C;
-    const int py = pix / w, px = pix % w;
-#pragma unroll
-    for (int round = 1; round <= 3; ++round) {
-      const int r = 2 * round;                                   // window radius: 2, 4, 6 (kernel 5, 9, 13; stride 1, same padding)
-      const int y0 = max(py - r, 0), y1 = min(py + r, h - 1), x0 = max(px - r, 0), x1 = min(px + r, w - 1);
+  for (int round = 1; round <= 3; ++round) {
+    const int r = 2 * round;                                     // window radius: 2, 4, 6 (kernel 5, 9, 13; stride 1, same padding)
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {      // row pass
+      const int pix = i / SPPB_C, ch = i % SPPB_C;
+      const int px = pix % w, row0 = pix - px;
+      const int x0 = max(px - r, 0), x1 = min(px + r, w - 1);
       float best = -CUDART_INF_F;
-      int arg = y0 * w + x0;
-      for (int yy = y0; yy <= y1; ++yy)
-        for (int xx = x0; xx <= x1; ++xx) {
-          const float v = to_f<T>(xs[(yy * w + xx) * SPPB_C + ch]);
-          if (v > best) { best = v; arg = yy * w + xx; }
-        }
+      int arg = x0;
+      for (int xx = x0; xx <= x1; ++xx) {
+        const float v = to_f<T>(xs[(row0 + xx) * SPPB_C + ch]);
+        if (v > best) { best = v; arg = xx; }
+      }
+      rv[i] = xs[(row0 + arg) * SPPB_C + ch]; ra[i] = (unsigned char)arg;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {      // column pass + scatter
+      const int pix = i / SPPB_C, ch = i % SPPB_C;
+      const int py = pix / w, px = pix - py * w;
+      const int y0 = max(py - r, 0), y1 = min(py + r, h - 1);
+      float best = -CUDART_INF_F;
+      int arg = y0 * w + ra[(y0 * w + px) * SPPB_C + ch];
+      for (int yy = y0; yy <= y1; ++yy) {
+        const int j = (yy * w + px) * SPPB_C + ch;
+        const float v = to_f<T>(rv[j]);
+        if (v > best) { best = v; arg = yy * w + ra[j]; }
+      }
       atomicAdd(&gs[arg * SPPB_C + ch], to_f<T>(dyi[(long long)pix * dy_ld + round * c + ch]));
     }
+    __syncthreads();
   }
-  __syncthreads();
   T* dxi = dx + (long long)img * hw * dx_ld + c0;
   for (int i = threadIdx.x; i < items; i += blockDim.x) dxi[(long long)(i / SPPB_C) * dx_ld + i % SPPB_C] = from_f<T>(gs[i]);
 }
@@ -473,16 +490,16 @@ int ppy_spp_backward(const void* x, int x_ld, const void* dy, int dy_ld, void* d
                      ppy_stream_t s) {
   PPY_REQUIRE(x && dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && c % SPPB_C == 0 && x_ld >= c && dx_ld >= c && dy_ld >= 4 * c);
   PPY_REQUIRE(dtype == PPY_BF16 || dtype == PPY_F32);
-  const size_t smem = (size_t)h * w * SPPB_C * (4 + dtype_size(dtype));
-  PPY_REQUIRE(smem <= 200 * 1024);
+  const size_t smem = (size_t)h * w * SPPB_C * (4 + 2 * dtype_size(dtype) + 1);
+  PPY_REQUIRE(smem <= 200 * 1024 && w <= 255);
   dim3 grid((unsigned)(c / SPPB_C), (unsigned)n);
   if (dtype == PPY_BF16) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(spp_backward_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spp_backward_kernel<__nv_bfloat16><<<grid, 256, smem, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, (const __nv_bfloat16*)dy, dy_ld,
+    spp_backward_kernel<__nv_bfloat16><<<grid, 1024, smem, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, (const __nv_bfloat16*)dy, dy_ld,
                                                                           (__nv_bfloat16*)dx, dx_ld, h, w, c);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(spp_backward_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    spp_backward_kernel<float><<<grid, 256, smem, as_stream(s)>>>((const float*)x, x_ld, (const float*)dy, dy_ld, (float*)dx, dx_ld, h, w, c);
+    spp_backward_kernel<float><<<grid, 1024, smem, as_stream(s)>>>((const float*)x, x_ld, (const float*)dy, dy_ld, (float*)dx, dx_ld, h, w, c);
   }
   return check_launch();
 }

@@ -114,7 +114,7 @@ constexpr int kBnFusedMaxC = 2048;
 template <typename T, int LC>
 __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, long long rows,
                                                              int c, double* __restrict__ sums, BnFinal fin, const T* __restrict__ res,
-                                                             int res_ld, int act, int gx) {
+                                                             int res_ld, int act, int gx, int flat_apply) {
   constexpr int V = VecT<T>::N;
   constexpr int RL = 256 / LC;
   __shared__ float red[2][256][V];
@@ -189,6 +189,48 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
   if (last) {
     for (int i = threadIdx.x; i < 2 * c + 1; i += 256) sums[i] = 0.0;
   }
+  if (!flat_apply) {
+    // Same thread -> (channel vector, row lane) map as phase 1: the thread's V scales / shifts live in registers (no per-element
+    // index division, no shared-memory lookups), four rows (+ residual rows) in flight per thread, and the sweep runs BACKWARDS
+    // over phase 1's row order so the rows read last -- the ones still in L2 -- are re-read first.
+    if (vec * V >= c || by >= gy) return;
+    float sc[V], sf[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = s_scale[vec * V + k]; sf[k] = s_shift[vec * V + k]; }
+    const long long step = (long long)gy * RL, first = (long long)by * RL + rl;
+    if (first >= rows) return;
+    const T* xcol = x + vec * V;
+    const T* rcol = res ? res + vec * V : nullptr;
+    T* ycol = y + vec * V;
+    for (long long r0 = first + (rows - 1 - first) / (4 * step) * (4 * step); r0 >= first; r0 -= 4 * step) {
+      uint4 xa[4], ra[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * step;
+        if (r < rows) {
+          xa[u] = __ldg(reinterpret_cast<const uint4*>(xcol + r * x_ld));
+          if (rcol) ra[u] = __ldg(reinterpret_cast<const uint4*>(rcol + r * res_ld));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long r = r0 + u * step;
+        if (r >= rows) continue;
+        const T* e = reinterpret_cast<const T*>(&xa[u]);
+        const T* f = reinterpret_cast<const T*>(&ra[u]);
+        uint4 raw;
+        T* o = reinterpret_cast<T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float a = to_f<T>(e[k]) * sc[k] + sf[k];
+          if (rcol) a += to_f<T>(f[k]);
+          o[k] = from_f<T>(apply_act(a, act));
+        }
+        *reinterpret_cast<uint4*>(ycol + r * y_ld) = raw;
+      }
+    }
+    return;
+  }
   const int cv = c / V;
   const long long total = rows * cv;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -210,6 +252,135 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
 #pragma unroll
     for (int k = 0; k < V; ++k) e[k] = from_f<T>(apply_act(a[k], act));
     *reinterpret_cast<uint4*>(y + r * y_ld + v * V) = raw;
+  }
+}
+
+// Backward of train-mode BatchNorm + relu / leaky(0.1) of a head layer in ONE cooperative launch (ATen: activation backward +
+// batch_norm_backward_reduce + batch_norm_backward_elemt, three launches and 6 reads + 2 writes of small L2-resident tensors).
+//   g = dy * act'(y);  dbeta = sum g;  dgamma = sum g * xhat  (xhat = (x - mean) * invstd)
+//   dx = gamma * invstd * (g - dbeta / N - xhat * dgamma / N)
+// Phase 1: per-thread fp32 partials of the two sums over the thread's V channels (bn_train_fused's thread map), fp64 atomics per
+// CTA; grid barrier; phase 2 re-reads dy / y / x (L2 hits) backwards and writes dx.  Workspace: 2c + 1 doubles, zero on entry and
+// left zero.
+template <typename T, int LC>
+__global__ void __launch_bounds__(256) bn_act_backward_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
+                                                              const T* __restrict__ y, int y_ld, T* __restrict__ dx, int dx_ld, long long rows,
+                                                              int c, const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, int act, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, double* __restrict__ sums, int gx) {
+  constexpr int V = VecT<T>::N;
+  constexpr int RL = 256 / LC;
+  __shared__ float red[2][256][V];
+  const int bx = blockIdx.x % gx, by = blockIdx.x / gx, gy = gridDim.x / gx;
+  const int vl = threadIdx.x % LC, rl = threadIdx.x / LC;
+  const int vec = bx * LC + vl;
+  const bool live = vec * V < c;
+  const float slope = act == PPY_ACT_RELU ? 0.f : act == PPY_ACT_LEAKY ? 0.1f : 1.f;
+  const bool masked = act != PPY_ACT_NONE && y != nullptr;
+  float mu[V], is[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { mu[k] = live ? mean[vec * V + k] : 0.f; is[k] = live ? invstd[vec * V + k] : 0.f; }
+  float s[V], q[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  const long long step = (long long)gy * RL, first = (long long)by * RL + rl;
+  const T* dcol = dy + vec * V;
+  const T* xcol = x + vec * V;
+  const T* ycol = masked ? y + vec * V : nullptr;
+  if (live) {
+    for (long long r0 = first; r0 < rows; r0 += 2 * step) {
+      uint4 da[2], xa[2], ya[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long long r = r0 + u * step;
+        if (r < rows) {
+          da[u] = __ldg(reinterpret_cast<const uint4*>(dcol + r * dy_ld));
+          xa[u] = __ldg(reinterpret_cast<const uint4*>(xcol + r * x_ld));
+          if (masked) ya[u] = __ldg(reinterpret_cast<const uint4*>(ycol + r * y_ld));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (r0 + u * step >= rows) continue;
+        const T* de = reinterpret_cast<const T*>(&da[u]);
+        const T* xe = reinterpret_cast<const T*>(&xa[u]);
+        const T* ye = reinterpret_cast<const T*>(&ya[u]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float g = to_f<T>(de[k]);
+          if (masked && !(to_f<T>(ye[k]) > 0.f)) g *= slope;
+          s[k] += g;
+          q[k] += g * ((to_f<T>(xe[k]) - mu[k]) * is[k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red[0][threadIdx.x][k] = s[k]; red[1][threadIdx.x][k] = q[k]; }
+  __syncthreads();
+  if (rl == 0 && live) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      double ds = 0.0, dq = 0.0;
+      for (int j = 0; j < RL; ++j) { ds += red[0][j * LC + vl][k]; dq += red[1][j * LC + vl][k]; }
+      atomicAdd(&sums[vec * V + k], ds);
+      atomicAdd(&sums[c + vec * V + k], dq);
+    }
+  }
+  __threadfence();
+  cooperative_groups::this_grid().sync();
+  float k1[V], k2[V], gi[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const double sg = live ? __ldcg(sums + vec * V + k) : 0.0, sq = live ? __ldcg(sums + c + vec * V + k) : 0.0;
+    k1[k] = (float)(sg / (double)rows); k2[k] = (float)(sq / (double)rows);
+    gi[k] = live ? (gamma ? gamma[vec * V + k] : 1.f) * is[k] : 0.f;
+    if (live && by == 0 && rl == 0) {
+      if (dbeta) dbeta[vec * V + k] = (float)sg;
+      if (dgamma) dgamma[vec * V + k] = (float)sq;
+    }
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(sums + 2 * c);
+    last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    for (int i = threadIdx.x; i < 2 * c + 1; i += 256) sums[i] = 0.0;
+  }
+  if (!live || first >= rows) return;
+  T* ocol = dx + vec * V;
+  for (long long r0 = first + (rows - 1 - first) / (2 * step) * (2 * step); r0 >= first; r0 -= 2 * step) {
+    uint4 da[2], xa[2], ya[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long r = r0 + u * step;
+      if (r < rows) {
+        da[u] = __ldg(reinterpret_cast<const uint4*>(dcol + r * dy_ld));
+        xa[u] = __ldg(reinterpret_cast<const uint4*>(xcol + r * x_ld));
+        if (masked) ya[u] = __ldg(reinterpret_cast<const uint4*>(ycol + r * y_ld));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long r = r0 + u * step;
+      if (r >= rows) continue;
+      const T* de = reinterpret_cast<const T*>(&da[u]);
+      const T* xe = reinterpret_cast<const T*>(&xa[u]);
+      const T* ye = reinterpret_cast<const T*>(&ya[u]);
+      uint4 raw;
+      T* o = reinterpret_cast<T*>(&raw);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float g = to_f<T>(de[k]);
+        if (masked && !(to_f<T>(ye[k]) > 0.f)) g *= slope;
+        const float xh = (to_f<T>(xe[k]) - mu[k]) * is[k];
+        o[k] = from_f<T>((g - k1[k] - xh * k2[k]) * gi[k]);
+      }
+      *reinterpret_cast<uint4*>(ocol + r * dx_ld) = raw;
+    }
   }
 }
 
@@ -359,9 +530,37 @@ static int launch_bn_fused(const void* x, int x_ld, void* y, int y_ld, long long
   if (gy < 1) gy = 1;
   const T* xp = (const T*)x; T* yp = (T*)y; const T* rp = (const T*)res;
   BnFinal f = fin;
+  static const int flat_knob = getenv("PPY_BN_FLAT_APPLY") != nullptr;
+  int flat_apply = flat_knob;
   void* args[] = {(void*)&xp, (void*)&x_ld, (void*)&yp, (void*)&y_ld, (void*)&rows, (void*)&c, (void*)&ws, (void*)&f, (void*)&rp,
-                  (void*)&res_ld, (void*)&act, (void*)&gx};
+                  (void*)&res_ld, (void*)&act, (void*)&gx, (void*)&flat_apply};
   rc = check_cuda(cudaLaunchCooperativeKernel((const void*)bn_train_fused_kernel<T, LC>, dim3((unsigned)(gx * gy)), dim3(256), args, 0, st));
+  if (rc) return rc;
+  count_launch();
+  return PPY_OK;
+}
+
+template <typename T, int LC>
+static int launch_bn_act_backward(const void* dy, int dy_ld, const void* x, int x_ld, const void* y, int y_ld, void* dx, int dx_ld, long long rows,
+                                  int c, const float* gamma, const float* mean, const float* invstd, int act, float* dgamma, float* dbeta,
+                                  double* ws, int gx, cudaStream_t st) {
+  int dev = 0, sms = 0, per_sm = 0;
+  int rc = check_cuda(cudaGetDevice(&dev));
+  if (rc) return rc;
+  if ((rc = check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)))) return rc;
+  if ((rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_act_backward_kernel<T, LC>, 256, 0)))) return rc;
+  if (per_sm < 1) return PPY_ERR_UNSUPPORTED;
+  if (per_sm > 4) per_sm = 4;
+  const int rl = 256 / LC;
+  long long gy = ceil_div(rows, (long long)rl * 4);
+  const long long cap = (long long)sms * per_sm / gx;          // every CTA resident (grid barrier)
+  if (cap < 1) return PPY_ERR_UNSUPPORTED;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  const T* dyp = (const T*)dy; const T* xp = (const T*)x; const T* yp = (const T*)y; T* dxp = (T*)dx;
+  void* args[] = {(void*)&dyp, (void*)&dy_ld, (void*)&xp, (void*)&x_ld, (void*)&yp, (void*)&y_ld, (void*)&dxp, (void*)&dx_ld, (void*)&rows,
+                  (void*)&c, (void*)&gamma, (void*)&mean, (void*)&invstd, (void*)&act, (void*)&dgamma, (void*)&dbeta, (void*)&ws, (void*)&gx};
+  rc = check_cuda(cudaLaunchCooperativeKernel((const void*)bn_act_backward_kernel<T, LC>, dim3((unsigned)(gx * gy)), dim3(256), args, 0, st));
   if (rc) return rc;
   count_launch();
   return PPY_OK;
@@ -440,6 +639,30 @@ int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long row
   PPY_BNF_LC(float);
 #undef PPY_BNF_LC
 #undef PPY_BNF
+}
+
+int ppy_bn_act_backward(const void* dy, int dy_ld, const void* x, int x_ld, const void* y, int y_ld, void* dx, int dx_ld, long long rows, int c,
+                        int dtype, const float* gamma, const float* save_mean, const float* save_invstd, int act, float* dgamma, float* dbeta,
+                        double* workspace /* 2*c + 1 doubles, ZERO on entry, zero on exit */, ppy_stream_t s) {
+  PPY_REQUIRE(dy && x && dx && save_mean && save_invstd && workspace && rows > 0 && c > 0 && dy_ld >= c && x_ld >= c && dx_ld >= c);
+  PPY_REQUIRE(dtype == PPY_BF16 || dtype == PPY_F32);
+  PPY_REQUIRE(act == PPY_ACT_NONE || ((act == PPY_ACT_RELU || act == PPY_ACT_LEAKY) && y && y_ld >= c));
+  const int v = 16 / dtype_size(dtype);
+  PPY_REQUIRE(c % v == 0 && dy_ld % v == 0 && x_ld % v == 0 && dx_ld % v == 0 && (!y || y_ld % v == 0));
+  PPY_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0);
+  const int cv = c / v;
+  int lc = 32;
+  while (lc > 1 && lc / 2 >= cv) lc >>= 1;
+  const int gx = (int)ceil_div(cv, lc);
+  cudaStream_t st = as_stream(s);
+#define PPY_BNB(T, LC) return launch_bn_act_backward<T, LC>(dy, dy_ld, x, x_ld, y, y_ld, dx, dx_ld, rows, c, gamma, save_mean, save_invstd, act, \
+                                                            dgamma, dbeta, workspace, gx, st)
+#define PPY_BNB_LC(T) do { switch (lc) { case 32: PPY_BNB(T, 32); case 16: PPY_BNB(T, 16); case 8: PPY_BNB(T, 8); case 4: PPY_BNB(T, 4); \
+                                        case 2: PPY_BNB(T, 2); default: PPY_BNB(T, 1); } } while (0)
+  if (dtype == PPY_BF16) PPY_BNB_LC(__nv_bfloat16);
+  PPY_BNB_LC(float);
+#undef PPY_BNB_LC
+#undef PPY_BNB
 }
 
 int ppy_scale_shift_act(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* scale,

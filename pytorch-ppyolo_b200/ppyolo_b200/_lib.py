@@ -12,7 +12,7 @@ c_int, c_ll, c_float, c_double, c_void_p, c_size_t = (ctypes.c_int, ctypes.c_lon
                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t)
 
 PPY_F32, PPY_BF16, PPY_F16X2 = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_MISH = 0, 1, 2, 3
 
 
@@ -74,6 +74,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ppy_bn_train_fused': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ppy_bn_act_backward': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ppy_scale_shift_act': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                     c_int, c_void_p]),
     'ppy_dropblock_mask': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_float, c_void_p,

@@ -165,6 +165,21 @@ class _BnActFn(torch.autograd.Function):
     def backward(ctx, dy):
         xh, y, weight, mean, invstd = ctx.saved_tensors
         act_code, eps = ctx.meta
+        if BN_BWD_KERNEL and act_code in (0, 1, 2):
+            # activation backward + both BatchNorm reductions + dx in ONE cooperative launch (ppy_bn_act_backward)
+            from . import ops
+            from ._lib import lib, check, PPY_BF16, PPY_F32
+            n, h, w, c = xh.shape
+            dyh = dy.permute(0, 2, 3, 1)
+            if not dyh.is_contiguous() or dyh.dtype != xh.dtype:
+                dyh = dyh.to(xh.dtype).contiguous()
+            dxh = torch.empty_like(xh)
+            dw, db = torch.empty(c, dtype=torch.float32, device=xh.device), torch.empty(c, dtype=torch.float32, device=xh.device)
+            code = PPY_BF16 if xh.dtype == torch.bfloat16 else PPY_F32
+            check(lib.ppy_bn_act_backward(ops.ptr(dyh), c, ops.ptr(xh), c, ops.ptr(y), c, ops.ptr(dxh), c, n * h * w, c, code,
+                                          ops.ptr(weight.detach()), ops.ptr(mean), ops.ptr(invstd), act_code, ops.ptr(dw), ops.ptr(db),
+                                          ops.ptr(_bn_workspace(c, xh.device)), ops.stream_ptr()), 'bn_act_backward')
+            return dxh.permute(0, 3, 1, 2), dw.to(weight.dtype), db.to(weight.dtype), None, None, None, None, None
         x = xh.permute(0, 3, 1, 2)
         g = dy
         if act_code == 1:
@@ -190,11 +205,12 @@ def _bn_workspace(c, device):
 
 
 BN_KERNELS = os.environ.get('PPY_HEAD_BN_KERNELS', '1') != '0'
+BN_BWD_KERNEL = os.environ.get('PPY_HEAD_BN_BWD_KERNEL', '1') != '0'
 
 
 def spp_kernels_ok(x):
     return x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.shape[1] % 32 == 0 and \
-        x.shape[2] * x.shape[3] * 32 * (4 + x.element_size()) <= 200 * 1024
+        x.shape[2] * x.shape[3] * 32 * (5 + 2 * x.element_size()) <= 200 * 1024 and x.shape[3] <= 255
 
 
 _PENDING_BN = []

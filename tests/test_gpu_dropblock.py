@@ -62,9 +62,11 @@ def test_dropblock_known_answer_statistics():
     assert float((F.max_pool2d(holes, 3, 1, 1) - holes).clamp(min=0).sum()) >= 0.0
 
 
-def test_dropblock_rng_stream_and_layouts():
+@pytest.mark.parametrize('channels', [8, 32, 48])
+def test_dropblock_rng_stream_and_layouts(channels):
+    """(channels % 16 == 0 in channels_last takes the 16-channels-per-thread kernels: same numbers as the generic ones)"""
     o = ops()
-    x = torch.randn((2, 8, 19, 19), device=DEV)
+    x = torch.randn((2, channels, 19, 19), device=DEV)
     o.dropblock_seed(123)
     a = o.drop_block(x, 3, 0.9)
     b = o.drop_block(x, 3, 0.9)                                # offset advanced: a fresh draw
