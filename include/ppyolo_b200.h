@@ -217,16 +217,18 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
                        double* workspace, ppy_stream_t s);
 /* ppy_bn_batch_stats + ppy_scale_shift_act of one layer in ONE cooperative launch (statistics, grid barrier, normalise +
  * activation + residual; the second read of x mostly hits L2): the train-mode BatchNorm of a frozen-backbone layer as one graph node
- * instead of four.  scale / shift receive the folded parameters as before.  workspace: 2*c + 1 doubles that are ZERO on entry; the
- * call leaves them zero (no memset).  save_mean / save_invstd (optional, [c]): the batch mean and 1/sqrt(var + eps) a BatchNorm
+ * instead of four.  scale / shift receive the folded parameters as before.  workspace: PPY_BN_WORKSPACE_DOUBLES(c) doubles (up to 16
+ * replicas of the 2c per-channel sums -- CTAs of one channel column add to different addresses -- and a counter) that are ZERO on
+ * entry; the call leaves them zero (no memset).  save_mean / save_invstd (optional, [c]): the batch mean and 1/sqrt(var + eps) a BatchNorm
  * backward needs.  c <= 2048; PPY_ERR_UNSUPPORTED when the device cannot launch cooperatively. */
+#define PPY_BN_WORKSPACE_DOUBLES(c) (32 * (size_t)(c) + 1)
 int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                        const void* residual, int res_ld, int act, double* workspace, float* save_mean, float* save_invstd, ppy_stream_t s);
 /* Backward of train-mode BatchNorm2d + relu / leaky(0.1) of a head Conv2dUnit (model/custom_layers.py:243-253 under autograd) in ONE
  * cooperative launch: g = dy * act'(y); dbeta = sum g; dgamma = sum g * xhat; dx = gamma * invstd * (g - dbeta/N - xhat * dgamma/N),
  * xhat = (x - save_mean) * save_invstd (the forward's batch statistics, ppy_bn_train_fused).  y (the forward's output) is needed for
- * relu / leaky only.  dgamma / dbeta: fp32 [c], optional.  workspace: 2*c + 1 doubles, ZERO on entry, left zero. */
+ * relu / leaky only.  dgamma / dbeta: fp32 [c], optional.  workspace: PPY_BN_WORKSPACE_DOUBLES(c) doubles, ZERO on entry, left zero. */
 int ppy_bn_act_backward(const void* dy, int dy_ld, const void* x, int x_ld, const void* y, int y_ld, void* dx, int dx_ld, long long rows, int c,
                         int dtype, const float* gamma, const float* save_mean, const float* save_invstd, int act, float* dgamma, float* dbeta,
                         double* workspace, ppy_stream_t s);

@@ -111,21 +111,43 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 // the conv has just written it).  The workspace is ZERO on entry and left zero on exit (the last CTA to have read the sums clears
 // them): no memset node.  c <= kBnFusedMaxC.
 constexpr int kBnFusedMaxC = 2048;
+constexpr int kBnMaxReplicas = 16;      // workspace: kBnMaxReplicas * 2c + 1 doubles (PPY_BN_WORKSPACE_DOUBLES)
+
+// CTA-level tail of a statistics phase: the 256 threads' fp32 partials (two sums per channel) are folded by ONE THREAD PER CHANNEL
+// (LC*V threads, RL terms each, fp64) and added to replica `rep` of the global sums.  Replicas spread the CTAs of one channel column
+// over several addresses: with 296 CTAs adding to the same 2c doubles, the same-address fp64 atomics (serialised in L2) were ~70 %
+// of a small layer's launch (ncu: warps parked at the grid barrier waiting for them).
+template <int LC, int V>
+__device__ __forceinline__ void cta_fold_atomic(float (&red)[2][256][V], double* __restrict__ sums, int c, int cbase, int rep) {
+  constexpr int RL = 256 / LC;
+  const int t = threadIdx.x;
+  if (t < LC * V && cbase + t < c) {
+    const int vl = t / V, k = t % V;
+    double ds = 0.0, dq = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < RL; ++j) { ds += red[0][j * LC + vl][k]; dq += red[1][j * LC + vl][k]; }
+    double* dst = sums + (size_t)rep * 2 * c;
+    atomicAdd(dst + cbase + t, ds);
+    atomicAdd(dst + c + cbase + t, dq);
+  }
+}
+
 template <typename T, int LC>
 __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, long long rows,
                                                              int c, double* __restrict__ sums, BnFinal fin, const T* __restrict__ res,
-                                                             int res_ld, int act, int gx, int flat_apply) {
+                                                             int res_ld, int act, int gx, int reps) {
   constexpr int V = VecT<T>::N;
   constexpr int RL = 256 / LC;
   __shared__ float red[2][256][V];
-  __shared__ float s_scale[kBnFusedMaxC], s_shift[kBnFusedMaxC];
+  __shared__ float s_scale[LC * V], s_shift[LC * V];
   const int bx = blockIdx.x % gx, by = blockIdx.x / gx, gy = gridDim.x / gx;      // 1-D grid (cooperative), viewed as gx x gy
   const int vl = threadIdx.x % LC, rl = threadIdx.x / LC;
   const int vec = bx * LC + vl;
+  const int cbase = bx * LC * V;
   float s[V], q[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) { s[k] = 0.f; q[k] = 0.f; }
-  if (vec * V < c && by < gy) {
+  if (vec * V < c) {
     const long long step = (long long)gy * RL;
     const T* col = x + vec * V;
     for (long long r0 = (long long)by * RL + rl; r0 < rows; r0 += 4 * step) {
@@ -148,26 +170,21 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
 #pragma unroll
   for (int k = 0; k < V; ++k) { red[0][threadIdx.x][k] = s[k]; red[1][threadIdx.x][k] = q[k]; }
   __syncthreads();
-  if (rl == 0 && vec * V < c && by < gy) {
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      double ds = 0.0, dq = 0.0;
-      for (int j = 0; j < RL; ++j) { ds += red[0][j * LC + vl][k]; dq += red[1][j * LC + vl][k]; }
-      atomicAdd(&sums[vec * V + k], ds);
-      atomicAdd(&sums[c + vec * V + k], dq);
-    }
-  }
+  cta_fold_atomic<LC, V>(red, sums, c, cbase, by % reps);
   __threadfence();
   cooperative_groups::this_grid().sync();
-  // ---- phase 2: scale / shift of every channel (block 0 also publishes them and moves the running statistics)
-  for (int ch = threadIdx.x; ch < c; ch += 256) {
-    const double mean = __ldcg(sums + ch) / (double)rows;
-    double var = __ldcg(sums + c + ch) / (double)rows - mean * mean;
+  // ---- phase 2: scale / shift of this CTA's channels (the by == 0 CTAs also publish them and move the running statistics)
+  if (threadIdx.x < LC * V && cbase + threadIdx.x < c) {
+    const int ch = cbase + threadIdx.x;
+    double sm = 0.0, sq = 0.0;
+    for (int r = 0; r < reps; ++r) { sm += __ldcg(sums + (size_t)r * 2 * c + ch); sq += __ldcg(sums + (size_t)r * 2 * c + c + ch); }
+    const double mean = sm / (double)rows;
+    double var = sq / (double)rows - mean * mean;
     if (var < 0.0) var = 0.0;
     const float inv = rsqrtf((float)var + fin.eps) * (fin.gamma ? fin.gamma[ch] : 1.f);
     const float sh = (fin.beta ? fin.beta[ch] : 0.f) - (float)mean * inv;
-    s_scale[ch] = inv; s_shift[ch] = sh;
-    if (blockIdx.x == 0) {
+    s_scale[threadIdx.x] = inv; s_shift[threadIdx.x] = sh;
+    if (by == 0) {
       fin.scale[ch] = inv; fin.shift[ch] = sh;
       if (fin.save_mean) fin.save_mean[ch] = (float)mean;
       if (fin.save_invstd) fin.save_invstd[ch] = rsqrtf((float)var + fin.eps);
@@ -182,21 +199,22 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
   // the last CTA to have read the sums clears them (and the counter) for the next launch
   __shared__ bool last;
   if (threadIdx.x == 0) {
-    unsigned int* done = reinterpret_cast<unsigned int*>(sums + 2 * c);
+    unsigned int* done = reinterpret_cast<unsigned int*>(sums + (size_t)kBnMaxReplicas * 2 * c);
     last = atomicAdd(done, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (last) {
-    for (int i = threadIdx.x; i < 2 * c + 1; i += 256) sums[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * c * reps; i += 256) sums[i] = 0.0;
+    if (threadIdx.x == 0) sums[(size_t)kBnMaxReplicas * 2 * c] = 0.0;
   }
-  if (!flat_apply) {
+  {
     // Same thread -> (channel vector, row lane) map as phase 1: the thread's V scales / shifts live in registers (no per-element
-    // index division, no shared-memory lookups), four rows (+ residual rows) in flight per thread, and the sweep runs BACKWARDS
-    // over phase 1's row order so the rows read last -- the ones still in L2 -- are re-read first.
-    if (vec * V >= c || by >= gy) return;
+    // index division), four rows (+ residual rows) in flight per thread, and the sweep runs BACKWARDS over phase 1's row order
+    // so the rows read last -- the ones still in L2 -- are re-read first.
+    if (vec * V >= c) return;
     float sc[V], sf[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { sc[k] = s_scale[vec * V + k]; sf[k] = s_shift[vec * V + k]; }
+    for (int k = 0; k < V; ++k) { sc[k] = s_scale[vl * V + k]; sf[k] = s_shift[vl * V + k]; }
     const long long step = (long long)gy * RL, first = (long long)by * RL + rl;
     if (first >= rows) return;
     const T* xcol = x + vec * V;
@@ -229,29 +247,6 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
         *reinterpret_cast<uint4*>(ycol + r * y_ld) = raw;
       }
     }
-    return;
-  }
-  const int cv = c / V;
-  const long long total = rows * cv;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int v = (int)(i % cv);
-    const long long r = i / cv;
-    float a[V];
-    ldv<T>(x + r * x_ld + v * V, a);
-    if (res) {
-      float b[V];
-      ldv<T>(res + r * res_ld + v * V, b);
-#pragma unroll
-      for (int k = 0; k < V; ++k) a[k] = a[k] * s_scale[v * V + k] + s_shift[v * V + k] + b[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < V; ++k) a[k] = a[k] * s_scale[v * V + k] + s_shift[v * V + k];
-    }
-    uint4 raw;
-    T* e = reinterpret_cast<T*>(&raw);
-#pragma unroll
-    for (int k = 0; k < V; ++k) e[k] = from_f<T>(apply_act(a[k], act));
-    *reinterpret_cast<uint4*>(y + r * y_ld + v * V) = raw;
   }
 }
 
@@ -260,20 +255,21 @@ __global__ void __launch_bounds__(256) bn_train_fused_kernel(const T* __restrict
 //   g = dy * act'(y);  dbeta = sum g;  dgamma = sum g * xhat  (xhat = (x - mean) * invstd)
 //   dx = gamma * invstd * (g - dbeta / N - xhat * dgamma / N)
 // Phase 1: per-thread fp32 partials of the two sums over the thread's V channels (bn_train_fused's thread map), fp64 atomics per
-// CTA; grid barrier; phase 2 re-reads dy / y / x (L2 hits) backwards and writes dx.  Workspace: 2c + 1 doubles, zero on entry and
-// left zero.
+// CTA (replicated sums, cta_fold_atomic); grid barrier; phase 2 re-reads dy / y / x (L2 hits) backwards and writes dx.  Workspace:
+// PPY_BN_WORKSPACE_DOUBLES(c), zero on entry and left zero.
 template <typename T, int LC>
 __global__ void __launch_bounds__(256) bn_act_backward_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                                                               const T* __restrict__ y, int y_ld, T* __restrict__ dx, int dx_ld, long long rows,
                                                               int c, const float* __restrict__ gamma, const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, int act, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, double* __restrict__ sums, int gx) {
+                                                              float* __restrict__ dbeta, double* __restrict__ sums, int gx, int reps) {
   constexpr int V = VecT<T>::N;
   constexpr int RL = 256 / LC;
   __shared__ float red[2][256][V];
   const int bx = blockIdx.x % gx, by = blockIdx.x / gx, gy = gridDim.x / gx;
   const int vl = threadIdx.x % LC, rl = threadIdx.x / LC;
   const int vec = bx * LC + vl;
+  const int cbase = bx * LC * V;
   const bool live = vec * V < c;
   const float slope = act == PPY_ACT_RELU ? 0.f : act == PPY_ACT_LEAKY ? 0.1f : 1.f;
   const bool masked = act != PPY_ACT_NONE && y != nullptr;
@@ -318,37 +314,36 @@ __global__ void __launch_bounds__(256) bn_act_backward_kernel(const T* __restric
 #pragma unroll
   for (int k = 0; k < V; ++k) { red[0][threadIdx.x][k] = s[k]; red[1][threadIdx.x][k] = q[k]; }
   __syncthreads();
-  if (rl == 0 && live) {
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      double ds = 0.0, dq = 0.0;
-      for (int j = 0; j < RL; ++j) { ds += red[0][j * LC + vl][k]; dq += red[1][j * LC + vl][k]; }
-      atomicAdd(&sums[vec * V + k], ds);
-      atomicAdd(&sums[c + vec * V + k], dq);
-    }
-  }
+  cta_fold_atomic<LC, V>(red, sums, c, cbase, by % reps);
   __threadfence();
   cooperative_groups::this_grid().sync();
-  float k1[V], k2[V], gi[V];
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    const double sg = live ? __ldcg(sums + vec * V + k) : 0.0, sq = live ? __ldcg(sums + c + vec * V + k) : 0.0;
-    k1[k] = (float)(sg / (double)rows); k2[k] = (float)(sq / (double)rows);
-    gi[k] = live ? (gamma ? gamma[vec * V + k] : 1.f) * is[k] : 0.f;
-    if (live && by == 0 && rl == 0) {
-      if (dbeta) dbeta[vec * V + k] = (float)sg;
-      if (dgamma) dgamma[vec * V + k] = (float)sq;
+  __shared__ float s_k1[LC * V], s_k2[LC * V];
+  if (threadIdx.x < LC * V && cbase + threadIdx.x < c) {
+    const int ch = cbase + threadIdx.x;
+    double sg = 0.0, sq = 0.0;
+    for (int r = 0; r < reps; ++r) { sg += __ldcg(sums + (size_t)r * 2 * c + ch); sq += __ldcg(sums + (size_t)r * 2 * c + c + ch); }
+    s_k1[threadIdx.x] = (float)(sg / (double)rows); s_k2[threadIdx.x] = (float)(sq / (double)rows);
+    if (by == 0) {
+      if (dbeta) dbeta[ch] = (float)sg;
+      if (dgamma) dgamma[ch] = (float)sq;
     }
   }
   __syncthreads();
+  float k1[V], k2[V], gi[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    k1[k] = live ? s_k1[vl * V + k] : 0.f; k2[k] = live ? s_k2[vl * V + k] : 0.f;
+    gi[k] = live ? (gamma ? gamma[vec * V + k] : 1.f) * is[k] : 0.f;
+  }
   __shared__ bool last;
   if (threadIdx.x == 0) {
-    unsigned int* done = reinterpret_cast<unsigned int*>(sums + 2 * c);
+    unsigned int* done = reinterpret_cast<unsigned int*>(sums + (size_t)kBnMaxReplicas * 2 * c);
     last = atomicAdd(done, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (last) {
-    for (int i = threadIdx.x; i < 2 * c + 1; i += 256) sums[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * c * reps; i += 256) sums[i] = 0.0;
+    if (threadIdx.x == 0) sums[(size_t)kBnMaxReplicas * 2 * c] = 0.0;
   }
   if (!live || first >= rows) return;
   T* ocol = dx + vec * V;
@@ -512,6 +507,14 @@ __global__ void __launch_bounds__(256) sgd_ema_multi_kernel(float* const* __rest
   }
 }
 
+// replicas of the per-channel sums: ~16 CTAs per address, at most kBnMaxReplicas (PPY_BN_REPLICAS overrides: experiments)
+inline int bn_replicas(long long gy) {
+  static const char* knob = getenv("PPY_BN_REPLICAS");
+  int r = knob ? atoi(knob) : (int)(gy / 16);
+  if (r > kBnMaxReplicas) r = kBnMaxReplicas;
+  return r < 1 ? 1 : r;
+}
+
 template <typename T, int LC>
 static int launch_bn_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, double* ws, const BnFinal& fin, const void* res,
                            int res_ld, int act, int gx, cudaStream_t st) {
@@ -530,10 +533,9 @@ static int launch_bn_fused(const void* x, int x_ld, void* y, int y_ld, long long
   if (gy < 1) gy = 1;
   const T* xp = (const T*)x; T* yp = (T*)y; const T* rp = (const T*)res;
   BnFinal f = fin;
-  static const int flat_knob = getenv("PPY_BN_FLAT_APPLY") != nullptr;
-  int flat_apply = flat_knob;
+  int reps = bn_replicas(gy);
   void* args[] = {(void*)&xp, (void*)&x_ld, (void*)&yp, (void*)&y_ld, (void*)&rows, (void*)&c, (void*)&ws, (void*)&f, (void*)&rp,
-                  (void*)&res_ld, (void*)&act, (void*)&gx, (void*)&flat_apply};
+                  (void*)&res_ld, (void*)&act, (void*)&gx, (void*)&reps};
   rc = check_cuda(cudaLaunchCooperativeKernel((const void*)bn_train_fused_kernel<T, LC>, dim3((unsigned)(gx * gy)), dim3(256), args, 0, st));
   if (rc) return rc;
   count_launch();
@@ -558,8 +560,10 @@ static int launch_bn_act_backward(const void* dy, int dy_ld, const void* x, int 
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
   const T* dyp = (const T*)dy; const T* xp = (const T*)x; const T* yp = (const T*)y; T* dxp = (T*)dx;
+  int reps = bn_replicas(gy);
   void* args[] = {(void*)&dyp, (void*)&dy_ld, (void*)&xp, (void*)&x_ld, (void*)&yp, (void*)&y_ld, (void*)&dxp, (void*)&dx_ld, (void*)&rows,
-                  (void*)&c, (void*)&gamma, (void*)&mean, (void*)&invstd, (void*)&act, (void*)&dgamma, (void*)&dbeta, (void*)&ws, (void*)&gx};
+                  (void*)&c, (void*)&gamma, (void*)&mean, (void*)&invstd, (void*)&act, (void*)&dgamma, (void*)&dbeta, (void*)&ws, (void*)&gx,
+                  (void*)&reps};
   rc = check_cuda(cudaLaunchCooperativeKernel((const void*)bn_act_backward_kernel<T, LC>, dim3((unsigned)(gx * gy)), dim3(256), args, 0, st));
   if (rc) return rc;
   count_launch();
@@ -618,7 +622,7 @@ int ppy_bn_batch_stats(const void* x, int x_ld, long long rows, int c, int dtype
 
 int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long rows, int c, int dtype, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                       const void* residual, int res_ld, int act, double* workspace /* 2*c + 1 doubles, ZERO on entry, zero on exit */,
+                       const void* residual, int res_ld, int act, double* workspace /* PPY_BN_WORKSPACE_DOUBLES(c), ZERO on entry, zero on exit */,
                        float* save_mean, float* save_invstd, ppy_stream_t s) {
   PPY_REQUIRE(x && y && scale && shift && workspace && rows > 0 && c > 0 && c <= kBnFusedMaxC && x_ld >= c && y_ld >= c);
   PPY_REQUIRE(dtype == PPY_BF16 || dtype == PPY_F32);
@@ -643,7 +647,7 @@ int ppy_bn_train_fused(const void* x, int x_ld, void* y, int y_ld, long long row
 
 int ppy_bn_act_backward(const void* dy, int dy_ld, const void* x, int x_ld, const void* y, int y_ld, void* dx, int dx_ld, long long rows, int c,
                         int dtype, const float* gamma, const float* save_mean, const float* save_invstd, int act, float* dgamma, float* dbeta,
-                        double* workspace /* 2*c + 1 doubles, ZERO on entry, zero on exit */, ppy_stream_t s) {
+                        double* workspace /* PPY_BN_WORKSPACE_DOUBLES(c), ZERO on entry, zero on exit */, ppy_stream_t s) {
   PPY_REQUIRE(dy && x && dx && save_mean && save_invstd && workspace && rows > 0 && c > 0 && dy_ld >= c && x_ld >= c && dx_ld >= c);
   PPY_REQUIRE(dtype == PPY_BF16 || dtype == PPY_F32);
   PPY_REQUIRE(act == PPY_ACT_NONE || ((act == PPY_ACT_RELU || act == PPY_ACT_LEAKY) && y && y_ld >= c));

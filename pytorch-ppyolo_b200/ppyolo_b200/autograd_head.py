@@ -199,7 +199,7 @@ def _bn_workspace(c, device):
     key = (c, str(device))
     ws = _BN_WS.get(key)
     if ws is None:
-        ws = torch.zeros(2 * c + 1, dtype=torch.float64, device=device)
+        ws = torch.zeros(32 * c + 1, dtype=torch.float64, device=device)       # PPY_BN_WORKSPACE_DOUBLES(c)
         _BN_WS[key] = ws
     return ws
 

@@ -455,7 +455,7 @@ class InferenceEngine(object):
             dst = TensorRef(self._new(raw.n, raw.h, raw.w, ops.round_up(cout, 8)), c=cout)
         scale = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
         shift = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
-        ws = self._keep(torch.zeros(2 * cout + 1, dtype=torch.float64, device=self.dev))
+        ws = self._keep(torch.zeros(32 * cout + 1, dtype=torch.float64, device=self.dev))      # PPY_BN_WORKSPACE_DOUBLES(cout)
         rows = raw.n * raw.h * raw.w
         momentum = 0.1 if bn.momentum is None else float(bn.momentum)
         a1 = (ctypes.c_void_p(raw.ptr), raw.ld, rows, cout, raw.code, ops.ptr(bn.weight.data), ops.ptr(bn.bias.data), float(bn.eps),

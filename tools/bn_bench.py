@@ -15,6 +15,7 @@ from ppyolo_b200._lib import lib, check, PPY_BF16
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=8); ap.add_argument('--size', type=int, default=608)
+ap.add_argument('--only', default=None, help='one layer shape by name (ncu captures)')
 a = ap.parse_args()
 dev = torch.device('cuda', 0)
 S = a.size
@@ -29,6 +30,8 @@ SHAPES = [('stem.conv1_1/2', S // 2, 32, False, 2), ('stem.conv1_3', S // 2, 64,
           ('stage5.short', S // 32, 2048, False, 1)]
 total_us, total_bytes, out = 0.0, 0.0, []
 for name, hw, c, has_res, count in SHAPES:
+    if a.only and name != a.only:
+        continue
     rows = a.batch * hw * hw
     nbytes = rows * c * 2
     nbuf = max(2, min(8, int(400e6 // nbytes) + 1))
@@ -38,7 +41,7 @@ for name, hw, c, has_res, count in SHAPES:
     g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
     rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
     sc, sh = torch.empty(c, device=dev), torch.empty(c, device=dev)
-    ws = torch.zeros(2 * c + 1, dtype=torch.float64, device=dev)
+    ws = torch.zeros(32 * c + 1, dtype=torch.float64, device=dev)
 
     def launch(i):
         check(lib.ppy_bn_train_fused(ops.ptr(xs[i]), c, ops.ptr(ys[i]), c, rows, c, PPY_BF16, ops.ptr(g), ops.ptr(b), 1e-5, 0.1, ops.ptr(rm),
@@ -72,4 +75,4 @@ for name, hw, c, has_res, count in SHAPES:
     del xs, ys, rs
     torch.cuda.empty_cache()
 print(json.dumps({'backbone_bn_layers': sum(s[4] for s in SHAPES), 'total_ms': total_us * 1e-3, 'algorithmic_GB': total_bytes * 1e-9,
-                  'mean_GBps': total_bytes / total_us * 1e-3, 'flat_apply': bool(os.environ.get('PPY_BN_FLAT_APPLY')), 'layers': out}))
+                  'mean_GBps': total_bytes / total_us * 1e-3, 'replicas_knob': os.environ.get('PPY_BN_REPLICAS'), 'layers': out}))
