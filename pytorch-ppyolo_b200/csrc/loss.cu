@@ -75,7 +75,7 @@ __device__ __forceinline__ void cell_geometry(const LossCfg& cfg, int a, int h, 
   c.iou = c.inter / c.uni;
 }
 
-// grid: ceil(N*A*S / WARPS) blocks of WARPS warps; warp = one (n, a, h) row
+// grid: ceil(N*A*S*chunks / WARPS) blocks of WARPS warps; warp = one 32-cell chunk of an (n, a, h) row
 template <bool BWD>
 __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg, const float* __restrict__ out,
                                                                const float* __restrict__ tgt, const float* __restrict__ gt_box,
@@ -86,9 +86,13 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
   __shared__ bool is_last;
   const int S = cfg.s, A = cfg.a, C = cfg.c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = cfg.n * A * S;
-  const int row = blockIdx.x * WARPS + warp;
-  const bool live = row < rows;
+  // (a row wider than 32 cells is shared by ceil(S / 32) warps, one 32-cell chunk each: three times the warps in flight on the
+  // 76 x 76 scale, whose launch is latency-bound on the per-cell ground-truth IoU loop)
+  const int chunks = (S + 31) / 32;
+  const int rows = cfg.n * A * S * chunks;
+  const int row_c = blockIdx.x * WARPS + warp;
+  const bool live = row_c < rows;
+  const int chunk = live ? row_c % chunks : 0, row = row_c / chunks;
   const int n = live ? row / (A * S) : 0, a = live ? (row / S) % A : 0, h = live ? row % S : 0;
   const size_t plane = (size_t)S * S;
   const int per = 5 + C, CH = A * (per + (cfg.iou_aware ? 1 : 0));
@@ -100,6 +104,16 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
   float* g_a = BWD ? g_n + (size_t)((cfg.iou_aware ? A : 0) + a * per) * plane + (size_t)h * S : nullptr;
   float* g_iou = BWD ? g_n + (size_t)a * plane + (size_t)h * S : nullptr;
 
+  // forward: the image's ground-truth boxes staged once per warp in shared memory -- the per-cell IoU loop read them from global
+  // memory one dependent L2 round trip per box (~20 us of a ~55 us launch whatever the grid size)
+  __shared__ float4 s_gt[BWD ? 1 : WARPS][BWD ? 1 : MAX_GT];
+  if (!BWD) {
+    if (live) {
+      const float4* gb4 = reinterpret_cast<const float4*>(gt_box) + (size_t)n * cfg.g;
+      for (int k = lane; k < cfg.g; k += 32) s_gt[BWD ? 0 : warp][BWD ? 0 : k] = __ldg(gb4 + k);
+    }
+    __syncwarp();
+  }
   // T_row = sum_w tobj (the IoU-aware loss meets the objectness target after its own sum over w)
   float trow = 0.f;
   if (live) for (int w = lane; w < S; w += 32) trow += __ldg(t_a + 5 * plane + w);
@@ -114,7 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
   }
   float row_la = 0.f;                          // forward: sum_w iou * -log(ioup) of this row
   if (live) {
-    for (int w = lane; w < S; w += 32) {
+    for (int w = chunk * 32 + lane; w < S && w < (chunk + 1) * 32; w += 32) {
       const float xl = __ldg(o_a + w), yl = __ldg(o_a + plane + w), wl = __ldg(o_a + 2 * plane + w), hl = __ldg(o_a + 3 * plane + w);
       const float ol = __ldg(o_a + 4 * plane + w);
       const float tx = __ldg(t_a + w), ty = __ldg(t_a + plane + w), tw = __ldg(t_a + 2 * plane + w), th = __ldg(t_a + 3 * plane + w);
@@ -152,9 +166,8 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
           const float area_a = (px1 - px0) * (py1 - py0);
           float best = -INFINITY;
           bool nan_seen = false;
-          const float* gb = gt_box + (size_t)n * cfg.g * 4;
           for (int k = 0; k < cfg.g; ++k) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(gb) + k);       // cx, cy, w, h
+            const float4 b = s_gt[BWD ? 0 : warp][BWD ? 0 : k];       // cx, cy, w, h
             const float gx0 = b.x - b.z / 2.f, gy0 = b.y - b.w / 2.f, gx1 = b.x + b.z / 2.f, gy1 = b.y + b.w / 2.f;
             const float iw = fmaxf(fminf(px1, gx1) - fmaxf(px0, gx0), 0.f), ih = fmaxf(fminf(py1, gy1) - fmaxf(py0, gy0), 0.f);
             const float inter = iw * ih;
@@ -167,12 +180,22 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
         float maxprob = 0.f;
         double lcls = 0.;
         if (tobj != 0.f || cfg.match_score) {
-          for (int k = 0; k < C; ++k) {
-            const float pc = sigm(__ldg(o_a + (size_t)(5 + k) * plane + w));
-            if (cfg.match_score) maxprob = fmaxf(maxprob, p * pc);
-            if (tobj != 0.f) {
-              const float t = __ldg(t_a + (size_t)(6 + k) * plane + w);
-              lcls += (double)(t * nlog(pc) + (1.f - t) * nlog(1.f - pc));
+          // (eight classes' logits and targets are requested together: one dependent L2 round trip per class was ~30 us of
+          // every launch -- the warps holding a positive cell set its duration; same summation order)
+          for (int k0 = 0; k0 < C; k0 += 8) {
+            float lg[8], tg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = k0 + j < C ? k0 + j : C - 1;
+              lg[j] = __ldg(o_a + (size_t)(5 + k) * plane + w);
+              tg[j] = tobj != 0.f ? __ldg(t_a + (size_t)(6 + k) * plane + w) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (k0 + j >= C) break;
+              const float pc = sigm(lg[j]);
+              if (cfg.match_score) maxprob = fmaxf(maxprob, p * pc);
+              if (tobj != 0.f) lcls += (double)(tg[j] * nlog(pc) + (1.f - tg[j]) * nlog(1.f - pc));
             }
           }
         }
@@ -222,10 +245,20 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
         if (cfg.iou_aware)
           g_iou[w] = g_aw * trow * cfg.aware_w * c.iou * (0.f - 1.f / (c.ioup + 1e-9f)) * (c.ioup * (1.f - c.ioup));
         if (tobj != 0.f) {
-          for (int k = 0; k < C; ++k) {
-            const float pc = sigm(__ldg(o_a + (size_t)(5 + k) * plane + w));
-            const float t = __ldg(t_a + (size_t)(6 + k) * plane + w);
-            g_a[(size_t)(5 + k) * plane + w] = g_cls * tobj * ((0.f - t / (pc + 1e-9f)) + (1.f - t) / (1.f - pc + 1e-9f)) * (pc * (1.f - pc));
+          for (int k0 = 0; k0 < C; k0 += 8) {
+            float lg[8], tg[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k = k0 + j < C ? k0 + j : C - 1;
+              lg[j] = __ldg(o_a + (size_t)(5 + k) * plane + w);
+              tg[j] = __ldg(t_a + (size_t)(6 + k) * plane + w);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (k0 + j >= C) break;
+              const float pc = sigm(lg[j]), t = tg[j];
+              g_a[(size_t)(5 + k0 + j) * plane + w] = g_cls * tobj * ((0.f - t / (pc + 1e-9f)) + (1.f - t) / (1.f - pc + 1e-9f)) * (pc * (1.f - pc));
+            }
           }
         } else {
           for (int k = 0; k < C; ++k) g_a[(size_t)(5 + k) * plane + w] = 0.f;
@@ -253,13 +286,16 @@ __global__ void __launch_bounds__(WARPS * 32) yolo_loss_kernel(const LossCfg cfg
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (is_last && threadIdx.x < 6) {
+  if (is_last && warp < 6) {
+    // warp k folds loss k: lane-strided partial sums (independent loads in flight instead of one 700-cycle round trip per
+    // block), then the shuffle tree -- a fixed order, so the result is run-to-run deterministic
     __threadfence();
     double t = 0.;
-    for (unsigned b = 0; b < gridDim.x; ++b) t += partial[(size_t)b * 6 + threadIdx.x];      // fixed order
-    losses[threadIdx.x] += (float)(t / (double)cfg.n);     // mean over the batch of the per-image sums; scales add up in launch order
-    if (threadIdx.x == 0) *counter = 0u;
+    for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(partial + (size_t)b * 6 + warp);
+    t = warp_sum(t);
+    if (lane == 0) losses[warp] += (float)(t / (double)cfg.n);     // mean over the batch of the per-image sums; scales add up in launch order
   }
+  if (is_last && threadIdx.x == 0) *counter = 0u;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -337,7 +373,7 @@ extern "C" {
 using namespace ppy;
 
 int ppy_yolo_loss_workspace_bytes(int n, int a, int size) {
-  return (int)(ceil_div((long long)n * a * size, WARPS) * 6 * sizeof(double) + 16);
+  return (int)(ceil_div((long long)n * a * size * ((size + 31) / 32), WARPS) * 6 * sizeof(double) + 16);
 }
 
 int ppy_yolo_loss_forward(const float* out, const float* target, const float* gt_box, int n, int a, int num_classes, int size, int g,
@@ -350,7 +386,7 @@ int ppy_yolo_loss_forward(const float* out, const float* target, const float* gt
   int rc = fill_loss_cfg(&cfg, n, a, num_classes, size, g, anchors_host, stride, scale_x_y, ignore_thresh, iou_aware, has_iou_loss,
                          iou_loss_weight, loss_square, iou_aware_weight, match_score);
   if (rc) return rc;
-  const unsigned blocks = (unsigned)ceil_div((long long)n * a * size, WARPS);
+  const unsigned blocks = (unsigned)ceil_div((long long)n * a * size * ((size + 31) / 32), WARPS);
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);            // zero before the first use; the kernel re-zeroes it
   double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
   yolo_loss_kernel<false><<<blocks, WARPS * 32, 0, as_stream(s)>>>(cfg, out, target, gt_box, noobj_mask, partial, counter, losses, nullptr, nullptr);
@@ -365,7 +401,7 @@ int ppy_yolo_loss_backward(const float* out, const float* target, int n, int a, 
   int rc = fill_loss_cfg(&cfg, n, a, num_classes, size, 0, anchors_host, stride, scale_x_y, 0.f, iou_aware, has_iou_loss, iou_loss_weight,
                          loss_square, iou_aware_weight, 0);
   if (rc) return rc;
-  const unsigned blocks = (unsigned)ceil_div((long long)n * a * size, WARPS);
+  const unsigned blocks = (unsigned)ceil_div((long long)n * a * size * ((size + 31) / 32), WARPS);
   yolo_loss_kernel<true><<<blocks, WARPS * 32, 0, as_stream(s)>>>(cfg, out, target, nullptr, const_cast<float*>(noobj_mask), nullptr, nullptr,
                                                                    nullptr, grad_losses, grad_out);
   return check_launch();
