@@ -80,6 +80,12 @@ int ppy_activation(void* x, long long count, int act, int dtype, ppy_stream_t s)
  * zero padded; channels [c_begin, c_begin+c_count) of the source are taken (CoordConv weight split). */
 int ppy_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int kh, int kw, int c_begin, int c_count,
                          void* packed, int cout_pad, int cin_pad, int k_pad, int dtype, ppy_stream_t s);
+/* Packed weight of the INPUT-GRADIENT conv of a k x k conv (training head; torch autograd's conv backward, reference train.py:437):
+ * the dgrad conv reads dY (o_pad >= cout channels) and writes c_main channels with the 180-degree-rotated, transposed weight --
+ * packed[ci][tap * o_pad + co] = w[co][ci][kh*kw - 1 - tap], rows ci in [c_main, rows_pad) and columns co >= cout zero.
+ * Same layout as ppy_pack_conv_weight(cout = c_main, cin = o_pad); PPY_BF16 only. */
+int ppy_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin_total, int kh, int kw, int c_main, void* packed, int rows_pad, int o_pad,
+                               int k_pad, int dtype, ppy_stream_t s);
 
 typedef struct ppy_conv_params {
   const void* x;            /* input NHWC, dtype = in_dtype */

@@ -28,6 +28,37 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// Packing of the INPUT-GRADIENT conv's weight straight from the forward weight (conv_autograd._dgrad): the dgrad conv reads dY
+// (o_pad channels) and produces c_main channels with wt[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx], so
+// packed[ci][tap * o_pad + co] = w[co][ci][taps - 1 - tap] -- one launch instead of flip + transposing copy + pack.  32 x 32
+// (co, ci) tiles through shared memory: reads walk ci (contiguous for 1x1, the taps of a row are one contiguous run), writes walk
+// co.  blockIdx.z = tap; the extra z slice zero-fills the K tail [taps * o_pad, k_pad).
+__global__ void __launch_bounds__(256) pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, int cin_total, int taps, int c_main,
+                                                                __nv_bfloat16* __restrict__ out, int rows_pad, int o_pad, int k_pad) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  if (tap == taps) {                     // K tail
+    const int tail = k_pad - taps * o_pad;
+    for (int r = ty; r < 32; r += 8) {
+      const int ci = ci0 + r;
+      for (int col = co0 + tx; col < tail && ci < rows_pad; col += gridDim.x * 32) out[(size_t)ci * k_pad + taps * o_pad + col] = from_f<__nv_bfloat16>(0.f);
+    }
+    return;
+  }
+  const int src_tap = taps - 1 - tap;
+  for (int r = ty; r < 32; r += 8) {     // r = co within the tile, tx = ci
+    const int co = co0 + r, ci = ci0 + tx;
+    tile[r][tx] = (co < cout && ci < c_main) ? __ldg(w + ((size_t)co * cin_total + ci) * taps + src_tap) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {     // r = ci within the tile, tx = co
+    const int ci = ci0 + r, co = co0 + tx;
+    if (ci < rows_pad && co < o_pad) out[(size_t)ci * k_pad + (size_t)tap * o_pad + co] = from_f<__nv_bfloat16>(tile[tx][r]);
+  }
+}
+
 // PPY_F16X2 packing: [2][cout_pad][k_pad] fp16 -- hi plane, then lo plane (w ~ hi + lo to 2^-22).  The caller pre-scales every
 // output channel by a power of two so that the lo parts stay clear of the fp16 subnormal range.
 __global__ void pack_weight_pair_kernel(const float* __restrict__ w, int cout, int cin_total, int kh, int kw, int c_begin,
@@ -205,6 +236,17 @@ int ppy_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int kh, i
     pack_weight_pair_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, kh, kw, c_begin, c_count,
                                                                          (__half*)packed, cout_pad, cin_pad, k_pad);
   else return PPY_ERR_INVALID;
+  return check_launch();
+}
+
+int ppy_pack_conv_weight_dgrad(const float* w_oihw, int cout, int cin_total, int kh, int kw, int c_main, void* packed, int rows_pad, int o_pad,
+                               int k_pad, int dtype, ppy_stream_t s) {
+  PPY_REQUIRE(w_oihw && packed && cout > 0 && cin_total > 0 && kh > 0 && kw > 0 && c_main > 0 && c_main <= cin_total);
+  PPY_REQUIRE(rows_pad >= c_main && o_pad >= cout && k_pad >= kh * kw * o_pad);
+  if (dtype != PPY_BF16) return PPY_ERR_UNSUPPORTED;
+  const int taps = kh * kw;
+  dim3 grid((unsigned)ceil_div(o_pad, 32), (unsigned)ceil_div(rows_pad, 32), (unsigned)(taps + (k_pad > taps * o_pad ? 1 : 0)));
+  pack_weight_dgrad_kernel<<<grid, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, taps, c_main, (__nv_bfloat16*)packed, rows_pad, o_pad, k_pad);
   return check_launch();
 }
 

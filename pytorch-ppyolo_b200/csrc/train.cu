@@ -496,14 +496,25 @@ __global__ void __launch_bounds__(256) sgd_ema_multi_kernel(float* const* __rest
   float* __restrict__ buf = mom + begin;
   float* __restrict__ sh = shadow ? shadow + shadow_offsets[t] : nullptr;
   const float lr_t = lr * lr_mult[t], wd_t = wd[t];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const float w = p[i];
-    const float d = g[i] * grad_scale + wd_t * w;
-    const float b = first_step ? d : momentum * buf[i] + d;
-    buf[i] = b;
-    const float w2 = w - lr_t * b;
-    p[i] = w2;
-    if (sh) sh[i] = __fadd_rn(__fmul_rn(decay, sh[i]), __fmul_rn(one_minus_decay, w2));
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < count; i0 += 4 * stride) {
+    float w[4], gr[4], bu[4], so[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                      // four independent elements in flight per thread and array
+      const long long i = i0 + u * stride;
+      if (i < count) { w[u] = p[i]; gr[u] = g[i]; bu[u] = first_step ? 0.f : buf[i]; so[u] = sh ? sh[i] : 0.f; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= count) continue;
+      const float d = gr[u] * grad_scale + wd_t * w[u];
+      const float b = first_step ? d : momentum * bu[u] + d;
+      buf[i] = b;
+      const float w2 = w[u] - lr_t * b;
+      p[i] = w2;
+      if (sh) sh[i] = __fadd_rn(__fmul_rn(decay, so[u]), __fmul_rn(one_minus_decay, w2));
+    }
   }
 }
 
@@ -581,7 +592,7 @@ int ppy_sgd_ema_multi(float* const* params, const float* grad_flat, float* momen
                       float momentum, float grad_scale, int first_step, float ema_decay, float ema_one_minus_decay, ppy_stream_t s) {
   PPY_REQUIRE(params && grad_flat && momentum_flat && offsets && lr_mult && weight_decay && num_tensors > 0);
   PPY_REQUIRE(!shadow_flat || shadow_offsets);
-  sgd_ema_multi_kernel<<<dim3(64, (unsigned)num_tensors), 256, 0, as_stream(s)>>>(params, grad_flat, momentum_flat, shadow_flat, offsets,
+  sgd_ema_multi_kernel<<<dim3(128, (unsigned)num_tensors), 256, 0, as_stream(s)>>>(params, grad_flat, momentum_flat, shadow_flat, offsets,
                                                                                   shadow_offsets, lr_mult, weight_decay, lr, momentum,
                                                                                   grad_scale, first_step, ema_decay, ema_one_minus_decay);
   return check_launch();

@@ -51,6 +51,7 @@ SIGNATURES = {
     'ppy_copy_channels': (c_int, [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p]),
     'ppy_coord_channels': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_activation': (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p]),
+    'ppy_pack_conv_weight_dgrad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'ppy_pack_conv_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                      c_int, c_void_p]),
     'ppy_stem_conv3x3s2': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float),

@@ -57,12 +57,8 @@ def _dgrad(dyh, weight, c_main, stride, pad, in_hw, out_f32):
         z = torch.zeros((n, hz, wz, o_pad), dtype=dyh.dtype, device=dev)
         z[:, 0:ho * stride:stride, 0:wo * stride:stride] = dyh
         dyh = z
-    if o_pad == cout:                                          # no padded output channels to zero: one flip + one transposing copy
-        wt = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3).contiguous()
-    else:
-        wt = torch.zeros((c_main, o_pad, k, k), dtype=torch.float32, device=dev)
-        wt[:, :cout] = weight.detach()[:, :c_main].flip(2, 3).permute(1, 0, 2, 3)
-    packed_t = ops.pack_weight(wt, PPY_BF16, cache=False)
+    # rotated + transposed + packed in one launch (was: flip, transposing copy, pack)
+    packed_t = ops.pack_weight_dgrad(weight, c_main, o_pad)
     dxh = ops.conv_nhwc(dyh, packed_t, o_pad, c_main, k, 1, k - 1 - pad, _const('one', c_main, dev), _const('zero', c_main, dev),
                         0, PPY_BF16, out_code=PPY_F32 if out_f32 else PPY_BF16)
     return dxh

@@ -115,6 +115,24 @@ def pack_weight(weight, code, c_begin=0, c_count=None, cache=True):
     return result
 
 
+def pack_weight_dgrad(weight, c_main, o_pad):
+    """Packed bf16 weight of the input-gradient conv (dY with ``o_pad`` channels -> ``c_main`` channels) straight from the forward
+    OIHW fp32 weight: 180-degree rotation + transposition + packing in one launch (ppy_pack_conv_weight_dgrad).  Returns the
+    same tuple as ``pack_weight`` of the transposed weight."""
+    _cuda(weight, 'weight')
+    cout, cin_total, kh, kw = weight.shape
+    w32 = weight.detach()
+    if w32.dtype != torch.float32 or not w32.is_contiguous():
+        w32 = w32.float().contiguous()
+    cin_pad = round_up(o_pad, 8)
+    k_pad = round_up(kh * kw * cin_pad, 64)
+    rows_pad = round_up(c_main, 32)
+    packed = torch.empty((rows_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
+    check(lib.ppy_pack_conv_weight_dgrad(ptr(w32), cout, cin_total, kh, kw, c_main, ptr(packed), rows_pad, cin_pad, k_pad, PPY_BF16,
+                                         stream_ptr()), 'pack_conv_weight_dgrad')
+    return packed, cin_pad, k_pad, rows_pad
+
+
 def split_halves(t):
     """fp32 tensor -> (hi, lo) fp16 tensors with t = hi + lo to 2^-22 (torch ops; used for small host-built operands)."""
     hi = t.to(torch.float16)
