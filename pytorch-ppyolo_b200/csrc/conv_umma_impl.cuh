@@ -184,29 +184,32 @@ __device__ __forceinline__ void add_pair8(float4& a, float4& b, const uint4& hi,
 }
 
 // nearest x2 upsample fused into the store: one output pixel -> its 2x2 block (aligned 8-channel vectors)
-__device__ __noinline__ void store_upsampled(const ppy_conv_params& p, int m, int co, int ho, int wo, float4 a, float4 b) {
+// (arguments by value: a reference to the parameter block would make every access a local-memory load -- an L2 round trip next
+// to 200+ KB of shared memory, see epilogue_acc)
+__device__ __noinline__ void store_upsampled(void* y, int y_ld, long long y_plane, int out_dtype, int* overflow, int m, int co, int ho, int wo,
+                                            float4 a, float4 b) {
   const unsigned hw_out = (unsigned)(ho * wo);
   const unsigned pix = (unsigned)m % hw_out, img = (unsigned)m / hw_out;
   const unsigned oy = pix / (unsigned)wo, ox = pix % (unsigned)wo;
   const size_t r0 = ((size_t)img * 2 * ho + 2 * oy) * 2 * wo + 2 * ox;
   const size_t rows[4] = {r0, r0 + 1, r0 + 2 * (size_t)wo, r0 + 2 * (size_t)wo + 1};
-  if (p.out_dtype == PPY_F16X2) {
+  if (out_dtype == PPY_F16X2) {
     uint4 hi, lo;
-    split8(a, b, hi, lo, p.overflow);
+    split8(a, b, hi, lo, overflow);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      __half* d = reinterpret_cast<__half*>(p.y) + rows[q] * p.y_ld + co;
+      __half* d = reinterpret_cast<__half*>(y) + rows[q] * y_ld + co;
       *reinterpret_cast<uint4*>(d) = hi;
-      *reinterpret_cast<uint4*>(d + p.y_plane) = lo;
+      *reinterpret_cast<uint4*>(d + y_plane) = lo;
     }
-  } else if (p.out_dtype == PPY_BF16) {
+  } else if (out_dtype == PPY_BF16) {
     const uint4 v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
 #pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + rows[q] * p.y_ld + co) = v;
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + rows[q] * y_ld + co) = v;
   } else {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + rows[q] * p.y_ld + co);
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + rows[q] * y_ld + co);
       dst[0] = a; dst[1] = b;
     }
   }
@@ -1020,7 +1023,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
                 b.x = fmaxf(b.x, b.x * slope); b.y = fmaxf(b.y, b.y * slope); b.z = fmaxf(b.z, b.z * slope); b.w = fmaxf(b.w, b.w * slope);
               }
               if (p.upsample2x) {
-                store_upsampled(p, m, co, ho, wo, a, b);
+                store_upsampled(p.y, p.y_ld, p.y_plane, p.out_dtype, p.overflow, m, co, ho, wo, a, b);
               } else if (SPLIT && out_bf16) {
                 uint4 hi, lo;
                 split8(a, b, hi, lo, p.overflow);
