@@ -181,9 +181,12 @@ class InferenceEngine(object):
         out = TensorRef(self._new(x.n, x.h, x.w, 4 * x.c))
         return self._simple('spp', lib.ppy_spp, x, out)
 
-    def _stem(self, unit):
+    def _stem(self, unit, raw=False):
+        """``raw``: the conv output itself (scale 1, shift 0, no activation) -- the train-mode BatchNorm kernel follows."""
         from model.custom_layers import ACT_CODES
         scale, shift = unit.folded_scale_shift()
+        if raw:
+            scale, shift = torch.ones_like(scale), torch.zeros_like(shift)
         w_host = np.ascontiguousarray(unit.conv.weight.detach().float().cpu().numpy())
         sc_host = np.ascontiguousarray(scale.cpu().numpy())
         sh_host = np.ascontiguousarray(shift.cpu().numpy())
@@ -193,7 +196,7 @@ class InferenceEngine(object):
         ho, wo = (self.h - 1) // 2 + 1, (self.w - 1) // 2 + 1
         out = TensorRef(self._new(self.n, ho, wo, 32))
         fp = ctypes.POINTER(ctypes.c_float)
-        wargs = (w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp), sh_host.ctypes.data_as(fp), 32, ACT_CODES[unit.act_name],
+        wargs = (w_host.ctypes.data_as(fp), sc_host.ctypes.data_as(fp), sh_host.ctypes.data_as(fp), 32, 0 if raw else ACT_CODES[unit.act_name],
                  ctypes.c_void_p(out.ptr), out.ld)
         if self.input_u8:
             lut = self._keep(torch.from_numpy(normalize_lut(**self.normalize)).to(self.dev))
@@ -412,7 +415,20 @@ class InferenceEngine(object):
         [N,H,W/2,2*cout] is bit-for-bit the [N,H,W,cout] tensor.  Half of the issued MACs multiply structural
         zeros -- the layer is HBM/L2-bound, the tensor pipe has the headroom -- and conv_flops counts the original."""
         from model.custom_layers import ACT_CODES
-        w = unit.conv.weight.detach().float()
+        cout = unit.conv.weight.shape[0]
+        w2 = self._pixel_pair_weight(unit.conv.weight)
+        scale, shift = unit.folded_scale_shift()
+        scale2, shift2 = torch.cat([scale, scale]).contiguous(), torch.cat([shift, shift]).contiguous()
+        xp = x.pixel_pairs()
+        flops_before = self.conv_flops
+        out = self._conv(name, xp, self._keep(w2), scale2, shift2, 1, ACT_CODES[unit.act_name])
+        self.conv_flops = flops_before + 2 * x.n * x.h * x.w * cout * 32 * 9
+        return out.pixel_unpairs(cout)
+
+    @staticmethod
+    def _pixel_pair_weight(weight):
+        """[cout, cin, 3, 3] -> the 3x3 weight over pixel pairs [2 cout, 2 cin, 3, 3] of ``_unit_pixel_pairs``."""
+        w = weight.detach().float()
         cout, cin, k, _ = w.shape
         w2 = torch.zeros((2 * cout, 2 * cin, 3, 3), dtype=torch.float32, device=w.device)
         for px in range(2):
@@ -421,22 +437,18 @@ class InferenceEngine(object):
                     kx = 2 * d + qx - px + 1
                     if 0 <= kx <= 2:
                         w2[px * cout:(px + 1) * cout, qx * cin:(qx + 1) * cin, :, d + 1] = w[:, :, :, kx]
-        scale, shift = unit.folded_scale_shift()
-        scale2, shift2 = torch.cat([scale, scale]).contiguous(), torch.cat([shift, shift]).contiguous()
-        xp = x.pixel_pairs()
-        flops_before = self.conv_flops
-        out = self._conv(name, xp, self._keep(w2), scale2, shift2, 1, ACT_CODES[unit.act_name])
-        self.conv_flops = flops_before + 2 * x.n * x.h * x.w * cout * cin * 9
-        return out.pixel_unpairs(cout)
+        return w2
 
-    def _unit_batch_stats(self, name, unit, x, residual, act, dst, coord):
+    def _unit_batch_stats(self, name, unit, x, residual, act, dst, coord, raw=None):
         """conv (raw) -> per-channel batch statistics (+ running-stat update) -> normalise + residual + act."""
         from model.custom_layers import DCNv2
         bn = unit.bn
         cout = bn.num_features
         one = torch.ones(cout, dtype=torch.float32, device=self.dev)
         zero = torch.zeros(cout, dtype=torch.float32, device=self.dev)
-        if isinstance(unit.conv, DCNv2):
+        if raw is not None:
+            pass                               # (the caller ran the conv: the fused stem kernel)
+        elif isinstance(unit.conv, DCNv2):
             d = unit.conv
             n_om = d.conv_offset.weight.shape[0]
             om = self._conv(name + '.offset', x, d.conv_offset.weight.detach(), torch.ones(n_om, dtype=torch.float32, device=self.dev),
@@ -450,7 +462,19 @@ class InferenceEngine(object):
                 raw = self._conv(name + '.raw', x, d.dcn_weight.detach(), one, bias, unit.stride, 0, offset_mask=om)
         else:
             bias = unit.conv.bias.detach().float() if unit.conv.bias is not None else zero
-            raw = self._conv(name + '.raw', x, unit.conv.weight.detach(), one, bias, unit.stride, 0, coord=coord)
+            pairable = (self.code == PPY_BF16 and unit.stride == 1 and tuple(unit.conv.weight.shape[1:]) == (32, 3, 3) and x.c == 32 and
+                        x.ld == 32 and x.c_off == 0 and x.w % 2 == 0 and cout % 8 == 0 and unit.conv.bias is None and not coord and
+                        not os.environ.get('PPY_NO_TRAIN_PIXEL_PAIRS'))
+            if pairable:
+                # the stem's 32-channel 3x3 convs on the pixel-pair view (see _unit_pixel_pairs): full 128-byte K rows through the
+                # 4-D TMA patch loader instead of the cp.async gather mode (2 launches of a bs-8 step: 0.39 -> ~0.1 ms); the raw
+                # output [N,H,W/2,2 cout] IS the [N,H,W,cout] tensor the statistics kernel reads
+                flops_before = self.conv_flops
+                raw = self._conv(name + '.raw', x.pixel_pairs(), self._keep(self._pixel_pair_weight(unit.conv.weight)),
+                                 torch.cat([one, one]).contiguous(), torch.cat([zero, zero]).contiguous(), 1, 0).pixel_unpairs(cout)
+                self.conv_flops = flops_before + 2 * x.n * x.h * x.w * cout * 32 * 9
+            else:
+                raw = self._conv(name + '.raw', x, unit.conv.weight.detach(), one, bias, unit.stride, 0, coord=coord)
         if dst is None:
             dst = TensorRef(self._new(raw.n, raw.h, raw.w, ops.round_up(cout, 8)), c=cout)
         scale = self._keep(torch.empty(cout, dtype=torch.float32, device=self.dev))
@@ -646,10 +670,17 @@ class InferenceEngine(object):
         self.im_size = torch.zeros((n, 2), dtype=torch.float32, device=self.dev)
         stem_units = list(zip(bb._stem_units(), ('conv1_1', 'conv1_2', 'conv1_3')))
         u0 = stem_units[0][0]
-        if (not self.train_bn and tuple(u0.conv.weight.shape) == (32, 3, 3, 3) and u0.stride == 2 and
-                u0.act_name in (None, 'relu', 'leaky')):
+        stem_ok = tuple(u0.conv.weight.shape) == (32, 3, 3, 3) and u0.stride == 2 and u0.act_name in (None, 'relu', 'leaky')
+        if stem_ok and not self.train_bn:
             # conv1_1 fused with the NCHW->NHWC change (K = 27: HBM-bound, fp32 SIMT, weights in the constant bank)
             x0 = self._stem(u0)
+            stem_units = stem_units[1:]
+        elif (stem_ok and self.code == PPY_BF16 and u0.bn is not None and u0.conv.bias is None and not self.input_u8 and
+              not os.environ.get('PPY_NO_TRAIN_STEM')):
+            # train-mode BatchNorm: the same kernel writes the RAW conv output (scale 1, shift 0, no activation) for the statistics
+            # kernel -- instead of a layout pass + the generic gather-mode conv over 3 channels padded to 8
+            from model.custom_layers import ACT_CODES
+            x0 = self._unit_batch_stats('stem.conv1_1', u0, None, None, ACT_CODES[u0.act_name], None, False, raw=self._stem(u0, raw=True))
             stem_units = stem_units[1:]
         elif self.input_u8:
             raise NotImplementedError('uint8 input needs the fused 3 -> 32 stride-2 stem conv (both PP-YOLO backbones have it)')
