@@ -17,14 +17,18 @@ constexpr int BM = 64, BN = 64, BK = 16, THREADS = 256;
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin_total, int kh, int kw, int c_begin,
                                    int c_count, T* __restrict__ out, int cout_pad, int cin_pad, int k_pad) {
-  const long long total = (long long)cout_pad * k_pad;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i / k_pad), k = (int)(i % k_pad);
-    const int tap = k / cin_pad, c = k % cin_pad;
-    float v = 0.f;
-    if (co < cout && tap < kh * kw && c < c_count)
-      v = __ldg(w + (((long long)co * cin_total + c_begin + c) * kh + tap / kw) * kw + tap % kw);
-    out[i] = from_f<T>(v);
+  // one row (output channel) per blockIdx.y, 32-bit index arithmetic inside the row (two 64-bit divisions per element were most
+  // of these small launches)
+  const int taps = kh * kw;
+  for (int co = blockIdx.y; co < cout_pad; co += gridDim.y) {
+    T* row = out + (size_t)co * k_pad;
+    const float* wrow = w + ((size_t)co * cin_total + c_begin) * taps;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < (unsigned)k_pad; k += gridDim.x * blockDim.x) {
+      const unsigned tap = k / (unsigned)cin_pad, c = k - tap * (unsigned)cin_pad;
+      float v = 0.f;
+      if (co < cout && tap < (unsigned)taps && c < (unsigned)c_count) v = __ldg(wrow + (size_t)c * taps + tap);
+      row[k] = from_f<T>(v);
+    }
   }
 }
 
@@ -226,12 +230,13 @@ int ppy_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int kh, i
   const long long total = (long long)cout_pad * k_pad;
   long long blocks = ceil_div(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  const dim3 grid2((unsigned)(k_pad >= 1024 ? 4 : 1), (unsigned)(cout_pad < 65535 ? cout_pad : 65535));      // (row, K chunk) blocks
   if (dtype == PPY_BF16)
-    pack_weight_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, as_stream(s)>>>(
+    pack_weight_kernel<__nv_bfloat16><<<grid2, 256, 0, as_stream(s)>>>(
         w_oihw, cout, cin_total, kh, kw, c_begin, c_count, (__nv_bfloat16*)packed, cout_pad, cin_pad, k_pad);
   else if (dtype == PPY_F32)
-    pack_weight_kernel<float><<<(unsigned)blocks, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, kh, kw, c_begin,
-                                                                           c_count, (float*)packed, cout_pad, cin_pad, k_pad);
+    pack_weight_kernel<float><<<grid2, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, kh, kw, c_begin,
+                                                                c_count, (float*)packed, cout_pad, cin_pad, k_pad);
   else if (dtype == PPY_F16X2)
     pack_weight_pair_kernel<<<(unsigned)blocks, 256, 0, as_stream(s)>>>(w_oihw, cout, cin_total, kh, kw, c_begin, c_count,
                                                                          (__half*)packed, cout_pad, cin_pad, k_pad);

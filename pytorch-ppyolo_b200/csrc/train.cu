@@ -433,37 +433,49 @@ inline unsigned blocks_for(long long work, int threads, long long cap = 148ll * 
 // 128-byte channel runs of NHWC pixels, writes 128-byte pixel runs of one output row.
 __global__ void __launch_bounds__(256) kmajor_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, int n, int h, int w, int c, int k, int pad,
                                                      int stride, int ho, int wo, __nv_bfloat16* __restrict__ out, long long m_pad) {
-  __shared__ __nv_bfloat16 tile[64][64 + 2];
+  // tile[pixel row][16-byte chunk of 8 channels], chunk index XOR-swizzled with (row / 8): the 16-byte row stores and the 32-bit
+  // column reads of the transpose are both bank-conflict free (the first version moved every element with 2-byte shared-memory
+  // accesses: 32 per thread, instruction-bound at ~1.6 TB/s of writes)
+  __shared__ uint4 tile[64][8];
   const long long m0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64, tap = blockIdx.z, ky = tap / k, kx = tap % k;
   const long long M = (long long)n * ho * wo;          // columns = OUTPUT pixels (stride 1: the input's own grid)
-  // load: thread -> (pixel row r = tid / 4 (+ 0 / 64 stride over two passes), 16 channels = two 16-byte vectors)
+  // load: thread -> (pixel row r, 8 channels = one 16-byte vector), two passes
   for (int e = threadIdx.x; e < 64 * 8; e += 256) {
     const int r = e >> 3, v = e & 7;
     const long long m = m0 + r;
     uint4 val = make_uint4(0u, 0u, 0u, 0u);
     if (m < M && c0 + v * 8 < c) {
-      const int px = (int)(m % wo), py = (int)((m / wo) % ho);
-      const long long img = m / ((long long)wo * ho);
+      // (32-bit index arithmetic: M < 2^31 is checked by the caller; three 64-bit divisions per vector were most of the kernel)
+      const unsigned mu = (unsigned)m, rowi = mu / (unsigned)wo;
+      const int px = (int)(mu - rowi * (unsigned)wo), py = (int)(rowi % (unsigned)ho);
+      const long long img = rowi / (unsigned)ho;
       const int iy = py * stride + ky - pad, ix = px * stride + kx - pad;
       if (iy >= 0 && iy < h && ix >= 0 && ix < w)
         val = __ldg(reinterpret_cast<const uint4*>(x + ((img * h + iy) * w + ix) * x_ld + c0 + v * 8));
     }
-    const __nv_bfloat16* ev = reinterpret_cast<const __nv_bfloat16*>(&val);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) tile[r][v * 8 + j] = ev[j];
+    tile[r][v ^ ((r >> 3) & 7)] = val;
   }
   __syncthreads();
-  // store: thread -> (channel row cc = e / 8, eight consecutive pixels)
+  // store: thread -> (channel PAIR cp, eight consecutive pixels 8v .. 8v+7): eight 32-bit reads (two channels of one pixel each),
+  // byte-permuted into the two channels' 16-byte pixel runs
   const int taps = k * k;
-  for (int e = threadIdx.x; e < 64 * 8; e += 256) {
-    const int cc = e >> 3, v = e & 7;
-    if (c0 + cc >= c || m0 + v * 8 >= m_pad) continue;
-    uint4 val;
-    __nv_bfloat16* ev = reinterpret_cast<__nv_bfloat16*>(&val);
+  const int cp = threadIdx.x >> 3, v = threadIdx.x & 7;
+  const int chunk = cp >> 2, wi = cp & 3;
+  uint32_t q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ev[j] = tile[v * 8 + j][cc];
-    *reinterpret_cast<uint4*>(out + ((long long)(c0 + cc) * taps + tap) * m_pad + m0 + v * 8) = val;
+  for (int j = 0; j < 8; ++j) q[j] = reinterpret_cast<const uint32_t*>(&tile[v * 8 + j][chunk ^ v])[wi];
+  if (m0 + v * 8 >= m_pad) return;
+  const int cc = c0 + 2 * cp;
+  if (cc < c) {
+    const uint4 lo = make_uint4(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410), __byte_perm(q[4], q[5], 0x5410),
+                                __byte_perm(q[6], q[7], 0x5410));
+    *reinterpret_cast<uint4*>(out + ((long long)cc * taps + tap) * m_pad + m0 + v * 8) = lo;
+  }
+  if (cc + 1 < c) {
+    const uint4 hi = make_uint4(__byte_perm(q[0], q[1], 0x7632), __byte_perm(q[2], q[3], 0x7632), __byte_perm(q[4], q[5], 0x7632),
+                                __byte_perm(q[6], q[7], 0x7632));
+    *reinterpret_cast<uint4*>(out + ((long long)(cc + 1) * taps + tap) * m_pad + m0 + v * 8) = hi;
   }
 }
 
@@ -713,7 +725,7 @@ int ppy_im2col_kmajor_strided(const void* x, int x_ld, int n, int h, int w, int 
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   PPY_REQUIRE(ho > 0 && wo > 0);
   const long long M = (long long)n * ho * wo;
-  PPY_REQUIRE(m_pad >= M && m_pad % 64 == 0 && m_pad / 64 < 0x7FFFFFFFll);
+  PPY_REQUIRE(m_pad >= M && m_pad % 64 == 0 && m_pad < 0x7FFFFFFFll);      // (the kernel indexes pixels with 32 bits)
   dim3 grid((unsigned)(m_pad / 64), (unsigned)ceil_div(c, 64), (unsigned)(k * k));
   kmajor_kernel<<<grid, 256, 0, as_stream(s)>>>((const __nv_bfloat16*)x, x_ld, n, h, w, c, k, pad, stride, ho, wo, (__nv_bfloat16*)out, m_pad);
   return check_launch();
