@@ -94,17 +94,10 @@ __global__ void __launch_bounds__(512, 2) allreduce_sgd_ema_kernel(const PeerSte
   const long long lo = per * a.rank, hi = lo + per < a.total4 ? lo + per : a.total4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (a.grad_mc != nullptr) {
-    // four in-switch reductions in flight per thread (each is an NVLink round trip of a few microseconds; one at a time left
-    // the slice latency-bound), then their four multicast stores
-    for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += 4 * stride) {
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i0 + u * stride < hi) v[u] = multimem_ld_reduce_add(a.grad_mc + 4 * (i0 + u * stride));
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (i0 + u * stride < hi) multimem_st(a.grad_mc + 4 * (i0 + u * stride), v[u]);
-    }
+    // (four reductions in flight per thread were measured: no gain at 2 GPUs, 0.40 -> 0.45 ms at 8 -- the phase is bound by the
+    // barriers and the rank skew, not by requests in flight)
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
+      multimem_st(a.grad_mc + 4 * i, multimem_ld_reduce_add(a.grad_mc + 4 * i));
   } else {
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
