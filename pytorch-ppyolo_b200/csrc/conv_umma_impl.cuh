@@ -1385,7 +1385,13 @@ int dispatch(const ppy_conv_params* p, int ho, int wo, cudaStream_t st) {
     // CTA pairs (cta_group::2, 256 x BN tiles, B split across the pair) for every TMA-fed layer with at least two M tiles
     static const bool no_pair = knob_off("PPY_NO_CTA2");
     if (!no_pair && (long long)p->n * ho * wo > BLOCK_M) {
-      if (c % 256 == 0) return tma_epi ? launch<256, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
+      // few tiles (small batches: the 19 x 19 maps of a bs-8 training step give 24 pair tiles at BLOCK_N 256 -- 48 of 148 SMs):
+      // 128-wide tiles when twice as many CTAs still fit one wave
+      static const bool no_narrow = knob_off("PPY_NO_NARROW_TILES");
+      const long long ctas256 = 2 * ceil_div((long long)p->n * ho * wo, 2ll * BLOCK_M) * (c / 256);
+      const bool narrow = !no_narrow && c % 256 == 0 && 2 * ctas256 <= num_sms();
+      if (c % 256 == 0 && !narrow)
+        return tma_epi ? launch<256, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<256, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
       return tma_epi ? launch<128, MODE, EPI_TMA, false, true>(p, ho, wo, st) : launch<128, MODE, EPI_SLAB, false, true>(p, ho, wo, st);
     }
   }
