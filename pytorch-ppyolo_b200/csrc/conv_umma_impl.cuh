@@ -129,8 +129,10 @@ template <int BN, int MODE, int EPI, bool CTA2 = false> struct TileCfg {
   static constexpr int kResBufs = kSlab ? 1 : 2;
   static constexpr int kEpiWarpBytes = (kResBufs + 1) * BOX_BYTES;
   static constexpr int kEpiBytes = EPI == EPI_TMA ? EPI_WARPS * (kEpiWarpBytes + EPI_TABLE_FLOATS * 4) : STAGING_BYTES;
-  static constexpr int kFixedBytes = kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kParamBytes = 320;      // shared-memory copy of the parameter block for the out-of-line generic epilogue
+  static constexpr int kFixedBytes = kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kParamBytes;
   static constexpr int kFit = (232448 - kFixedBytes) / (kAStageBytes + kBStageBytes);
+  static_assert(kFit == (232448 - (kFixedBytes - kParamBytes)) / (kAStageBytes + kBStageBytes), "the parameter copy must not cost a pipeline stage");
   static constexpr int kWant = CTA2 ? (EPI == EPI_TMA ? (BN == 256 ? 4 : 6) : (BN == 256 ? 6 : 8))
                                     : (EPI == EPI_TMA ? (BN == 256 ? 3 : (BN == 128 ? 4 : 6)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int kStages = (kSlab || SPLIT) ? (kFit < 4 ? kFit : 4) : (kFit < kWant ? kFit : kWant);
@@ -217,13 +219,14 @@ __device__ __noinline__ void store_upsampled(void* y, int y_ld, long long y_plan
 
 // Generic (unaligned / partial-vector / upsampling / fp32-residual) epilogue for 8 channels of one output row.
 // Kept out of line so the hot path of the kernel stays small enough for the instruction cache.
-__device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, const float* acc8, int m, int co, int ho, int wo, float slope) {
+__device__ __noinline__ void epilogue_slow(const ppy_conv_params& p, float4 va, float4 vb, int m, int co, int ho, int wo, float slope) {
+  // (p: the CTA's shared-memory copy of the parameter block; the eight values by value -- registers, not a local array)
   const int ncol = (p.cout - co) < 8 ? (p.cout - co) : 8;
   const int hw_out = ho * wo;
   const int pix = m % hw_out, img = m / hw_out;
   const int oy = pix / wo, ox = pix % wo;
   for (int e = 0; e < ncol; ++e) {
-    float f = acc8[e];
+    float f = e == 0 ? va.x : e == 1 ? va.y : e == 2 ? va.z : e == 3 ? va.w : e == 4 ? vb.x : e == 5 ? vb.y : e == 6 ? vb.z : vb.w;
     if (p.bias_map) f += __ldg(p.bias_map + (size_t)pix * p.cout + co + e);
     if (p.coord_w) f += __ldg(p.coord_w + co + e) * (__fdiv_rn((float)ox, (float)(wo - 1)) * 2.f - 1.f) +
                         __ldg(p.coord_w + p.cout + co + e) * (__fdiv_rn((float)oy, (float)(ho - 1)) * 2.f - 1.f);
@@ -350,6 +353,13 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform for the compiler: role branches are not divergent
+  // The out-of-line generic epilogue takes the parameter block by reference.  Handing it the kernel parameter itself makes the
+  // compiler keep a per-thread copy in LOCAL memory -- and next to 200+ KB of shared memory the L1 holds nothing, so every field
+  // access there is an L2 round trip (~2,400 cycles per call: the 2-channel tail convs of the head outputs and the 27-channel DCN
+  // offset convs take that path for every row).  One copy per CTA in shared memory instead.
+  static_assert(sizeof(ppy_conv_params) <= Cfg::kParamBytes, "parameter block larger than its shared-memory slot");
+  ppy_conv_params* const p_smem = reinterpret_cast<ppy_conv_params*>(gen_base + stg_off + Cfg::kEpiBytes + 512);
+  if (tid == 32) *p_smem = p;                                      // (published by the barrier below)
   const long long M = (long long)p.n * ho * wo;
   const int num_tiles = ACC ? num_m_tiles * num_n_tiles * num_splits * num_taps : num_m_tiles * num_n_tiles;
 
@@ -1048,9 +1058,7 @@ conv_umma_kernel(const ppy_conv_params p, const int ho, const int wo, const int 
               if constexpr (ACC) {
                 epilogue_acc(reinterpret_cast<float*>(p.y), p.y_ld, p.cout, p.scale, p.shift, a, b, mrow[ps], co, u.tap * p.wgrad_tap_stride, u.sp == 0);
               } else {
-                float tmp[8];
-                tmp[0] = a.x; tmp[1] = a.y; tmp[2] = a.z; tmp[3] = a.w; tmp[4] = b.x; tmp[5] = b.y; tmp[6] = b.z; tmp[7] = b.w;
-                epilogue_slow(p, tmp, mrow[ps], co, ho, wo, slope);
+                epilogue_slow(*p_smem, a, b, mrow[ps], co, ho, wo, slope);
               }
             }
           }
