@@ -7,6 +7,10 @@
 //   bn_finalize   mean / biased var -> folded scale, shift; running stats <- (1-m)*running + m*(mean, unbiased var)
 //   scale_shift   y = act(x*scale[c] + shift[c] (+ residual)), 16-byte channel vectors
 //   sgd_momentum  g' = g*grad_scale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
+//   bn_train_fused   statistics + finalize + normalise (+ residual, + activation) of one layer as ONE cooperative launch
+//   bn_act_backward  activation' * dy, both BatchNorm reductions and dx of a head layer as ONE cooperative launch
+//   kmajor           K-major (pixel-contiguous) operands of the weight-gradient GEMM: transposed im2col
+//   sgd_ema_multi    optimizer step + EMA of all trainable tensors in one launch
 #include <stdlib.h>
 #include <cooperative_groups.h>
 #include "common.cuh"
